@@ -1,0 +1,209 @@
+/*
+ * rebound_b200.h -- C ABI of the B200-native force / collision / kick-drift hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only.  Every hot-path
+ * entry point names the reference function (file:line in hannorein/rebound v5.0.0,
+ * paths relative to the reference root) whose behaviour it replaces.  The shim
+ * translation units under rebound_b200/shim/ forward the reference's own symbols
+ * (reb_gravity_basic_calculate_acceleration, ...) to these functions, see
+ * INTEGRATION.md.
+ *
+ * The same structs are used by the CPU oracle (oracle/oracle.c, prefix orc_) and by
+ * the reference harness (oracle/ref_harness.c, prefix refh_) so that the parity
+ * tests can drive all three through one ctypes binding.
+ *
+ * All arithmetic is IEEE binary64.  All functions returning int return 0 on success
+ * and a negative REBCU_ERR_* code on failure; rebcu_last_error() gives the message
+ * (the text equals the reference's reb_simulation_error() text where one exists).
+ */
+#ifndef REBOUND_B200_H
+#define REBOUND_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REBCU_SIZE_MAX UINT64_MAX
+
+/* Layout of struct reb_particle (src/rebound.h:86-104): 11 doubles + 3 pointers = 112 B. */
+typedef struct rebcu_particle {
+    double x, y, z;
+    double vx, vy, vz;
+    double ax, ay, az;
+    double m;
+    double r;
+    uint64_t name;   /* const char*            -- carried through untouched */
+    uint64_t ap;     /* void*                  -- carried through untouched */
+    uint64_t sim;    /* struct reb_simulation* -- carried through untouched */
+} rebcu_particle;
+
+/* Layout of struct reb_vec6d (src/rebound.h:134-141). */
+typedef struct rebcu_vec6d { double x, y, z, vx, vy, vz; } rebcu_vec6d;
+
+/* Layout of struct reb_collision (src/rebound.h:144-149): 72 B. */
+typedef struct rebcu_collision {
+    uint64_t p1;
+    uint64_t p2;
+    rebcu_vec6d gb;
+    uint64_t ri;
+} rebcu_collision;
+
+/* Enum values are the reference's (src/rebound.h:372-393). */
+enum { REBCU_COLLISION_NONE = 0, REBCU_COLLISION_DIRECT = 1, REBCU_COLLISION_TREE = 2 };
+enum { REBCU_BOUNDARY_NONE = 0, REBCU_BOUNDARY_OPEN = 1, REBCU_BOUNDARY_PERIODIC = 2, REBCU_BOUNDARY_SHEAR = 3 };
+enum { REBCU_GRAVITY_NONE = 0, REBCU_GRAVITY_BASIC = 1, REBCU_GRAVITY_COMPENSATED = 2, REBCU_GRAVITY_TREE = 3 };
+enum { REBCU_IGNORE_TERMS_NONE = 0, REBCU_IGNORE_TERMS_BETWEEN_0_AND_1 = 1, REBCU_IGNORE_TERMS_INVOLVING_0 = 2 };
+/* Integrators are selected by name in the reference (src/simulation.c:217-238). */
+enum { REBCU_INTEGRATOR_NONE = 0, REBCU_INTEGRATOR_LEAPFROG = 1, REBCU_INTEGRATOR_SEI = 2 };
+/* Arithmetic mode of the direct-summation and tree-walk kernels:
+ *   STRICT: per-particle ascending-j accumulation, no FMA contraction, IEEE sqrt and divide
+ *           => bit-identical to the reference C build (-std=c99, src/Makefile.defs:5).
+ *   FAST:   FMA + rsqrt/Newton, j split across lanes; <= 1e-12 relative of STRICT. */
+enum { REBCU_MODE_STRICT = 0, REBCU_MODE_FAST = 1 };
+
+/* The scalar fields of struct reb_simulation (src/rebound.h:238-413) the hot path reads.
+ * The shim fills this from `r` before each call and writes back t / dt_last_done /
+ * gravity_ignore_terms after it. */
+typedef struct rebcu_config {
+    double t;
+    double G;
+    double softening;
+    double OMEGA;
+    double OMEGAZ;
+    double dt;
+    double dt_last_done;
+    double opening_angle2;
+    double root_size;
+    uint64_t N_active;            /* REBCU_SIZE_MAX: all particles are active */
+    int32_t testparticle_type;
+    int32_t gravity_ignore_terms;
+    int32_t N_root_x, N_root_y, N_root_z;
+    int32_t N_ghost_x, N_ghost_y, N_ghost_z;
+    int32_t boundary;
+    int32_t gravity;
+    int32_t collision;
+    int32_t integrator;
+    int32_t leapfrog_order;       /* struct reb_integrator_leapfrog_state.order (integrator_leapfrog.h:30-32) */
+    int32_t mode;                 /* REBCU_MODE_* */
+} rebcu_config;
+
+/* One cell of the octree in depth-first pre-order (octants ascending), the order in which the
+ * reference's recursive functions visit its pointer tree (src/tree.h:34-56, src/tree.c:285-289).
+ * `skip` is the pre-order index of the first cell after this cell's subtree. */
+typedef struct rebcu_treecell {
+    double x, y, z, w;        /* geometric centre and width (tree.c:87-102) */
+    double m, mx, my, mz;     /* mass and centre of mass    (tree.c:147-207) */
+    int32_t pt;               /* particle index (leaf) or -(number of particles) (tree.c:112,127,129) */
+    int32_t skip;
+    int32_t depth;            /* 0 = root cell */
+    int32_t rootbox;
+} rebcu_treecell;
+
+enum {
+    REBCU_OK = 0,
+    REBCU_ERR_CUDA = -1,              /* CUDA runtime failure */
+    REBCU_ERR_ARG = -2,               /* invalid argument */
+    REBCU_ERR_ROOT_SIZE = -3,         /* tree.c:255-258 */
+    REBCU_ERR_OUTSIDE_BOX = -4,       /* tree.c:265-268 */
+    REBCU_ERR_NONFINITE = -5,         /* tree.c:66-69 */
+    REBCU_ERR_SAME_COORDINATES = -6,  /* tree.c:119-123 */
+    REBCU_ERR_LEAPFROG_ORDER = -7,    /* integrator_leapfrog.c:204-206 */
+    REBCU_ERR_CAPACITY = -8,          /* caller-provided output buffer too small */
+    REBCU_ERR_CELL_SIZE_ZERO = -9,    /* tree.c:107-111 */
+    REBCU_ERR_NOT_RESIDENT = -10      /* resident call without a prior rebcu_upload */
+};
+
+typedef struct rebcu_handle rebcu_handle;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* One handle per simulation (the reference keeps all state in the caller-owned struct
+ * reb_simulation, src/simulation.c:98; the struct is size-frozen, so device state lives here).
+ * `stream` is a cudaStream_t (NULL = a private non-blocking stream). */
+rebcu_handle* rebcu_create(int device, void* stream);
+void rebcu_destroy(rebcu_handle* h);
+const char* rebcu_last_error(const rebcu_handle* h);
+int rebcu_version(void);
+int rebcu_device_count(void);
+void* rebcu_stream(const rebcu_handle* h);
+int rebcu_synchronize(rebcu_handle* h);
+/* Pin / unpin a caller-owned host buffer (e.g. r->particles) for full-rate PCIe copies. */
+int rebcu_host_register(void* ptr, uint64_t bytes);
+int rebcu_host_unregister(void* ptr);
+
+/* ---- residency (r->particles AoS <-> device SoA) ---------------------------------------- */
+/* Modelled on the reference's is_synchronized / did_modify_particles protocol
+ * (src/simulation.c:633-637, src/particle.c:75,345,371). */
+int rebcu_upload(rebcu_handle* h, const rebcu_particle* particles, uint64_t N);
+int rebcu_download(rebcu_handle* h, rebcu_particle* particles, uint64_t N);
+/* Only ax,ay,az are written back (what a gravity routine produces). */
+int rebcu_download_acc(rebcu_handle* h, rebcu_particle* particles, uint64_t N);
+uint64_t rebcu_N(const rebcu_handle* h);
+/* Device pointer of one resident SoA field (0..10 = x,y,z,vx,vy,vz,ax,ay,az,m,r), for
+ * torch.distributed plumbing; length rebcu_N(h) doubles. */
+void* rebcu_device_field(rebcu_handle* h, int field);
+
+/* ---- resident hot path ------------------------------------------------------------------- */
+/* reb_simulation_update_acceleration, src/simulation.c:640-689 (NONE/BASIC/COMPENSATED/TREE).
+ * For TREE this includes the boundary check at gravity.c:56, so N may change. */
+int rebcu_update_acceleration(rebcu_handle* h, rebcu_config* cfg);
+/* reb_integrator_leapfrog_step (integrator_leapfrog.c:97-209) / reb_integrator_sei_step
+ * (integrator_sei.c:86-117), selected by cfg->integrator.  Advances cfg->t, sets dt_last_done. */
+int rebcu_integrator_step(rebcu_handle* h, rebcu_config* cfg);
+/* reb_boundary_check, src/boundary.c:35-141.  OPEN removes particles (order preserving,
+ * N_active decremented as in particle.c:364-366): cfg->N_active and rebcu_N() change. */
+int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg);
+/* The search part of reb_collision_search (src/collision.c:49-331): fills a device list in the
+ * serial build's order and copies it to `out` (capacity `cap` entries); *n_found is the full count.
+ * The shuffle and the resolve loop (collision.c:336-404) stay with the caller. */
+int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg,
+                           rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+/* reb_simulation_steps for a simulation without host callbacks (src/simulation.c:504-603):
+ * n x { integrator step; boundary check; collision search }.  With cfg->collision != NONE the
+ * collision list of the LAST step is left on the device (rebcu_collisions_fetch). */
+int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps);
+int rebcu_collisions_fetch(rebcu_handle* h, rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+
+/* ---- tree inspection (parity tests; reb_tree_construct + reb_tree_calculate_gravity_data,
+ *      src/tree.c:254-271, 209-229) --------------------------------------------------------- */
+int rebcu_tree_build(rebcu_handle* h, const rebcu_config* cfg);
+uint64_t rebcu_tree_cell_count(const rebcu_handle* h);
+int rebcu_tree_fetch(rebcu_handle* h, rebcu_treecell* out, uint64_t cap);
+
+/* ---- host-buffer drop-ins (what the shim calls when the data lives in r->particles) ------ */
+/* reb_gravity_basic_calculate_acceleration        src/gravity.c:167-282
+ * reb_gravity_compensated_calculate_acceleration  src/gravity.c:284-531
+ * reb_gravity_tree_calculate_acceleration         src/gravity.c:47-106
+ * Upload x,y,z,m -> kernel -> write ax,ay,az into the caller's AoS.  cfg->gravity selects. */
+int rebcu_gravity_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N);
+/* reb_collision_search (search part) on a host AoS. */
+int rebcu_collision_search_host(rebcu_handle* h, const rebcu_config* cfg,
+                                const rebcu_particle* particles, uint64_t N,
+                                rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+/* reb_simulation_steps on a host AoS: upload, n steps resident, download. */
+int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N,
+                     uint64_t n_steps);
+
+/* ---- multi-GPU sharding ------------------------------------------------------- */
+/* Rank `rank` of `world` owns the contiguous i-block [N*rank/world, N*(rank+1)/world): the direct
+ * and tree force kernels and kick/drift touch only that block; positions of the other blocks are
+ * refreshed by the caller's all-gather on rebcu_device_field(0..2) between drift and force. */
+int rebcu_set_shard(rebcu_handle* h, int rank, int world);
+void rebcu_shard_range(const rebcu_handle* h, uint64_t* begin, uint64_t* end);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+/* Number of kernels this handle launched since creation (bench.py's gpu_launches). */
+uint64_t rebcu_launch_count(const rebcu_handle* h);
+/* Device time in ms (CUDA events on the handle's stream) accumulated per kernel class since the
+ * last reset; classes: 0 direct force, 1 kick/drift, 2 tree build, 3 tree walk, 4 collision,
+ * 5 boundary, 6 pack/unpack.  Enabled by rebcu_timing_enable (adds event records per launch). */
+int rebcu_timing_enable(rebcu_handle* h, int on);
+int rebcu_timing_read(rebcu_handle* h, double* ms_out, uint64_t* launches_out, int n_classes);
+int rebcu_timing_reset(rebcu_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBOUND_B200_H */

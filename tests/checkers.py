@@ -1,0 +1,161 @@
+"""CPU checkers for the parity tests: the oracle restatement (oracle/liboracle.so) and, when it has
+been built in this container, the unmodified reference behind oracle/ref_harness.c
+(oracle/_ref/libref_harness*.so).  TEST INFRASTRUCTURE ONLY -- the product never imports this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from rebound_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+class CheckerError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class Checker:
+    """Uniform Python face of liboracle.so (prefix orc_) and libref_harness*.so (prefix refh_)."""
+
+    def __init__(self, path, prefix, kind):
+        self.lib = C.CDLL(path)
+        self.f = abi.bind(self.lib, prefix, abi.CHECKER_SIGNATURES)
+        self.kind = kind
+        self.path = path
+
+    def _check(self, err):
+        if err != 0:
+            raise CheckerError(err, self.f["last_error"]().decode())
+
+    def gravity(self, cfg, p):
+        p = p.copy()
+        c = cfg.copy()
+        n = C.c_uint64(len(p))
+        self._check(self.f["gravity"](C.byref(c), abi.as_ptr(p), C.byref(n)))
+        return p[: n.value], c
+
+    def gravity_timed(self, cfg, p, n_evals=1):
+        p = p.copy()
+        c = cfg.copy()
+        n = C.c_uint64(len(p))
+        sec = C.c_double(0)
+        self._check(self.f["gravity_timed"](C.byref(c), abi.as_ptr(p), C.byref(n), n_evals, C.byref(sec)))
+        return p[: n.value], sec.value
+
+    def boundary_check(self, cfg, p):
+        p = p.copy()
+        c = cfg.copy()
+        n = C.c_uint64(len(p))
+        self._check(self.f["boundary_check"](C.byref(c), abi.as_ptr(p), C.byref(n)))
+        return p[: n.value], c
+
+    def integrator_step(self, cfg, p):
+        p = p.copy()
+        c = cfg.copy()
+        n = C.c_uint64(len(p))
+        self._check(self.f["integrator_step"](C.byref(c), abi.as_ptr(p), C.byref(n)))
+        return p[: n.value], c
+
+    def collision_search(self, cfg, p, cap=None):
+        p = p.copy()
+        c = cfg.copy()
+        cap = cap or max(64, 8 * len(p))
+        out = np.zeros(cap, dtype=abi.COLLISION_DTYPE)
+        n = C.c_uint64(0)
+        self._check(self.f["collision_search"](C.byref(c), abi.as_ptr(p), len(p), abi.as_ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            return self.collision_search(cfg, p, cap=n.value)
+        return out[: n.value]
+
+    def steps(self, cfg, p, n_steps, resolve=0, minimum_collision_velocity=0.0):
+        p = p.copy()
+        c = cfg.copy()
+        n = C.c_uint64(len(p))
+        aux = (C.c_double * 3)()
+        self._check(self.f["steps"](C.byref(c), abi.as_ptr(p), C.byref(n), n_steps, resolve,
+                                    minimum_collision_velocity, aux))
+        return p[: n.value], c, {"collisions_log_n": int(aux[0]), "collisions_plog": aux[1], "seconds": aux[2]}
+
+    def energy(self, cfg, p):
+        p = p.copy()
+        c = cfg.copy()
+        return self.f["energy"](C.byref(c), abi.as_ptr(p), len(p))
+
+    def tree_dump(self, cfg, p):
+        p = p.copy()
+        c = cfg.copy()
+        cap = 4 * len(p) + 64
+        while True:
+            out = np.zeros(cap, dtype=abi.TREECELL_DTYPE)
+            n = C.c_uint64(0)
+            self._check(self.f["tree_dump"](C.byref(c), abi.as_ptr(p), len(p), abi.as_ptr(out), cap, C.byref(n)))
+            if n.value <= cap:
+                return out[: n.value]
+            cap = n.value
+
+    def threads(self):
+        return self.f["openmp_threads"]()
+
+    def set_threads(self, n):
+        self.f["set_threads"](n)
+
+
+def build_oracle():
+    """Compiles oracle/liboracle.so (and oracle/_ref when the reference sources are present)."""
+    subprocess.run(["make", "-C", ORACLE_DIR, "all"], check=True, capture_output=True)
+
+
+_cache = {}
+
+
+def oracle():
+    if "oracle" not in _cache:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so"], check=True, capture_output=True)
+        _cache["oracle"] = Checker(path, "orc_", "port")
+    return _cache["oracle"]
+
+
+def reference(openmp=False):
+    """The unmodified reference, or None if oracle/_ref has not been built (it is built in the
+    authoring container, where /root/reference exists, and travels to the GPU box as a binary)."""
+    key = "ref_omp" if openmp else "ref"
+    if key not in _cache:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_harness_omp.so" if openmp else "libref_harness.so")
+        _cache[key] = Checker(path, "refh_", "reference") if os.path.exists(path) else None
+    return _cache[key]
+
+
+DOUBLE_FIELDS = ("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az", "m", "r")
+
+
+def bits_equal(a, b, fields=DOUBLE_FIELDS):
+    """True iff the given double fields agree bit for bit (NaN-safe, distinguishes -0.0)."""
+    if len(a) != len(b):
+        return False
+    return all(np.array_equal(a[f].view(np.uint64), b[f].view(np.uint64)) for f in fields)
+
+
+def max_rel_acc_error(a, b):
+    """max_i |a_i - b_i| / |b_i| over acceleration vectors."""
+    da = np.stack([a["ax"] - b["ax"], a["ay"] - b["ay"], a["az"] - b["az"]], axis=1)
+    nb = np.sqrt(b["ax"] ** 2 + b["ay"] ** 2 + b["az"] ** 2)
+    nd = np.sqrt((da**2).sum(axis=1))
+    ok = nb > 0
+    return float((nd[ok] / nb[ok]).max()) if ok.any() else 0.0
+
+
+def collisions_equal(a, b, with_ri=True):
+    """Bitwise list equality.  `ri` is left uninitialised by the reference's DIRECT search
+    (src/collision.c:114-117 never writes it), so it is only compared for TREE lists."""
+    if len(a) != len(b):
+        return False
+    fields = [f for f in abi.COLLISION_DTYPE.names if with_ri or f != "ri"]
+    return all(np.array_equal(a[f].view(np.uint64), b[f].view(np.uint64)) for f in fields)

@@ -1,0 +1,216 @@
+"""Pins the CPU restatement (oracle/oracle.c) against the UNMODIFIED reference compiled from
+/root/reference/src into oracle/_ref (oracle/Makefile).  Everything is compared bit for bit.
+The same cases are stored as fixtures (tests/golden) for machines without the reference build."""
+import numpy as np
+import pytest
+
+import checkers
+from checkers import bits_equal
+from rebound_b200 import abi, ics
+
+pytestmark = pytest.mark.needs_ref
+
+
+def cases_direct():
+    p = ics.plummer(300, seed=1)
+    yield "plummer_basic", ics.plummer_config(300), p
+    yield "plummer_comp", ics.plummer_config(300, gravity=abi.GRAVITY_COMPENSATED), p
+    yield "nosoft", ics.plummer_config(300, softening=0.0), p
+    for typ in (0, 1):
+        for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
+            q = ics.planetesimal_disk(200, seed=3)
+            q["m"][10:] = 1e-9
+            yield f"testp{typ}_g{grav}", ics.planetesimal_config(testparticle_type=typ, gravity=grav), q
+    for terms in (1, 2):
+        for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
+            yield f"ignore{terms}_g{grav}", ics.plummer_config(300, gravity_ignore_terms=terms, gravity=grav), p
+    # N_active = 1 with type 1: exercises the (j==1 && i==0) corner of gravity.c:263
+    q = ics.planetesimal_disk(50, seed=4)
+    q["m"][1:] = 1e-6
+    yield "nactive1_ignore1", ics.planetesimal_config(N_active=1, testparticle_type=1, gravity_ignore_terms=1), q
+
+
+@pytest.mark.parametrize("name,cfg,p", list(cases_direct()), ids=lambda v: v if isinstance(v, str) else "")
+def test_direct_gravity_bitwise(name, cfg, p):
+    ref, _ = checkers.reference().gravity(cfg, p)
+    refomp, _ = checkers.reference(openmp=True).gravity(cfg, p)
+    orc, _ = checkers.oracle().gravity(cfg, p)
+    assert bits_equal(ref, refomp), "reference serial and OpenMP builds differ"
+    assert bits_equal(orc, ref)
+
+
+def test_basic_ghostboxes_matches_openmp_build():
+    # With ghost boxes the reference's serial build applies the shifted pair antisymmetrically
+    # (gravity.c:199-212) and is NOT bitwise equal to its own OpenMP build; the gather form is the
+    # OpenMP build's (gravity.c:216-232).
+    p = ics.plummer(200, seed=5)
+    for b in (abi.BOUNDARY_PERIODIC, abi.BOUNDARY_OPEN, abi.BOUNDARY_SHEAR):
+        cfg = ics.plummer_config(200, boundary=b, root_size=30.0, N_ghost_x=1, N_ghost_y=2, N_ghost_z=1,
+                                 OMEGA=1.0, t=0.37)
+        refomp, _ = checkers.reference(openmp=True).gravity(cfg, p)
+        ref, _ = checkers.reference().gravity(cfg, p)
+        orc, _ = checkers.oracle().gravity(cfg, p)
+        assert bits_equal(orc, refomp)
+        assert checkers.max_rel_acc_error(ref, refomp) < 1e-12
+
+
+@pytest.mark.parametrize("order", [2, 4, 6, 8])
+def test_leapfrog_steps_bitwise(order):
+    p = ics.plummer(128, seed=7)
+    cfg = ics.plummer_config(128, leapfrog_order=order, dt=1e-3)
+    ref, cr, _ = checkers.reference().steps(cfg, p, 5)
+    orc, co, _ = checkers.oracle().steps(cfg, p, 5)
+    assert bits_equal(orc, ref)
+    assert cr.t == co.t and cr.dt_last_done == co.dt_last_done
+
+
+def test_leapfrog_bad_order():
+    p = ics.plummer(8, seed=7)
+    cfg = ics.plummer_config(8, leapfrog_order=3)
+    with pytest.raises(checkers.CheckerError) as e1:
+        checkers.reference().integrator_step(cfg, p)
+    with pytest.raises(checkers.CheckerError) as e2:
+        checkers.oracle().integrator_step(cfg, p)
+    assert e1.value.msg == e2.value.msg == "Leapfrog order not supported."
+
+
+def tree_cases():
+    yield "disc", ics.selfgravity_disc_config(), ics.selfgravity_disc(2000, seed=2)
+    yield "disc_theta1.5", ics.selfgravity_disc_config(opening_angle2=1.5), ics.selfgravity_disc(500, seed=3)
+    p = ics.plummer(1000, seed=4)
+    yield "plummer_box", ics.plummer_config(1000, gravity=abi.GRAVITY_TREE, root_size=200.0, opening_angle2=0.25), p
+    yield "sheet", ics.shearing_sheet_config(root_size=40.0, t=123.4), ics.shearing_sheet(root_size=40.0, seed=5)
+    yield "rootboxes_3d", ics.plummer_config(1000, gravity=abi.GRAVITY_TREE, root_size=50.0, N_root_x=2,
+                                            N_root_y=3, N_root_z=2, boundary=abi.BOUNDARY_PERIODIC,
+                                            N_ghost_x=1, N_ghost_y=1, N_ghost_z=1), p
+
+
+@pytest.mark.parametrize("name,cfg,p", list(tree_cases()), ids=lambda v: v if isinstance(v, str) else "")
+def test_tree_cells_bitwise(name, cfg, p):
+    p, cfg = checkers.reference().boundary_check(cfg, p)
+    ref = checkers.reference().tree_dump(cfg, p)
+    orc = checkers.oracle().tree_dump(cfg, p)
+    assert len(ref) == len(orc)
+    assert ref.tobytes() == orc.tobytes()
+
+
+@pytest.mark.parametrize("name,cfg,p", list(tree_cases()), ids=lambda v: v if isinstance(v, str) else "")
+def test_tree_gravity_bitwise(name, cfg, p):
+    ref, cr = checkers.reference().gravity(cfg, p)
+    orc, co = checkers.oracle().gravity(cfg, p)
+    assert len(ref) == len(orc)
+    assert bits_equal(orc, ref)
+    assert cr.N_active == co.N_active
+
+
+def test_tree_errors():
+    cfg = ics.selfgravity_disc_config()
+    p = ics.selfgravity_disc(50, seed=2)
+    bad = p.copy(); bad["x"][7] = bad["x"][3]; bad["y"][7] = bad["y"][3]; bad["z"][7] = bad["z"][3]
+    nan = p.copy(); nan["y"][5] = np.nan
+    noroot = ics.selfgravity_disc_config(root_size=-1.0)
+    outside = p.copy(); outside["x"][9] = 100.0
+    cfg_nob = ics.selfgravity_disc_config(boundary=abi.BOUNDARY_NONE)
+    for c, q in ((cfg, bad), (cfg, nan), (noroot, p), (cfg_nob, outside)):
+        with pytest.raises(checkers.CheckerError) as e1:
+            checkers.reference().tree_dump(c, q)
+        with pytest.raises(checkers.CheckerError) as e2:
+            checkers.oracle().tree_dump(c, q)
+        assert e1.value.msg == e2.value.msg
+
+
+@pytest.mark.parametrize("boundary", [abi.BOUNDARY_OPEN, abi.BOUNDARY_PERIODIC, abi.BOUNDARY_SHEAR])
+def test_boundary_bitwise(boundary):
+    rng = np.random.default_rng(11)
+    n = 500
+    p = abi.particles(n)
+    for f in ("x", "y", "z"):
+        p[f] = rng.uniform(-14, 14, n)
+    for f in ("vx", "vy", "vz"):
+        p[f] = rng.normal(0, 1, n)
+    p["m"] = 1.0
+    cfg = abi.default_config(boundary=boundary, root_size=10.0, N_root_x=2, N_root_y=1, N_root_z=1,
+                             OMEGA=0.7, t=3.3, N_active=40)
+    ref, cr = checkers.reference().boundary_check(cfg, p)
+    orc, co = checkers.oracle().boundary_check(cfg, p)
+    assert len(ref) == len(orc)
+    assert bits_equal(orc, ref)
+    assert cr.N_active == co.N_active
+
+
+def test_boundary_open_removes_everything():
+    p = abi.particles(5)
+    p["x"] = 100.0
+    cfg = abi.default_config(boundary=abi.BOUNDARY_OPEN, root_size=10.0, N_active=3)
+    ref, cr = checkers.reference().boundary_check(cfg, p)
+    orc, co = checkers.oracle().boundary_check(cfg, p)
+    assert len(ref) == len(orc) == 0
+    assert cr.N_active == co.N_active
+
+
+def collision_cases():
+    p = ics.shearing_sheet(root_size=40.0, seed=5)
+    yield "sheet_tree", ics.shearing_sheet_config(root_size=40.0, t=55.5), p
+    yield "sheet_direct", ics.shearing_sheet_config(root_size=40.0, t=55.5, collision=abi.COLLISION_DIRECT), p
+    rng = np.random.default_rng(3)
+    n = 400
+    q = abi.particles(n)
+    for f in ("x", "y", "z"):
+        q[f] = rng.uniform(-4.9, 4.9, n)
+    for f in ("vx", "vy", "vz"):
+        q[f] = rng.normal(0, 1, n)
+    q["r"] = rng.uniform(0.05, 0.4, n)
+    q["m"] = 1.0
+    for col in (abi.COLLISION_DIRECT, abi.COLLISION_TREE):
+        yield f"box_open_c{col}", abi.default_config(collision=col, root_size=10.0, boundary=abi.BOUNDARY_OPEN), q
+        yield f"box_per_c{col}", abi.default_config(collision=col, root_size=10.0, boundary=abi.BOUNDARY_PERIODIC,
+                                                    N_ghost_x=1, N_ghost_y=1, N_ghost_z=1), q
+        yield f"box_2root_c{col}", abi.default_config(collision=col, root_size=5.0, N_root_x=2, N_root_y=2, N_root_z=2,
+                                                      boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=2, N_ghost_y=1), q
+
+
+@pytest.mark.parametrize("name,cfg,p", list(collision_cases()), ids=lambda v: v if isinstance(v, str) else "")
+def test_collision_list_bitwise(name, cfg, p):
+    ref = checkers.reference().collision_search(cfg, p)
+    orc = checkers.oracle().collision_search(cfg, p)
+    assert len(ref) > 0
+    assert len(ref) == len(orc)
+    assert checkers.collisions_equal(ref, orc, with_ri=(cfg.collision == abi.COLLISION_TREE))
+
+
+def test_sei_step_bitwise():
+    p = ics.shearing_sheet(root_size=30.0, seed=8)
+    cfg = ics.shearing_sheet_config(root_size=30.0, collision=abi.COLLISION_NONE)
+    ref, cr = checkers.reference().integrator_step(cfg, p)
+    orc, co = checkers.oracle().integrator_step(cfg, p)
+    assert bits_equal(orc, ref)
+    assert cr.t == co.t and cr.OMEGAZ == co.OMEGAZ
+
+
+@pytest.mark.parametrize("resolve", [1, 2])
+def test_shearing_sheet_full_steps_bitwise(resolve):
+    # examples/shearing_sheet: SEI + shear boundary + tree gravity + tree collisions + hard spheres
+    p = ics.shearing_sheet(root_size=30.0, seed=9)
+    cfg = ics.shearing_sheet_config(root_size=30.0)
+    mcv = 1.0 * ics.SHEET_OMEGA * 0.001
+    ref, cr, ar = checkers.reference().steps(cfg, p, 20, resolve=resolve, minimum_collision_velocity=mcv)
+    orc, co, ao = checkers.oracle().steps(cfg, p, 20, resolve=resolve, minimum_collision_velocity=mcv)
+    assert ar["collisions_log_n"] > 0
+    assert ar["collisions_log_n"] == ao["collisions_log_n"]
+    assert ar["collisions_plog"] == ao["collisions_plog"]
+    assert bits_equal(orc, ref)
+
+
+def test_disc_full_steps_bitwise():
+    p = ics.selfgravity_disc(1500, seed=12)
+    cfg = ics.selfgravity_disc_config(collision=abi.COLLISION_NONE)
+    ref, cr, _ = checkers.reference().steps(cfg, p, 5)
+    orc, co, _ = checkers.oracle().steps(cfg, p, 5)
+    assert len(ref) == len(orc)
+    assert bits_equal(orc, ref)
+
+
+def test_energy():
+    p = ics.plummer(200, seed=1)
+    cfg = ics.plummer_config(200)
+    assert checkers.reference().energy(cfg, p) == checkers.oracle().energy(cfg, p)
