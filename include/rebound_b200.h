@@ -165,6 +165,10 @@ int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg,
  * collision list of the LAST step is left on the device (rebcu_collisions_fetch). */
 int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps);
 int rebcu_collisions_fetch(rebcu_handle* h, rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+/* Hook run after each step's collision search inside rebcu_steps: the place of the shuffle + resolve
+ * loop (collision.c:336-404), which stays on the host because r->collision_resolve is a user callback.
+ * The callback may call rebcu_collisions_fetch / rebcu_download / rebcu_upload; non-zero aborts. */
+int rebcu_set_collision_callback(rebcu_handle* h, int (*cb)(void* user), void* user);
 
 /* ---- tree inspection (parity tests; reb_tree_construct + reb_tree_calculate_gravity_data,
  *      src/tree.c:254-271, 209-229) --------------------------------------------------------- */
@@ -191,6 +195,10 @@ int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particl
  * and tree force kernels and kick/drift touch only that block; positions of the other blocks are
  * refreshed by the caller's all-gather on rebcu_device_field(0..2) between drift and force. */
 int rebcu_set_shard(rebcu_handle* h, int rank, int world);
+/* Called inside every integrator step between the drift and the force evaluation (where the
+ * reference's MPI build calls reb_communication_mpi_distribute_particles, gravity.c:58-61): the caller
+ * all-gathers the x,y,z fields of the other ranks' blocks (torch.distributed / NCCL on this stream). */
+int rebcu_set_exchange_callback(rebcu_handle* h, void (*cb)(void* user), void* user);
 void rebcu_shard_range(const rebcu_handle* h, uint64_t* begin, uint64_t* end);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */

@@ -172,6 +172,8 @@ PRODUCT_SIGNATURES = {
     "steps_host": (C.c_int, [_P, _CFG, _P, _U64P, C.c_uint64]),
     "set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "shard_range": (None, [_P, _U64P, _U64P]),
+    "set_exchange_callback": (C.c_int, [_P, _P, _P]),
+    "set_collision_callback": (C.c_int, [_P, _P, _P]),
     "launch_count": (C.c_uint64, [_P]),
     "timing_enable": (C.c_int, [_P, C.c_int]),
     "timing_read": (C.c_int, [_P, _DBLP, _U64P, C.c_int]),

@@ -1,0 +1,144 @@
+// api.cu -- the extern "C" hot-path entry points of include/rebound_b200.h that compose the kernels:
+// force dispatch, integrator step, whole steps, and the host-buffer drop-ins the shim calls.
+#include "engine.cuh"
+
+// reb_simulation_update_acceleration, src/simulation.c:640-689 (the GPU-resident gravity modes).
+int update_acceleration(rebcu_handle* h, rebcu_config* c) {
+    switch (c->gravity) {
+        case REBCU_GRAVITY_NONE: return zero_acceleration(h);
+        case REBCU_GRAVITY_BASIC:
+        case REBCU_GRAVITY_COMPENSATED: return direct_gravity(h, c);
+        case REBCU_GRAVITY_TREE: return tree_gravity(h, c);
+        default: return rebcu_fail(h, REBCU_ERR_ARG, "Gravity calculation not yet implemented.");
+    }
+}
+
+static int integrator_step(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry_out, bool write_acc) {
+    switch (c->integrator) {
+        case REBCU_INTEGRATOR_LEAPFROG: return leapfrog_step_ex(h, c, carry_in, carry_out, write_acc);
+        case REBCU_INTEGRATOR_SEI: return sei_step(h, c);
+        case REBCU_INTEGRATOR_NONE: c->t += c->dt; c->dt_last_done = c->dt; return REBCU_OK;   // reb_integrator_none
+        default: return rebcu_fail(h, REBCU_ERR_ARG, "Integrator not found.");
+    }
+}
+
+extern "C" {
+
+int rebcu_update_acceleration(rebcu_handle* h, rebcu_config* cfg) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    return update_acceleration(h, cfg);
+}
+
+int rebcu_integrator_step(rebcu_handle* h, rebcu_config* cfg) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    return integrator_step(h, cfg, false, false, true);
+}
+
+int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    return boundary_check(h, cfg);
+}
+
+int rebcu_collisions_fetch(rebcu_handle* h, rebcu_collision* out, uint64_t cap, uint64_t* n_found) {
+    *n_found = h->col_n;
+    const uint64_t n = h->col_n < cap ? h->col_n : cap;
+    if (n && out) {
+        CU_TRY(h, cudaMemcpyAsync(out, h->col_list, n * sizeof(rebcu_collision), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return REBCU_OK;
+}
+
+int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg, rebcu_collision* out, uint64_t cap, uint64_t* n_found) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    int err = collision_search(h, cfg);
+    if (err) return err;
+    return rebcu_collisions_fetch(h, out, cap, n_found);
+}
+
+// reb_simulation_steps (src/simulation.c:504-513) for a simulation without host callbacks: per step
+// integrator (:527-529), boundary check (:575), collision search (:584).  Consecutive leapfrog steps
+// share one kick+drift+drift launch when nothing observes the state in between.
+int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const bool can_carry = cfg->integrator == REBCU_INTEGRATOR_LEAPFROG && cfg->boundary == REBCU_BOUNDARY_NONE
+                        && cfg->collision == REBCU_COLLISION_NONE && h->exchange == nullptr;
+    bool carried = false;
+    for (uint64_t s = 0; s < n_steps; s++) {
+        const bool last = (s + 1 == n_steps);
+        const bool carry_out = can_carry && !last;
+        int err = integrator_step(h, cfg, carried, carry_out, last);
+        if (err) return err;
+        carried = carry_out;
+        err = boundary_check(h, cfg);
+        if (err) return err;
+        if (cfg->collision != REBCU_COLLISION_NONE) {
+            err = collision_search(h, cfg);
+            if (err) return err;
+            if (h->collision_hook) {
+                err = h->collision_hook(h->collision_hook_user);
+                if (err) return err;
+            }
+        }
+    }
+    return REBCU_OK;
+}
+
+int rebcu_gravity_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N) {
+    int err = rebcu_upload(h, particles, *N);
+    if (err) return err;
+    err = update_acceleration(h, cfg);
+    if (err) return err;
+    *N = h->N;
+    return rebcu_download(h, particles, *N);
+}
+
+int rebcu_collision_search_host(rebcu_handle* h, const rebcu_config* cfg, const rebcu_particle* particles, uint64_t N,
+                                rebcu_collision* out, uint64_t cap, uint64_t* n_found) {
+    int err = rebcu_upload(h, particles, N);
+    if (err) return err;
+    return rebcu_collision_search(h, cfg, out, cap, n_found);
+}
+
+int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N, uint64_t n_steps) {
+    int err = rebcu_upload(h, particles, *N);
+    if (err) return err;
+    err = rebcu_steps(h, cfg, n_steps);
+    if (err) return err;
+    *N = h->N;
+    return rebcu_download(h, particles, *N);
+}
+
+int rebcu_set_exchange_callback(rebcu_handle* h, void (*cb)(void*), void* user) {
+    h->exchange = cb; h->exchange_user = user;
+    return REBCU_OK;
+}
+
+int rebcu_set_collision_callback(rebcu_handle* h, int (*cb)(void*), void* user) {
+    h->collision_hook = cb; h->collision_hook_user = user;
+    return REBCU_OK;
+}
+
+int rebcu_tree_build(rebcu_handle* h, const rebcu_config* cfg) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    return tree_build(h, cfg);
+}
+
+uint64_t rebcu_tree_cell_count(const rebcu_handle* h) { return h->tree.n_cells; }
+
+int rebcu_tree_fetch(rebcu_handle* h, rebcu_treecell* out, uint64_t cap) {
+    if (cap < h->tree.n_cells) return rebcu_fail(h, REBCU_ERR_CAPACITY, "tree cell buffer too small");
+    if (h->tree.n_cells) {
+        CU_TRY(h, cudaMemcpyAsync(out, h->tree.cells, h->tree.n_cells * sizeof(rebcu_treecell), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return REBCU_OK;
+}
+
+}  // extern "C"

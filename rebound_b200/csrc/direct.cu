@@ -1,0 +1,274 @@
+// direct.cu -- FP64 direct-summation gravity.
+//
+// Replaces reb_gravity_basic_calculate_acceleration (src/gravity.c:167-282) and
+// reb_gravity_compensated_calculate_acceleration (src/gravity.c:284-531).
+//
+// Gather form: particle i accumulates its own sum over its sources j in ascending order, which is
+// what the reference's OpenMP build does (gravity.c:216-232, 309-414) and what its serial build
+// produces bit for bit when there are no ghost boxes.
+//   sources(i) = [0, N_active)  U  ([N_active, N) if i is active and testparticle_type==1)
+//   minus j==i and the pairs excluded by gravity_ignore_terms (gravity.c:219-221).
+//
+// STRICT kernels: one thread per i, j-tiles of (x,y,z,m) staged in shared memory (next tile
+// prefetched into registers), arithmetic in the reference's expression order with
+// __dadd_rn/__dmul_rn/__dsqrt_rn/__ddiv_rn => bit-identical accelerations.
+// FAST kernels: 32 i per block, the j range split across the warps of the block, FMA + rsqrt;
+// partial sums are combined in a fixed warp order (deterministic, <=1e-12 relative of STRICT).
+//
+// Bound: FP64 pipe.  HBM traffic is 32 B read per source per CTA tile + 24 B written per particle.
+#include "engine.cuh"
+
+namespace {
+
+constexpr uint64_t NO_SKIP = ~0ull;
+
+struct DirectArgs {
+    const double* x; const double* y; const double* z; const double* m;
+    double* ax; double* ay; double* az;
+    uint64_t N, Na;
+    uint64_t i_begin, i_end;
+    int type, terms;
+    double G, soft2;
+    const GhostShifts* ghosts;   // device
+    int use_ghosts;              // 0: compensated (no shift at all, gravity.c:315-317)
+};
+
+// Per-particle source range and the (at most two) excluded source indices.
+__device__ __forceinline__ void source_set(const DirectArgs& a, uint64_t i, uint64_t& ns, uint64_t& skip0, uint64_t& skip1) {
+    ns = (i < a.Na && a.type) ? a.N : a.Na;
+    skip0 = i;
+    skip1 = NO_SKIP;
+    if (a.terms == REBCU_IGNORE_TERMS_BETWEEN_0_AND_1) { if (i < 2) skip1 = 1 - i; }
+    else if (a.terms == REBCU_IGNORE_TERMS_INVOLVING_0) { if (i == 0) ns = 0; else skip1 = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// STRICT
+// ------------------------------------------------------------------------------------------------
+template <bool KAHAN, int BLOCK, int JPT>
+__global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a) {
+    constexpr int TJ = BLOCK * JPT;
+    __shared__ double4 tile[TJ];
+
+    const uint64_t i0 = a.i_begin + (uint64_t)blockIdx.x * BLOCK;
+    const uint64_t i = i0 + threadIdx.x;
+    const bool valid = i < a.i_end;
+    uint64_t ns = 0, skip0 = NO_SKIP, skip1 = NO_SKIP;
+    double pxi = 0, pyi = 0, pzi = 0;
+    if (valid) {
+        source_set(a, i, ns, skip0, skip1);
+        pxi = a.x[i]; pyi = a.y[i]; pzi = a.z[i];
+    }
+    // block-uniform upper bound of the source range
+    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;
+    const double negG = -a.G;
+
+    double sx = 0, sy = 0, sz = 0;     // running sums
+    double cx = 0, cy = 0, cz = 0;     // Kahan compensation (r->gravity_cs[i])
+
+    const int ngb = a.use_ghosts ? a.ghosts->n : 1;
+    for (int g = 0; g < ngb; g++) {
+        double xi = pxi, yi = pyi, zi = pzi;
+        if (a.use_ghosts) {
+            xi = s_add(a.ghosts->gb[g].x, pxi);
+            yi = s_add(a.ghosts->gb[g].y, pyi);
+            zi = s_add(a.ghosts->gb[g].z, pzi);
+        }
+        // prefetch tile 0
+        double4 pre[JPT];
+#pragma unroll
+        for (int k = 0; k < JPT; k++) {
+            const uint64_t j = (uint64_t)k * BLOCK + threadIdx.x;
+            pre[k] = (j < ns_blk) ? make_double4(a.x[j], a.y[j], a.z[j], a.m[j]) : make_double4(0, 0, 0, 0);
+        }
+        for (uint64_t t0 = 0; t0 < ns_blk; t0 += TJ) {
+            __syncthreads();   // previous tile fully consumed
+#pragma unroll
+            for (int k = 0; k < JPT; k++) tile[k * BLOCK + threadIdx.x] = pre[k];
+            __syncthreads();
+            const uint64_t tn = t0 + TJ;
+            if (tn < ns_blk) {
+#pragma unroll
+                for (int k = 0; k < JPT; k++) {
+                    const uint64_t j = tn + (uint64_t)k * BLOCK + threadIdx.x;
+                    pre[k] = (j < ns_blk) ? make_double4(a.x[j], a.y[j], a.z[j], a.m[j]) : make_double4(0, 0, 0, 0);
+                }
+            }
+            const int jn = (ns_blk - t0 < (uint64_t)TJ) ? (int)(ns_blk - t0) : TJ;
+#pragma unroll 4
+            for (int jj = 0; jj < jn; jj++) {
+                const uint64_t j = t0 + jj;
+                const double4 s = tile[jj];
+                const double dx = s_sub(xi, s.x);
+                const double dy = s_sub(yi, s.y);
+                const double dz = s_sub(zi, s.z);
+                const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);
+                const double r = s_sqrt(r2);
+                const bool ok = (j < ns) & (j != skip0) & (j != skip1);
+                if (!KAHAN) {
+                    // prefact = -G/(_r*_r*_r)*particles[j].m   (gravity.c:226)
+                    const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), s.w);
+                    if (ok) {
+                        sx = s_add(sx, s_mul(p, dx));
+                        sy = s_add(sy, s_mul(p, dy));
+                        sz = s_add(sz, s_mul(p, dz));
+                    }
+                } else {
+                    // prefact = G/(r2*r); prefactj = -prefact*m_j   (gravity.c:320-321)
+                    const double p = s_mul(-s_div(a.G, s_mul(r2, r)), s.w);
+                    if (ok) {
+                        double y, t;
+                        y = s_sub(s_mul(p, dx), cx); t = s_add(sx, y); cx = s_sub(s_sub(t, sx), y); sx = t;
+                        y = s_sub(s_mul(p, dy), cy); t = s_add(sy, y); cy = s_sub(s_sub(t, sy), y); sy = t;
+                        y = s_sub(s_mul(p, dz), cz); t = s_add(sz, y); cz = s_sub(s_sub(t, sz), y); sz = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (valid) { a.ax[i] = sx; a.ay[i] = sy; a.az[i] = sz; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST
+// ------------------------------------------------------------------------------------------------
+// Block = 32 particles x W warps.  Warp w handles source chunks w, w+W, ... of 32 sources each,
+// staged in a private shared-memory slab (double buffered through registers).
+template <bool KAHAN, int W>
+__global__ void __launch_bounds__(32 * W) direct_fast_kernel(const DirectArgs a) {
+    __shared__ double4 slab[W][32];
+    __shared__ double red[W][6][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t i0 = a.i_begin + (uint64_t)blockIdx.x * 32;
+    const uint64_t i = i0 + lane;
+    const bool valid = i < a.i_end;
+    uint64_t ns = 0, skip0 = NO_SKIP, skip1 = NO_SKIP;
+    double pxi = 0, pyi = 0, pzi = 0;
+    if (valid) {
+        source_set(a, i, ns, skip0, skip1);
+        pxi = a.x[i]; pyi = a.y[i]; pzi = a.z[i];
+    }
+    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;
+    const double negG = -a.G;
+    double sx = 0, sy = 0, sz = 0, cx = 0, cy = 0, cz = 0;
+
+    const int ngb = a.use_ghosts ? a.ghosts->n : 1;
+    for (int g = 0; g < ngb; g++) {
+        double xi = pxi, yi = pyi, zi = pzi;
+        if (a.use_ghosts) { xi += a.ghosts->gb[g].x; yi += a.ghosts->gb[g].y; zi += a.ghosts->gb[g].z; }
+        uint64_t t0 = (uint64_t)w * 32;
+        double4 pre = make_double4(0, 0, 0, 0);
+        if (t0 + lane < ns_blk) { const uint64_t j = t0 + lane; pre = make_double4(a.x[j], a.y[j], a.z[j], negG * a.m[j]); }
+        for (; t0 < ns_blk; t0 += 32 * W) {
+            __syncwarp();
+            slab[w][lane] = pre;
+            __syncwarp();
+            const uint64_t tn = t0 + 32 * W + lane;
+            pre = make_double4(0, 0, 0, 0);
+            if (tn < ns_blk) pre = make_double4(a.x[tn], a.y[tn], a.z[tn], negG * a.m[tn]);
+            const int jn = (ns_blk - t0 < 32ull) ? (int)(ns_blk - t0) : 32;
+#pragma unroll 8
+            for (int jj = 0; jj < jn; jj++) {
+                const uint64_t j = t0 + jj;
+                const double4 s = slab[w][jj];
+                const double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
+                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
+                const double ri = rsqrt(r2);
+                const bool ok = (j < ns) & (j != skip0) & (j != skip1);
+                const double p = ok ? s.w * (ri * ri * ri) : 0.0;
+                if (!KAHAN) {
+                    sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
+                } else {
+                    double y, t;
+                    y = fma(p, dx, -cx); t = sx + y; cx = (t - sx) - y; sx = t;
+                    y = fma(p, dy, -cy); t = sy + y; cy = (t - sy) - y; sy = t;
+                    y = fma(p, dz, -cz); t = sz + y; cz = (t - sz) - y; sz = t;
+                }
+            }
+        }
+    }
+    // combine the W partial sums in warp order (fixed => deterministic)
+    red[w][0][lane] = sx; red[w][1][lane] = sy; red[w][2][lane] = sz;
+    red[w][3][lane] = cx; red[w][4][lane] = cy; red[w][5][lane] = cz;
+    __syncthreads();
+    if (w == 0 && valid) {
+        double tx = 0, ty = 0, tz = 0, ex = 0, ey = 0, ez = 0;
+        for (int k = 0; k < W; k++) {
+            // two-sum of the partials; the per-warp Kahan residuals are folded into the error term
+            double v, t, bb;
+            v = red[k][0][lane]; t = tx + v; bb = t - tx; ex += (tx - (t - bb)) + (v - bb) - red[k][3][lane]; tx = t;
+            v = red[k][1][lane]; t = ty + v; bb = t - ty; ey += (ty - (t - bb)) + (v - bb) - red[k][4][lane]; ty = t;
+            v = red[k][2][lane]; t = tz + v; bb = t - tz; ez += (tz - (t - bb)) + (v - bb) - red[k][5][lane]; tz = t;
+        }
+        a.ax[i] = tx + ex; a.ay[i] = ty + ey; a.az[i] = tz + ez;
+    }
+}
+
+__global__ void zero3_kernel(double* ax, double* ay, double* az, uint64_t b, uint64_t e) {
+    const uint64_t i = b + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e) { ax[i] = 0; ay[i] = 0; az[i] = 0; }
+}
+
+template <bool KAHAN>
+void launch_strict(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
+    // Spread small problems over all 148 SMs: one warp per CTA until there are >= 2 CTAs per SM.
+    if (n_i >= 148ull * 128 * 2) direct_strict_kernel<KAHAN, 128, 1><<<div_up(n_i, 128), 128, 0, h->stream>>>(a);
+    else if (n_i >= 148ull * 64 * 2) direct_strict_kernel<KAHAN, 64, 2><<<div_up(n_i, 64), 64, 0, h->stream>>>(a);
+    else direct_strict_kernel<KAHAN, 32, 4><<<div_up(n_i, 32), 32, 0, h->stream>>>(a);
+}
+
+template <bool KAHAN>
+void launch_fast(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
+    const unsigned int blocks = div_up(n_i, 32);
+    // aim for >= 16 warps per SM
+    const uint64_t want = (148ull * 16 + blocks - 1) / blocks;
+    if (want >= 8 && a.Na >= 2048) direct_fast_kernel<KAHAN, 8><<<blocks, 256, 0, h->stream>>>(a);
+    else if (want >= 4 && a.Na >= 1024) direct_fast_kernel<KAHAN, 4><<<blocks, 128, 0, h->stream>>>(a);
+    else if (want >= 2 && a.Na >= 512) direct_fast_kernel<KAHAN, 2><<<blocks, 64, 0, h->stream>>>(a);
+    else direct_fast_kernel<KAHAN, 1><<<blocks, 32, 0, h->stream>>>(a);
+}
+
+}  // namespace
+
+int zero_acceleration(rebcu_handle* h) {
+    uint64_t b, e; engine_shard(h, &b, &e);
+    if (e <= b) return REBCU_OK;
+    LaunchScope ls(h, TC_KICKDRIFT);
+    zero3_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(h->f(F_AX), h->f(F_AY), h->f(F_AZ), b, e);
+    CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}
+
+int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
+    const uint64_t N = h->N;
+    if (N == 0) return REBCU_OK;
+    DirectArgs a;
+    a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z); a.m = h->f(F_M);
+    a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
+    a.N = N;
+    a.Na = (c->N_active == REBCU_SIZE_MAX) ? N : (c->N_active < N ? c->N_active : N);
+    engine_shard(h, &a.i_begin, &a.i_end);
+    a.type = c->testparticle_type;
+    a.terms = c->gravity_ignore_terms;
+    a.G = c->G;
+    a.soft2 = c->softening * c->softening;
+    a.ghosts = h->ghosts_dev;
+    const bool kahan = c->gravity == REBCU_GRAVITY_COMPENSATED;
+    a.use_ghosts = kahan ? 0 : 1;
+    if (!kahan) {
+        GhostShifts g;
+        engine_ghost_shifts(c, c->N_ghost_x, c->N_ghost_y, c->N_ghost_z, &g);
+        int err = engine_upload_ghosts(h, &g);
+        if (err) return err;
+    }
+    const uint64_t n_i = a.i_end - a.i_begin;
+    if (n_i == 0) return REBCU_OK;
+    {
+        LaunchScope ls(h, TC_DIRECT);
+        if (c->mode == REBCU_MODE_FAST) { if (kahan) launch_fast<true>(h, a, n_i); else launch_fast<false>(h, a, n_i); }
+        else { if (kahan) launch_strict<true>(h, a, n_i); else launch_strict<false>(h, a, n_i); }
+    }
+    CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}

@@ -1,0 +1,140 @@
+// engine.cuh -- shared declarations of the B200 engine behind include/rebound_b200.h.
+//
+// Data layout in HBM (per handle = per simulation):
+//   soa      14 contiguous arrays of `cap` 8-byte words: x y z vx vy vz ax ay az m r | name ap sim
+//            (struct reb_particle, src/rebound.h:86-104, transposed).  Kernels touch only the arrays
+//            they need: force kernels read x,y,z,m (32 B/particle) and write ax,ay,az; kick/drift
+//            streams x,v,a in and x,v out; the three tag arrays only move in pack/unpack/compaction.
+//   aos      staging copy of the caller's AoS (112 B/particle) for the PCIe transfers.
+//   tree_*   sorted keys / permutation / pre-order cell arrays (see tree.cu).
+//   col_*    collision candidate counts and the output list (see collision.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stddef.h>
+#include <vector>
+#include "../../include/rebound_b200.h"
+
+enum { F_X = 0, F_Y, F_Z, F_VX, F_VY, F_VZ, F_AX, F_AY, F_AZ, F_M, F_R, F_NAME, F_AP, F_SIM, F_COUNT };
+enum { TC_DIRECT = 0, TC_KICKDRIFT, TC_TREEBUILD, TC_TREEWALK, TC_COLLISION, TC_BOUNDARY, TC_PACK, TC_COUNT };
+
+#define REBCU_MAX_GHOST 729   // (2*4+1)^3
+#define GHOST_RING 8
+
+struct GhostShifts {          // ghost-box offsets, computed on the host exactly as src/boundary.c:145-201
+    int n;
+    rebcu_vec6d gb[REBCU_MAX_GHOST];
+};
+
+struct TimedRange { cudaEvent_t a, b; int cls; };
+
+struct TreeBuffers {
+    uint64_t cap_n = 0;       // particle capacity of the per-particle arrays
+    uint64_t cap_cells = 0;
+    uint64_t* keys = nullptr;      // [cap_n] 64-bit keys (rootbox | 3 bits/level), unsorted
+    uint64_t* keys_sorted = nullptr;
+    uint32_t* perm = nullptr;      // [cap_n] sorted position -> particle index
+    uint32_t* perm_in = nullptr;
+    int32_t* lcp = nullptr;        // [cap_n+1] common prefix (levels) of sorted neighbours k-1,k ; -1 across root boxes
+    uint32_t* cell_off = nullptr;  // [cap_n+1] exclusive scan of cells opened per sorted particle
+    uint32_t* cell_cnt = nullptr;
+    rebcu_treecell* cells = nullptr; // [cap_cells] pre-order
+    int32_t* parent = nullptr;     // [cap_cells]
+    uint32_t* ready = nullptr;     // [cap_cells] children-done counters for the moment pass
+    double4* walk_pos = nullptr;   // [cap_cells] (mx,my,mz,m) packed for the walk
+    double4* walk_geo = nullptr;   // [cap_cells] (x,y,z,w) packed for the collision walk
+    int2* walk_meta = nullptr;     // [cap_cells] (pt, skip)
+    void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+    void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+    uint64_t n_cells = 0;
+    int* flags = nullptr;          // device error flags [8]
+    int built_for_n = -1;
+};
+
+struct rebcu_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t N = 0, cap = 0;
+    double* soa = nullptr;
+    rebcu_particle* aos = nullptr;
+    bool resident = false;
+    int rank = 0, world = 1;
+    char err[512] = {0};
+    uint64_t launches = 0;
+    bool timing = false;
+    std::vector<TimedRange> ranges;
+    std::vector<cudaEvent_t> event_pool;
+    GhostShifts* ghosts_dev = nullptr;   // device copy
+    GhostShifts ghosts_host;             // what ghosts_dev holds (valid if ghosts_valid)
+    bool ghosts_valid = false;
+    GhostShifts* ghost_ring = nullptr;   // pinned staging ring
+    cudaEvent_t ghost_ring_ev[GHOST_RING] = {};
+    bool ghost_ring_used[GHOST_RING] = {};
+    int ghost_ring_next = 0;
+    TreeBuffers tree;
+    // collision buffers
+    uint32_t* col_count = nullptr; uint64_t* col_off = nullptr; uint64_t col_cap_n = 0;
+    rebcu_collision* col_list = nullptr; uint64_t col_cap = 0; uint64_t col_n = 0;
+    void* col_scan_tmp = nullptr; size_t col_scan_tmp_bytes = 0;
+    // small device scratch
+    double* scratch = nullptr;            // 64 doubles
+    unsigned long long* counters = nullptr; // 16 counters
+    void* compact_tmp = nullptr; size_t compact_tmp_bytes = 0; double* compact_buf = nullptr; uint64_t compact_cap = 0;
+    uint32_t* compact_flag = nullptr; uint32_t* compact_pos = nullptr;
+    double* scratch_big = nullptr;        // 2 x 7 x 256 doubles: massive-body snapshots of the fused test-particle step
+    int tp_phase = 0;
+    void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)
+    void* exchange_user = nullptr;
+    int (*collision_hook)(void*) = nullptr;   // called after each step's collision search (host resolve)
+    void* collision_hook_user = nullptr;
+    // pinned staging for small host<->device exchanges
+    unsigned long long* pinned = nullptr;  // 32 words
+
+    inline double* f(int field) const { return soa + (size_t)field * cap; }
+    inline uint64_t* tag(int field) const { return (uint64_t*)(soa + (size_t)field * cap); }
+};
+
+int rebcu_fail(rebcu_handle* h, int code, const char* msg);
+int rebcu_cuda_fail(rebcu_handle* h, cudaError_t e, const char* where);
+
+#define CU_TRY(h, expr)                                                       \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return rebcu_cuda_fail((h), _e, #expr);        \
+    } while (0)
+
+// Timing bracket: records an event pair around a region when timing is enabled, and counts launches.
+struct LaunchScope {
+    rebcu_handle* h; int idx;
+    LaunchScope(rebcu_handle* h_, int cls, int n_launches = 1);
+    ~LaunchScope();
+};
+
+// internal entry points (one per translation unit)
+int engine_reserve(rebcu_handle* h, uint64_t n);
+void engine_ghost_shifts(const rebcu_config* c, int gx, int gy, int gz, GhostShifts* out);
+int engine_upload_ghosts(rebcu_handle* h, const GhostShifts* g);
+int direct_gravity(rebcu_handle* h, const rebcu_config* c);
+int zero_acceleration(rebcu_handle* h);
+int leapfrog_step(rebcu_handle* h, rebcu_config* c, bool fuse_ok);
+int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry_out, bool write_acc);
+int sei_step(rebcu_handle* h, rebcu_config* c);
+int boundary_check(rebcu_handle* h, rebcu_config* c);
+int tree_build(rebcu_handle* h, const rebcu_config* c);
+int tree_gravity(rebcu_handle* h, rebcu_config* c);
+int collision_search(rebcu_handle* h, const rebcu_config* c);
+int update_acceleration(rebcu_handle* h, rebcu_config* c);
+void engine_shard(const rebcu_handle* h, uint64_t* b, uint64_t* e);
+void tree_free(rebcu_handle* h);
+
+// ---- strict IEEE helpers: never contracted into FMA, correctly rounded sqrt and divide --------
+__device__ __forceinline__ double s_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double s_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double s_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double s_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double s_sqrt(double a) { return __dsqrt_rn(a); }
+
+static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }

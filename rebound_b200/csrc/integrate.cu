@@ -1,0 +1,324 @@
+// integrate.cu -- leapfrog kick/drift and SEI operators on the resident SoA.
+//
+// Replaces drift / kick / reb_integrator_leapfrog_step (src/integrator_leapfrog.c:72-93, 97-209) and
+// operator_H012 / operator_phi1 / reb_integrator_sei_step (src/integrator_sei.c:126-174, 86-117).
+//
+// All arithmetic is strict (separately rounded multiply and add, as the reference's -std=c99 build),
+// so trajectories are bit-identical as long as the accelerations are.
+// Bound: HBM.  Algorithmic bytes per particle: drift 72 (x,v in; x out), kick+drift 120
+// (x,v,a in; x,v out), fused test-particle step 96 (x,v in; x,v out; accelerations stay in registers).
+#include "engine.cuh"
+#include <math.h>
+
+namespace {
+
+// Composition coefficients, integrator_leapfrog.c:68-70.
+const double LF4 = 0.675603595979828817023843904485;
+const double LF6[5] = {0.1867, 0.5554970237124784, 0.1294669489134754, -0.843265623387734, 0.9432033015235604};
+const double LF8[9] = {0.128865979381443, 0.581514087105251, -0.410175371469850, 0.1851469357165877, -0.4095523434208514,
+                       0.1444059410800120, 0.2783355003936797, 0.3149566839162949, -0.6269948254051343979};
+
+// Drift / kick coefficients of one step, each product formed as the reference writes it
+// (integrator_leapfrog.c:102-203).  Returns the number of kicks (drifts = kicks + 1) or -1.
+int lf_schedule(int order, double dt, double* drift, double* kick) {
+    if (order == 2) { drift[0] = dt * 0.5; kick[0] = dt; drift[1] = dt * 0.5; return 1; }
+    if (order == 4) {
+        drift[0] = dt * LF4;          kick[0] = dt * 2. * LF4;
+        drift[1] = dt * (0.5 - LF4);  kick[1] = dt * (1. - 4. * LF4);
+        drift[2] = dt * (0.5 - LF4);  kick[2] = dt * 2. * LF4;
+        drift[3] = dt * LF4;
+        return 3;
+    }
+    if (order == 6 || order == 8) {
+        const double* a = (order == 6) ? LF6 : LF8;
+        const int s = (order == 6) ? 5 : 9;
+        const int nk = 2 * s - 1;
+        for (int k = 0; k < nk; k++) kick[k] = dt * a[(k < s) ? k : (2 * s - 2 - k)];
+        drift[0] = dt * a[0] * 0.5;
+        for (int k = 1; k < nk; k++) { const int lo = (k < s) ? (k - 1) : (2 * s - 2 - k); drift[k] = dt * (a[lo] + a[lo + 1]) * 0.5; }
+        drift[nk] = dt * a[0] * 0.5;
+        return nk;
+    }
+    return -1;
+}
+
+struct Soa {
+    double *x, *y, *z, *vx, *vy, *vz, *ax, *ay, *az, *m;
+};
+Soa soa_of(const rebcu_handle* h) {
+    return Soa{h->f(F_X), h->f(F_Y), h->f(F_Z), h->f(F_VX), h->f(F_VY), h->f(F_VZ), h->f(F_AX), h->f(F_AY), h->f(F_AZ), h->f(F_M)};
+}
+
+// x += d*v   (integrator_leapfrog.c:77-79)
+__global__ void __launch_bounds__(256) drift_kernel(Soa s, double d, uint64_t b, uint64_t e) {
+    const uint64_t i = b + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= e) return;
+    s.x[i] = s_add(s.x[i], s_mul(d, s.vx[i]));
+    s.y[i] = s_add(s.y[i], s_mul(d, s.vy[i]));
+    s.z[i] = s_add(s.z[i], s_mul(d, s.vz[i]));
+}
+
+// v += k*a ; x += d1*v ; [x += d2*v]   (kick :89-91 followed by one or two drifts)
+__global__ void __launch_bounds__(256) kick_drift_kernel(Soa s, double k, double d1, int has_d2, double d2, uint64_t b, uint64_t e) {
+    const uint64_t i = b + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= e) return;
+    const double vx = s_add(s.vx[i], s_mul(k, s.ax[i]));
+    const double vy = s_add(s.vy[i], s_mul(k, s.ay[i]));
+    const double vz = s_add(s.vz[i], s_mul(k, s.az[i]));
+    double x = s_add(s.x[i], s_mul(d1, vx));
+    double y = s_add(s.y[i], s_mul(d1, vy));
+    double z = s_add(s.z[i], s_mul(d1, vz));
+    if (has_d2) { x = s_add(x, s_mul(d2, vx)); y = s_add(y, s_mul(d2, vy)); z = s_add(z, s_mul(d2, vz)); }
+    s.vx[i] = vx; s.vy[i] = vy; s.vz[i] = vz;
+    s.x[i] = x; s.y[i] = y; s.z[i] = z;
+}
+
+// ---- fused leapfrog step for "few massive bodies + many test particles" (testparticle_type 0) ----
+// Every CTA keeps the N_active massive bodies in shared memory and advances them itself (the same
+// strictly rounded operations in every CTA, so all copies agree bit for bit); each thread then does
+// drift -> force from the massive bodies -> kick -> drift for its own particle with the
+// accelerations never leaving registers.  One launch = one whole leapfrog step, 96 B/particle.
+constexpr int TP_MAX_ACTIVE = 256;
+constexpr int TP_BLOCK = 128;
+
+struct TpArgs {
+    Soa s;
+    const double* act_in;   // snapshot of the massive bodies before the step: 7 arrays of Na (x y z vx vy vz m)
+    double* act_out;        // snapshot after the step
+    uint64_t N; int Na;
+    double d0; int has_d0;  // leading drift (absent if the previous launch already applied it)
+    double k, d1, d2; int has_d2;
+    double G, soft2;
+    double gbx, gby, gbz;   // offset of ghost box (0,0,0), added as the reference does (gravity.c:222-224)
+    int kahan, fast, write_acc;
+};
+
+template <bool FAST>
+__device__ __forceinline__ void tp_force(const double* sx, const double* sy, const double* sz, const double* sm, int Na, int self,
+                                         double xi, double yi, double zi, double G, double soft2, bool kahan,
+                                         double& ax, double& ay, double& az) {
+    double cx = 0, cy = 0, cz = 0;
+    ax = ay = az = 0;
+    const double negG = -G;
+    for (int j = 0; j < Na; j++) {
+        if (j == self) continue;
+        if (FAST) {
+            const double dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+            const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
+            const double ri = rsqrt(r2);
+            const double p = negG * sm[j] * (ri * ri * ri);
+            ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az);
+        } else {
+            const double dx = s_sub(xi, sx[j]), dy = s_sub(yi, sy[j]), dz = s_sub(zi, sz[j]);
+            const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
+            const double r = s_sqrt(r2);
+            if (!kahan) {
+                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), sm[j]);
+                ax = s_add(ax, s_mul(p, dx)); ay = s_add(ay, s_mul(p, dy)); az = s_add(az, s_mul(p, dz));
+            } else {
+                const double p = s_mul(-s_div(G, s_mul(r2, r)), sm[j]);
+                double y, t;
+                y = s_sub(s_mul(p, dx), cx); t = s_add(ax, y); cx = s_sub(s_sub(t, ax), y); ax = t;
+                y = s_sub(s_mul(p, dy), cy); t = s_add(ay, y); cy = s_sub(s_sub(t, ay), y); ay = t;
+                y = s_sub(s_mul(p, dz), cz); t = s_add(az, y); cz = s_sub(s_sub(t, az), y); az = t;
+            }
+        }
+    }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
+    __shared__ double sx[TP_MAX_ACTIVE], sy[TP_MAX_ACTIVE], sz[TP_MAX_ACTIVE], sm[TP_MAX_ACTIVE];
+    const int Na = a.Na;
+    for (int j = threadIdx.x; j < Na; j += TP_BLOCK) {
+        double x = a.act_in[0 * Na + j], y = a.act_in[1 * Na + j], z = a.act_in[2 * Na + j];
+        if (a.has_d0) {
+            x = s_add(x, s_mul(a.d0, a.act_in[3 * Na + j]));
+            y = s_add(y, s_mul(a.d0, a.act_in[4 * Na + j]));
+            z = s_add(z, s_mul(a.d0, a.act_in[5 * Na + j]));
+        }
+        sx[j] = x; sy[j] = y; sz[j] = z; sm[j] = a.act_in[6 * Na + j];
+    }
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * TP_BLOCK + threadIdx.x;
+    if (i >= a.N) return;
+    double x = a.s.x[i], y = a.s.y[i], z = a.s.z[i];
+    double vx = a.s.vx[i], vy = a.s.vy[i], vz = a.s.vz[i];
+    if (a.has_d0) { x = s_add(x, s_mul(a.d0, vx)); y = s_add(y, s_mul(a.d0, vy)); z = s_add(z, s_mul(a.d0, vz)); }
+    double ax, ay, az;
+    {
+        double xi = x, yi = y, zi = z;
+        if (!a.kahan) { xi = s_add(a.gbx, x); yi = s_add(a.gby, y); zi = s_add(a.gbz, z); }
+        tp_force<FAST>(sx, sy, sz, sm, Na, (i < (uint64_t)Na) ? (int)i : -1, xi, yi, zi, a.G, a.soft2, a.kahan != 0, ax, ay, az);
+    }
+    vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
+    x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));
+    if (a.has_d2) { x = s_add(x, s_mul(a.d2, vx)); y = s_add(y, s_mul(a.d2, vy)); z = s_add(z, s_mul(a.d2, vz)); }
+    a.s.x[i] = x; a.s.y[i] = y; a.s.z[i] = z;
+    a.s.vx[i] = vx; a.s.vy[i] = vy; a.s.vz[i] = vz;
+    if (a.write_acc) { a.s.ax[i] = ax; a.s.ay[i] = ay; a.s.az[i] = az; }
+    if (i < (uint64_t)Na) {
+        a.act_out[0 * Na + i] = x; a.act_out[1 * Na + i] = y; a.act_out[2 * Na + i] = z;
+        a.act_out[3 * Na + i] = vx; a.act_out[4 * Na + i] = vy; a.act_out[5 * Na + i] = vz;
+        a.act_out[6 * Na + i] = a.s.m[i];
+    }
+}
+
+__global__ void tp_snapshot_kernel(Soa s, double* act, int Na) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Na) return;
+    act[0 * Na + j] = s.x[j]; act[1 * Na + j] = s.y[j]; act[2 * Na + j] = s.z[j];
+    act[3 * Na + j] = s.vx[j]; act[4 * Na + j] = s.vy[j]; act[5 * Na + j] = s.vz[j];
+    act[6 * Na + j] = s.m[j];
+}
+
+// ---- SEI -------------------------------------------------------------------------------------
+struct SeiConsts { double sindt, tandt, sindtz, tandtz, OMEGA, OMEGAZ, dt; };
+
+// operator_H012, integrator_sei.c:126-157 (expression order preserved)
+__device__ __forceinline__ void sei_h012(const SeiConsts& c, double& x, double& y, double& z, double& vx, double& vy, double& vz) {
+    const double zx = s_mul(z, c.OMEGAZ);
+    const double zy = vz;
+    const double zt1 = s_sub(zx, s_mul(c.tandtz, zy));
+    const double zyt = s_add(s_mul(c.sindtz, zt1), zy);
+    const double zxt = s_sub(zt1, s_mul(c.tandtz, zyt));
+    z = s_div(zxt, c.OMEGAZ);
+    vz = zyt;
+    const double aO = s_add(s_mul(2., vy), s_mul(s_mul(4., x), c.OMEGA));
+    const double bO = s_sub(s_mul(y, c.OMEGA), s_mul(2., vx));
+    const double ys = s_div(s_sub(s_mul(y, c.OMEGA), bO), 2.);
+    const double xs = s_sub(s_mul(x, c.OMEGA), aO);
+    const double xst1 = s_sub(xs, s_mul(c.tandt, ys));
+    const double yst = s_add(s_mul(c.sindt, xst1), ys);
+    const double xst = s_sub(xst1, s_mul(c.tandt, yst));
+    x = s_div(s_add(xst, aO), c.OMEGA);
+    y = s_sub(s_div(s_add(s_mul(yst, 2.), bO), c.OMEGA), s_mul(s_mul(3. / 4., aO), c.dt));
+    vx = yst;
+    vy = s_sub(s_mul(-xst, 2.), s_mul(3. / 2., aO));
+}
+
+// phase 0: H012 ; phase 1: phi1 (integrator_sei.c:168-174) then H012
+__global__ void __launch_bounds__(256) sei_kernel(Soa s, SeiConsts c, int phase, uint64_t b, uint64_t e) {
+    const uint64_t i = b + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= e) return;
+    double x = s.x[i], y = s.y[i], z = s.z[i], vx = s.vx[i], vy = s.vy[i], vz = s.vz[i];
+    if (phase == 1) {
+        vx = s_add(vx, s_mul(s.ax[i], c.dt));
+        vy = s_add(vy, s_mul(s.ay[i], c.dt));
+        vz = s_add(vz, s_mul(s.az[i], c.dt));
+    }
+    sei_h012(c, x, y, z, vx, vy, vz);
+    s.x[i] = x; s.y[i] = y; s.z[i] = z; s.vx[i] = vx; s.vy[i] = vy; s.vz[i] = vz;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// Leapfrog.  `carry_in`: the leading drift of this step was already applied by the previous step's
+// last launch; `carry_out`: also apply the leading drift of the NEXT step (same dt) in this step's
+// last launch.  Both are only used by rebcu_steps when nothing observes the state between steps.
+// -------------------------------------------------------------------------------------------------
+static bool tp_path_ok(const rebcu_handle* h, const rebcu_config* c) {
+    const uint64_t Na = (c->N_active == REBCU_SIZE_MAX) ? h->N : c->N_active;
+    return h->world == 1 && Na > 0 && Na <= TP_MAX_ACTIVE && Na < h->N && c->testparticle_type == 0
+        && (c->gravity == REBCU_GRAVITY_BASIC || c->gravity == REBCU_GRAVITY_COMPENSATED)
+        && c->N_ghost_x == 0 && c->N_ghost_y == 0 && c->N_ghost_z == 0
+        && (c->leapfrog_order == 2 || c->leapfrog_order == 0);
+}
+
+int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry_out, bool write_acc) {
+    c->gravity_ignore_terms = REBCU_IGNORE_TERMS_NONE;        // integrator_leapfrog.c:98
+    double drift[20], kick[20];
+    const int order = c->leapfrog_order ? c->leapfrog_order : 2;
+    const int nk = lf_schedule(order, c->dt, drift, kick);
+    if (nk < 0) return rebcu_fail(h, REBCU_ERR_LEAPFROG_ORDER, "Leapfrog order not supported.");
+    uint64_t b, e; engine_shard(h, &b, &e);
+    const uint64_t n = e - b;
+    Soa s = soa_of(h);
+
+    if (tp_path_ok(h, c)) {
+        const int Na = (int)c->N_active;
+        double* act = h->scratch_big;
+        if (!act) return rebcu_fail(h, REBCU_ERR_CUDA, "scratch missing");
+        double* act_in = act + (size_t)h->tp_phase * 7 * TP_MAX_ACTIVE;
+        double* act_out = act + (size_t)(1 - h->tp_phase) * 7 * TP_MAX_ACTIVE;
+        if (!carry_in) {
+            LaunchScope ls(h, TC_KICKDRIFT);
+            tp_snapshot_kernel<<<div_up(Na, 128), 128, 0, h->stream>>>(s, act_in, Na);
+        }
+        TpArgs a;
+        a.s = s; a.act_in = act_in; a.act_out = act_out; a.N = h->N; a.Na = Na;
+        a.d0 = drift[0]; a.has_d0 = carry_in ? 0 : 1;
+        a.k = kick[0]; a.d1 = drift[1]; a.d2 = drift[0]; a.has_d2 = carry_out ? 1 : 0;
+        a.G = c->G; a.soft2 = c->softening * c->softening;
+        { GhostShifts g0; engine_ghost_shifts(c, 0, 0, 0, &g0); a.gbx = g0.gb[0].x; a.gby = g0.gb[0].y; a.gbz = g0.gb[0].z; }
+        a.kahan = c->gravity == REBCU_GRAVITY_COMPENSATED; a.fast = c->mode == REBCU_MODE_FAST;
+        a.write_acc = write_acc ? 1 : 0;
+        {
+            LaunchScope ls(h, TC_DIRECT);
+            if (a.fast) tp_leapfrog_kernel<true><<<div_up(h->N, TP_BLOCK), TP_BLOCK, 0, h->stream>>>(a);
+            else tp_leapfrog_kernel<false><<<div_up(h->N, TP_BLOCK), TP_BLOCK, 0, h->stream>>>(a);
+        }
+        CU_TRY(h, cudaGetLastError());
+        h->tp_phase = 1 - h->tp_phase;
+        c->t += drift[0]; c->t += drift[1];
+        c->dt_last_done = c->dt;
+        return REBCU_OK;
+    }
+
+    for (int k = 0; k < nk; k++) {
+        if (k == 0 && !carry_in && n) {
+            LaunchScope ls(h, TC_KICKDRIFT);
+            drift_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(s, drift[0], b, e);
+        }
+        c->t += drift[k];
+        if (h->exchange) h->exchange(h->exchange_user);
+        int err = update_acceleration(h, c);
+        if (err) return err;
+        engine_shard(h, &b, &e);   // N may shrink (tree gravity + open boundary)
+        s = soa_of(h);
+        const bool last = (k == nk - 1);
+        if (e > b) {
+            LaunchScope ls(h, TC_KICKDRIFT);
+            kick_drift_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(s, kick[k], drift[k + 1], (last && carry_out) ? 1 : 0, drift[0], b, e);
+        }
+    }
+    CU_TRY(h, cudaGetLastError());
+    c->t += drift[nk];
+    c->dt_last_done = c->dt;
+    return REBCU_OK;
+}
+
+int leapfrog_step(rebcu_handle* h, rebcu_config* c, bool fuse_ok) {
+    (void)fuse_ok;
+    return leapfrog_step_ex(h, c, false, false, true);
+}
+
+int sei_step(rebcu_handle* h, rebcu_config* c) {
+    c->gravity_ignore_terms = REBCU_IGNORE_TERMS_NONE;        // integrator_sei.c:88
+    if (c->OMEGAZ == -1) c->OMEGAZ = c->OMEGA;                // integrator_sei.c:93-95
+    SeiConsts k;
+    k.sindt = sin(c->OMEGA * (-c->dt / 2.));
+    k.tandt = tan(c->OMEGA * (-c->dt / 4.));
+    k.sindtz = sin(c->OMEGAZ * (-c->dt / 2.));
+    k.tandtz = tan(c->OMEGAZ * (-c->dt / 4.));
+    k.OMEGA = c->OMEGA; k.OMEGAZ = c->OMEGAZ; k.dt = c->dt;
+    uint64_t b, e; engine_shard(h, &b, &e);
+    if (e > b) {
+        LaunchScope ls(h, TC_KICKDRIFT);
+        sei_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(soa_of(h), k, 0, b, e);
+    }
+    c->t += c->dt / 2.;
+    if (h->exchange) h->exchange(h->exchange_user);
+    int err = update_acceleration(h, c);
+    if (err) return err;
+    engine_shard(h, &b, &e);
+    if (e > b) {
+        LaunchScope ls(h, TC_KICKDRIFT);
+        sei_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(soa_of(h), k, 1, b, e);
+    }
+    CU_TRY(h, cudaGetLastError());
+    c->t += c->dt / 2.;
+    c->dt_last_done = c->dt;
+    return REBCU_OK;
+}

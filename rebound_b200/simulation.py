@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's simulation interface for the hot path.
+
+`Engine` is a 1:1 ctypes binding of include/rebound_b200.h (the drop-in C ABI).  `Simulation`
+mirrors the part of the reference's `rebound.Simulation` that drives the hot path -- the attribute
+names (`gravity`, `collision`, `boundary`, `integrator`, `N_active`, `testparticle_type`,
+`softening`, `opening_angle2`, `root_size`, `N_ghost_x`, ...), `add`, `steps`, `integrate`,
+`synchronize` (rebound/simulation.py:1276-1325 in the reference) and its error behaviour (pending
+error => RuntimeError with the reference's message text).
+
+There is no CPU path: if the CUDA library is missing or no device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librebound_b200.so")
+
+
+class LibraryMissing(ImportError):
+    pass
+
+
+class ReboundCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{abi.ERRORS.get(code, code)}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+_fn = None
+
+
+def load_library():
+    """Loads rebound_b200/librebound_b200.so and binds every symbol declared in the header."""
+    global _lib, _fn
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C rebound_b200/csrc).  rebound_b200 has no CPU fallback."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        sigs = dict(abi.PRODUCT_SIGNATURES)
+        _fn = abi.bind(_lib, "rebcu_", sigs)
+    return _fn
+
+
+EXCHANGE_CB = C.CFUNCTYPE(None, C.c_void_p)
+COLLISION_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class Engine:
+    """One rebcu_handle (= one simulation's device state)."""
+
+    def __init__(self, device=0, stream=None):
+        self.f = load_library()
+        self.h = self.f["create"](device, stream)
+        if not self.h:
+            raise ReboundCudaError(-1, f"rebcu_create(device={device}) failed: no usable CUDA device")
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.f["destroy"](self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, err):
+        if err != 0:
+            raise ReboundCudaError(err, self.f["last_error"](self.h).decode())
+
+    # residency
+    def upload(self, p):
+        assert p.dtype == abi.PARTICLE_DTYPE and p.flags.c_contiguous
+        self._check(self.f["upload"](self.h, abi.as_ptr(p), len(p)))
+
+    def download(self, out=None):
+        n = self.N
+        if out is None:
+            out = abi.particles(n)
+        self._check(self.f["download"](self.h, abi.as_ptr(out), len(out)))
+        return out[:n]
+
+    @property
+    def N(self):
+        return int(self.f["N"](self.h))
+
+    def synchronize(self):
+        self._check(self.f["synchronize"](self.h))
+
+    def device_field(self, field):
+        return self.f["device_field"](self.h, field)
+
+    # hot path
+    def update_acceleration(self, cfg):
+        self._check(self.f["update_acceleration"](self.h, C.byref(cfg)))
+
+    def integrator_step(self, cfg):
+        self._check(self.f["integrator_step"](self.h, C.byref(cfg)))
+
+    def boundary_check(self, cfg):
+        self._check(self.f["boundary_check"](self.h, C.byref(cfg)))
+
+    def steps(self, cfg, n):
+        self._check(self.f["steps"](self.h, C.byref(cfg), n))
+
+    def collision_search(self, cfg, cap=None):
+        cap = cap or max(1024, 4 * self.N)
+        out = np.zeros(cap, dtype=abi.COLLISION_DTYPE)
+        n = C.c_uint64(0)
+        self._check(self.f["collision_search"](self.h, C.byref(cfg), abi.as_ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            out = np.zeros(n.value, dtype=abi.COLLISION_DTYPE)
+            self._check(self.f["collisions_fetch"](self.h, abi.as_ptr(out), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def collisions_fetch(self):
+        n = C.c_uint64(0)
+        self._check(self.f["collisions_fetch"](self.h, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=abi.COLLISION_DTYPE)
+        self._check(self.f["collisions_fetch"](self.h, abi.as_ptr(out), len(out), C.byref(n)))
+        return out[: n.value]
+
+    def tree(self, cfg):
+        self._check(self.f["tree_build"](self.h, C.byref(cfg)))
+        n = int(self.f["tree_cell_count"](self.h))
+        out = np.zeros(max(n, 1), dtype=abi.TREECELL_DTYPE)
+        self._check(self.f["tree_fetch"](self.h, abi.as_ptr(out), len(out)))
+        return out[:n]
+
+    # host-buffer drop-ins
+    def gravity_host(self, cfg, p):
+        n = C.c_uint64(len(p))
+        self._check(self.f["gravity_host"](self.h, C.byref(cfg), abi.as_ptr(p), C.byref(n)))
+        return n.value
+
+    def steps_host(self, cfg, p, n_steps):
+        n = C.c_uint64(len(p))
+        self._check(self.f["steps_host"](self.h, C.byref(cfg), abi.as_ptr(p), C.byref(n), n_steps))
+        return n.value
+
+    def collision_search_host(self, cfg, p, cap=None):
+        cap = cap or max(1024, 4 * len(p))
+        out = np.zeros(cap, dtype=abi.COLLISION_DTYPE)
+        n = C.c_uint64(0)
+        self._check(self.f["collision_search_host"](self.h, C.byref(cfg), abi.as_ptr(p), len(p), abi.as_ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            return self.collision_search_host(cfg, p, cap=n.value)
+        return out[: n.value]
+
+    # sharding
+    def set_shard(self, rank, world):
+        self._check(self.f["set_shard"](self.h, rank, world))
+
+    def shard_range(self):
+        b, e = C.c_uint64(0), C.c_uint64(0)
+        self.f["shard_range"](self.h, C.byref(b), C.byref(e))
+        return b.value, e.value
+
+    def set_exchange_callback(self, fn):
+        cb = EXCHANGE_CB(lambda _u: fn()) if fn else None
+        self._keep.append(cb)
+        self._check(self.f["set_exchange_callback"](self.h, C.cast(cb, C.c_void_p) if cb else None, None))
+
+    def set_collision_callback(self, fn):
+        cb = COLLISION_CB(lambda _u: int(fn() or 0)) if fn else None
+        self._keep.append(cb)
+        self._check(self.f["set_collision_callback"](self.h, C.cast(cb, C.c_void_p) if cb else None, None))
+
+    # instrumentation
+    @property
+    def launch_count(self):
+        return int(self.f["launch_count"](self.h))
+
+    def timing_enable(self, on=True):
+        self._check(self.f["timing_enable"](self.h, 1 if on else 0))
+
+    def timing_reset(self):
+        self._check(self.f["timing_reset"](self.h))
+
+    def timing_read(self):
+        ms = (C.c_double * 7)()
+        n = (C.c_uint64 * 7)()
+        self._check(self.f["timing_read"](self.h, ms, n, 7))
+        names = ("direct", "kickdrift", "treebuild", "treewalk", "collision", "boundary", "pack")
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
+
+
+_GRAVITY = {"none": 0, "basic": 1, "compensated": 2, "tree": 3}
+_COLLISION = {"none": 0, "direct": 1, "tree": 2}
+_BOUNDARY = {"none": 0, "open": 1, "periodic": 2, "shear": 3}
+_INTEGRATOR = {"none": 0, "leapfrog": 1, "sei": 2}
+_ENUMS = {"gravity": _GRAVITY, "collision": _COLLISION, "boundary": _BOUNDARY, "integrator": _INTEGRATOR}
+_CFG_FIELDS = {name for name, _ in abi.Config._fields_}
+
+
+class Simulation:
+    """The hot-path subset of the reference's `rebound.Simulation`, resident on one B200.
+
+    Enum-valued attributes accept the reference's string names (rebound/simulation.py:18-20).
+    Particles added with `add` live in a host array until the next step, then stay in HBM until
+    `synchronize()` / `particles` is read (the is_synchronized protocol, src/simulation.c:633-637).
+    """
+
+    def __init__(self, device=0, stream=None):
+        object.__setattr__(self, "_cfg", abi.default_config())
+        object.__setattr__(self, "_engine", Engine(device, stream))
+        object.__setattr__(self, "_host", abi.particles(0))
+        object.__setattr__(self, "_host_valid", True)   # host copy is current
+        object.__setattr__(self, "_dev_valid", False)   # device copy is current
+        object.__setattr__(self, "steps_done", 0)
+        object.__setattr__(self, "collision_resolve", None)
+
+    def __setattr__(self, name, value):
+        if name in _ENUMS:
+            if isinstance(value, str):
+                if value not in _ENUMS[name]:
+                    raise ValueError(f"{name} '{value}' not found")
+                value = _ENUMS[name][value]
+            setattr(self._cfg, name, value)
+        elif name == "N_active":
+            self._cfg.N_active = abi.SIZE_MAX if value in (-1, None) else value
+        elif name in _CFG_FIELDS:
+            setattr(self._cfg, name, value)
+        else:
+            object.__setattr__(self, name, value)
+
+    def __getattr__(self, name):
+        if name in _CFG_FIELDS:
+            return getattr(self._cfg, name)
+        raise AttributeError(name)
+
+    @property
+    def config(self):
+        return self._cfg
+
+    @property
+    def engine(self):
+        return self._engine
+
+    @property
+    def N(self):
+        return self._engine.N if self._dev_valid else len(self._host)
+
+    def add(self, particles=None, **kw):
+        """reb_simulation_add (src/particle.c:47-76): appends particles; marks the device copy stale."""
+        self.synchronize()
+        if particles is None:
+            particles = abi.particles(1)
+            for k, v in kw.items():
+                particles[k] = v
+        object.__setattr__(self, "_host", np.concatenate([self._host, particles.astype(abi.PARTICLE_DTYPE)]))
+        object.__setattr__(self, "_dev_valid", False)
+
+    @property
+    def particles(self):
+        self.synchronize()
+        return self._host
+
+    def did_modify_particles(self):
+        """The caller edited `particles` in place (r->did_modify_particles, src/rebound.h:247)."""
+        object.__setattr__(self, "_dev_valid", False)
+        object.__setattr__(self, "_host_valid", True)
+
+    def synchronize(self):
+        if not self._host_valid:
+            object.__setattr__(self, "_host", self._engine.download())
+            object.__setattr__(self, "_host_valid", True)
+
+    def _to_device(self):
+        if not self._dev_valid:
+            self._engine.upload(np.ascontiguousarray(self._host))
+            object.__setattr__(self, "_dev_valid", True)
+
+    def update_acceleration(self):
+        self._to_device()
+        self._engine.update_acceleration(self._cfg)
+        object.__setattr__(self, "_host_valid", False)
+
+    def steps(self, n):
+        """reb_simulation_steps (src/simulation.c:504-513)."""
+        self._to_device()
+        self._engine.steps(self._cfg, int(n))
+        object.__setattr__(self, "_host_valid", False)
+        object.__setattr__(self, "steps_done", self.steps_done + int(n))
+
+    def step(self):
+        self.steps(1)
+
+    def integrate(self, tmax):
+        """reb_simulation_integrate with exact_finish_time=0 semantics (src/simulation.c:465): whole
+        steps of size dt until t >= tmax."""
+        c = self._cfg
+        if c.dt == 0:
+            raise RuntimeError("dt is zero")
+        n = 0
+        t = c.t
+        while (t < tmax) if c.dt > 0 else (t > tmax):
+            t += c.dt
+            n += 1
+        if n:
+            self.steps(n)
+
+    def collision_search(self):
+        self._to_device()
+        return self._engine.collision_search(self._cfg)
+
+    def tree(self):
+        self._to_device()
+        return self._engine.tree(self._cfg)
+
+    def close(self):
+        self._engine.close()

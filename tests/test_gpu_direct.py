@@ -1,0 +1,177 @@
+"""GPU parity: direct-summation gravity and leapfrog through the C ABI against the CPU oracle
+(oracle/oracle.c, pinned bitwise to the reference in test_oracle_vs_reference.py).
+
+STRICT mode must be bit-identical; FAST mode within 1e-12 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import checkers
+from checkers import bits_equal, max_rel_acc_error
+from rebound_b200 import abi, ics
+from rebound_b200.simulation import Engine, ReboundCudaError
+
+pytestmark = pytest.mark.gpu
+
+ACC = ("ax", "ay", "az")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def gpu_gravity(eng, cfg, p):
+    q = p.copy()
+    c = cfg.copy()
+    n = eng.gravity_host(c, q)
+    return q[:n], c
+
+
+def direct_cases():
+    p = ics.plummer(1000, seed=1)
+    yield "plummer_basic", ics.plummer_config(1000), p
+    yield "plummer_comp", ics.plummer_config(1000, gravity=abi.GRAVITY_COMPENSATED), p
+    yield "nosoft", ics.plummer_config(1000, softening=0.0), p
+    yield "ragged_37", ics.plummer_config(37), ics.plummer(37, seed=2)
+    yield "single", ics.plummer_config(1), ics.plummer(1, seed=2)
+    yield "two", ics.plummer_config(2), ics.plummer(2, seed=2)
+    yield "n5000", ics.plummer_config(5000), ics.plummer(5000, seed=3)
+    yield "n20000_comp", ics.plummer_config(20000, gravity=abi.GRAVITY_COMPENSATED), ics.plummer(20000, seed=3)
+    for typ in (0, 1):
+        for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
+            q = ics.planetesimal_disk(3000, seed=3)
+            q["m"][10:] = 1e-9
+            yield f"testp{typ}_g{grav}", ics.planetesimal_config(testparticle_type=typ, gravity=grav), q
+    for terms in (1, 2):
+        for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
+            yield f"ignore{terms}_g{grav}", ics.plummer_config(1000, gravity_ignore_terms=terms, gravity=grav), p
+    q = ics.planetesimal_disk(50, seed=4)
+    q["m"][1:] = 1e-6
+    yield "nactive1_ignore1", ics.planetesimal_config(N_active=1, testparticle_type=1, gravity_ignore_terms=1), q
+    for b in (abi.BOUNDARY_PERIODIC, abi.BOUNDARY_OPEN, abi.BOUNDARY_SHEAR):
+        yield f"ghost_b{b}", ics.plummer_config(300, boundary=b, root_size=30.0, N_ghost_x=1, N_ghost_y=2,
+                                                N_ghost_z=1, OMEGA=1.0, t=0.37), ics.plummer(300, seed=5)
+
+
+CASES = list(direct_cases())
+
+
+@pytest.mark.parametrize("name,cfg,p", CASES, ids=[c[0] for c in CASES])
+def test_direct_strict_bitwise(eng, name, cfg, p):
+    want, _ = checkers.oracle().gravity(cfg, p)
+    got, _ = gpu_gravity(eng, cfg, p)
+    assert bits_equal(got, want)                      # accelerations AND untouched fields
+
+
+@pytest.mark.parametrize("name,cfg,p", CASES, ids=[c[0] for c in CASES])
+def test_direct_fast_within_1e12(eng, name, cfg, p):
+    want, _ = checkers.oracle().gravity(cfg, p)
+    c = cfg.copy()
+    c.mode = abi.MODE_FAST
+    got, _ = gpu_gravity(eng, c, p)
+    assert max_rel_acc_error(got, want) <= 1e-12
+
+
+def test_golden_plummer_reference_vector(eng):
+    """Accelerations the unmodified reference produced (tests/golden/make_golden.py)."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "direct_plummer512.npz")
+    g = np.load(path)
+    p = g["particles_in"].view(abi.PARTICLE_DTYPE).reshape(-1)
+    for key, grav in (("basic", abi.GRAVITY_BASIC), ("compensated", abi.GRAVITY_COMPENSATED)):
+        cfg = ics.plummer_config(512, gravity=grav)
+        cfg.softening = float(g["softening"])
+        got, _ = gpu_gravity(eng, cfg, p)
+        want = g["acc_" + key]
+        got_acc = np.stack([got[f] for f in ACC], axis=1)
+        assert np.array_equal(got_acc.view(np.uint64), want.view(np.uint64))
+
+
+@pytest.mark.parametrize("order", [2, 4, 6, 8])
+def test_leapfrog_steps_bitwise(eng, order):
+    p = ics.plummer(700, seed=7)
+    cfg = ics.plummer_config(700, leapfrog_order=order, dt=1e-3)
+    want, cw, _ = checkers.oracle().steps(cfg, p, 4)
+    q = p.copy()
+    c = cfg.copy()
+    eng.steps_host(c, q, 4)
+    assert bits_equal(q, want)
+    assert c.t == cw.t and c.dt_last_done == cw.dt_last_done
+
+
+def test_leapfrog_step_by_step_equals_batched(eng):
+    p = ics.plummer(300, seed=8)
+    cfg = ics.plummer_config(300, dt=1e-3)
+    q1, c1 = p.copy(), cfg.copy()
+    eng.steps_host(c1, q1, 6)
+    q2, c2 = p.copy(), cfg.copy()
+    for _ in range(6):
+        eng.steps_host(c2, q2, 1)
+    assert bits_equal(q1, q2) and c1.t == c2.t
+
+
+def test_leapfrog_bad_order(eng):
+    p = ics.plummer(8, seed=7)
+    cfg = ics.plummer_config(8, leapfrog_order=3)
+    with pytest.raises(ReboundCudaError) as e:
+        eng.steps_host(cfg.copy(), p.copy(), 1)
+    assert e.value.msg == "Leapfrog order not supported."
+
+
+@pytest.mark.parametrize("grav", [abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED])
+@pytest.mark.parametrize("mode", [abi.MODE_STRICT, abi.MODE_FAST])
+def test_planetesimal_fused_step(eng, grav, mode):
+    """Config C2 shape: 10 massive bodies + test particles, testparticle_type 0 (fused step kernel)."""
+    p = ics.planetesimal_disk(5000, seed=9)
+    cfg = ics.planetesimal_config(gravity=grav, mode=mode)
+    want, cw, _ = checkers.oracle().steps(cfg, p, 7)
+    q, c = p.copy(), cfg.copy()
+    eng.steps_host(c, q, 7)
+    assert c.t == cw.t
+    if mode == abi.MODE_STRICT:
+        assert bits_equal(q, want)
+    else:
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            np.testing.assert_allclose(q[f], want[f], rtol=1e-11, atol=1e-13)
+        assert max_rel_acc_error(q, want) <= 1e-12 * 50
+
+
+def test_energy_error_matches_reference_path(eng):
+    """Energy error after n steps equals the oracle's (bitwise trajectories => identical energies)."""
+    p = ics.plummer(512, seed=11)
+    cfg = ics.plummer_config(512)
+    e0 = checkers.oracle().energy(cfg, p)
+    want, _, _ = checkers.oracle().steps(cfg, p, 20)
+    q, c = p.copy(), cfg.copy()
+    eng.steps_host(c, q, 20)
+    e_gpu = checkers.oracle().energy(cfg, q)
+    e_ref = checkers.oracle().energy(cfg, want)
+    assert e_gpu == e_ref
+    assert abs((e_gpu - e0) / e0) < 1e-6
+
+
+def test_linearity_in_G_and_translation_full_size(eng):
+    """Size-independent properties at config C1's N=16384: a(2G) = 2 a(G) exactly in strict mode,
+    sum_i m_i a_i ~ 0 (Newton's third law)."""
+    n = 16384
+    p = ics.plummer(n, seed=42)
+    cfg = ics.plummer_config(n)
+    a1, _ = gpu_gravity(eng, cfg, p)
+    c2 = cfg.copy(); c2.G = 2.0
+    a2, _ = gpu_gravity(eng, c2, p)
+    for f in ACC:
+        assert np.array_equal(a2[f], 2.0 * a1[f])
+        assert abs(np.sum(p["m"] * a1[f])) < 1e-12 * np.sum(np.abs(p["m"] * a1[f]))
+    # sampled rows against the oracle arithmetic (numpy restatement of gravity.c:222-230)
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, n, 16):
+        dx, dy, dz = p["x"][i] - p["x"], p["y"][i] - p["y"], p["z"][i] - p["z"]
+        r = np.sqrt(dx * dx + dy * dy + dz * dz + cfg.softening**2)
+        pre = -cfg.G / (r * r * r) * p["m"]
+        pre[i] = 0.0
+        acc = 0.0
+        for v in pre * dx:
+            acc += v
+        assert acc == a1["ax"][i]
