@@ -178,7 +178,10 @@ def main():
     p, cfg, inter, desc = workload(args.workload, rank)
     inner = args.inner or INNER_STEPS[args.workload]
     n = len(p)
-    stream = torch.cuda.current_stream()
+    # An explicit (non-default) torch stream: the engine launches on it and torch.cuda.Event times it.
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng = Engine(local_rank, stream.cuda_stream)
 
     # pinned host AoS (the role of r->particles after rebcu_host_register)

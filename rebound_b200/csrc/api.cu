@@ -135,6 +135,8 @@ uint64_t rebcu_tree_cell_count(const rebcu_handle* h) { return h->tree.n_cells; 
 int rebcu_tree_fetch(rebcu_handle* h, rebcu_treecell* out, uint64_t cap) {
     if (cap < h->tree.n_cells) return rebcu_fail(h, REBCU_ERR_CAPACITY, "tree cell buffer too small");
     if (h->tree.n_cells) {
+        int err = tree_export(h);
+        if (err) return err;
         CU_TRY(h, cudaMemcpyAsync(out, h->tree.cells, h->tree.n_cells * sizeof(rebcu_treecell), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }

@@ -1,3 +1,255 @@
-// collision.cu -- placeholder, replaced below in this round.
+// collision.cu -- the search part of reb_collision_search (src/collision.c:49-331).
+//
+// DIRECT (collision.c:64-124): all ordered pairs (i, j != i) in every ghost box of the innermost ring;
+//   a pair is reported when the spheres overlap (r2 <= (r_i+r_j)^2) and approach (dv.dx <= 0).
+// TREE (collision.c:197-269, helper :422-503): per projectile, ghost box, root box: depth-first descent
+//   pruned with  r2 < (r_i + r_2nd + 0.866 w)^2  on the GEOMETRIC cell centre; same leaf test.
+//
+// Both are two-pass (count -> exclusive scan -> fill) so that the list comes out in the order the
+// reference's serial build produces it -- DIRECT: ghost box, projectile, target; TREE: projectile,
+// ghost box, root box, pre-order -- because the list order feeds the rand_r shuffle and the
+// order-dependent resolve loop (collision.c:336-404), which stay on the host.
+// All predicates use strictly rounded arithmetic in the reference's expression order, so the pair set is
+// bit-exact.  `ri` is written for TREE only (the reference leaves it uninitialised in DIRECT).
+// r->map / N_targets subsets (used by MERCURIUS/TRACE) are not part of this path.
+// Bound: DIRECT FP64 pipe (N^2 predicates); TREE L2/HBM latency on the cell arrays.
 #include "engine.cuh"
-int collision_search(rebcu_handle* h, const rebcu_config* c) { (void)c; return rebcu_fail(h, REBCU_ERR_ARG, "collision search not built yet"); }
+#include <cub/device/device_scan.cuh>
+
+namespace {
+
+struct ColSoa { const double *x, *y, *z, *vx, *vy, *vz, *r; };
+
+ColSoa col_soa(const rebcu_handle* h) {
+    return ColSoa{h->f(F_X), h->f(F_Y), h->f(F_Z), h->f(F_VX), h->f(F_VY), h->f(F_VZ), h->f(F_R)};
+}
+
+// collision.c:95-106 / :457-469
+__device__ __forceinline__ bool hit(const rebcu_vec6d& s, double r1, double x2, double y2, double z2, double r2p,
+                                    const ColSoa& P, uint32_t j) {
+    const double dx = s_sub(s.x, x2), dy = s_sub(s.y, y2), dz = s_sub(s.z, z2);
+    const double sr = s_add(r1, r2p);
+    const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+    if (r2 > s_mul(sr, sr)) return false;
+    const double dvx = s_sub(s.vx, P.vx[j]), dvy = s_sub(s.vy, P.vy[j]), dvz = s_sub(s.vz, P.vz[j]);
+    if (s_add(s_add(s_mul(dvx, dx), s_mul(dvy, dy)), s_mul(dvz, dz)) > 0) return false;
+    return true;
+}
+
+__device__ __forceinline__ rebcu_vec6d shifted(const rebcu_vec6d& gb, const ColSoa& P, uint32_t i) {
+    rebcu_vec6d s;
+    s.x = s_add(gb.x, P.x[i]); s.y = s_add(gb.y, P.y[i]); s.z = s_add(gb.z, P.z[i]);
+    s.vx = s_add(gb.vx, P.vx[i]); s.vy = s_add(gb.vy, P.vy[i]); s.vz = s_add(gb.vz, P.vz[i]);
+    return s;
+}
+
+__device__ __forceinline__ void emit(rebcu_collision* out, uint64_t at, uint32_t p1, uint32_t p2, const rebcu_vec6d& gb, uint64_t ri) {
+    rebcu_collision c;
+    c.p1 = p1; c.p2 = p2; c.gb = gb; c.ri = ri;
+    out[at] = c;
+}
+
+// ---- DIRECT ------------------------------------------------------------------------------------
+// grid.y = ghost box, thread = projectile, targets tiled through shared memory.
+template <bool FILL>
+__global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_t n, const GhostShifts* ghosts,
+                                                               uint32_t* __restrict__ count, const uint32_t* __restrict__ off,
+                                                               rebcu_collision* __restrict__ out) {
+    __shared__ double4 tile[128];
+    const uint32_t g = blockIdx.y;
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = i < n;
+    const rebcu_vec6d gb = ghosts->gb[g];
+    rebcu_vec6d s = gb;
+    double r1 = 0;
+    if (valid) { s = shifted(gb, P, i); r1 = P.r[i]; }
+    uint32_t found = 0;
+    const uint64_t base = (FILL && valid) ? off[(uint64_t)g * n + i] : 0;
+    for (uint32_t t0 = 0; t0 < n; t0 += 128) {
+        __syncthreads();
+        const uint32_t j0 = t0 + threadIdx.x;
+        tile[threadIdx.x] = (j0 < n) ? make_double4(P.x[j0], P.y[j0], P.z[j0], P.r[j0]) : make_double4(0, 0, 0, 0);
+        __syncthreads();
+        const int jn = min(128u, n - t0);
+        if (valid) {
+            for (int jj = 0; jj < jn; jj++) {
+                const uint32_t j = t0 + jj;
+                if (j == i) continue;
+                const double4 q = tile[jj];
+                if (hit(s, r1, q.x, q.y, q.z, q.w, P, j)) {
+                    if (FILL) emit(out, base + found, i, j, gb, 0);
+                    found++;
+                }
+            }
+        }
+    }
+    if (!FILL && valid) count[(uint64_t)g * n + i] = found;
+}
+
+// ---- TREE ---------------------------------------------------------------------------------------
+struct TreeColArgs {
+    const double4* pos; const double4* geo; const int4* meta; uint32_t n_cells;
+    const uint32_t* perm; uint32_t n;
+    const GhostShifts* ghosts;
+    double r2nd;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColArgs a, uint32_t* __restrict__ count,
+                                                             const uint32_t* __restrict__ off, rebcu_collision* __restrict__ out) {
+    const uint32_t k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= a.n) return;
+    const uint32_t i = a.perm[k];            // key order => neighbouring lanes walk neighbouring paths
+    const double r1 = P.r[i];
+    const double reach = s_add(r1, a.r2nd);
+    uint32_t found = 0;
+    const uint64_t base = FILL ? off[i] : 0;
+    const int ngb = a.ghosts->n;
+    for (int g = 0; g < ngb; g++) {
+        const rebcu_vec6d gb = a.ghosts->gb[g];
+        const rebcu_vec6d s = shifted(gb, P, i);
+        uint32_t c = 0;
+        while (c < a.n_cells) {
+            const int4 mt = a.meta[c];
+            if (mt.x >= 0) {
+                if ((uint32_t)mt.x != i) {
+                    const double4 q = a.pos[c];                      // leaf: the particle's own position
+                    if (hit(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x)) {
+                        if (FILL) emit(out, base + found, i, (uint32_t)mt.x, gb, (uint64_t)mt.w);
+                        found++;
+                    }
+                }
+                c = mt.y;
+            } else {
+                const double4 q = a.geo[c];
+                const double dx = s_sub(s.x, q.x), dy = s_sub(s.y, q.y), dz = s_sub(s.z, q.z);
+                const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+                const double rp = s_add(reach, s_mul(0.86602540378443, q.w));       // collision.c:492
+                c = (r2 < s_mul(rp, rp)) ? c + 1 : (uint32_t)mt.y;
+            }
+        }
+    }
+    if (!FILL) count[i] = found;
+}
+
+// Radius of the second largest particle (reb_simulation_two_largest_particles, simulation.c:718-799).
+__global__ void __launch_bounds__(1024) second_largest_kernel(const double* __restrict__ r, uint32_t n, double* out) {
+    __shared__ double s1[1024], s2[1024];
+    double l1 = -1.0, l2 = -1.0;
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+        const double v = r[i];
+        if (v > l1) { l2 = l1; l1 = v; } else if (v > l2) l2 = v;
+    }
+    s1[threadIdx.x] = l1; s2[threadIdx.x] = l2;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            const double a1 = s1[threadIdx.x], a2 = s2[threadIdx.x], b1 = s1[threadIdx.x + w], b2 = s2[threadIdx.x + w];
+            // two largest of the multiset {a1,a2,b1,b2}
+            const double m1 = a1 > b1 ? a1 : b1;
+            const double lo = a1 > b1 ? b1 : a1;
+            const double hi2 = a1 > b1 ? a2 : b2;
+            s1[threadIdx.x] = m1; s2[threadIdx.x] = lo > hi2 ? lo : hi2;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (n >= 2) ? s2[0] : 0.0;
+}
+
+int ensure_lists(rebcu_handle* h, uint64_t n_counts) {
+    if (h->col_cap_n < n_counts + 1) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->col_count); cudaFree(h->col_off); cudaFree(h->col_scan_tmp);
+        h->col_count = nullptr; h->col_off = nullptr; h->col_scan_tmp = nullptr;
+        const uint64_t cap = n_counts + n_counts / 8 + 1024;
+        CU_TRY(h, cudaMalloc(&h->col_count, cap * sizeof(uint32_t)));
+        CU_TRY(h, cudaMalloc(&h->col_off, cap * sizeof(uint32_t)));
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, h->col_count, (uint32_t*)h->col_off, (int)cap, h->stream);
+        CU_TRY(h, cudaMalloc(&h->col_scan_tmp, tb));
+        h->col_scan_tmp_bytes = tb;
+        h->col_cap_n = cap;
+    }
+    return REBCU_OK;
+}
+
+// scan the counts (n_counts entries + a zero sentinel) and fetch the total
+int scan_counts(rebcu_handle* h, uint64_t n_counts, uint64_t* total) {
+    CU_TRY(h, cudaMemsetAsync(h->col_count + n_counts, 0, sizeof(uint32_t), h->stream));
+    size_t tb = h->col_scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(h->col_scan_tmp, tb, h->col_count, (uint32_t*)h->col_off, (int)n_counts + 1, h->stream);
+    uint32_t* pin = (uint32_t*)h->pinned;
+    CU_TRY(h, cudaMemcpyAsync(pin, (uint32_t*)h->col_off + n_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    *total = pin[0];
+    if (*total > h->col_cap) {
+        cudaFree(h->col_list); h->col_list = nullptr;
+        const uint64_t cap = *total + *total / 4 + 1024;
+        CU_TRY(h, cudaMalloc(&h->col_list, cap * sizeof(rebcu_collision)));
+        h->col_cap = cap;
+    }
+    return REBCU_OK;
+}
+
+}  // namespace
+
+int collision_search(rebcu_handle* h, const rebcu_config* c) {
+    h->col_n = 0;
+    const uint64_t n = h->N;
+    if (c->collision == REBCU_COLLISION_NONE || n == 0) return REBCU_OK;
+    if (c->collision != REBCU_COLLISION_DIRECT && c->collision != REBCU_COLLISION_TREE)
+        return rebcu_fail(h, REBCU_ERR_ARG, "Collision routine not implemented.");
+    if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "collision search supports N < 2^31");
+    // only the innermost ring of ghost boxes (collision.c:67-69, 214-216)
+    GhostShifts g;
+    engine_ghost_shifts(c, c->N_ghost_x > 1 ? 1 : c->N_ghost_x, c->N_ghost_y > 1 ? 1 : c->N_ghost_y,
+                        c->N_ghost_z > 1 ? 1 : c->N_ghost_z, &g);
+    int err;
+    ColSoa P = col_soa(h);
+    uint64_t total = 0;
+    if (c->collision == REBCU_COLLISION_DIRECT) {
+        if ((err = engine_upload_ghosts(h, &g))) return err;
+        const uint64_t n_counts = (uint64_t)g.n * n;
+        if ((err = ensure_lists(h, n_counts))) return err;
+        dim3 grid(div_up(n, 128), g.n);
+        {
+            LaunchScope ls(h, TC_COLLISION, 2);
+            direct_collision_kernel<false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, h->col_count, nullptr, nullptr);
+        }
+        CU_TRY(h, cudaGetLastError());
+        if ((err = scan_counts(h, n_counts, &total))) return err;
+        if (total) {
+            LaunchScope ls(h, TC_COLLISION);
+            direct_collision_kernel<true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list);
+        }
+    } else {
+        if ((err = tree_build(h, c))) return err;                       // collision.c:200
+        if ((err = engine_upload_ghosts(h, &g))) return err;
+        if ((err = ensure_lists(h, n))) return err;
+        TreeBuffers& T = h->tree;
+        TreeColArgs a;
+        a.pos = T.walk_pos; a.geo = T.walk_geo; a.meta = (const int4*)T.walk_meta; a.n_cells = (uint32_t)T.n_cells;
+        a.perm = T.perm; a.n = (uint32_t)n; a.ghosts = h->ghosts_dev;
+        {
+            LaunchScope ls(h, TC_COLLISION, 2);
+            second_largest_kernel<<<1, 1024, 0, h->stream>>>(P.r, (uint32_t)n, h->scratch);
+        }
+        double* pin = (double*)(h->pinned + 8);
+        CU_TRY(h, cudaMemcpyAsync(pin, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        a.r2nd = pin[0];
+        {
+            LaunchScope ls(h, TC_COLLISION);
+            tree_collision_kernel<false><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr);
+        }
+        CU_TRY(h, cudaGetLastError());
+        if ((err = scan_counts(h, n, &total))) return err;
+        if (total) {
+            LaunchScope ls(h, TC_COLLISION);
+            tree_collision_kernel<true><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, nullptr, (const uint32_t*)h->col_off, h->col_list);
+        }
+    }
+    CU_TRY(h, cudaGetLastError());
+    h->col_n = total;
+    return REBCU_OK;
+}

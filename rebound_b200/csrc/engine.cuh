@@ -49,6 +49,7 @@ struct TreeBuffers {
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
     uint64_t n_cells = 0;
+    uint32_t* shard_list = nullptr; // [cap_n] sorted positions owned by this rank (multi-GPU walk)
     int* flags = nullptr;          // device error flags [8]
     int built_for_n = -1;
 };
@@ -76,7 +77,7 @@ struct rebcu_handle {
     int ghost_ring_next = 0;
     TreeBuffers tree;
     // collision buffers
-    uint32_t* col_count = nullptr; uint64_t* col_off = nullptr; uint64_t col_cap_n = 0;
+    uint32_t* col_count = nullptr; uint32_t* col_off = nullptr; uint64_t col_cap_n = 0;
     rebcu_collision* col_list = nullptr; uint64_t col_cap = 0; uint64_t col_n = 0;
     void* col_scan_tmp = nullptr; size_t col_scan_tmp_bytes = 0;
     // small device scratch
@@ -125,6 +126,7 @@ int sei_step(rebcu_handle* h, rebcu_config* c);
 int boundary_check(rebcu_handle* h, rebcu_config* c);
 int tree_build(rebcu_handle* h, const rebcu_config* c);
 int tree_gravity(rebcu_handle* h, rebcu_config* c);
+int tree_export(rebcu_handle* h);
 int collision_search(rebcu_handle* h, const rebcu_config* c);
 int update_acceleration(rebcu_handle* h, rebcu_config* c);
 void engine_shard(const rebcu_handle* h, uint64_t* b, uint64_t* e);

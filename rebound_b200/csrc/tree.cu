@@ -1,5 +1,516 @@
-// tree.cu -- placeholder, replaced below in this round.
+// tree.cu -- octree build, multipole (mass / centre-of-mass) pass and Barnes-Hut walk.
+//
+// Replaces reb_tree_construct / reb_tree_add_particle_to_cell (src/tree.c:254-271, 80-134),
+// reb_tree_calculate_gravity_data (src/tree.c:147-229), reb_tree_calculate_acceleration_for_particle
+// (src/tree.c:275-328), reb_tree_delete (src/tree.c:231-252, nothing to do here: arena buffers) and
+// reb_gravity_tree_calculate_acceleration (src/gravity.c:47-106).
+//
+// The reference inserts particles one by one into a pointer octree with one particle per leaf and
+// unbounded depth.  Its topology does not depend on the insertion order: a cell exists iff it
+// contains >= 1 particle and its parent contains >= 2.  So the identical tree is built in bulk:
+//   1. keys      per particle: root box (particle.c:119-126) and the octant path obtained by REPLAYING
+//                the reference's `p < centre` comparisons with its exact centre recurrence
+//                (centre = parent centre +- w/4, tree.c:99-102, which rounds when root_size is not a
+//                power of two) -- octant bit 1 = low side, so ascending key order = the reference's
+//                depth-first octant order.  64-bit key = root box | 3 bits per level.
+//   2. sort      stable LSD radix sort of (key, index) [cub::DeviceRadixSort as the staging sorter].
+//   3. ties      particles agreeing in all key levels are ordered (and duplicates detected,
+//                tree.c:119-123) by continuing the exact descent pairwise.
+//   4. lcp       common path length of sorted neighbours; cells opened at sorted position k are the
+//                internal cells at depths (lcp[k], lcp[k+1]] plus the leaf at 1+max(lcp[k],lcp[k+1]).
+//   5. cells     emitted in depth-first pre-order (= sorted order) with the reference's geometry,
+//                pt = particle index or -(particle count), and skip = first cell after the subtree.
+//   6. moments   bottom-up with per-cell child counters; each parent combines its children in octant
+//                order with the reference's expression (tree.c:162-179), so m, mx, my, mz are bitwise.
+//   7. walk      one thread per particle in key order (spatially coherent warps), stackless pre-order
+//                traversal with per-lane opening decisions: every particle sees exactly the
+//                reference's interaction list in the reference's order (ghost boxes, root boxes,
+//                octants ascending) => bitwise accelerations in STRICT mode.
+// Bounds: build steps are HBM-streaming (keys 24 B in / 12 B out per particle, sort ~8 passes x 24 B,
+// cells ~1.5/particle x 80 B out); the walk is FP64-pipe / L2-latency bound.
 #include "engine.cuh"
-void tree_free(rebcu_handle* h) { (void)h; }
-int tree_build(rebcu_handle* h, const rebcu_config* c) { (void)c; return rebcu_fail(h, REBCU_ERR_ARG, "tree not built yet"); }
-int tree_gravity(rebcu_handle* h, rebcu_config* c) { (void)c; return rebcu_fail(h, REBCU_ERR_ARG, "tree not built yet"); }
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <math.h>
+
+namespace {
+
+constexpr int MAX_DESCENT = 1200;   // below 2^-1074 x root_size a cell has width zero (tree.c:107-111)
+constexpr int W_TABLE = 64;
+
+struct TreeParams {
+    double root_size;
+    int Nx, Ny, Nz;
+    int L0;        // octant levels stored in the key
+    int rbits;     // bits of root box index above the path
+    uint64_t n;
+};
+
+struct Geo { double cx, cy, cz, w; };
+
+// Root box of a particle and that root cell's centre: particle.c:119-126 and tree.c:87-97.
+__device__ __forceinline__ int root_cell(const TreeParams& P, double x, double y, double z, Geo& g) {
+    const double rs = P.root_size;
+    const double bx = s_mul(rs, (double)P.Nx), by = s_mul(rs, (double)P.Ny), bz = s_mul(rs, (double)P.Nz);
+    const int i = ((int)floor(s_div(s_add(x, s_div(bx, 2.)), rs)) + P.Nx) % P.Nx;
+    const int j = ((int)floor(s_div(s_add(y, s_div(by, 2.)), rs)) + P.Ny) % P.Ny;
+    const int k = ((int)floor(s_div(s_add(z, s_div(bz, 2.)), rs)) + P.Nz) % P.Nz;
+    g.w = rs;
+    g.cx = s_add(s_div(-bx, 2.), s_mul(rs, s_add(0.5, (double)i)));
+    g.cy = s_add(s_div(-by, 2.), s_mul(rs, s_add(0.5, (double)j)));
+    g.cz = s_add(s_div(-bz, 2.), s_mul(rs, s_add(0.5, (double)k)));
+    return (k * P.Ny + j) * P.Nx + i;
+}
+
+// Octant of (x,y,z) in cell g (tree.c:136-142), then g becomes that child cell (tree.c:99-102).
+__device__ __forceinline__ int descend(Geo& g, double x, double y, double z) {
+    const int o = (x < g.cx ? 1 : 0) | (y < g.cy ? 2 : 0) | (z < g.cz ? 4 : 0);
+    g.w = s_div(g.w, 2.);
+    const double q = s_div(g.w, 2.);
+    g.cx = s_add(g.cx, (o & 1) ? -q : q);
+    g.cy = s_add(g.cy, (o & 2) ? -q : q);
+    g.cz = s_add(g.cz, (o & 4) ? -q : q);
+    return o;
+}
+
+// flags: [0] min index outside box, [1] min index non-finite, [2] min (larger index) of a duplicate pair,
+//        [3] cell size zero
+__global__ void __launch_bounds__(256) key_kernel(TreeParams P, const double* __restrict__ x, const double* __restrict__ y,
+                                                  const double* __restrict__ z, uint64_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ idx, int* flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.n) return;
+    const double px = x[i], py = y[i], pz = z[i];
+    idx[i] = (uint32_t)i;
+    const double rs = P.root_size;
+    // tree.c:265-268 then tree.c:66-69
+    if (fabs(px) > s_div(s_mul(rs, (double)P.Nx), 2.) || fabs(py) > s_div(s_mul(rs, (double)P.Ny), 2.) ||
+        fabs(pz) > s_div(s_mul(rs, (double)P.Nz), 2.)) { atomicMin(&flags[0], (int)i); keys[i] = ~0ull; return; }
+    if (!isfinite(px) || !isfinite(py) || !isfinite(pz)) { atomicMin(&flags[1], (int)i); keys[i] = ~0ull; return; }
+    Geo g;
+    const int rb = root_cell(P, px, py, pz, g);
+    uint64_t key = (uint64_t)rb;
+    for (int l = 0; l < P.L0; l++) key = (key << 3) | (uint64_t)descend(g, px, py, pz);
+    keys[i] = key;
+}
+
+// Number of common octant levels of two particles known to share all L0 key levels (or -2 if identical
+// coordinates); *less = a sorts before b.
+__device__ int deep_common(const TreeParams& P, double ax, double ay, double az, double bx, double by, double bz,
+                           bool* less, int* flags) {
+    if (ax == bx && ay == by && az == bz) { *less = false; return -2; }
+    Geo g;
+    root_cell(P, ax, ay, az, g);
+    int c = 0;
+    for (; c < MAX_DESCENT; c++) {
+        Geo ga = g;
+        const int oa = descend(ga, ax, ay, az);
+        Geo gb = g;
+        const int ob = descend(gb, bx, by, bz);
+        if (oa != ob) { *less = oa < ob; return c; }
+        g = ga;
+        if (!(g.w > 0.0)) { atomicMin(&flags[3], 1); break; }
+    }
+    *less = false;
+    return c;
+}
+
+// Orders runs of equal keys by the deeper path (insertion sort by the thread owning the run start).
+__global__ void __launch_bounds__(256) tie_kernel(TreeParams P, const uint64_t* __restrict__ keys, uint32_t* __restrict__ perm,
+                                                  const double* __restrict__ x, const double* __restrict__ y,
+                                                  const double* __restrict__ z, int* flags) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k + 1 >= P.n) return;
+    if (keys[k] != keys[k + 1]) return;
+    if (k > 0 && keys[k - 1] == keys[k]) return;     // not the run start
+    uint64_t e = k + 1;
+    while (e + 1 < P.n && keys[e + 1] == keys[k]) e++;
+    for (uint64_t a = k + 1; a <= e; a++) {
+        const uint32_t pa = perm[a];
+        const double ax = x[pa], ay = y[pa], az = z[pa];
+        uint64_t b = a;
+        while (b > k) {
+            const uint32_t pb = perm[b - 1];
+            bool less;
+            const int c = deep_common(P, ax, ay, az, x[pb], y[pb], z[pb], &less, flags);
+            if (c == -2) { atomicMin(&flags[2], (int)max(pa, pb)); break; }
+            if (!less) break;
+            perm[b] = pb;
+            b--;
+        }
+        perm[b] = pa;
+    }
+}
+
+// lcp[k] = common octant levels of sorted particles k-1 and k (same root box), -1 across root boxes and
+// at both ends (k = 0 and k = n).
+__global__ void __launch_bounds__(256) lcp_kernel(TreeParams P, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+                                                  const double* __restrict__ x, const double* __restrict__ y,
+                                                  const double* __restrict__ z, int32_t* __restrict__ lcp, int* flags) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k > P.n) return;
+    if (k == 0 || k == P.n) { lcp[k] = -1; return; }
+    const uint64_t a = keys[k - 1], b = keys[k];
+    int c;
+    if (a != b) {
+        const uint64_t d = a ^ b;
+        const int hb = 63 - __clzll((long long)d);
+        c = (hb >= 3 * P.L0) ? -1 : (P.L0 - 1 - hb / 3);
+    } else {
+        const uint32_t pa = perm[k - 1], pb = perm[k];
+        bool less;
+        c = deep_common(P, x[pa], y[pa], z[pa], x[pb], y[pb], z[pb], &less, flags);
+        if (c == -2) { atomicMin(&flags[2], (int)max(pa, pb)); c = P.L0; }
+        else c += 0;
+    }
+    lcp[k] = c;
+}
+
+__global__ void __launch_bounds__(256) count_kernel(uint64_t n, const int32_t* __restrict__ lcp, uint32_t* __restrict__ cnt) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const int d = lcp[k + 1] - lcp[k];
+    cnt[k] = (uint32_t)((d > 0 ? d : 0) + 1);
+}
+
+struct CellArrays {
+    double4* pos;    // mx,my,mz,m
+    double4* geo;    // x,y,z,w
+    int4* meta;      // pt, skip, depth, rootbox
+    int32_t* parent;
+    uint32_t* ready; // children still missing
+};
+
+// Emits the cells opened at sorted position k (geometry, pt, skip, depth, rootbox; leaf moments).
+__global__ void __launch_bounds__(128) emit_kernel(TreeParams P, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+                                                   const int32_t* __restrict__ lcp, const uint32_t* __restrict__ off,
+                                                   const double* __restrict__ x, const double* __restrict__ y,
+                                                   const double* __restrict__ z, const double* __restrict__ m, CellArrays C) {
+    const uint64_t k = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (k >= P.n) return;
+    const int lo = lcp[k], hi = lcp[k + 1];
+    const int n_int = hi > lo ? hi - lo : 0;
+    const int leaf_depth = 1 + (lo > hi ? lo : hi);
+    const uint32_t base = off[k];
+    const uint32_t p = perm[k];
+    const double px = x[p], py = y[p], pz = z[p];
+    Geo g;
+    const int rb = root_cell(P, px, py, pz, g);
+    const uint64_t key = keys[k];
+    for (int d = 0; d <= leaf_depth; d++) {
+        if (d > 0) descend(g, px, py, pz);
+        const bool internal = (d > lo && d <= hi);
+        if (!internal && d != leaf_depth) continue;
+        const uint32_t c = internal ? base + (uint32_t)(d - lo - 1) : base + (uint32_t)n_int;
+        C.geo[c] = make_double4(g.cx, g.cy, g.cz, g.w);
+        if (!internal) {
+            C.meta[c] = make_int4((int)p, (int)c + 1, d, rb);
+            C.pos[c] = make_double4(px, py, pz, m[p]);      // tree.c:201-205
+            C.ready[c] = 0;
+            continue;
+        }
+        // last sorted position whose path shares the first d levels with particle k
+        uint64_t e;
+        if (d <= P.L0) {
+            const int sh = 3 * (P.L0 - d);
+            const uint64_t pref = key >> sh;
+            uint64_t step = 1, loj = k + 1;         // loj is known to be inside (lcp[k+1] >= d)
+            uint64_t hij = P.n;                      // first position known to be outside (exclusive bound)
+            while (loj + step < P.n && (keys[loj + step] >> sh) == pref) { loj += step; step <<= 1; }
+            if (loj + step < hij) hij = loj + step;
+            while (loj + 1 < hij) {                   // invariant: loj inside, hij outside or n
+                const uint64_t mid = loj + (hij - loj) / 2;
+                if ((keys[mid] >> sh) == pref) loj = mid; else hij = mid;
+            }
+            e = loj;
+        } else {
+            e = k + 1;
+            while (e + 1 < P.n && lcp[e + 1] >= d) e++;
+        }
+        C.meta[c] = make_int4(-(int)(e - k + 1), (int)off[e + 1], d, rb);
+    }
+}
+
+// Every internal cell adopts its children (the first child follows it, the next one starts where the
+// previous subtree ends) and counts them.
+__global__ void __launch_bounds__(256) adopt_kernel(uint64_t n_cells, CellArrays C) {
+    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cells) return;
+    const int4 mt = C.meta[c];
+    if (mt.z == 0) C.parent[c] = -1;
+    if (mt.x >= 0) return;
+    uint32_t nch = 0;
+    for (int ch = (int)c + 1; ch < mt.y; ch = C.meta[ch].y) { C.parent[ch] = (int)c; nch++; }
+    C.ready[c] = nch;
+}
+
+// Bottom-up moments: the thread that delivers the last child of a cell computes that cell
+// (tree.c:156-179: children in octant order, sum of mx*m, then divide by the total mass).
+__global__ void __launch_bounds__(256) moment_kernel(uint64_t n_cells, CellArrays C) {
+    const uint64_t c0 = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c0 >= n_cells) return;
+    if (C.meta[c0].x < 0) return;            // start from leaves only
+    int c = C.parent[c0];
+    while (c >= 0) {
+        __threadfence();
+        if (atomicSub(&C.ready[c], 1u) != 1u) return;    // siblings still pending
+        __threadfence();
+        const int end = C.meta[c].y;
+        double mm = 0., mx = 0., my = 0., mz = 0.;
+        for (int ch = c + 1; ch < end; ch = C.meta[ch].y) {
+            const volatile double4* q = (const volatile double4*)&C.pos[ch];
+            const double dx = q->x, dy = q->y, dz = q->z, dm = q->w;
+            mx = s_add(mx, s_mul(dx, dm));
+            my = s_add(my, s_mul(dy, dm));
+            mz = s_add(mz, s_mul(dz, dm));
+            mm = s_add(mm, dm);
+        }
+        if (mm > 0) { mx = s_div(mx, mm); my = s_div(my, mm); mz = s_div(mz, mm); }
+        volatile double4* o = (volatile double4*)&C.pos[c];
+        o->x = mx; o->y = my; o->z = mz; o->w = mm;
+        c = C.parent[c];
+    }
+}
+
+__global__ void __launch_bounds__(256) export_kernel(uint64_t n_cells, CellArrays C, rebcu_treecell* out) {
+    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cells) return;
+    const double4 g = C.geo[c], p = C.pos[c];
+    const int4 mt = C.meta[c];
+    rebcu_treecell t;
+    t.x = g.x; t.y = g.y; t.z = g.z; t.w = g.w; t.m = p.w; t.mx = p.x; t.my = p.y; t.mz = p.z;
+    t.pt = mt.x; t.skip = mt.y; t.depth = mt.z; t.rootbox = mt.w;
+    out[c] = t;
+}
+
+// ---- Barnes-Hut walk -----------------------------------------------------------------------------
+struct WalkArgs {
+    const double4* pos; const int4* meta; uint64_t n_cells;
+    const uint32_t* perm; const uint32_t* list; uint64_t n_work;     // work item t -> sorted position (list[t] or t)
+    const double* x; const double* y; const double* z;
+    double* ax; double* ay; double* az;
+    const GhostShifts* ghosts;
+    double G, soft2, theta2;
+    double w2[W_TABLE];      // squared cell width by depth
+    double root_size;
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (t >= a.n_work) return;
+    const uint64_t k = a.list ? a.list[t] : t;
+    const uint32_t self = a.perm[k];
+    const double px = a.x[self], py = a.y[self], pz = a.z[self];
+    double sx = 0., sy = 0., sz = 0.;
+    const double negG = -a.G;
+    const int ngb = a.ghosts->n;
+    const int n_cells = (int)a.n_cells;
+    for (int g = 0; g < ngb; g++) {
+        // gravity.c:93-97: shifted position = ghost box offset + particle position
+        const double gx = s_add(a.ghosts->gb[g].x, px), gy = s_add(a.ghosts->gb[g].y, py), gz = s_add(a.ghosts->gb[g].z, pz);
+        int c = 0;
+        while (c < n_cells) {
+            const double4 q = a.pos[c];
+            const int4 mt = a.meta[c];
+            const double dx = s_sub(gx, q.x), dy = s_sub(gy, q.y), dz = s_sub(gz, q.z);
+            const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+            if (mt.x < 0) {
+                double w2;
+                if (mt.z < W_TABLE) w2 = a.w2[mt.z];
+                else { double w = a.root_size; for (int d = 0; d < mt.z; d++) w = s_div(w, 2.); w2 = s_mul(w, w); }
+                if (w2 > s_mul(a.theta2, r2)) { c++; continue; }          // tree.c:284: open the cell
+            } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }    // tree.c:311
+            if (FAST) {
+                const double ri = rsqrt(r2 + a.soft2);
+                const double p = negG * q.w * (ri * ri * ri);
+                sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
+            } else {
+                const double r = s_sqrt(s_add(r2, a.soft2));
+                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), q.w);   // tree.c:292,313
+                sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
+            }
+            c = mt.y;
+        }
+    }
+    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+}
+
+__global__ void __launch_bounds__(256) shard_flag_kernel(uint64_t n, const uint32_t* __restrict__ perm, uint32_t b, uint32_t e,
+                                                         uint32_t* __restrict__ flag) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k < n) { const uint32_t p = perm[k]; flag[k] = (p >= b && p < e) ? 1u : 0u; }
+}
+__global__ void __launch_bounds__(256) shard_list_kernel(uint64_t n, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                                                         uint32_t* __restrict__ list) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k < n && flag[k]) list[pos[k]] = (uint32_t)k;
+}
+
+template <typename T>
+int ensure(rebcu_handle* h, T** ptr, size_t count) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    CU_TRY(h, cudaMalloc(ptr, count * sizeof(T)));
+    return REBCU_OK;
+}
+
+}  // namespace
+
+void tree_free(rebcu_handle* h) {
+    TreeBuffers& T = h->tree;
+    cudaFree(T.keys); cudaFree(T.keys_sorted); cudaFree(T.perm); cudaFree(T.perm_in); cudaFree(T.lcp);
+    cudaFree(T.cell_off); cudaFree(T.cell_cnt); cudaFree(T.cells); cudaFree(T.parent); cudaFree(T.ready);
+    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
+    cudaFree(T.shard_list);
+    T = TreeBuffers();
+}
+
+static int tree_error(rebcu_handle* h, const int* f) {
+    // The reference stops at the first offending particle in index order (tree.c:263-270).
+    int best = 0x7fffffff, which = -1;
+    for (int k = 0; k < 3; k++) if (f[k] < best) { best = f[k]; which = k; }
+    if (which == 0) return rebcu_fail(h, REBCU_ERR_OUTSIDE_BOX, "Particle is outside of simulation box. Cannot add to tree.");
+    if (which == 1) return rebcu_fail(h, REBCU_ERR_NONFINITE, "Particle has non-finite coordinates. Cannot add to tree.");
+    if (which == 2) return rebcu_fail(h, REBCU_ERR_SAME_COORDINATES, "Cannot add two particles with the same coordinates to the tree.");
+    if (f[3] != 0x7fffffff) return rebcu_fail(h, REBCU_ERR_CELL_SIZE_ZERO, "Tree cell has size zero.");
+    return REBCU_OK;
+}
+
+int tree_build(rebcu_handle* h, const rebcu_config* c) {
+    TreeBuffers& T = h->tree;
+    if (c->root_size <= 0.0)
+        return rebcu_fail(h, REBCU_ERR_ROOT_SIZE, "Set root_size to a finite value to use a tree based gravity or collision solver.");
+    const uint64_t n = h->N;
+    T.n_cells = 0;
+    if (n == 0) return REBCU_OK;
+    if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "tree supports N < 2^31 (int indices, tree.h:52)");
+    TreeParams P;
+    P.root_size = c->root_size; P.Nx = c->N_root_x; P.Ny = c->N_root_y; P.Nz = c->N_root_z; P.n = n;
+    const uint64_t n_root = (uint64_t)P.Nx * P.Ny * P.Nz;
+    P.rbits = 0;
+    while ((1ull << P.rbits) < n_root) P.rbits++;
+    P.L0 = (63 - P.rbits) / 3;
+    if (P.L0 < 1) return rebcu_fail(h, REBCU_ERR_ARG, "too many root boxes");
+
+    if (T.cap_n < n) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        const uint64_t cap = h->cap > n ? h->cap : n;
+        int err;
+        if ((err = ensure(h, &T.keys, cap))) return err;
+        if ((err = ensure(h, &T.keys_sorted, cap))) return err;
+        if ((err = ensure(h, &T.perm, cap))) return err;
+        if ((err = ensure(h, &T.perm_in, cap))) return err;
+        if ((err = ensure(h, &T.lcp, cap + 1))) return err;
+        if ((err = ensure(h, &T.cell_off, cap + 1))) return err;
+        if ((err = ensure(h, &T.cell_cnt, cap + 1))) return err;
+        if ((err = ensure(h, &T.shard_list, cap))) return err;
+        if (!T.flags) { if ((err = ensure(h, &T.flags, 8))) return err; }
+        size_t sb = 0, cb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sb, T.keys, T.keys_sorted, T.perm_in, T.perm, (int)cap, 0, 64, h->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, cb, T.cell_cnt, T.cell_off, (int)cap + 1, h->stream);
+        cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); T.sort_tmp = T.scan_tmp = nullptr;
+        CU_TRY(h, cudaMalloc(&T.sort_tmp, sb)); T.sort_tmp_bytes = sb;
+        CU_TRY(h, cudaMalloc(&T.scan_tmp, cb)); T.scan_tmp_bytes = cb;
+        T.cap_n = cap;
+    }
+    const double *x = h->f(F_X), *y = h->f(F_Y), *z = h->f(F_Z), *m = h->f(F_M);
+    {
+        LaunchScope ls(h, TC_TREEBUILD, 6);
+        CU_TRY(h, cudaMemsetAsync(T.flags, 0x7f, 8 * sizeof(int), h->stream));   // 0x7f7f7f7f: "no error"
+        key_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(P, x, y, z, T.keys, T.perm_in, T.flags);
+        size_t sb = T.sort_tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(T.sort_tmp, sb, T.keys, T.keys_sorted, T.perm_in, T.perm, (int)n, 0, P.rbits + 3 * P.L0, h->stream);
+        tie_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(P, T.keys_sorted, T.perm, x, y, z, T.flags);
+        lcp_kernel<<<div_up(n + 1, 256), 256, 0, h->stream>>>(P, T.keys_sorted, T.perm, x, y, z, T.lcp, T.flags);
+        count_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.lcp, T.cell_cnt);
+        CU_TRY(h, cudaMemsetAsync(T.cell_cnt + n, 0, sizeof(uint32_t), h->stream));
+        size_t cb = T.scan_tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(T.scan_tmp, cb, T.cell_cnt, T.cell_off, (int)n + 1, h->stream);
+    }
+    CU_TRY(h, cudaGetLastError());
+    // cell count and error flags back to the host
+    int* pin = (int*)h->pinned;
+    CU_TRY(h, cudaMemcpyAsync(pin, T.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(pin + 4, T.cell_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    int f[4];
+    for (int k = 0; k < 4; k++) f[k] = (pin[k] == 0x7f7f7f7f) ? 0x7fffffff : pin[k];
+    if (f[0] != 0x7fffffff || f[1] != 0x7fffffff || f[2] != 0x7fffffff || f[3] != 0x7fffffff) return tree_error(h, f);
+    const uint64_t n_cells = (uint32_t)pin[4];
+    if (T.cap_cells < n_cells) {
+        const uint64_t cap = n_cells + n_cells / 8 + 1024;
+        int err;
+        if ((err = ensure(h, &T.walk_pos, cap))) return err;
+        if ((err = ensure(h, &T.walk_geo, cap))) return err;
+        if ((err = ensure(h, (int4**)&T.walk_meta, cap))) return err;
+        if ((err = ensure(h, &T.parent, cap))) return err;
+        if ((err = ensure(h, &T.ready, cap))) return err;
+        cudaFree(T.cells); T.cells = nullptr;
+        T.cap_cells = cap;
+    }
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready};
+    {
+        LaunchScope ls(h, TC_TREEBUILD, 3);
+        emit_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(P, T.keys_sorted, T.perm, T.lcp, T.cell_off, x, y, z, m, C);
+        adopt_kernel<<<div_up(n_cells, 256), 256, 0, h->stream>>>(n_cells, C);
+        moment_kernel<<<div_up(n_cells, 256), 256, 0, h->stream>>>(n_cells, C);
+    }
+    CU_TRY(h, cudaGetLastError());
+    T.n_cells = n_cells;
+    T.built_for_n = (int)n;
+    return REBCU_OK;
+}
+
+// Copies the tree out as rebcu_treecell records (parity tests).
+int tree_export(rebcu_handle* h) {
+    TreeBuffers& T = h->tree;
+    if (T.n_cells == 0) return REBCU_OK;
+    if (!T.cells) CU_TRY(h, cudaMalloc(&T.cells, T.cap_cells * sizeof(rebcu_treecell)));
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready};
+    export_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, C, T.cells);
+    CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}
+
+int tree_gravity(rebcu_handle* h, rebcu_config* c) {
+    int err = boundary_check(h, c);                       // gravity.c:56
+    if (err) return err;
+    err = tree_build(h, c);                               // gravity.c:63-71
+    if (err) return err;
+    const uint64_t n = h->N;
+    if (n == 0) return REBCU_OK;
+    TreeBuffers& T = h->tree;
+    GhostShifts g;
+    engine_ghost_shifts(c, c->N_ghost_x, c->N_ghost_y, c->N_ghost_z, &g);
+    err = engine_upload_ghosts(h, &g);
+    if (err) return err;
+    WalkArgs a;
+    a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.n_cells = T.n_cells;
+    a.perm = T.perm; a.list = nullptr; a.n_work = n;
+    a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
+    a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
+    a.ghosts = h->ghosts_dev;
+    a.G = c->G; a.soft2 = c->softening * c->softening; a.theta2 = c->opening_angle2;
+    a.root_size = c->root_size;
+    double w = c->root_size;
+    for (int d = 0; d < W_TABLE; d++) { a.w2[d] = w * w; w = w / 2.; }
+    if (h->world > 1) {
+        // walk only the particles of this rank's index block, visited in key order
+        uint64_t b, e; engine_shard(h, &b, &e);
+        uint32_t* flag = T.cell_cnt; uint32_t* pos = T.cell_off;      // reuse (build is finished)
+        LaunchScope ls(h, TC_TREEWALK, 3);
+        shard_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.perm, (uint32_t)b, (uint32_t)e, flag);
+        size_t cb = T.scan_tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(T.scan_tmp, cb, flag, pos, (int)n, h->stream);
+        shard_list_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, flag, pos, T.shard_list);
+        a.list = T.shard_list; a.n_work = e - b;
+    }
+    if (a.n_work) {
+        LaunchScope ls(h, TC_TREEWALK);
+        if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<div_up(a.n_work, 128), 128, 0, h->stream>>>(a);
+        else walk_kernel<false><<<div_up(a.n_work, 128), 128, 0, h->stream>>>(a);
+    }
+    CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}

@@ -130,7 +130,7 @@ def selfgravity_disc(n, boxsize=10.2, disc_mass=0.2, seed=42):
     p["z"][1:] = a * rng.normal(0, math.sqrt(0.001), n)
     p["vx"][1:] = vkep * np.sin(phi)
     p["vy"][1:] = -vkep * np.cos(phi)
-    p["m"][1:] = disc_mass / n
+    p["m"][1:] = disc_mass / max(n, 1)
     return p
 
 

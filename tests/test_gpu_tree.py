@@ -1,0 +1,262 @@
+"""GPU parity for the tree path through the C ABI: octree cells (bit-exact leaf / cell assignment,
+geometry and moments), Barnes-Hut accelerations, boundary check, SEI, collision lists, whole steps.
+Checked against the CPU oracle (pinned to the reference) and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import checkers
+from checkers import bits_equal, collisions_equal, max_rel_acc_error
+from rebound_b200 import abi, ics
+from rebound_b200.simulation import Engine, ReboundCudaError
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def tree_cases():
+    yield "disc", ics.selfgravity_disc_config(), ics.selfgravity_disc(3000, seed=2)
+    yield "disc_theta1.5", ics.selfgravity_disc_config(opening_angle2=1.5), ics.selfgravity_disc(700, seed=3)
+    p = ics.plummer(2000, seed=4)
+    yield "plummer_box", ics.plummer_config(2000, gravity=abi.GRAVITY_TREE, root_size=200.0, opening_angle2=0.25), p
+    yield "sheet", ics.shearing_sheet_config(root_size=40.0, t=123.4), ics.shearing_sheet(root_size=40.0, seed=5)
+    yield "rootboxes_3d", ics.plummer_config(2000, gravity=abi.GRAVITY_TREE, root_size=50.0, N_root_x=2, N_root_y=3,
+                                            N_root_z=2, boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=1, N_ghost_y=1, N_ghost_z=1), p
+    yield "single", ics.selfgravity_disc_config(), ics.selfgravity_disc(0, seed=1)
+    yield "pair", ics.selfgravity_disc_config(), ics.selfgravity_disc(1, seed=1)
+    # deep tree: pairs closer than 2^-21 of the box force the tie-break path beyond the 63-bit key
+    q = ics.selfgravity_disc(400, seed=6)
+    q["x"][201:] = q["x"][1:201] + 1e-9 * np.arange(1, 201)
+    q["y"][201:] = q["y"][1:201] - 3e-10
+    q["z"][201:] = q["z"][1:201]
+    yield "deep_pairs", ics.selfgravity_disc_config(), q
+    t = ics.selfgravity_disc(300, seed=7)
+    t["x"][101:201] = t["x"][1:101] * (1 + 2.0**-50)
+    t["y"][101:201] = t["y"][1:101]
+    t["z"][101:201] = t["z"][1:101]
+    t["x"][201:] = t["x"][1:101] * (1 + 2.0**-49)
+    t["y"][201:] = t["y"][1:101]
+    t["z"][201:] = t["z"][1:101]
+    yield "ulp_triples", ics.selfgravity_disc_config(), t
+
+
+TREE_CASES = list(tree_cases())
+IDS = [c[0] for c in TREE_CASES]
+
+
+@pytest.mark.parametrize("name,cfg,p", TREE_CASES, ids=IDS)
+def test_tree_cells_bitwise(eng, name, cfg, p):
+    pb, cb = checkers.oracle().boundary_check(cfg, p)
+    want = checkers.oracle().tree_dump(cb, pb)
+    eng.upload(np.ascontiguousarray(pb))
+    got = eng.tree(cb.copy())
+    assert len(got) == len(want)
+    for f in abi.TREECELL_DTYPE.names:
+        assert np.array_equal(got[f].view(np.uint64 if got[f].dtype == np.float64 else np.int32),
+                              want[f].view(np.uint64 if want[f].dtype == np.float64 else np.int32)), f
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("name,cfg,p", TREE_CASES, ids=IDS)
+def test_tree_gravity_bitwise(eng, name, cfg, p):
+    want, cw = checkers.oracle().gravity(cfg, p)
+    q, c = p.copy(), cfg.copy()
+    n = eng.gravity_host(c, q)
+    assert n == len(want)
+    assert bits_equal(q[:n], want)
+    assert c.N_active == cw.N_active
+
+
+@pytest.mark.parametrize("name,cfg,p", TREE_CASES[:5], ids=IDS[:5])
+def test_tree_gravity_fast_mode(eng, name, cfg, p):
+    want, _ = checkers.oracle().gravity(cfg, p)
+    q, c = p.copy(), cfg.copy()
+    c.mode = abi.MODE_FAST
+    n = eng.gravity_host(c, q)
+    assert max_rel_acc_error(q[:n], want) <= 1e-12
+
+
+def test_tree_error_vs_direct_matches_reference_level(eng):
+    """Tree accuracy against direct summation is the reference's own (identical interaction lists):
+    rms relative error at theta^2=0.25 on a Plummer sphere stays at the few-1e-3 level."""
+    n = 16384
+    p = ics.plummer(n, seed=42)
+    cd = ics.plummer_config(n)
+    ct = ics.plummer_config(n, gravity=abi.GRAVITY_TREE, root_size=400.0, opening_angle2=0.25)
+    inside = (np.abs(p["x"]) < 200) & (np.abs(p["y"]) < 200) & (np.abs(p["z"]) < 200)
+    p = np.ascontiguousarray(p[inside])
+    qd, qt = p.copy(), p.copy()
+    eng.gravity_host(cd.copy(), qd)
+    eng.gravity_host(ct.copy(), qt)
+    a_d = np.stack([qd["ax"], qd["ay"], qd["az"]], 1)
+    a_t = np.stack([qt["ax"], qt["ay"], qt["az"]], 1)
+    rel = np.linalg.norm(a_t - a_d, axis=1) / np.linalg.norm(a_d, axis=1)
+    assert 1e-4 < np.sqrt(np.mean(rel**2)) < 1e-2
+
+
+def test_tree_errors(eng):
+    cfg = ics.selfgravity_disc_config()
+    p = ics.selfgravity_disc(50, seed=2)
+    bad = p.copy(); bad["x"][7] = bad["x"][3]; bad["y"][7] = bad["y"][3]; bad["z"][7] = bad["z"][3]
+    nan = p.copy(); nan["y"][5] = np.nan
+    noroot = ics.selfgravity_disc_config(root_size=-1.0)
+    outside = p.copy(); outside["x"][9] = 100.0
+    cfg_nob = ics.selfgravity_disc_config(boundary=abi.BOUNDARY_NONE)
+    both = outside.copy(); both["y"][5] = np.nan        # index 5 < 9: non-finite is reported first
+    for c, q in ((cfg, bad), (cfg, nan), (noroot, p), (cfg_nob, outside), (cfg_nob, both)):
+        with pytest.raises(checkers.CheckerError) as e1:
+            checkers.oracle().tree_dump(c, q)
+        eng.upload(np.ascontiguousarray(q))
+        with pytest.raises(ReboundCudaError) as e2:
+            eng.tree(c.copy())
+        assert e1.value.msg == e2.value.msg
+        assert e1.value.code == e2.value.code
+
+
+def test_tree_golden(eng):
+    g = np.load(os.path.join(GOLD, "tree_disc400.npz"))
+    p = np.frombuffer(g["particles_in"].tobytes(), dtype=abi.PARTICLE_DTYPE).copy()
+    cfg = ics.selfgravity_disc_config()
+    q, c = p.copy(), cfg.copy()
+    n = eng.gravity_host(c, q)
+    assert n == int(g["n_out"])
+    got = np.stack([q["ax"][:n], q["ay"][:n], q["az"][:n]], 1)
+    assert np.array_equal(got.view(np.uint64), g["acc"].view(np.uint64))
+    eng.boundary_check(c)
+    cells = eng.tree(c)
+    assert cells.tobytes() == g["cells"].tobytes()
+
+
+@pytest.mark.parametrize("boundary", [abi.BOUNDARY_OPEN, abi.BOUNDARY_PERIODIC, abi.BOUNDARY_SHEAR])
+def test_boundary_bitwise(eng, boundary):
+    rng = np.random.default_rng(11)
+    n = 5000
+    p = abi.particles(n)
+    for f in ("x", "y", "z"):
+        p[f] = rng.uniform(-14, 14, n)
+    for f in ("vx", "vy", "vz"):
+        p[f] = rng.normal(0, 1, n)
+    p["m"] = 1.0
+    p["name"] = np.arange(n)          # pointer fields must travel with their particle
+    cfg = abi.default_config(boundary=boundary, root_size=10.0, N_root_x=2, N_root_y=1, N_root_z=1, OMEGA=0.7, t=3.3, N_active=40)
+    want, cw = checkers.oracle().boundary_check(cfg, p)
+    eng.upload(p)
+    c = cfg.copy()
+    eng.boundary_check(c)
+    got = eng.download()
+    assert len(got) == len(want)
+    assert bits_equal(got, want)
+    assert np.array_equal(got["name"], want["name"])
+    assert c.N_active == cw.N_active
+
+
+def test_boundary_open_removes_everything(eng):
+    p = abi.particles(5)
+    p["x"] = 100.0
+    cfg = abi.default_config(boundary=abi.BOUNDARY_OPEN, root_size=10.0, N_active=3)
+    want, cw = checkers.oracle().boundary_check(cfg, p)
+    eng.upload(p)
+    c = cfg.copy()
+    eng.boundary_check(c)
+    assert eng.N == 0 == len(want)
+    assert c.N_active == cw.N_active
+
+
+def collision_cases():
+    p = ics.shearing_sheet(root_size=40.0, seed=5)
+    yield "sheet_tree", ics.shearing_sheet_config(root_size=40.0, t=55.5), p
+    yield "sheet_direct", ics.shearing_sheet_config(root_size=40.0, t=55.5, collision=abi.COLLISION_DIRECT), p
+    rng = np.random.default_rng(3)
+    n = 1500
+    q = abi.particles(n)
+    for f in ("x", "y", "z"):
+        q[f] = rng.uniform(-4.9, 4.9, n)
+    for f in ("vx", "vy", "vz"):
+        q[f] = rng.normal(0, 1, n)
+    q["r"] = rng.uniform(0.02, 0.25, n)
+    q["m"] = 1.0
+    for col in (abi.COLLISION_DIRECT, abi.COLLISION_TREE):
+        yield f"box_open_c{col}", abi.default_config(collision=col, root_size=10.0, boundary=abi.BOUNDARY_OPEN), q
+        yield f"box_per_c{col}", abi.default_config(collision=col, root_size=10.0, boundary=abi.BOUNDARY_PERIODIC,
+                                                    N_ghost_x=1, N_ghost_y=1, N_ghost_z=1), q
+        yield f"box_2root_c{col}", abi.default_config(collision=col, root_size=5.0, N_root_x=2, N_root_y=2, N_root_z=2,
+                                                      boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=2, N_ghost_y=1), q
+    e = abi.particles(3)
+    e["x"] = [0.0, 3.0, -3.0]
+    e["r"] = 0.1
+    yield "no_collisions_tree", abi.default_config(collision=abi.COLLISION_TREE, root_size=10.0), e
+    yield "no_collisions_direct", abi.default_config(collision=abi.COLLISION_DIRECT, root_size=10.0), e
+
+
+COL_CASES = list(collision_cases())
+
+
+@pytest.mark.parametrize("name,cfg,p", COL_CASES, ids=[c[0] for c in COL_CASES])
+def test_collision_list_bitwise(eng, name, cfg, p):
+    want = checkers.oracle().collision_search(cfg, p)
+    got = eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p))
+    assert len(got) == len(want)
+    assert collisions_equal(got, want, with_ri=(cfg.collision == abi.COLLISION_TREE))
+
+
+def test_collision_golden(eng):
+    g = np.load(os.path.join(GOLD, "sheet_root30.npz"))
+    p = np.frombuffer(g["particles_in"].tobytes(), dtype=abi.PARTICLE_DTYPE).copy()
+    cfg = ics.shearing_sheet_config(root_size=30.0, t=55.5)
+    got = eng.collision_search_host(cfg.copy(), p)
+    want = np.frombuffer(g["col_tree"].tobytes(), dtype=abi.COLLISION_DTYPE)
+    assert collisions_equal(got, want)
+    cfg_d = ics.shearing_sheet_config(root_size=30.0, t=55.5, collision=abi.COLLISION_DIRECT)
+    got = eng.collision_search_host(cfg_d.copy(), p)
+    want = np.frombuffer(g["col_direct"].tobytes(), dtype=abi.COLLISION_DTYPE)
+    assert collisions_equal(got, want, with_ri=False)
+    q, c = p.copy(), cfg.copy()
+    n = eng.gravity_host(c, q)
+    got = np.stack([q["ax"][:n], q["ay"][:n], q["az"][:n]], 1)
+    assert np.array_equal(got.view(np.uint64), g["acc"].view(np.uint64))
+
+
+def test_sei_step_bitwise(eng):
+    p = ics.shearing_sheet(root_size=30.0, seed=8)
+    cfg = ics.shearing_sheet_config(root_size=30.0, collision=abi.COLLISION_NONE)
+    want, cw = checkers.oracle().integrator_step(cfg, p)
+    eng.upload(p.copy())
+    c = cfg.copy()
+    eng.integrator_step(c)
+    got = eng.download()
+    assert bits_equal(got, want)
+    assert c.t == cw.t and c.OMEGAZ == cw.OMEGAZ and c.dt_last_done == cw.dt_last_done
+
+
+def test_disc_full_steps_bitwise(eng):
+    """Config C4 shape: leapfrog + tree gravity + open boundary (particles leave the box)."""
+    p = ics.selfgravity_disc(4000, seed=12)
+    cfg = ics.selfgravity_disc_config(collision=abi.COLLISION_NONE)
+    want, cw, _ = checkers.oracle().steps(cfg, p, 5)
+    q, c = p.copy(), cfg.copy()
+    n = eng.steps_host(c, q, 5)
+    assert n == len(want)
+    assert bits_equal(q[:n], want)
+    assert c.t == cw.t
+
+
+def test_sheet_steps_no_resolve_bitwise(eng):
+    """Config C5 shape without the resolve loop: SEI + shear boundary + tree gravity (25 ghost boxes)
+    + tree collision search every step."""
+    p = ics.shearing_sheet(root_size=30.0, seed=9)
+    cfg = ics.shearing_sheet_config(root_size=30.0)
+    want, cw, _ = checkers.oracle().steps(cfg, p, 6, resolve=0)
+    q, c = p.copy(), cfg.copy()
+    n = eng.steps_host(c, q, 6)
+    assert bits_equal(q[:n], want)
+    want_col = checkers.oracle().collision_search(cw, want)
+    got_col = eng.collisions_fetch()
+    assert collisions_equal(got_col, want_col)
