@@ -1,0 +1,102 @@
+/* shim_common.c -- side table simulation -> device handle, config marshalling, residency helpers. */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "shim_common.h"
+#include "integrator_leapfrog.h"
+
+#define SHIM_MAX 256
+static struct shim_state table[SHIM_MAX];
+static int table_n = 0;
+static pthread_mutex_t table_lock = PTHREAD_MUTEX_INITIALIZER;
+
+struct shim_state* shim_get(struct reb_simulation* r){
+    pthread_mutex_lock(&table_lock);
+    struct shim_state* s = NULL;
+    for (int i=0;i<table_n;i++) if (table[i].r==r){ s = &table[i]; break; }
+    if (!s){
+        for (int i=0;i<table_n && !s;i++) if (table[i].r==NULL) s = &table[i];
+        if (!s && table_n<SHIM_MAX) s = &table[table_n++];
+        if (s){
+            memset(s, 0, sizeof(*s));
+            int device = 0;
+            const char* env = getenv("REBOUND_B200_DEVICE");
+            if (env) device = atoi(env);
+            s->h = rebcu_create(device, NULL);
+            if (s->h) s->r = r; else s = NULL;
+        }
+    }
+    pthread_mutex_unlock(&table_lock);
+    if (!s) reb_simulation_error(r, "rebound_b200: no usable CUDA device (or too many simulations); the GPU hot path has no CPU fallback.");
+    return s;
+}
+
+void shim_forget(struct reb_simulation* r){
+    pthread_mutex_lock(&table_lock);
+    for (int i=0;i<table_n;i++) if (table[i].r==r){
+        rebcu_destroy(table[i].h);
+        memset(&table[i], 0, sizeof(table[i]));
+    }
+    pthread_mutex_unlock(&table_lock);
+}
+
+int shim_resident_mode(void){
+    const char* env = getenv("REBOUND_B200_RESIDENT");
+    return env && env[0]=='1';
+}
+
+void shim_fill_config(const struct reb_simulation* r, rebcu_config* c){
+    memset(c, 0, sizeof(*c));
+    c->t = r->t; c->G = r->G; c->softening = r->softening;
+    c->OMEGA = r->OMEGA; c->OMEGAZ = r->OMEGAZ;
+    c->dt = r->dt; c->dt_last_done = r->dt_last_done;
+    c->opening_angle2 = r->opening_angle2;
+    c->root_size = r->root_size;
+    c->N_active = (r->N_active==SIZE_MAX)?REBCU_SIZE_MAX:(uint64_t)r->N_active;
+    c->testparticle_type = r->testparticle_type;
+    c->gravity_ignore_terms = (int32_t)r->gravity_ignore_terms;
+    c->N_root_x = (int32_t)r->N_root_x; c->N_root_y = (int32_t)r->N_root_y; c->N_root_z = (int32_t)r->N_root_z;
+    c->N_ghost_x = r->N_ghost_x; c->N_ghost_y = r->N_ghost_y; c->N_ghost_z = r->N_ghost_z;
+    c->boundary = (int32_t)r->boundary;
+    c->gravity = (int32_t)r->gravity;
+    c->collision = (int32_t)r->collision;
+    c->integrator = REBCU_INTEGRATOR_NONE;
+    if (r->integrator.name && strcmp(r->integrator.name, "leapfrog")==0){
+        c->integrator = REBCU_INTEGRATOR_LEAPFROG;
+        const struct reb_integrator_leapfrog_state* st = r->integrator.state;
+        c->leapfrog_order = st ? (int32_t)st->order : 2;
+    }else if (r->integrator.name && strcmp(r->integrator.name, "sei")==0){
+        c->integrator = REBCU_INTEGRATOR_SEI;
+    }
+    const char* mode = getenv("REBOUND_B200_MODE");
+    c->mode = (mode && strcmp(mode, "fast")==0) ? REBCU_MODE_FAST : REBCU_MODE_STRICT;
+}
+
+int shim_report(struct reb_simulation* r, struct shim_state* s, int err){
+    if (err) reb_simulation_error(r, rebcu_last_error(s->h));
+    return err;
+}
+
+int shim_to_device(struct reb_simulation* r, struct shim_state* s){
+    /* Only resident mode trusts the device copy across calls; the default mode re-uploads every time. */
+    if (shim_resident_mode() && s->device_valid && !r->did_modify_particles && s->uploaded_from==r->particles && s->uploaded_N==r->N) return 0;
+    int err = rebcu_upload(s->h, (const rebcu_particle*)r->particles, r->N);
+    if (err) return shim_report(r, s, err);
+    s->uploaded_from = r->particles; s->uploaded_N = r->N;
+    s->device_valid = 1;
+    s->host_stale = 0;
+    return 0;
+}
+
+int shim_to_host(struct reb_simulation* r, struct shim_state* s){
+    if (!s->host_stale) return 0;
+    const uint64_t n = rebcu_N(s->h);
+    if (n > r->N_allocated) return shim_report(r, s, REBCU_ERR_CAPACITY);
+    int err = rebcu_download(s->h, (rebcu_particle*)r->particles, n);
+    if (err) return shim_report(r, s, err);
+    r->N = n;
+    s->uploaded_N = n;
+    s->host_stale = 0;
+    return 0;
+}

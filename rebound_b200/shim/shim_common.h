@@ -1,0 +1,51 @@
+/*
+ * shim_common.h -- glue shared by the drop-in translation units.
+ *
+ * The shim files are compiled against the reference's OWN headers (-I<reference>/src, nothing is
+ * copied) and linked with the reference's unmodified sources into a librebound whose hot-path
+ * symbols forward to the CUDA engine (include/rebound_b200.h).  See INTEGRATION.md.
+ *
+ * Device state cannot live in struct reb_simulation (its size is frozen: the Python package checks
+ * sizeof at import, rebound/simulation.py:1478-1482), so it lives in a side table keyed by the
+ * simulation pointer.
+ */
+#ifndef REBOUND_B200_SHIM_COMMON_H
+#define REBOUND_B200_SHIM_COMMON_H
+
+#include "rebound.h"
+#include "../../include/rebound_b200.h"
+
+/* shim-internal symbols are not exported (the reference's CI requires every exported symbol of
+ * librebound to start with reb_, .github/workflows/c.yml:17-22) */
+#pragma GCC visibility push(hidden)
+
+struct shim_state {
+    struct reb_simulation* r;
+    rebcu_handle* h;
+    int device_valid;            /* the device SoA holds the current particle state */
+    int host_stale;              /* r->particles is behind the device copy (resident mode, is_synchronized==0) */
+    struct reb_particle* uploaded_from;
+    size_t uploaded_N;
+};
+
+/* Returns the per-simulation state (creating the rebcu handle on first use); NULL + reb_simulation_error
+ * if no CUDA device is usable -- there is no CPU fallback for the replaced functions. */
+struct shim_state* shim_get(struct reb_simulation* r);
+void shim_forget(struct reb_simulation* r);
+
+/* 1 if REBOUND_B200_RESIDENT=1: the leapfrog / SEI steps keep particles in HBM between steps and set
+ * r->is_synchronized = 0 (the protocol WHFast uses, src/simulation.c:633-637). */
+int shim_resident_mode(void);
+
+void shim_fill_config(const struct reb_simulation* r, rebcu_config* c);
+/* Forwards a rebcu error to reb_simulation_error (src/simulation.c:82-86); returns err. */
+int shim_report(struct reb_simulation* r, struct shim_state* s, int err);
+
+/* Make the device copy current: uploads r->particles unless the device already holds this state
+ * (same array, same N, r->did_modify_particles not set -- the flag WHFast relies on, rebound.h:247). */
+int shim_to_device(struct reb_simulation* r, struct shim_state* s);
+/* Make r->particles current: downloads if the device is ahead. */
+int shim_to_host(struct reb_simulation* r, struct shim_state* s);
+
+#pragma GCC visibility pop
+#endif

@@ -1,0 +1,169 @@
+/*
+ * shim_hotpath.c -- the reference's hot-path symbols, forwarding to the CUDA engine.
+ *
+ * Defines (same names, same signatures as the reference):
+ *   reb_gravity_basic_calculate_acceleration        src/gravity.c:167
+ *   reb_gravity_compensated_calculate_acceleration  src/gravity.c:284
+ *   reb_gravity_tree_calculate_acceleration         src/gravity.c:47
+ *   reb_boundary_check                              src/boundary.c:35
+ *   reb_collision_search                            src/collision.c:49
+ * The reference's own definitions are compiled under the names *_cpuref (-D renames in
+ * rebound_b200/shim/Makefile); they are only used for the modes outside the GPU hot path
+ * (REB_COLLISION_LINE/LINETREE, r->map / N_targets subsets, track_energy_offset, free_particle_ap).
+ *
+ * Default mode: host-authoritative -- every call uploads r->particles, runs on the GPU and writes
+ * the result back, so every host hook of the reference keeps working unchanged.
+ * REBOUND_B200_RESIDENT=1: see shim_integrators.c.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "shim_common.h"
+#include "gravity.h"
+#include "boundary.h"
+#include "collision.h"
+#include "particle.h"
+
+void reb_boundary_check_cpuref(struct reb_simulation* r);
+void reb_collision_search_cpuref(struct reb_simulation* const r);
+
+/* ---- gravity ------------------------------------------------------------------------------- */
+static void gravity_gpu(struct reb_simulation* r){
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
+    rebcu_config c;
+    shim_fill_config(r, &c);
+    if (s->host_stale){
+        /* resident mode: called from inside the device-side integrator step is impossible (the step
+         * computes forces itself); a direct call while the host is stale works on the device copy. */
+        int err = rebcu_update_acceleration(s->h, &c);
+        if (shim_report(r, s, err)) return;
+        r->N = rebcu_N(s->h);
+        r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
+        return;
+    }
+    uint64_t N = r->N;
+    int err = rebcu_gravity_host(s->h, &c, (rebcu_particle*)r->particles, &N);
+    s->device_valid = 0;
+    if (shim_report(r, s, err)) return;
+    if (N != r->N){                       /* tree gravity + open boundary removed particles (gravity.c:56) */
+        r->N = N;
+        r->did_modify_particles = 1;
+    }
+    r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
+}
+
+void reb_gravity_basic_calculate_acceleration(struct reb_simulation* r){ gravity_gpu(r); }
+void reb_gravity_compensated_calculate_acceleration(struct reb_simulation* r){ gravity_gpu(r); }
+void reb_gravity_tree_calculate_acceleration(struct reb_simulation* r){
+    if (r->boundary==REB_BOUNDARY_OPEN && (r->track_energy_offset || r->free_particle_ap || r->integrator.callbacks.will_remove_particle)){
+        /* per-removal host side effects (boundary.c:66-72, particle.c:338-358): run the boundary pass on the host */
+        struct shim_state* s = shim_get(r);
+        if (!s) return;
+        if (shim_to_host(r, s)) return;
+        reb_boundary_check_cpuref(r);
+        s->device_valid = 0;
+    }
+    gravity_gpu(r);
+}
+
+/* ---- boundary ------------------------------------------------------------------------------ */
+void reb_boundary_check(struct reb_simulation* r){
+    if (r->boundary==REB_BOUNDARY_NONE) return;
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
+    if (r->boundary==REB_BOUNDARY_OPEN && (r->track_energy_offset || r->free_particle_ap || r->integrator.callbacks.will_remove_particle)){
+        if (shim_to_host(r, s)) return;
+        reb_boundary_check_cpuref(r);
+        s->device_valid = 0;
+        return;
+    }
+    rebcu_config c;
+    shim_fill_config(r, &c);
+    const int resident = s->host_stale;
+    if (!resident){
+        int err = rebcu_upload(s->h, (const rebcu_particle*)r->particles, r->N);
+        if (shim_report(r, s, err)) return;
+    }
+    int err = rebcu_boundary_check(s->h, &c);
+    if (shim_report(r, s, err)) return;
+    const uint64_t N = rebcu_N(s->h);
+    if (!resident){
+        err = rebcu_download(s->h, (rebcu_particle*)r->particles, N);
+        if (shim_report(r, s, err)) return;
+        s->device_valid = 0;
+    }
+    if (N != r->N){
+        if (N==0 && r->N>0) reb_simulation_warning(r, "Last particle removed.");      /* particle.c:346 */
+        r->N = N;
+        r->did_modify_particles = resident ? r->did_modify_particles : 1;
+        s->uploaded_N = N;
+    }
+    r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
+}
+
+/* ---- collisions ---------------------------------------------------------------------------- */
+void reb_collision_search(struct reb_simulation* const r){
+    const int gpu_mode = (r->collision==REB_COLLISION_DIRECT || r->collision==REB_COLLISION_TREE)
+                       && r->map==NULL && r->N_targets==SIZE_MAX;
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
+    if (!gpu_mode){
+        if (shim_to_host(r, s)) return;
+        reb_collision_search_cpuref(r);
+        s->device_valid = 0;
+        return;
+    }
+    r->N_collisions = 0;
+    rebcu_config c;
+    shim_fill_config(r, &c);
+    if (!s->host_stale){
+        int err = rebcu_upload(s->h, (const rebcu_particle*)r->particles, r->N);
+        if (shim_report(r, s, err)) return;
+    }
+    uint64_t n_found = 0;
+    int err = rebcu_collision_search(s->h, &c, (rebcu_collision*)r->collisions, r->N_allocated_collisions, &n_found);
+    if (shim_report(r, s, err)) return;
+    if (n_found > r->N_allocated_collisions){
+        /* grow as collision.c:108-113 does (doubling from 32) and fetch the full list */
+        size_t cap = r->N_allocated_collisions ? r->N_allocated_collisions : 32;
+        while (cap < n_found) cap *= 2;
+        r->collisions = realloc(r->collisions, sizeof(struct reb_collision)*cap);
+        r->N_allocated_collisions = cap;
+        err = rebcu_collisions_fetch(s->h, (rebcu_collision*)r->collisions, cap, &n_found);
+        if (shim_report(r, s, err)) return;
+    }
+    r->N_collisions = n_found;
+    if (n_found==0) return;
+    /* The shuffle and the resolve loop work on r->particles (user callback ABI). */
+    if (shim_to_host(r, s)) return;
+    s->device_valid = 0;
+
+    /* collision.c:336-342 */
+    for (size_t i=0;i<r->N_collisions;i++){
+        size_t new = rand_r(&(r->rand_seed))%r->N_collisions;
+        struct reb_collision c1 = r->collisions[i];
+        r->collisions[i] = r->collisions[new];
+        r->collisions[new] = c1;
+    }
+    /* collision.c:345-404 */
+    enum REB_COLLISION_RESOLVE_OUTCOME (*resolve) (struct reb_simulation* const r, struct reb_collision c) = r->collision_resolve;
+    if (resolve==NULL) resolve = reb_collision_resolve_halt;
+    for (size_t i=0;i<r->N_collisions;i++){
+        struct reb_collision col = r->collisions[i];
+        if (col.p1 == SIZE_MAX || col.p2 == SIZE_MAX) continue;
+        enum REB_COLLISION_RESOLVE_OUTCOME outcome = resolve(r, col);
+        for (int which=0; which<2; which++){
+            const int bit = which==0 ? REB_COLLISION_RESOLVE_OUTCOME_REMOVE_P1 : REB_COLLISION_RESOLVE_OUTCOME_REMOVE_P2;
+            if (!(outcome & bit)) continue;
+            const size_t gone = which==0 ? col.p1 : col.p2;
+            if (reb_simulation_remove_particle(r, gone)) continue;
+            if (which==0 && col.p2 > col.p1 && col.p2!=SIZE_MAX) col.p2--;
+            for (size_t j=i+1;j<r->N_collisions;j++){
+                struct reb_collision* cp = &(r->collisions[j]);
+                if (cp->p1==gone || cp->p2==gone){ cp->p1 = SIZE_MAX; cp->p2 = SIZE_MAX; }
+                if (cp->p1 > gone && cp->p1!=SIZE_MAX) cp->p1--;
+                if (cp->p2 > gone && cp->p2!=SIZE_MAX) cp->p2--;
+            }
+        }
+    }
+}

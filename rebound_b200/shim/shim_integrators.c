@@ -1,0 +1,103 @@
+/*
+ * shim_integrators.c -- the `leapfrog` and `sei` entries of the reference's integrator registry,
+ * backed by the fused kick/drift and SEI kernels.
+ *
+ * Defines the data symbols reb_integrator_leapfrog (src/integrator_leapfrog.c:32-48) and
+ * reb_integrator_sei (src/integrator_sei.c:47-63) referenced by the X-macro in rebound.h:205 /
+ * simulation.c:222-224.  The reference's own structs are compiled as *_cpuref; its step functions
+ * (reb_integrator_leapfrog_step, reb_integrator_sei_step), create/free functions, field descriptor
+ * lists and the lf4/lf6/lf8 constants keep their names and are reused here.
+ *
+ * A step runs entirely on the device when the force is one the engine owns (gravity NONE / BASIC /
+ * COMPENSATED / TREE, no variational particles, no additional_forces callback).  Otherwise the
+ * reference's host step runs and only its force call lands on the GPU (shim_hotpath.c).
+ *
+ * REBOUND_B200_RESIDENT=1: particles stay in HBM between steps; r->is_synchronized is cleared and the
+ * `synchronize` callback (called by reb_simulation_synchronize at src/simulation.c:331,336,455,511,521,562)
+ * brings r->particles up to date -- the protocol of the reference's WHFast integrators.
+ */
+#include <string.h>
+#include "shim_common.h"
+#include "integrator_leapfrog.h"
+#include "integrator_sei.h"
+
+void reb_integrator_leapfrog_step(struct reb_simulation* r, void* state);
+void* reb_integrator_leapfrog_create();
+void reb_integrator_leapfrog_free(void* p);
+extern const struct reb_binarydata_field_descriptor reb_integrator_leapfrog_field_descriptor_list[];
+void reb_integrator_sei_step(struct reb_simulation* r, void* state);
+void* reb_integrator_sei_create();
+void reb_integrator_sei_free(void* p);
+extern const struct reb_binarydata_field_descriptor reb_integrator_sei_field_descriptor_list[];
+
+static int device_step_possible(const struct reb_simulation* r){
+    if (r->N_var || r->additional_forces) return 0;
+    switch (r->gravity){
+        case REB_GRAVITY_NONE: case REB_GRAVITY_BASIC: case REB_GRAVITY_COMPENSATED: case REB_GRAVITY_TREE: break;
+        default: return 0;
+    }
+    if (r->gravity==REB_GRAVITY_TREE && r->boundary==REB_BOUNDARY_OPEN
+        && (r->track_energy_offset || r->free_particle_ap)) return 0;
+    return 1;
+}
+
+static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_simulation*, void*), void* state){
+    if (!device_step_possible(r)){
+        struct shim_state* s = shim_get(r);
+        if (s){ if (shim_to_host(r, s)) return; s->device_valid = 0; }
+        host_step(r, state);
+        return;
+    }
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
+    rebcu_config c;
+    shim_fill_config(r, &c);
+    if (shim_to_device(r, s)) return;
+    int err = rebcu_integrator_step(s->h, &c);
+    if (shim_report(r, s, err)) return;
+    r->t = c.t;
+    r->dt_last_done = c.dt_last_done;
+    r->gravity_ignore_terms = c.gravity_ignore_terms;
+    r->OMEGAZ = c.OMEGAZ;
+    r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
+    s->host_stale = 1;
+    if (shim_resident_mode()){
+        r->N = rebcu_N(s->h);            /* tree gravity + open boundary may have removed particles */
+        s->uploaded_N = r->N;
+        r->is_synchronized = 0;
+    }else{
+        shim_to_host(r, s);
+    }
+}
+
+static void synchronize(struct reb_simulation* r, void* state){
+    (void)state;
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
+    if (shim_to_host(r, s)) return;
+    r->is_synchronized = 1;
+}
+
+static void leapfrog_step(struct reb_simulation* r, void* state){ device_step(r, reb_integrator_leapfrog_step, state); }
+static void sei_step(struct reb_simulation* r, void* state){ device_step(r, reb_integrator_sei_step, state); }
+
+const struct reb_integrator reb_integrator_leapfrog = {
+    .documentation = "Leapfrog (drift-kick-drift), orders 2, 4, 6 and 8; kick/drift run as fused CUDA kernels on the resident particle arrays.",
+    .step = leapfrog_step,
+    .synchronize = synchronize,
+    .create = reb_integrator_leapfrog_create,
+    .free = reb_integrator_leapfrog_free,
+    .field_descriptor_list = reb_integrator_leapfrog_field_descriptor_list,
+};
+
+const struct reb_integrator reb_integrator_sei = {
+    .documentation = "Symplectic Epicycle Integrator for the shearing sheet (Rein & Tremaine 2011); operators run as CUDA kernels on the resident particle arrays.",
+    .step = sei_step,
+    .synchronize = synchronize,
+    .create = reb_integrator_sei_create,
+    .free = reb_integrator_sei_free,
+    .field_descriptor_list = reb_integrator_sei_field_descriptor_list,
+};
+
+/* Explicit release of the device state of a simulation (optional; everything is freed at exit). */
+void reb_b200_release(struct reb_simulation* r){ shim_forget(r); }

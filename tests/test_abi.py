@@ -54,3 +54,20 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert "liboracle" not in text and "libref_harness" not in text, f
+
+
+def test_dropin_librebound_exports_reference_symbols():
+    """The drop-in librebound (when built) exports the hot-path symbols under the reference's names and,
+    like the reference's CI demands (.github/workflows/c.yml:17-22), only reb_-prefixed symbols."""
+    import subprocess
+    lib = os.path.join(ROOT, "rebound_b200", "_dropin", "librebound.so")
+    if not os.path.exists(lib):
+        pytest.skip("drop-in librebound not built")
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    syms = [l.split()[-1] for l in out.splitlines() if l.split()[-2] in "TDRB"]
+    assert all(s.startswith("reb_") for s in syms), [s for s in syms if not s.startswith("reb_")]
+    for s in ("reb_gravity_basic_calculate_acceleration", "reb_gravity_compensated_calculate_acceleration",
+              "reb_gravity_tree_calculate_acceleration", "reb_boundary_check", "reb_collision_search",
+              "reb_integrator_leapfrog", "reb_integrator_sei", "reb_simulation_integrate", "reb_tree_construct",
+              "reb_boundary_get_ghostbox", "reb_integrator_leapfrog_lf4_a"):
+        assert s in syms, s
