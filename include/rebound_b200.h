@@ -210,6 +210,10 @@ uint64_t rebcu_launch_count(const rebcu_handle* h);
 int rebcu_timing_enable(rebcu_handle* h, int on);
 int rebcu_timing_read(rebcu_handle* h, double* ms_out, uint64_t* launches_out, int n_classes);
 int rebcu_timing_reset(rebcu_handle* h);
+/* Device self-test of the STRICT kernels' branch-free sqrt/divide against __dsqrt_rn/__ddiv_rn on
+ * n_samples pseudo-random operand pairs: result4 = {sqrt mismatches, divide mismatches (both must be 0),
+ * sqrt / divide operands of the ordinary families that were sent to the generic path}. */
+int rebcu_selftest_math(rebcu_handle* h, uint64_t n_samples, uint64_t seed, uint64_t* result4);
 
 #ifdef __cplusplus
 }

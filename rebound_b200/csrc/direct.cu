@@ -17,6 +17,7 @@
 //
 // Bound: FP64 pipe.  HBM traffic is 32 B read per source per CTA tile + 24 B written per particle.
 #include "engine.cuh"
+#include "strict_math.cuh"
 
 namespace {
 
@@ -45,6 +46,37 @@ __device__ __forceinline__ void source_set(const DirectArgs& a, uint64_t i, uint
 // ------------------------------------------------------------------------------------------------
 // STRICT
 // ------------------------------------------------------------------------------------------------
+// Generic-path recomputation of one particle (sources read straight from global memory); only runs for
+// particles whose branch-free pass met an operand outside the fast range of fsqrt_rn / fdiv_rn.
+template <bool KAHAN>
+__device__ __forceinline__ void direct_slow(const DirectArgs& a, uint64_t i, uint64_t ns, uint64_t skip0, uint64_t skip1,
+                                         double pxi, double pyi, double pzi, double& sx, double& sy, double& sz) {
+    sx = sy = sz = 0;
+    double cx = 0, cy = 0, cz = 0;
+    const double negG = -a.G;
+    const int ngb = a.use_ghosts ? a.ghosts->n : 1;
+    for (int g = 0; g < ngb; g++) {
+        double xi = pxi, yi = pyi, zi = pzi;
+        if (a.use_ghosts) { xi = s_add(a.ghosts->gb[g].x, pxi); yi = s_add(a.ghosts->gb[g].y, pyi); zi = s_add(a.ghosts->gb[g].z, pzi); }
+        for (uint64_t j = 0; j < ns; j++) {
+            if (j == skip0 || j == skip1) continue;
+            const double dx = s_sub(xi, a.x[j]), dy = s_sub(yi, a.y[j]), dz = s_sub(zi, a.z[j]);
+            const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);
+            const double r = s_sqrt(r2);
+            if (!KAHAN) {
+                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), a.m[j]);
+                sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
+            } else {
+                const double p = s_mul(-s_div(a.G, s_mul(r2, r)), a.m[j]);
+                double y, t;
+                y = s_sub(s_mul(p, dx), cx); t = s_add(sx, y); cx = s_sub(s_sub(t, sx), y); sx = t;
+                y = s_sub(s_mul(p, dy), cy); t = s_add(sy, y); cy = s_sub(s_sub(t, sy), y); sy = t;
+                y = s_sub(s_mul(p, dz), cz); t = s_add(sz, y); cz = s_sub(s_sub(t, sz), y); sz = t;
+            }
+        }
+    }
+}
+
 template <bool KAHAN, int BLOCK, int JPT>
 __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a) {
     constexpr int TJ = BLOCK * JPT;
@@ -65,6 +97,7 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
 
     double sx = 0, sy = 0, sz = 0;     // running sums
     double cx = 0, cy = 0, cz = 0;     // Kahan compensation (r->gravity_cs[i])
+    unsigned bad = 0;                  // a used term left the fast range of fsqrt_rn / fdiv_rn
 
     const int ngb = a.use_ghosts ? a.ghosts->n : 1;
     for (int g = 0; g < ngb; g++) {
@@ -103,20 +136,23 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
                 const double dy = s_sub(yi, s.y);
                 const double dz = s_sub(zi, s.z);
                 const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);
-                const double r = s_sqrt(r2);
+                unsigned b = 0;
+                const double r = fsqrt_rn(r2, b);
                 const bool ok = (j < ns) & (j != skip0) & (j != skip1);
                 if (!KAHAN) {
                     // prefact = -G/(_r*_r*_r)*particles[j].m   (gravity.c:226)
-                    const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), s.w);
+                    const double p = s_mul(fdiv_rn(negG, s_mul(s_mul(r, r), r), b), s.w);
                     if (ok) {
+                        bad |= b;
                         sx = s_add(sx, s_mul(p, dx));
                         sy = s_add(sy, s_mul(p, dy));
                         sz = s_add(sz, s_mul(p, dz));
                     }
                 } else {
                     // prefact = G/(r2*r); prefactj = -prefact*m_j   (gravity.c:320-321)
-                    const double p = s_mul(-s_div(a.G, s_mul(r2, r)), s.w);
+                    const double p = s_mul(-fdiv_rn(a.G, s_mul(r2, r), b), s.w);
                     if (ok) {
+                        bad |= b;
                         double y, t;
                         y = s_sub(s_mul(p, dx), cx); t = s_add(sx, y); cx = s_sub(s_sub(t, sx), y); sx = t;
                         y = s_sub(s_mul(p, dy), cy); t = s_add(sy, y); cy = s_sub(s_sub(t, sy), y); sy = t;
@@ -127,7 +163,10 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
         }
         __syncthreads();
     }
-    if (valid) { a.ax[i] = sx; a.ay[i] = sy; a.az[i] = sz; }
+    if (valid) {
+        if (bad) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, sx, sy, sz);
+        a.ax[i] = sx; a.ay[i] = sy; a.az[i] = sz;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

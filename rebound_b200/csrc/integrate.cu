@@ -8,6 +8,7 @@
 // Bound: HBM.  Algorithmic bytes per particle: drift 72 (x,v in; x out), kick+drift 120
 // (x,v,a in; x,v out), fused test-particle step 96 (x,v in; x,v out; accelerations stay in registers).
 #include "engine.cuh"
+#include "strict_math.cuh"
 #include <math.h>
 
 namespace {
@@ -93,30 +94,57 @@ struct TpArgs {
     int kahan, fast, write_acc;
 };
 
-template <bool FAST>
-__device__ __forceinline__ void tp_force(const double* sx, const double* sy, const double* sz, const double* sm, int Na, int self,
+// MODE 0: strict, branch-free fast-range sqrt/divide (sets *bad); 1: FAST; 2: strict, generic sqrt/divide
+template <int MODE>
+__device__ __forceinline__ void tp_force(const double4* src, int Na, int self,
                                          double xi, double yi, double zi, double G, double soft2, bool kahan,
-                                         double& ax, double& ay, double& az) {
+                                         double& ax, double& ay, double& az, unsigned* bad) {
+    constexpr bool FAST = MODE == 1;
     double cx = 0, cy = 0, cz = 0;
     ax = ay = az = 0;
     const double negG = -G;
+    unsigned anybad = 0;
+#pragma unroll 2
     for (int j = 0; j < Na; j++) {
+        const double4 sj = src[j];
+        const double sxj = sj.x, syj = sj.y, szj = sj.z, smj = sj.w;
+        if (MODE == 0) {
+            const double dx = s_sub(xi, sxj), dy = s_sub(yi, syj), dz = s_sub(zi, szj);
+            const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
+            unsigned b = 0;
+            const double r = fsqrt_rn(r2, b);
+            const bool ok = j != self;
+            if (!kahan) {
+                const double p = s_mul(fdiv_rn(negG, s_mul(s_mul(r, r), r), b), smj);
+                if (ok) { anybad |= b; ax = s_add(ax, s_mul(p, dx)); ay = s_add(ay, s_mul(p, dy)); az = s_add(az, s_mul(p, dz)); }
+            } else {
+                const double p = s_mul(-fdiv_rn(G, s_mul(r2, r), b), smj);
+                if (ok) {
+                    anybad |= b;
+                    double y, t;
+                    y = s_sub(s_mul(p, dx), cx); t = s_add(ax, y); cx = s_sub(s_sub(t, ax), y); ax = t;
+                    y = s_sub(s_mul(p, dy), cy); t = s_add(ay, y); cy = s_sub(s_sub(t, ay), y); ay = t;
+                    y = s_sub(s_mul(p, dz), cz); t = s_add(az, y); cz = s_sub(s_sub(t, az), y); az = t;
+                }
+            }
+            continue;
+        }
         if (j == self) continue;
         if (FAST) {
-            const double dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+            const double dx = xi - sxj, dy = yi - syj, dz = zi - szj;
             const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
             const double ri = rsqrt(r2);
-            const double p = negG * sm[j] * (ri * ri * ri);
+            const double p = negG * smj * (ri * ri * ri);
             ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az);
         } else {
-            const double dx = s_sub(xi, sx[j]), dy = s_sub(yi, sy[j]), dz = s_sub(zi, sz[j]);
+            const double dx = s_sub(xi, sxj), dy = s_sub(yi, syj), dz = s_sub(zi, szj);
             const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
             const double r = s_sqrt(r2);
             if (!kahan) {
-                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), sm[j]);
+                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), smj);
                 ax = s_add(ax, s_mul(p, dx)); ay = s_add(ay, s_mul(p, dy)); az = s_add(az, s_mul(p, dz));
             } else {
-                const double p = s_mul(-s_div(G, s_mul(r2, r)), sm[j]);
+                const double p = s_mul(-s_div(G, s_mul(r2, r)), smj);
                 double y, t;
                 y = s_sub(s_mul(p, dx), cx); t = s_add(ax, y); cx = s_sub(s_sub(t, ax), y); ax = t;
                 y = s_sub(s_mul(p, dy), cy); t = s_add(ay, y); cy = s_sub(s_sub(t, ay), y); ay = t;
@@ -124,11 +152,18 @@ __device__ __forceinline__ void tp_force(const double* sx, const double* sy, con
             }
         }
     }
+    if (bad) *bad = anybad;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void tp_force_generic(const double4* src, int Na, int self, double xi, double yi, double zi, double G,
+                                              double soft2, bool kahan, double& ax, double& ay, double& az) {
+    tp_force<2>(src, Na, self, xi, yi, zi, G, soft2, kahan, ax, ay, az, nullptr);
 }
 
 template <bool FAST>
 __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
-    __shared__ double sx[TP_MAX_ACTIVE], sy[TP_MAX_ACTIVE], sz[TP_MAX_ACTIVE], sm[TP_MAX_ACTIVE];
+    __shared__ double4 src[TP_MAX_ACTIVE];
     const int Na = a.Na;
     for (int j = threadIdx.x; j < Na; j += TP_BLOCK) {
         double x = a.act_in[0 * Na + j], y = a.act_in[1 * Na + j], z = a.act_in[2 * Na + j];
@@ -137,7 +172,7 @@ __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
             y = s_add(y, s_mul(a.d0, a.act_in[4 * Na + j]));
             z = s_add(z, s_mul(a.d0, a.act_in[5 * Na + j]));
         }
-        sx[j] = x; sy[j] = y; sz[j] = z; sm[j] = a.act_in[6 * Na + j];
+        src[j] = make_double4(x, y, z, a.act_in[6 * Na + j]);
     }
     __syncthreads();
     const uint64_t i = (uint64_t)blockIdx.x * TP_BLOCK + threadIdx.x;
@@ -149,7 +184,10 @@ __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
     {
         double xi = x, yi = y, zi = z;
         if (!a.kahan) { xi = s_add(a.gbx, x); yi = s_add(a.gby, y); zi = s_add(a.gbz, z); }
-        tp_force<FAST>(sx, sy, sz, sm, Na, (i < (uint64_t)Na) ? (int)i : -1, xi, yi, zi, a.G, a.soft2, a.kahan != 0, ax, ay, az);
+        const int self = (i < (uint64_t)Na) ? (int)i : -1;
+        unsigned bad = 0;
+        tp_force<FAST ? 1 : 0>(src, Na, self, xi, yi, zi, a.G, a.soft2, a.kahan != 0, ax, ay, az, &bad);
+        if (bad) tp_force_generic<FAST>(src, Na, self, xi, yi, zi, a.G, a.soft2, a.kahan != 0, ax, ay, az);
     }
     vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
     x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));

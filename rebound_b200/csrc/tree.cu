@@ -29,6 +29,7 @@
 // Bounds: build steps are HBM-streaming (keys 24 B in / 12 B out per particle, sort ~8 passes x 24 B,
 // cells ~1.5/particle x 80 B out); the walk is FP64-pipe / L2-latency bound.
 #include "engine.cuh"
+#include "strict_math.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <math.h>
@@ -295,14 +296,13 @@ struct WalkArgs {
     double root_size;
 };
 
-template <bool FAST>
-__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
-    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
-    if (t >= a.n_work) return;
-    const uint64_t k = a.list ? a.list[t] : t;
-    const uint32_t self = a.perm[k];
-    const double px = a.x[self], py = a.y[self], pz = a.z[self];
-    double sx = 0., sy = 0., sz = 0.;
+// MODE 0: strict with the branch-free fast-range sqrt/divide (returns the sticky out-of-range flag),
+//      1: FAST (FMA + rsqrt), 2: strict with the generic __dsqrt_rn/__ddiv_rn.
+template <int MODE>
+__device__ __forceinline__ unsigned walk_one(const WalkArgs& a, uint32_t self, double px, double py, double pz,
+                                             double& sx, double& sy, double& sz) {
+    sx = sy = sz = 0.;
+    unsigned bad = 0;
     const double negG = -a.G;
     const int ngb = a.ghosts->n;
     const int n_cells = (int)a.n_cells;
@@ -321,18 +321,40 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
                 else { double w = a.root_size; for (int d = 0; d < mt.z; d++) w = s_div(w, 2.); w2 = s_mul(w, w); }
                 if (w2 > s_mul(a.theta2, r2)) { c++; continue; }          // tree.c:284: open the cell
             } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }    // tree.c:311
-            if (FAST) {
+            if (MODE == 1) {
                 const double ri = rsqrt(r2 + a.soft2);
                 const double p = negG * q.w * (ri * ri * ri);
                 sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
+            } else if (MODE == 0) {
+                const double r = fsqrt_rn(s_add(r2, a.soft2), bad);
+                const double p = s_mul(fdiv_rn(negG, s_mul(s_mul(r, r), r), bad), q.w);   // tree.c:292,313
+                sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
             } else {
                 const double r = s_sqrt(s_add(r2, a.soft2));
-                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), q.w);   // tree.c:292,313
+                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), q.w);
                 sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
             }
             c = mt.y;
         }
     }
+    return bad;
+}
+
+__device__ __forceinline__ void walk_generic(const WalkArgs& a, uint32_t self, double px, double py, double pz,
+                                          double& sx, double& sy, double& sz) {
+    walk_one<2>(a, self, px, py, pz, sx, sy, sz);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (t >= a.n_work) return;
+    const uint64_t k = a.list ? a.list[t] : t;
+    const uint32_t self = a.perm[k];
+    const double px = a.x[self], py = a.y[self], pz = a.z[self];
+    double sx, sy, sz;
+    const unsigned bad = walk_one<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
+    if (bad) walk_generic(a, self, px, py, pz, sx, sy, sz);
     a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
 }
 

@@ -182,6 +182,11 @@ class Engine:
     def launch_count(self):
         return int(self.f["launch_count"](self.h))
 
+    def selftest_math(self, n_samples, seed=1):
+        out = (C.c_uint64 * 4)()
+        self._check(self.f["selftest_math"](self.h, n_samples, seed, out))
+        return {"sqrt_mismatch": int(out[0]), "div_mismatch": int(out[1]), "sqrt_flagged": int(out[2]), "div_flagged": int(out[3])}
+
     def timing_enable(self, on=True):
         self._check(self.f["timing_enable"](self.h, 1 if on else 0))
 

@@ -175,3 +175,12 @@ def test_linearity_in_G_and_translation_full_size(eng):
         for v in pre * dx:
             acc += v
         assert acc == a1["ax"][i]
+
+
+def test_strict_math_selftest(eng):
+    """The branch-free sqrt/divide used by the STRICT kernels equal __dsqrt_rn/__ddiv_rn bit for bit on
+    3e8 operand pairs (ordinary magnitudes, arbitrary bit patterns, near-square rounding ties)."""
+    n = 300_000_000
+    r = eng.selftest_math(n, seed=12345)
+    assert r["sqrt_mismatch"] == 0 and r["div_mismatch"] == 0
+    assert r["sqrt_flagged"] < 1e-3 * n and r["div_flagged"] < 1e-3 * n
