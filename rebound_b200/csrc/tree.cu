@@ -496,8 +496,16 @@ int tree_export(rebcu_handle* h) {
 }
 
 int tree_gravity(rebcu_handle* h, rebcu_config* c) {
-    int err = boundary_check(h, c);                       // gravity.c:56
+    // gravity.c:56.  Every rank holds all positions at this point (they were exchanged after the drift), and
+    // the replicated tree needs all of them wrapped, so the check covers the full range on every rank.
+    const int rank = h->rank, world = h->world;
+    const uint64_t n_before = h->N;
+    h->rank = 0; h->world = 1;
+    int err = boundary_check(h, c);
+    h->rank = rank; h->world = world;
     if (err) return err;
+    if (world > 1 && h->N != n_before)
+        return rebcu_fail(h, REBCU_ERR_ARG, "open-boundary removal while sharded over several GPUs needs a full-state exchange (not implemented)");
     err = tree_build(h, c);                               // gravity.c:63-71
     if (err) return err;
     const uint64_t n = h->N;
