@@ -32,6 +32,7 @@ struct DirectArgs {
     double G, soft2;
     const GhostShifts* ghosts;   // device
     int use_ghosts;              // 0: compensated (no shift at all, gravity.c:315-317)
+    int windowed;                // G inside the window of the branch-free sqrt/divide (strict_math.cuh)
 };
 
 // Per-particle source range and the (at most two) excluded source indices.
@@ -77,6 +78,90 @@ __device__ __forceinline__ void direct_slow(const DirectArgs& a, uint64_t i, uin
     }
 }
 
+struct StrictAcc { double sx, sy, sz, cx, cy, cz; unsigned wmax; };
+
+// One shared-memory tile of sources against one particle.
+//   WINDOWED: branch-free sqrt/divide (strict_math.cuh), the window key of the used terms is tracked in acc.wmax
+//   PRED:     per-term predicate (source range end, the particle itself, ignored pairs); tiles a whole warp
+//             can use unconditionally run with PRED=false and carry no integer work in the loop.
+template <bool KAHAN, bool WINDOWED, bool PRED>
+__device__ __forceinline__ void strict_tile(const double4* __restrict__ tile, int jn, uint64_t t0, uint64_t ns, uint64_t skip0,
+                                            uint64_t skip1, double xi, double yi, double zi, double G, double soft2, StrictAcc& A) {
+    const double negG = -G;
+#pragma unroll 4
+    for (int jj = 0; jj < jn; jj++) {
+        const double4 s = tile[jj];
+        const double dx = s_sub(xi, s.x);
+        const double dy = s_sub(yi, s.y);
+        const double dz = s_sub(zi, s.z);
+        const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
+        const double r = WINDOWED ? fsqrt_rn_w(r2) : s_sqrt(r2);
+        double p;
+        if (!KAHAN) {
+            const double b = s_mul(s_mul(r, r), r);          // prefact = -G/(_r*_r*_r)*particles[j].m   (gravity.c:226)
+            p = s_mul(WINDOWED ? fdiv_rn_w(negG, b) : s_div(negG, b), s.w);
+        } else {
+            const double b = s_mul(r2, r);                   // prefact = G/(r2*r); prefactj = -prefact*m_j (gravity.c:320-321)
+            p = s_mul(-(WINDOWED ? fdiv_rn_w(G, b) : s_div(G, b)), s.w);
+        }
+        if (PRED) {
+            const uint64_t j = t0 + jj;
+            if (!((j < ns) & (j != skip0) & (j != skip1))) continue;
+        }
+        if (WINDOWED) A.wmax = max(A.wmax, strict_window_key(r2));
+        if (!KAHAN) {
+            A.sx = s_add(A.sx, s_mul(p, dx));
+            A.sy = s_add(A.sy, s_mul(p, dy));
+            A.sz = s_add(A.sz, s_mul(p, dz));
+        } else {
+            double y, t;
+            y = s_sub(s_mul(p, dx), A.cx); t = s_add(A.sx, y); A.cx = s_sub(s_sub(t, A.sx), y); A.sx = t;
+            y = s_sub(s_mul(p, dy), A.cy); t = s_add(A.sy, y); A.cy = s_sub(s_sub(t, A.sy), y); A.sy = t;
+            y = s_sub(s_mul(p, dz), A.cz); t = s_add(A.sz, y); A.cz = s_sub(s_sub(t, A.sz), y); A.sz = t;
+        }
+    }
+}
+
+// The unconditional windowed tile with U source terms advanced in lock step (see strict_math.cuh); the
+// accumulation itself stays in ascending source order.
+template <bool KAHAN, int U>
+__device__ __forceinline__ void strict_tile_lockstep(const double4* __restrict__ tile, int jn, double xi, double yi, double zi,
+                                                     double G, double soft2, StrictAcc& A) {
+    const double negG = -G;
+    int jj = 0;
+    for (; jj + U <= jn; jj += U) {
+        double dx[U], dy[U], dz[U], r2[U], r[U], b[U], q[U], m[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double4 s = tile[jj + u];
+            dx[u] = s_sub(xi, s.x); dy[u] = s_sub(yi, s.y); dz[u] = s_sub(zi, s.z); m[u] = s.w;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) r2[u] = s_add(s_add(s_add(s_mul(dx[u], dx[u]), s_mul(dy[u], dy[u])), s_mul(dz[u], dz[u])), soft2);
+#pragma unroll
+        for (int u = 0; u < U; u++) A.wmax = max(A.wmax, strict_window_key(r2[u]));
+        fsqrt_rn_w_vec<U>(r2, r);
+#pragma unroll
+        for (int u = 0; u < U; u++) b[u] = KAHAN ? s_mul(r2[u], r[u]) : s_mul(s_mul(r[u], r[u]), r[u]);
+        fdiv_rn_w_vec<U>(KAHAN ? G : negG, b, q);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double p = KAHAN ? s_mul(-q[u], m[u]) : s_mul(q[u], m[u]);
+            if (!KAHAN) {
+                A.sx = s_add(A.sx, s_mul(p, dx[u]));
+                A.sy = s_add(A.sy, s_mul(p, dy[u]));
+                A.sz = s_add(A.sz, s_mul(p, dz[u]));
+            } else {
+                double y, t;
+                y = s_sub(s_mul(p, dx[u]), A.cx); t = s_add(A.sx, y); A.cx = s_sub(s_sub(t, A.sx), y); A.sx = t;
+                y = s_sub(s_mul(p, dy[u]), A.cy); t = s_add(A.sy, y); A.cy = s_sub(s_sub(t, A.sy), y); A.sy = t;
+                y = s_sub(s_mul(p, dz[u]), A.cz); t = s_add(A.sz, y); A.cz = s_sub(s_sub(t, A.sz), y); A.sz = t;
+            }
+        }
+    }
+    if (jj < jn) strict_tile<KAHAN, true, false>(tile + jj, jn - jj, 0, ~0ull, NO_SKIP, NO_SKIP, xi, yi, zi, G, soft2, A);
+}
+
 template <bool KAHAN, int BLOCK, int JPT>
 __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a) {
     constexpr int TJ = BLOCK * JPT;
@@ -85,19 +170,15 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
     const uint64_t i0 = a.i_begin + (uint64_t)blockIdx.x * BLOCK;
     const uint64_t i = i0 + threadIdx.x;
     const bool valid = i < a.i_end;
-    uint64_t ns = 0, skip0 = NO_SKIP, skip1 = NO_SKIP;
+    // block-uniform upper bound of the source range
+    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;
+    uint64_t ns = ns_blk, skip0 = NO_SKIP, skip1 = NO_SKIP;      // idle lanes behave like "clean" lanes and never store
     double pxi = 0, pyi = 0, pzi = 0;
     if (valid) {
         source_set(a, i, ns, skip0, skip1);
         pxi = a.x[i]; pyi = a.y[i]; pzi = a.z[i];
     }
-    // block-uniform upper bound of the source range
-    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;
-    const double negG = -a.G;
-
-    double sx = 0, sy = 0, sz = 0;     // running sums
-    double cx = 0, cy = 0, cz = 0;     // Kahan compensation (r->gravity_cs[i])
-    unsigned bad = 0;                  // a used term left the fast range of fsqrt_rn / fdiv_rn
+    StrictAcc A = {0, 0, 0, 0, 0, 0, 0};   // running sums, Kahan compensation (r->gravity_cs[i]), window key
 
     const int ngb = a.use_ghosts ? a.ghosts->n : 1;
     for (int g = 0; g < ngb; g++) {
@@ -128,44 +209,21 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
                 }
             }
             const int jn = (ns_blk - t0 < (uint64_t)TJ) ? (int)(ns_blk - t0) : TJ;
-#pragma unroll 4
-            for (int jj = 0; jj < jn; jj++) {
-                const uint64_t j = t0 + jj;
-                const double4 s = tile[jj];
-                const double dx = s_sub(xi, s.x);
-                const double dy = s_sub(yi, s.y);
-                const double dz = s_sub(zi, s.z);
-                const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);
-                unsigned b = 0;
-                const double r = fsqrt_rn(r2, b);
-                const bool ok = (j < ns) & (j != skip0) & (j != skip1);
-                if (!KAHAN) {
-                    // prefact = -G/(_r*_r*_r)*particles[j].m   (gravity.c:226)
-                    const double p = s_mul(fdiv_rn(negG, s_mul(s_mul(r, r), r), b), s.w);
-                    if (ok) {
-                        bad |= b;
-                        sx = s_add(sx, s_mul(p, dx));
-                        sy = s_add(sy, s_mul(p, dy));
-                        sz = s_add(sz, s_mul(p, dz));
-                    }
-                } else {
-                    // prefact = G/(r2*r); prefactj = -prefact*m_j   (gravity.c:320-321)
-                    const double p = s_mul(-fdiv_rn(a.G, s_mul(r2, r), b), s.w);
-                    if (ok) {
-                        bad |= b;
-                        double y, t;
-                        y = s_sub(s_mul(p, dx), cx); t = s_add(sx, y); cx = s_sub(s_sub(t, sx), y); sx = t;
-                        y = s_sub(s_mul(p, dy), cy); t = s_add(sy, y); cy = s_sub(s_sub(t, sy), y); sy = t;
-                        y = s_sub(s_mul(p, dz), cz); t = s_add(sz, y); cz = s_sub(s_sub(t, sz), y); sz = t;
-                    }
-                }
+            const uint64_t t1 = t0 + (uint64_t)jn;
+            const bool lane_clean = (t1 <= ns) && (skip0 < t0 || skip0 >= t1) && (skip1 < t0 || skip1 >= t1);
+            const bool clean = __all_sync(0xffffffffu, lane_clean);      // warp-uniform
+            if (a.windowed) {
+                if (clean) strict_tile_lockstep<KAHAN, 4>(tile, jn, xi, yi, zi, a.G, a.soft2, A);
+                else strict_tile<KAHAN, true, true>(tile, jn, t0, ns, skip0, skip1, xi, yi, zi, a.G, a.soft2, A);
+            } else {
+                strict_tile<KAHAN, false, true>(tile, jn, t0, ns, skip0, skip1, xi, yi, zi, a.G, a.soft2, A);
             }
         }
         __syncthreads();
     }
     if (valid) {
-        if (bad) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, sx, sy, sz);
-        a.ax[i] = sx; a.ay[i] = sy; a.az[i] = sz;
+        if (A.wmax >= STRICT_WINDOW_LIMIT) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, A.sx, A.sy, A.sz);
+        a.ax[i] = A.sx; a.ay[i] = A.sy; a.az[i] = A.sz;
     }
 }
 
@@ -295,6 +353,7 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
     a.ghosts = h->ghosts_dev;
     const bool kahan = c->gravity == REBCU_GRAVITY_COMPENSATED;
     a.use_ghosts = kahan ? 0 : 1;
+    a.windowed = strict_window_ok(c->G) ? 1 : 0;
     if (!kahan) {
         GhostShifts g;
         engine_ghost_shifts(c, c->N_ghost_x, c->N_ghost_y, c->N_ghost_z, &g);

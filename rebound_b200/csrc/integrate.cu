@@ -92,76 +92,71 @@ struct TpArgs {
     double G, soft2;
     double gbx, gby, gbz;   // offset of ghost box (0,0,0), added as the reference does (gravity.c:222-224)
     int kahan, fast, write_acc;
+    int windowed;           // G lies inside the window of the branch-free sqrt/divide (strict_math.cuh)
 };
 
-// MODE 0: strict, branch-free fast-range sqrt/divide (sets *bad); 1: FAST; 2: strict, generic sqrt/divide
-template <int MODE>
-__device__ __forceinline__ void tp_force(const double4* src, int Na, int self,
-                                         double xi, double yi, double zi, double G, double soft2, bool kahan,
-                                         double& ax, double& ay, double& az, unsigned* bad) {
-    constexpr bool FAST = MODE == 1;
+// Force of the massive bodies (shared memory) on one particle, strict arithmetic.
+//   WINDOWED: branch-free sqrt/divide (strict_math.cuh); returns the running window key, the caller falls
+//             back to the generic variant (WINDOWED=false) if it reaches STRICT_WINDOW_LIMIT.
+//   SELF:     the particle may be one of the sources (first warp only) and must skip itself.
+template <bool KAHAN, bool WINDOWED, bool SELF>
+__device__ __forceinline__ unsigned tp_force_strict(const double4* src, int Na, int self, double xi, double yi, double zi,
+                                                    double G, double soft2, double& ax, double& ay, double& az) {
     double cx = 0, cy = 0, cz = 0;
     ax = ay = az = 0;
     const double negG = -G;
-    unsigned anybad = 0;
+    unsigned wmax = 0;
 #pragma unroll 2
     for (int j = 0; j < Na; j++) {
         const double4 sj = src[j];
-        const double sxj = sj.x, syj = sj.y, szj = sj.z, smj = sj.w;
-        if (MODE == 0) {
-            const double dx = s_sub(xi, sxj), dy = s_sub(yi, syj), dz = s_sub(zi, szj);
-            const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
-            unsigned b = 0;
-            const double r = fsqrt_rn(r2, b);
-            const bool ok = j != self;
-            if (!kahan) {
-                const double p = s_mul(fdiv_rn(negG, s_mul(s_mul(r, r), r), b), smj);
-                if (ok) { anybad |= b; ax = s_add(ax, s_mul(p, dx)); ay = s_add(ay, s_mul(p, dy)); az = s_add(az, s_mul(p, dz)); }
-            } else {
-                const double p = s_mul(-fdiv_rn(G, s_mul(r2, r), b), smj);
-                if (ok) {
-                    anybad |= b;
-                    double y, t;
-                    y = s_sub(s_mul(p, dx), cx); t = s_add(ax, y); cx = s_sub(s_sub(t, ax), y); ax = t;
-                    y = s_sub(s_mul(p, dy), cy); t = s_add(ay, y); cy = s_sub(s_sub(t, ay), y); ay = t;
-                    y = s_sub(s_mul(p, dz), cz); t = s_add(az, y); cz = s_sub(s_sub(t, az), y); az = t;
-                }
-            }
-            continue;
-        }
-        if (j == self) continue;
-        if (FAST) {
-            const double dx = xi - sxj, dy = yi - syj, dz = zi - szj;
-            const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
-            const double ri = rsqrt(r2);
-            const double p = negG * smj * (ri * ri * ri);
-            ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az);
+        const double dx = s_sub(xi, sj.x), dy = s_sub(yi, sj.y), dz = s_sub(zi, sj.z);
+        const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
+        const double r = WINDOWED ? fsqrt_rn_w(r2) : s_sqrt(r2);
+        double p;
+        if (!KAHAN) {
+            const double b = s_mul(s_mul(r, r), r);                       // gravity.c:226
+            p = s_mul(WINDOWED ? fdiv_rn_w(negG, b) : s_div(negG, b), sj.w);
         } else {
-            const double dx = s_sub(xi, sxj), dy = s_sub(yi, syj), dz = s_sub(zi, szj);
-            const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), soft2);
-            const double r = s_sqrt(r2);
-            if (!kahan) {
-                const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), smj);
-                ax = s_add(ax, s_mul(p, dx)); ay = s_add(ay, s_mul(p, dy)); az = s_add(az, s_mul(p, dz));
-            } else {
-                const double p = s_mul(-s_div(G, s_mul(r2, r)), smj);
-                double y, t;
-                y = s_sub(s_mul(p, dx), cx); t = s_add(ax, y); cx = s_sub(s_sub(t, ax), y); ax = t;
-                y = s_sub(s_mul(p, dy), cy); t = s_add(ay, y); cy = s_sub(s_sub(t, ay), y); ay = t;
-                y = s_sub(s_mul(p, dz), cz); t = s_add(az, y); cz = s_sub(s_sub(t, az), y); az = t;
-            }
+            const double b = s_mul(r2, r);                                // gravity.c:320-321
+            p = s_mul(-(WINDOWED ? fdiv_rn_w(G, b) : s_div(G, b)), sj.w);
+        }
+        if (SELF && j == self) continue;
+        if (WINDOWED) wmax = max(wmax, strict_window_key(r2));
+        if (!KAHAN) {
+            ax = s_add(ax, s_mul(p, dx)); ay = s_add(ay, s_mul(p, dy)); az = s_add(az, s_mul(p, dz));
+        } else {
+            double y, t;
+            y = s_sub(s_mul(p, dx), cx); t = s_add(ax, y); cx = s_sub(s_sub(t, ax), y); ax = t;
+            y = s_sub(s_mul(p, dy), cy); t = s_add(ay, y); cy = s_sub(s_sub(t, ay), y); ay = t;
+            y = s_sub(s_mul(p, dz), cz); t = s_add(az, y); cz = s_sub(s_sub(t, az), y); az = t;
         }
     }
-    if (bad) *bad = anybad;
+    return wmax;
 }
 
-template <bool FAST>
-__device__ __forceinline__ void tp_force_generic(const double4* src, int Na, int self, double xi, double yi, double zi, double G,
-                                              double soft2, bool kahan, double& ax, double& ay, double& az) {
-    tp_force<2>(src, Na, self, xi, yi, zi, G, soft2, kahan, ax, ay, az, nullptr);
+__device__ __forceinline__ void tp_force_fast(const double4* src, int Na, int self, double xi, double yi, double zi,
+                                              double G, double soft2, bool kahan, double& ax, double& ay, double& az) {
+    double cx = 0, cy = 0, cz = 0;
+    ax = ay = az = 0;
+    const double negG = -G;
+    for (int j = 0; j < Na; j++) {
+        if (j == self) continue;
+        const double4 sj = src[j];
+        const double dx = xi - sj.x, dy = yi - sj.y, dz = zi - sj.z;
+        const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
+        const double ri = rsqrt(r2);
+        const double p = negG * sj.w * (ri * ri * ri);
+        if (!kahan) { ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az); }
+        else {
+            double y, t;
+            y = fma(p, dx, -cx); t = ax + y; cx = (t - ax) - y; ax = t;
+            y = fma(p, dy, -cy); t = ay + y; cy = (t - ay) - y; ay = t;
+            y = fma(p, dz, -cz); t = az + y; cz = (t - az) - y; az = t;
+        }
+    }
 }
 
-template <bool FAST>
+template <bool FAST, bool KAHAN>
 __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
     __shared__ double4 src[TP_MAX_ACTIVE];
     const int Na = a.Na;
@@ -183,11 +178,19 @@ __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
     double ax, ay, az;
     {
         double xi = x, yi = y, zi = z;
-        if (!a.kahan) { xi = s_add(a.gbx, x); yi = s_add(a.gby, y); zi = s_add(a.gbz, z); }
+        if (!KAHAN) { xi = s_add(a.gbx, x); yi = s_add(a.gby, y); zi = s_add(a.gbz, z); }
         const int self = (i < (uint64_t)Na) ? (int)i : -1;
-        unsigned bad = 0;
-        tp_force<FAST ? 1 : 0>(src, Na, self, xi, yi, zi, a.G, a.soft2, a.kahan != 0, ax, ay, az, &bad);
-        if (bad) tp_force_generic<FAST>(src, Na, self, xi, yi, zi, a.G, a.soft2, a.kahan != 0, ax, ay, az);
+        const bool warp_has_self = (i - (threadIdx.x & 31)) < (uint64_t)Na;        // warp-uniform
+        if (FAST) {
+            tp_force_fast(src, Na, self, xi, yi, zi, a.G, a.soft2, KAHAN, ax, ay, az);
+        } else {
+            unsigned w = STRICT_WINDOW_LIMIT;
+            if (a.windowed) {
+                if (warp_has_self) w = tp_force_strict<KAHAN, true, true>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
+                else w = tp_force_strict<KAHAN, true, false>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
+            }
+            if (w >= STRICT_WINDOW_LIMIT) tp_force_strict<KAHAN, false, true>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
+        }
     }
     vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
     x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));
@@ -294,8 +297,10 @@ int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry
         a.write_acc = write_acc ? 1 : 0;
         {
             LaunchScope ls(h, TC_DIRECT);
-            if (a.fast) tp_leapfrog_kernel<true><<<div_up(h->N, TP_BLOCK), TP_BLOCK, 0, h->stream>>>(a);
-            else tp_leapfrog_kernel<false><<<div_up(h->N, TP_BLOCK), TP_BLOCK, 0, h->stream>>>(a);
+            const unsigned int nb = div_up(h->N, TP_BLOCK);
+            a.windowed = strict_window_ok(c->G) ? 1 : 0;
+            if (a.fast) { if (a.kahan) tp_leapfrog_kernel<true, true><<<nb, TP_BLOCK, 0, h->stream>>>(a); else tp_leapfrog_kernel<true, false><<<nb, TP_BLOCK, 0, h->stream>>>(a); }
+            else { if (a.kahan) tp_leapfrog_kernel<false, true><<<nb, TP_BLOCK, 0, h->stream>>>(a); else tp_leapfrog_kernel<false, false><<<nb, TP_BLOCK, 0, h->stream>>>(a); }
         }
         CU_TRY(h, cudaGetLastError());
         h->tp_phase = 1 - h->tp_phase;

@@ -294,9 +294,10 @@ struct WalkArgs {
     double G, soft2, theta2;
     double w2[W_TABLE];      // squared cell width by depth
     double root_size;
+    int windowed;            // G inside the window of the branch-free sqrt/divide (strict_math.cuh)
 };
 
-// MODE 0: strict with the branch-free fast-range sqrt/divide (returns the sticky out-of-range flag),
+// MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
 //      1: FAST (FMA + rsqrt), 2: strict with the generic __dsqrt_rn/__ddiv_rn.
 template <int MODE>
 __device__ __forceinline__ unsigned walk_one(const WalkArgs& a, uint32_t self, double px, double py, double pz,
@@ -326,8 +327,10 @@ __device__ __forceinline__ unsigned walk_one(const WalkArgs& a, uint32_t self, d
                 const double p = negG * q.w * (ri * ri * ri);
                 sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
             } else if (MODE == 0) {
-                const double r = fsqrt_rn(s_add(r2, a.soft2), bad);
-                const double p = s_mul(fdiv_rn(negG, s_mul(s_mul(r, r), r), bad), q.w);   // tree.c:292,313
+                const double rs2 = s_add(r2, a.soft2);
+                bad = max(bad, strict_window_key(rs2));
+                const double r = fsqrt_rn_w(rs2);
+                const double p = s_mul(fdiv_rn_w(negG, s_mul(s_mul(r, r), r)), q.w);      // tree.c:292,313
                 sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
             } else {
                 const double r = s_sqrt(s_add(r2, a.soft2));
@@ -353,8 +356,9 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
     const uint32_t self = a.perm[k];
     const double px = a.x[self], py = a.y[self], pz = a.z[self];
     double sx, sy, sz;
-    const unsigned bad = walk_one<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
-    if (bad) walk_generic(a, self, px, py, pz, sx, sy, sz);
+    unsigned wkey = STRICT_WINDOW_LIMIT;
+    if (FAST || a.windowed) wkey = walk_one<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
+    if (!FAST && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
     a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
 }
 
@@ -523,6 +527,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     a.ghosts = h->ghosts_dev;
     a.G = c->G; a.soft2 = c->softening * c->softening; a.theta2 = c->opening_angle2;
     a.root_size = c->root_size;
+    a.windowed = strict_window_ok(c->G) ? 1 : 0;
     double w = c->root_size;
     for (int d = 0; d < W_TABLE; d++) { a.w2[d] = w * w; w = w / 2.; }
     if (h->world > 1) {

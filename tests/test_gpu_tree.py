@@ -260,3 +260,23 @@ def test_sheet_steps_no_resolve_bitwise(eng):
     want_col = checkers.oracle().collision_search(cw, want)
     got_col = eng.collisions_fetch()
     assert collisions_equal(got_col, want_col)
+
+
+def test_disc_2pow20_full_size_bitwise(eng):
+    """Config C4 recipe at N=2^20 (the largest size the CPU oracle finishes in seconds with OpenMP): the whole
+    acceleration array is bit-identical, and the device tree satisfies the pre-order invariants."""
+    n = 1 << 20
+    p = ics.selfgravity_disc(n - 1, seed=42)
+    cfg = ics.selfgravity_disc_config()
+    want, _ = checkers.oracle().gravity(cfg, p)
+    q, c = p.copy(), cfg.copy()
+    m = eng.gravity_host(c, q)
+    assert m == len(want)
+    assert bits_equal(q[:m], want)
+    cells = eng.tree(c)
+    leaves = cells[cells["pt"] >= 0]
+    assert len(leaves) == m and np.array_equal(np.sort(leaves["pt"]), np.arange(m))      # one leaf per particle
+    internal = cells[cells["pt"] < 0]
+    assert -internal["pt"][0] == m                                                          # root counts everything
+    assert np.all(cells["skip"] > np.arange(len(cells))) and cells["skip"][0] == len(cells)
+    assert abs(cells["m"][0] - p["m"].sum()) < 1e-12

@@ -35,9 +35,9 @@ def case(name):
         return ics.selfgravity_disc(n - 1, seed=42), cfg, 2, None
     if name.startswith("c5"):
         n = 1 << int(name.split("_")[1].replace("fast",""))
-        rs = 2655.0 * (n / 2**20) ** 0.5 / 1.0
-        cfg = ics.shearing_sheet_config(root_size=rs / 2 * 1.0)
-        p = ics.shearing_sheet(root_size=rs / 2 * 1.0, seed=42)
+        rs = 2655.0 * (n / 2**20) ** 0.5          # root_size ~ 2655 m gives N ~ 2^20 with 2x2 root boxes
+        cfg = ics.shearing_sheet_config(root_size=rs)
+        p = ics.shearing_sheet(root_size=rs, seed=42)
         if "fast" in name:
             cfg.mode = abi.MODE_FAST
         return p, cfg, 2, None
