@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(INNER_STEPS))
     ap.add_argument("--inner", type=int, default=0, help="leapfrog steps per bench step (default 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational measurements of the other configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -257,7 +258,8 @@ def main():
     if args.workload.startswith("c2"):
         alg_bytes = 96.0 * n                 # x,v read + x,v written per particle per fused step
         roof = {"bound": "hbm", "kernel": "tp_leapfrog_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "unit": "GB/s", "peak_source": peak_src,
+                "traffic": 50.98e6, "traffic_source": "dram read+write per launch, ncu --set full (profiles/r01_tp2_ncu.txt; cold L2: x,v read once, writes stay in L2)",
                 "note": "resident state (48 B x N = 50 MB) fits the 126 MB L2, so inner steps stream from L2; "
                         "strict-mode arithmetic makes the kernel FP64-pipe bound, see fp64"}
     else:
@@ -274,6 +276,38 @@ def main():
     roof["fp64"] = {"achieved_tflops": 20.0 * inter / (k_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                     "peak_source": "148 SM x 64 DFMA/clk x 2 flop x sampled SM clock (nominal)",
                     "frac": 20.0 * inter / (k_ms * 1e-3) / 1e12 / fp64_peak}
+
+    # ---------------- other BASELINE.json configurations, device-resident, informational ----------------
+    others = None
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_extra:
+        from rebound_b200 import ics
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e-3 / reps
+
+        others = {}
+        n1 = 16384
+        p1 = ics.plummer(n1, seed=42)
+        for tag, mode in (("c1_plummer16384_basic_strict", abi.MODE_STRICT), ("c1_plummer16384_basic_fast", abi.MODE_FAST)):
+            c1 = ics.plummer_config(n1, mode=mode)
+            eng.upload(np.ascontiguousarray(p1))
+            s1 = timed(lambda: eng.steps(c1, 10), 3) / 10
+            others[tag] = {"interactions_per_s": (n1 * n1 - n1) / s1, "ms_per_step": s1 * 1e3}
+        n4 = 1 << 20
+        p4 = ics.selfgravity_disc(n4 - 1, seed=42)
+        c4 = ics.selfgravity_disc_config()
+        eng.upload(np.ascontiguousarray(p4))
+        s4 = timed(lambda: eng.steps(c4, 2), 2) / 2
+        others["c4_disc_2pow20_tree_strict"] = {"particle_steps_per_s": n4 / s4, "ms_per_step": s4 * 1e3}
+        eng.upload(hp)
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
@@ -301,6 +335,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "other_configs": others,
         }
         print(json.dumps(line))
     eng.close()

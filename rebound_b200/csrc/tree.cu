@@ -33,6 +33,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -362,6 +363,73 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
     a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
 }
 
+// Warp-cooperative walk.  ncu showed the per-thread walk bound by L1 wavefronts (l1tex data pipe 93 % busy,
+// 23 sectors per request): 32 lanes chase 32 different cells.  Here the 32 key-adjacent particles of a warp
+// share ONE traversal cursor c: the cell record is fetched with a warp-uniform (broadcast, single wavefront)
+// load, every lane still takes its own opening decision and keeps `next` = the first cell it wants to see
+// again (c+1 after opening, skip after accepting), and the cursor advances to the minimum over the lanes.
+// Each lane therefore visits exactly the cells, in exactly the order, of its own stackless walk: the result
+// is bit-identical to walk_kernel, only the memory traffic is shared.
+template <int MODE>
+__global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    const bool live = t < a.n_work;
+    uint32_t self = 0xffffffffu;
+    double px = 0, py = 0, pz = 0;
+    if (live) {
+        const uint64_t k = a.list ? a.list[t] : t;
+        self = a.perm[k];
+        px = a.x[self]; py = a.y[self]; pz = a.z[self];
+    }
+    double sx = 0., sy = 0., sz = 0.;
+    unsigned wkey = 0;
+    const double negG = -a.G;
+    const int ngb = a.ghosts->n;
+    const int n_cells = (int)a.n_cells;
+    for (int g = 0; g < ngb; g++) {
+        const double gx = s_add(a.ghosts->gb[g].x, px), gy = s_add(a.ghosts->gb[g].y, py), gz = s_add(a.ghosts->gb[g].z, pz);
+        int next = live ? 0 : n_cells;
+        int c = 0;                                   // warp-uniform cursor = min over lanes of `next`
+        while (c < n_cells) {
+            const double4 q = a.pos[c];              // uniform address: one wavefront for the whole warp
+            const int4 mt = a.meta[c];
+            if (next == c) {
+                const double dx = s_sub(gx, q.x), dy = s_sub(gy, q.y), dz = s_sub(gz, q.z);
+                const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+                bool interact = true;
+                if (mt.x < 0) {
+                    double w2;
+                    if (mt.z < W_TABLE) w2 = a.w2[mt.z];
+                    else { double w = a.root_size; for (int d = 0; d < mt.z; d++) w = s_div(w, 2.); w2 = s_mul(w, w); }
+                    if (w2 > s_mul(a.theta2, r2)) { interact = false; next = c + 1; }     // tree.c:284: open the cell
+                } else if ((uint32_t)mt.x == self) interact = false;                     // tree.c:311
+                if (interact) {
+                    if (MODE == 1) {
+                        const double ri = rsqrt(r2 + a.soft2);
+                        const double p = negG * q.w * (ri * ri * ri);
+                        sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
+                    } else if (MODE == 0) {
+                        const double rs2 = s_add(r2, a.soft2);
+                        wkey = max(wkey, strict_window_key(rs2));
+                        const double r = fsqrt_rn_w(rs2);
+                        const double p = s_mul(fdiv_rn_w(negG, s_mul(s_mul(r, r), r)), q.w);      // tree.c:292,313
+                        sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
+                    } else {
+                        const double r = s_sqrt(s_add(r2, a.soft2));
+                        const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), q.w);
+                        sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
+                    }
+                }
+                if (next == c) next = mt.y;          // accepted, leaf, or own leaf: continue after the subtree
+            }
+            c = __reduce_min_sync(0xffffffffu, next);
+        }
+    }
+    if (!live) return;
+    if (MODE == 0 && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
+    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+}
+
 __global__ void __launch_bounds__(256) shard_flag_kernel(uint64_t n, const uint32_t* __restrict__ perm, uint32_t b, uint32_t e,
                                                          uint32_t* __restrict__ flag) {
     const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -543,8 +611,20 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     }
     if (a.n_work) {
         LaunchScope ls(h, TC_TREEWALK);
-        if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<div_up(a.n_work, 128), 128, 0, h->stream>>>(a);
-        else walk_kernel<false><<<div_up(a.n_work, 128), 128, 0, h->stream>>>(a);
+        // Both walks give identical bits.  Measured on B200 (profiles/r01_walk_ncu.txt, r01_walk_coop_ncu.txt):
+        // per-thread is L1-wavefront bound (l1tex 93 %, FP64 37 %), cooperative is FP64-issue bound (FP64 61 %,
+        // 18.7 of 32 lanes active); wall time 6.99 vs 7.24 ms at N=2^20, 2.1 vs 3.0 ms with 25 ghost boxes.
+        // Default: per-thread; REBOUND_B200_WALK=coop selects the cooperative kernel.
+        static const bool per_thread = [] { const char* e = getenv("REBOUND_B200_WALK"); return !(e && strcmp(e, "coop") == 0); }();
+        const unsigned int nb = div_up(a.n_work, 128);
+        if (per_thread) {
+            if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<nb, 128, 0, h->stream>>>(a);
+            else walk_kernel<false><<<nb, 128, 0, h->stream>>>(a);
+        } else {
+            if (c->mode == REBCU_MODE_FAST) walk_coop_kernel<1><<<nb, 128, 0, h->stream>>>(a);
+            else if (a.windowed) walk_coop_kernel<0><<<nb, 128, 0, h->stream>>>(a);
+            else walk_coop_kernel<2><<<nb, 128, 0, h->stream>>>(a);
+        }
     }
     CU_TRY(h, cudaGetLastError());
     return REBCU_OK;
