@@ -255,13 +255,18 @@ def main():
     eng.timing_enable(False)
     dom = max(tim, key=lambda k: tim[k]["ms"])
     k_ms = tim[dom]["ms"] / max(1, tim[dom]["launches"])
+    steps_in_launch = 1
     if args.workload.startswith("c2"):
-        alg_bytes = 96.0 * n                 # x,v read + x,v written per particle per fused step
-        roof = {"bound": "hbm", "kernel": "tp_leapfrog_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "peak_source": peak_src,
-                "traffic": 50.98e6, "traffic_source": "dram read+write per launch, ncu --set full (profiles/r01_tp2_ncu.txt; cold L2: x,v read once, writes stay in L2)",
-                "note": "resident state (48 B x N = 50 MB) fits the 126 MB L2, so inner steps stream from L2; "
-                        "strict-mode arithmetic makes the kernel FP64-pipe bound, see fp64"}
+        # tp_multistep_kernel: ONE launch advances every test particle through all `inner` steps with x,v in
+        # registers: 48 B read + 72 B written per particle per launch (x,v in; x,v,a out), DESIGN.md section 3.
+        steps_in_launch = inner
+        alg_bytes = 120.0 * n
+        roof = {"bound": "hbm", "kernel": "tp_multistep_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "limiting_resource": "fp64 pipe",
+                "note": f"one launch = {inner} leapfrog steps of all particles held in registers, so HBM traffic is 120 B per "
+                        "particle per launch by construction and the kernel is bound by the FP64 pipe (strict IEEE sqrt+divide: "
+                        "36 DP instructions per interaction); see fp64.pipe_frac"}
     else:
         flops = 20.0 * inter                 # 20 flop per interaction
         roof = {"bound": "hbm", "kernel": "direct_strict_kernel", "achieved": 32.0 * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -273,9 +278,14 @@ def main():
     # FP64 pipe view: interactions/s of the kernel alone x 20 flop against 148 SM x 64 DFMA/clk x 2 x clock
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
-    roof["fp64"] = {"achieved_tflops": 20.0 * inter / (k_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+    k_inter_per_s = inter * steps_in_launch / (k_ms * 1e-3)
+    dp_per_inter = 36.0 if cfg.mode == 0 else 22.0      # FP64-pipe instructions per interaction (SASS count)
+    roof["fp64"] = {"achieved_tflops": 20.0 * k_inter_per_s / 1e12, "peak_tflops": fp64_peak,
                     "peak_source": "148 SM x 64 DFMA/clk x 2 flop x sampled SM clock (nominal)",
-                    "frac": 20.0 * inter / (k_ms * 1e-3) / 1e12 / fp64_peak}
+                    "frac": 20.0 * k_inter_per_s / 1e12 / fp64_peak,
+                    "pipe_frac": k_inter_per_s * dp_per_inter / (148 * 64 * sm_mhz * 1e6),
+                    "pipe_frac_note": "issued FP64-pipe instructions per lane-slot: interactions/s x DP instructions per "
+                                      "interaction / (148 SM x 64 lanes x clock); 20 flop/interaction is BASELINE.md's algorithmic count"}
 
     # ---------------- other BASELINE.json configurations, device-resident, informational ----------------
     others = None

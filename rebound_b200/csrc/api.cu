@@ -66,6 +66,11 @@ int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg, rebcu_colli
 int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
+    {
+        // few massive bodies + many test particles: the whole batch of steps in two launches
+        const int fused = tp_steps_resident(h, cfg, n_steps);
+        if (fused <= 0) return fused;
+    }
     const bool can_carry = cfg->integrator == REBCU_INTEGRATOR_LEAPFROG && cfg->boundary == REBCU_BOUNDARY_NONE
                         && cfg->collision == REBCU_COLLISION_NONE && h->exchange == nullptr;
     bool carried = false;
@@ -118,6 +123,10 @@ int rebcu_collision_search_host(rebcu_handle* h, const rebcu_config* cfg, const 
 }
 
 int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N, uint64_t n_steps) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    // few massive bodies + many test particles: chunked, copies overlapped with the kernels
+    const int piped = tp_steps_host_pipelined(h, cfg, particles, *N, n_steps);
+    if (piped <= 0) return piped;
     int err = rebcu_upload(h, particles, *N);
     if (err) return err;
     err = rebcu_steps(h, cfg, n_steps);

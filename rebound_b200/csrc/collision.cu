@@ -20,6 +20,13 @@ namespace {
 
 struct ColSoa { const double *x, *y, *z, *vx, *vy, *vz, *r; };
 
+// one LDG.E.256 per 32-byte cell record (half the L1 wavefronts of two 128-bit loads in a divergent walk)
+__device__ __forceinline__ double4 ld256(const double4* p) {
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
 ColSoa col_soa(const rebcu_handle* h) {
     return ColSoa{h->f(F_X), h->f(F_Y), h->f(F_Z), h->f(F_VX), h->f(F_VY), h->f(F_VZ), h->f(F_R)};
 }
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
             const int4 mt = a.meta[c];
             if (mt.x >= 0) {
                 if ((uint32_t)mt.x != i) {
-                    const double4 q = a.pos[c];                      // leaf: the particle's own position
+                    const double4 q = ld256(a.pos + c);              // leaf: the particle's own position
                     if (hit(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x)) {
                         if (FILL) emit(out, base + found, i, (uint32_t)mt.x, gb, (uint64_t)mt.w);
                         found++;
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
                 }
                 c = mt.y;
             } else {
-                const double4 q = a.geo[c];
+                const double4 q = ld256(a.geo + c);
                 const double dx = s_sub(s.x, q.x), dy = s_sub(s.y, q.y), dz = s_sub(s.z, q.z);
                 const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
                 const double rp = s_add(reach, s_mul(0.86602540378443, q.w));       // collision.c:492

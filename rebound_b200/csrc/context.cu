@@ -69,6 +69,9 @@ void rebcu_destroy(rebcu_handle* h) {
     cudaFree(h->soa); cudaFree(h->aos); cudaFree(h->ghosts_dev); cudaFree(h->scratch); cudaFree(h->counters); cudaFree(h->scratch_big);
     cudaFree(h->col_count); cudaFree(h->col_off); cudaFree(h->col_list); cudaFree(h->col_scan_tmp);
     cudaFree(h->compact_tmp); cudaFree(h->compact_buf); cudaFree(h->compact_flag); cudaFree(h->compact_pos);
+    cudaFree(h->tp_hist);
+    for (int k = 0; k < AUX_STREAMS; k++) if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
+    for (int k = 0; k < 3; k++) if (h->aux_ev[k]) cudaEventDestroy(h->aux_ev[k]);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->ghost_ring) cudaFreeHost(h->ghost_ring);
     for (int i = 0; i < GHOST_RING; i++) if (h->ghost_ring_ev[i]) cudaEventDestroy(h->ghost_ring_ev[i]);
@@ -227,6 +230,26 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(uint64_t* __restrict
     __syncthreads();
     const uint64_t words = cnt * WORDS;
     for (uint64_t w = threadIdx.x; w < words; w += PACK_THREADS) aos[base * WORDS + w] = tile[w];
+}
+
+// Range versions on an arbitrary stream, for the chunk-pipelined host-buffer path (integrate.cu).
+// b must be a multiple of PACK_THREADS.
+int engine_upload_range(rebcu_handle* h, cudaStream_t s, const rebcu_particle* particles, uint64_t b, uint64_t e) {
+    if (e <= b) return REBCU_OK;
+    CU_TRY(h, cudaMemcpyAsync(h->aos + b, particles + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyHostToDevice, s));
+    h->launches++;
+    unpack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s>>>((const uint64_t*)(h->aos + b), (uint64_t*)h->soa + b, h->cap, e - b);
+    CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}
+
+int engine_download_range(rebcu_handle* h, cudaStream_t s, rebcu_particle* particles, uint64_t b, uint64_t e) {
+    if (e <= b) return REBCU_OK;
+    h->launches++;
+    pack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s>>>((uint64_t*)(h->aos + b), (const uint64_t*)h->soa + b, h->cap, e - b);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(particles + b, h->aos + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyDeviceToHost, s));
+    return REBCU_OK;
 }
 
 extern "C" {

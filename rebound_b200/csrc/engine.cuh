@@ -22,6 +22,7 @@ enum { TC_DIRECT = 0, TC_KICKDRIFT, TC_TREEBUILD, TC_TREEWALK, TC_COLLISION, TC_
 
 #define REBCU_MAX_GHOST 729   // (2*4+1)^3
 #define GHOST_RING 8
+#define AUX_STREAMS 4
 
 struct GhostShifts {          // ghost-box offsets, computed on the host exactly as src/boundary.c:145-201
     int n;
@@ -45,7 +46,8 @@ struct TreeBuffers {
     uint32_t* ready = nullptr;     // [cap_cells] children-done counters for the moment pass
     double4* walk_pos = nullptr;   // [cap_cells] (mx,my,mz,m) packed for the walk
     double4* walk_geo = nullptr;   // [cap_cells] (x,y,z,w) packed for the collision walk
-    int2* walk_meta = nullptr;     // [cap_cells] (pt, skip)
+    int2* walk_meta = nullptr;     // [cap_cells] int4 (pt, skip, depth, rootbox)
+    int2* walk_meta2 = nullptr;    // [cap_cells] (leaf: pt >= 0 | internal: -(depth+1), skip): all the gravity walk needs
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
     uint64_t n_cells = 0;
@@ -87,6 +89,9 @@ struct rebcu_handle {
     uint32_t* compact_flag = nullptr; uint32_t* compact_pos = nullptr;
     double* scratch_big = nullptr;        // 2 x 7 x 256 doubles: massive-body snapshots of the fused test-particle step
     int tp_phase = 0;
+    cudaStream_t aux[AUX_STREAMS] = {};         // copy/compute overlap streams of the chunk-pipelined host path
+    cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
+    double* tp_hist = nullptr; uint64_t tp_hist_cap = 0;   // per-step snapshots of the massive bodies
     void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)
     void* exchange_user = nullptr;
     int (*collision_hook)(void*) = nullptr;   // called after each step's collision search (host resolve)
@@ -123,6 +128,12 @@ int zero_acceleration(rebcu_handle* h);
 int leapfrog_step(rebcu_handle* h, rebcu_config* c, bool fuse_ok);
 int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry_out, bool write_acc);
 int sei_step(rebcu_handle* h, rebcu_config* c);
+// Chunk-pipelined reb_simulation_steps on a host AoS for the fused test-particle step; returns 1 if the
+// configuration is not eligible (caller falls back to upload / steps / download), 0 on success, <0 on error.
+int tp_steps_resident(rebcu_handle* h, rebcu_config* c, uint64_t n_steps);
+int tp_steps_host_pipelined(rebcu_handle* h, rebcu_config* c, rebcu_particle* particles, uint64_t N, uint64_t n_steps);
+int engine_upload_range(rebcu_handle* h, cudaStream_t s, const rebcu_particle* particles, uint64_t b, uint64_t e);
+int engine_download_range(rebcu_handle* h, cudaStream_t s, rebcu_particle* particles, uint64_t b, uint64_t e);
 int boundary_check(rebcu_handle* h, rebcu_config* c);
 int tree_build(rebcu_handle* h, const rebcu_config* c);
 int tree_gravity(rebcu_handle* h, rebcu_config* c);

@@ -87,6 +87,7 @@ struct TpArgs {
     const double* act_in;   // snapshot of the massive bodies before the step: 7 arrays of Na (x y z vx vy vz m)
     double* act_out;        // snapshot after the step
     uint64_t N; int Na;
+    uint64_t i_begin;       // first particle of this launch (chunk-pipelined host path), normally 0; N = end
     double d0; int has_d0;  // leading drift (absent if the previous launch already applied it)
     double k, d1, d2; int has_d2;
     double G, soft2;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
         src[j] = make_double4(x, y, z, a.act_in[6 * Na + j]);
     }
     __syncthreads();
-    const uint64_t i = (uint64_t)blockIdx.x * TP_BLOCK + threadIdx.x;
+    const uint64_t i = a.i_begin + (uint64_t)blockIdx.x * TP_BLOCK + threadIdx.x;
     if (i >= a.N) return;
     double x = a.s.x[i], y = a.s.y[i], z = a.s.z[i];
     double vx = a.s.vx[i], vy = a.s.vy[i], vz = a.s.vz[i];
@@ -202,6 +203,104 @@ __global__ void __launch_bounds__(TP_BLOCK) tp_leapfrog_kernel(const TpArgs a) {
         a.act_out[0 * Na + i] = x; a.act_out[1 * Na + i] = y; a.act_out[2 * Na + i] = z;
         a.act_out[3 * Na + i] = vx; a.act_out[4 * Na + i] = vy; a.act_out[5 * Na + i] = vz;
         a.act_out[6 * Na + i] = a.s.m[i];
+    }
+}
+
+// ---- many steps per launch --------------------------------------------------------------------
+// With testparticle_type 0 the massive bodies do not feel the test particles, so their whole trajectory over
+// n_steps can be computed first by ONE small CTA (tp_history_kernel) and recorded step by step (hist[st] = the
+// state the step kernel would receive as act_in: before the leading drift for st = 0, after the merged trailing
+// drift otherwise).  tp_multistep_kernel then advances every test particle through all n_steps in a single
+// launch with x, v held in registers: per particle 48 B are read and 72 B written once per call instead of
+// per step, and the launch count is independent of n_steps.  Every particle executes exactly the operation
+// sequence of tp_leapfrog_kernel, so the results are bit-identical.
+struct TpMultiArgs {
+    Soa s;
+    double* hist;           // (n_steps+1) x 7 x Na
+    uint64_t i_begin, i_end; int Na;
+    uint64_t n_steps;
+    double d0, k, d1, d2;
+    double G, soft2, gbx, gby, gbz;
+    int windowed, fast, kahan;
+};
+
+template <bool FAST, bool KAHAN>
+__device__ __forceinline__ void tp_force_any(const double4* src, int Na, int self, bool warp_has_self, double x, double y, double z,
+                                             const TpMultiArgs& a, double& ax, double& ay, double& az) {
+    double xi = x, yi = y, zi = z;
+    if (!KAHAN) { xi = s_add(a.gbx, x); yi = s_add(a.gby, y); zi = s_add(a.gbz, z); }
+    if (FAST) { tp_force_fast(src, Na, self, xi, yi, zi, a.G, a.soft2, KAHAN, ax, ay, az); return; }
+    unsigned w = STRICT_WINDOW_LIMIT;
+    if (a.windowed) {
+        if (warp_has_self) w = tp_force_strict<KAHAN, true, true>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
+        else w = tp_force_strict<KAHAN, true, false>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
+    }
+    if (w >= STRICT_WINDOW_LIMIT) tp_force_strict<KAHAN, false, true>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
+}
+
+// One CTA: the massive bodies alone, all steps; records hist[0..n_steps] and writes their final state.
+template <bool FAST, bool KAHAN>
+__global__ void __launch_bounds__(TP_MAX_ACTIVE) tp_history_kernel(const TpMultiArgs a) {
+    __shared__ double4 src[TP_MAX_ACTIVE];
+    const int j = threadIdx.x, Na = a.Na;
+    const bool live = j < Na;
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, m = 0, ax = 0, ay = 0, az = 0;
+    if (live) { x = a.s.x[j]; y = a.s.y[j]; z = a.s.z[j]; vx = a.s.vx[j]; vy = a.s.vy[j]; vz = a.s.vz[j]; m = a.s.m[j]; }
+    for (uint64_t st = 0; st < a.n_steps; st++) {
+        if (live) {
+            double* hs = a.hist + st * 7 * Na;
+            hs[0 * Na + j] = x; hs[1 * Na + j] = y; hs[2 * Na + j] = z; hs[3 * Na + j] = vx; hs[4 * Na + j] = vy; hs[5 * Na + j] = vz; hs[6 * Na + j] = m;
+            if (st == 0) { x = s_add(x, s_mul(a.d0, vx)); y = s_add(y, s_mul(a.d0, vy)); z = s_add(z, s_mul(a.d0, vz)); }
+            src[j] = make_double4(x, y, z, m);
+        }
+        __syncthreads();
+        if (live) {
+            tp_force_any<FAST, KAHAN>(src, Na, j, true, x, y, z, a, ax, ay, az);
+            vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
+            x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));
+            if (st + 1 < a.n_steps) { x = s_add(x, s_mul(a.d2, vx)); y = s_add(y, s_mul(a.d2, vy)); z = s_add(z, s_mul(a.d2, vz)); }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        double* hs = a.hist + a.n_steps * 7 * Na;
+        hs[0 * Na + j] = x; hs[1 * Na + j] = y; hs[2 * Na + j] = z; hs[3 * Na + j] = vx; hs[4 * Na + j] = vy; hs[5 * Na + j] = vz; hs[6 * Na + j] = m;
+        a.s.x[j] = x; a.s.y[j] = y; a.s.z[j] = z; a.s.vx[j] = vx; a.s.vy[j] = vy; a.s.vz[j] = vz;
+        a.s.ax[j] = ax; a.s.ay[j] = ay; a.s.az[j] = az;
+    }
+}
+
+// Test particles i in [max(i_begin, Na), i_end): all steps in one launch, massive bodies replayed from hist.
+template <bool FAST, bool KAHAN>
+__global__ void __launch_bounds__(TP_BLOCK) tp_multistep_kernel(const TpMultiArgs a) {
+    __shared__ double4 src[2][TP_MAX_ACTIVE];
+    const int Na = a.Na;
+    const uint64_t i = a.i_begin + (uint64_t)blockIdx.x * TP_BLOCK + threadIdx.x;
+    const bool live = i < a.i_end && i >= (uint64_t)Na;
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0;
+    if (live) { x = a.s.x[i]; y = a.s.y[i]; z = a.s.z[i]; vx = a.s.vx[i]; vy = a.s.vy[i]; vz = a.s.vz[i]; }
+    for (uint64_t st = 0; st < a.n_steps; st++) {
+        double4* buf = src[st & 1];
+        const double* hs = a.hist + st * 7 * Na;
+        for (int j = threadIdx.x; j < Na; j += TP_BLOCK) {
+            double sx = hs[0 * Na + j], sy = hs[1 * Na + j], sz = hs[2 * Na + j];
+            if (st == 0) {
+                sx = s_add(sx, s_mul(a.d0, hs[3 * Na + j])); sy = s_add(sy, s_mul(a.d0, hs[4 * Na + j])); sz = s_add(sz, s_mul(a.d0, hs[5 * Na + j]));
+            }
+            buf[j] = make_double4(sx, sy, sz, hs[6 * Na + j]);
+        }
+        __syncthreads();      // one barrier per step: the other buffer is only rewritten two steps later
+        if (live) {
+            if (st == 0) { x = s_add(x, s_mul(a.d0, vx)); y = s_add(y, s_mul(a.d0, vy)); z = s_add(z, s_mul(a.d0, vz)); }
+            tp_force_any<FAST, KAHAN>(buf, Na, -1, false, x, y, z, a, ax, ay, az);
+            vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
+            x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));
+            if (st + 1 < a.n_steps) { x = s_add(x, s_mul(a.d2, vx)); y = s_add(y, s_mul(a.d2, vy)); z = s_add(z, s_mul(a.d2, vz)); }
+        }
+    }
+    if (live) {
+        a.s.x[i] = x; a.s.y[i] = y; a.s.z[i] = z; a.s.vx[i] = vx; a.s.vy[i] = vy; a.s.vz[i] = vz;
+        a.s.ax[i] = ax; a.s.ay[i] = ay; a.s.az[i] = az;
     }
 }
 
@@ -288,7 +387,7 @@ int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry
             tp_snapshot_kernel<<<div_up(Na, 128), 128, 0, h->stream>>>(s, act_in, Na);
         }
         TpArgs a;
-        a.s = s; a.act_in = act_in; a.act_out = act_out; a.N = h->N; a.Na = Na;
+        a.s = s; a.act_in = act_in; a.act_out = act_out; a.N = h->N; a.Na = Na; a.i_begin = 0;
         a.d0 = drift[0]; a.has_d0 = carry_in ? 0 : 1;
         a.k = kick[0]; a.d1 = drift[1]; a.d2 = drift[0]; a.has_d2 = carry_out ? 1 : 0;
         a.G = c->G; a.soft2 = c->softening * c->softening;
@@ -328,6 +427,126 @@ int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry
     }
     CU_TRY(h, cudaGetLastError());
     c->t += drift[nk];
+    c->dt_last_done = c->dt;
+    return REBCU_OK;
+}
+
+static TpMultiArgs tp_multi_args(rebcu_handle* h, const rebcu_config* c, uint64_t n_steps, const double* drift, const double* kick) {
+    TpMultiArgs a;
+    a.s = soa_of(h); a.hist = h->tp_hist; a.i_begin = 0; a.i_end = h->N; a.Na = (int)c->N_active; a.n_steps = n_steps;
+    a.d0 = drift[0]; a.k = kick[0]; a.d1 = drift[1]; a.d2 = drift[0];
+    a.G = c->G; a.soft2 = c->softening * c->softening;
+    GhostShifts g0; engine_ghost_shifts(c, 0, 0, 0, &g0);
+    a.gbx = g0.gb[0].x; a.gby = g0.gb[0].y; a.gbz = g0.gb[0].z;
+    a.windowed = strict_window_ok(c->G) ? 1 : 0;
+    a.fast = c->mode == REBCU_MODE_FAST; a.kahan = c->gravity == REBCU_GRAVITY_COMPENSATED;
+    return a;
+}
+static void tp_launch_history(const TpMultiArgs& a, cudaStream_t s) {
+    if (a.fast) { if (a.kahan) tp_history_kernel<true, true><<<1, TP_MAX_ACTIVE, 0, s>>>(a); else tp_history_kernel<true, false><<<1, TP_MAX_ACTIVE, 0, s>>>(a); }
+    else { if (a.kahan) tp_history_kernel<false, true><<<1, TP_MAX_ACTIVE, 0, s>>>(a); else tp_history_kernel<false, false><<<1, TP_MAX_ACTIVE, 0, s>>>(a); }
+}
+static void tp_launch_multistep(const TpMultiArgs& a, cudaStream_t s) {
+    const unsigned int nb = div_up(a.i_end - a.i_begin, TP_BLOCK);
+    if (a.fast) { if (a.kahan) tp_multistep_kernel<true, true><<<nb, TP_BLOCK, 0, s>>>(a); else tp_multistep_kernel<true, false><<<nb, TP_BLOCK, 0, s>>>(a); }
+    else { if (a.kahan) tp_multistep_kernel<false, true><<<nb, TP_BLOCK, 0, s>>>(a); else tp_multistep_kernel<false, false><<<nb, TP_BLOCK, 0, s>>>(a); }
+}
+
+static int tp_reserve_history(rebcu_handle* h, uint64_t n_steps, int Na) {
+    const uint64_t hist_need = (n_steps + 1) * 7 * (uint64_t)Na;
+    if (h->tp_hist_cap < hist_need) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->tp_hist); h->tp_hist = nullptr; h->tp_hist_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->tp_hist, hist_need * sizeof(double)));
+        h->tp_hist_cap = hist_need;
+    }
+    return REBCU_OK;
+}
+
+// Resident version: reb_simulation_steps for the fused test-particle configuration in two launches
+// (massive-body history, then every test particle through all steps).  Returns 1 if not eligible.
+int tp_steps_resident(rebcu_handle* h, rebcu_config* c, uint64_t n_steps) {
+    if (!(tp_path_ok(h, c) && c->integrator == REBCU_INTEGRATOR_LEAPFROG && c->boundary == REBCU_BOUNDARY_NONE
+          && c->collision == REBCU_COLLISION_NONE && h->exchange == nullptr && n_steps >= 2 && n_steps <= 65536)) return 1;
+    const int Na = (int)c->N_active;
+    int err = tp_reserve_history(h, n_steps, Na);
+    if (err) return err;
+    c->gravity_ignore_terms = REBCU_IGNORE_TERMS_NONE;
+    double drift[20], kick[20];
+    lf_schedule(2, c->dt, drift, kick);
+    TpMultiArgs a = tp_multi_args(h, c, n_steps, drift, kick);
+    {
+        LaunchScope ls(h, TC_KICKDRIFT);
+        tp_launch_history(a, h->stream);
+    }
+    {
+        LaunchScope ls(h, TC_DIRECT);
+        tp_launch_multistep(a, h->stream);
+    }
+    CU_TRY(h, cudaGetLastError());
+    for (uint64_t st = 0; st < n_steps; st++) { c->t += drift[0]; c->t += drift[1]; }
+    c->dt_last_done = c->dt;
+    return REBCU_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// reb_simulation_steps on a HOST particle array for the fused test-particle configuration, pipelined:
+// the particles are cut into chunks; each chunk is uploaded, advanced through ALL n_steps and downloaded
+// on one of two streams, so the PCIe copies of one chunk overlap the kernels of another (test particles of
+// type 0 do not interact).  The massive bodies live in chunk 0, whose launches record their state after
+// every step (tp_hist); the later chunks replay that history, so every chunk sees, step by step, exactly
+// the massive-body positions the single-launch-per-step path would give it.  Bit-identical results.
+// -------------------------------------------------------------------------------------------------
+int tp_steps_host_pipelined(rebcu_handle* h, rebcu_config* c, rebcu_particle* particles, uint64_t N, uint64_t n_steps) {
+    const uint64_t N_saved = h->N;
+    h->N = N;
+    const bool ok = tp_path_ok(h, c) && c->integrator == REBCU_INTEGRATOR_LEAPFROG && c->boundary == REBCU_BOUNDARY_NONE
+                 && c->collision == REBCU_COLLISION_NONE && h->exchange == nullptr && !h->timing
+                 && N >= (1u << 18) && n_steps >= 1 && n_steps <= 65536;
+    h->N = N_saved;
+    if (!ok) return 1;
+    int err = engine_reserve(h, N);
+    if (err) return err;
+    h->N = N; h->resident = true; h->tree.built_for_n = -1;
+    const int Na = (int)c->N_active;
+    for (int k = 0; k < AUX_STREAMS; k++) if (!h->aux[k]) CU_TRY(h, cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 3; k++) if (!h->aux_ev[k]) CU_TRY(h, cudaEventCreateWithFlags(&h->aux_ev[k], cudaEventDisableTiming));
+    if ((err = tp_reserve_history(h, n_steps, Na))) return err;
+    c->gravity_ignore_terms = REBCU_IGNORE_TERMS_NONE;
+    double drift[20], kick[20];
+    lf_schedule(2, c->dt, drift, kick);
+    TpMultiArgs a = tp_multi_args(h, c, n_steps, drift, kick);
+
+    // everything queued on the handle's stream so far must be finished before the aux streams touch the buffers
+    CU_TRY(h, cudaEventRecord(h->aux_ev[0], h->stream));
+    for (int k = 0; k < AUX_STREAMS; k++) CU_TRY(h, cudaStreamWaitEvent(h->aux[k], h->aux_ev[0], 0));
+
+    // range 0 = the first 256 particles (holds the massive bodies): their history starts as early as possible
+    const int n_chunks = 16;
+    const uint64_t head = 256;
+    uint64_t cs = (N - head + n_chunks - 1) / n_chunks;
+    cs = ((cs + 255) / 256) * 256;
+    int idx = 0;
+    for (uint64_t b = 0; b < N; idx++) {
+        const uint64_t e = (idx == 0) ? head : ((b + cs < N) ? b + cs : N);
+        cudaStream_t s = h->aux[idx % AUX_STREAMS];
+        if ((err = engine_upload_range(h, s, particles, b, e))) return err;
+        if (idx == 0) {
+            h->launches++;
+            tp_launch_history(a, s);
+            CU_TRY(h, cudaEventRecord(h->aux_ev[1], s));
+        } else if (idx < AUX_STREAMS) {
+            CU_TRY(h, cudaStreamWaitEvent(s, h->aux_ev[1], 0));      // history complete (stream 0 is ordered anyway)
+        }
+        a.i_begin = b; a.i_end = e;
+        h->launches++;
+        tp_launch_multistep(a, s);
+        CU_TRY(h, cudaGetLastError());
+        if ((err = engine_download_range(h, s, particles, b, e))) return err;
+        b = e;
+    }
+    for (int k = 0; k < AUX_STREAMS; k++) CU_TRY(h, cudaStreamSynchronize(h->aux[k]));
+    for (uint64_t st = 0; st < n_steps; st++) { c->t += drift[0]; c->t += drift[1]; }
     c->dt_last_done = c->dt;
     return REBCU_OK;
 }

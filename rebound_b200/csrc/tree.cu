@@ -181,6 +181,7 @@ struct CellArrays {
     int4* meta;      // pt, skip, depth, rootbox
     int32_t* parent;
     uint32_t* ready; // children still missing
+    int2* meta2;     // (leaf: pt | internal: -(depth+1), skip) -- the 8 bytes the gravity walk reads per visit
 };
 
 // Emits the cells opened at sorted position k (geometry, pt, skip, depth, rootbox; leaf moments).
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(128) emit_kernel(TreeParams P, const uint64_t*
         C.geo[c] = make_double4(g.cx, g.cy, g.cz, g.w);
         if (!internal) {
             C.meta[c] = make_int4((int)p, (int)c + 1, d, rb);
+            C.meta2[c] = make_int2((int)p, (int)c + 1);
             C.pos[c] = make_double4(px, py, pz, m[p]);      // tree.c:201-205
             C.ready[c] = 0;
             continue;
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(128) emit_kernel(TreeParams P, const uint64_t*
             while (e + 1 < P.n && lcp[e + 1] >= d) e++;
         }
         C.meta[c] = make_int4(-(int)(e - k + 1), (int)off[e + 1], d, rb);
+        C.meta2[c] = make_int2(-(d + 1), (int)off[e + 1]);
     }
 }
 
@@ -286,8 +289,16 @@ __global__ void __launch_bounds__(256) export_kernel(uint64_t n_cells, CellArray
 }
 
 // ---- Barnes-Hut walk -----------------------------------------------------------------------------
+// 256-bit load of one (mx,my,mz,m) record: one LDG.E.256 instead of two LDG.E.128, which halves the L1
+// wavefronts of the divergent per-thread walk (its measured bottleneck).
+__device__ __forceinline__ double4 ld_pos256(const double4* p) {
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
 struct WalkArgs {
-    const double4* pos; const int4* meta; uint64_t n_cells;
+    const double4* pos; const int4* meta; const int2* meta2; uint64_t n_cells;
     const uint32_t* perm; const uint32_t* list; uint64_t n_work;     // work item t -> sorted position (list[t] or t)
     const double* x; const double* y; const double* z;
     double* ax; double* ay; double* az;
@@ -313,14 +324,15 @@ __device__ __forceinline__ unsigned walk_one(const WalkArgs& a, uint32_t self, d
         const double gx = s_add(a.ghosts->gb[g].x, px), gy = s_add(a.ghosts->gb[g].y, py), gz = s_add(a.ghosts->gb[g].z, pz);
         int c = 0;
         while (c < n_cells) {
-            const double4 q = a.pos[c];
-            const int4 mt = a.meta[c];
+            const double4 q = ld_pos256(a.pos + c);
+            const int2 mt = a.meta2[c];               // x: particle index (leaf) or -(depth+1); y: skip
             const double dx = s_sub(gx, q.x), dy = s_sub(gy, q.y), dz = s_sub(gz, q.z);
             const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
             if (mt.x < 0) {
+                const int depth = -mt.x - 1;
                 double w2;
-                if (mt.z < W_TABLE) w2 = a.w2[mt.z];
-                else { double w = a.root_size; for (int d = 0; d < mt.z; d++) w = s_div(w, 2.); w2 = s_mul(w, w); }
+                if (depth < W_TABLE) w2 = a.w2[depth];
+                else { double w = a.root_size; for (int d = 0; d < depth; d++) w = s_div(w, 2.); w2 = s_mul(w, w); }
                 if (w2 > s_mul(a.theta2, r2)) { c++; continue; }          // tree.c:284: open the cell
             } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }    // tree.c:311
             if (MODE == 1) {
@@ -455,7 +467,7 @@ void tree_free(rebcu_handle* h) {
     TreeBuffers& T = h->tree;
     cudaFree(T.keys); cudaFree(T.keys_sorted); cudaFree(T.perm); cudaFree(T.perm_in); cudaFree(T.lcp);
     cudaFree(T.cell_off); cudaFree(T.cell_cnt); cudaFree(T.cells); cudaFree(T.parent); cudaFree(T.ready);
-    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
+    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
     cudaFree(T.shard_list);
     T = TreeBuffers();
 }
@@ -540,10 +552,11 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
         if ((err = ensure(h, (int4**)&T.walk_meta, cap))) return err;
         if ((err = ensure(h, &T.parent, cap))) return err;
         if ((err = ensure(h, &T.ready, cap))) return err;
+        if ((err = ensure(h, &T.walk_meta2, cap))) return err;
         cudaFree(T.cells); T.cells = nullptr;
         T.cap_cells = cap;
     }
-    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready};
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2};
     {
         LaunchScope ls(h, TC_TREEBUILD, 3);
         emit_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(P, T.keys_sorted, T.perm, T.lcp, T.cell_off, x, y, z, m, C);
@@ -561,7 +574,7 @@ int tree_export(rebcu_handle* h) {
     TreeBuffers& T = h->tree;
     if (T.n_cells == 0) return REBCU_OK;
     if (!T.cells) CU_TRY(h, cudaMalloc(&T.cells, T.cap_cells * sizeof(rebcu_treecell)));
-    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready};
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2};
     export_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, C, T.cells);
     CU_TRY(h, cudaGetLastError());
     return REBCU_OK;
@@ -588,7 +601,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     err = engine_upload_ghosts(h, &g);
     if (err) return err;
     WalkArgs a;
-    a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.n_cells = T.n_cells;
+    a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
     a.perm = T.perm; a.list = nullptr; a.n_work = n;
     a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
     a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);

@@ -35,6 +35,7 @@ struct shim_state* shim_get(struct reb_simulation* r){
 void shim_forget(struct reb_simulation* r){
     pthread_mutex_lock(&table_lock);
     for (int i=0;i<table_n;i++) if (table[i].r==r){
+        if (table[i].pinned_ptr) rebcu_host_unregister(table[i].pinned_ptr);
         rebcu_destroy(table[i].h);
         memset(&table[i], 0, sizeof(table[i]));
     }
@@ -78,7 +79,24 @@ int shim_report(struct reb_simulation* r, struct shim_state* s, int err){
     return err;
 }
 
+/* REBOUND_B200_PIN=1: page-lock r->particles so the PCIe copies run at full rate (pageable copies reach
+ * about half).  Opt-in because librebound realloc()s the array when particles are added
+ * (src/particle.c:53-58); the registration follows the pointer, but the old block is released by libc
+ * before this code can unpin it, which is only safe if the run does not grow the array while stepping. */
+static void shim_pin(struct reb_simulation* r, struct shim_state* s){
+    static int want = -1;
+    if (want < 0){ const char* e = getenv("REBOUND_B200_PIN"); want = (e && e[0]=='1') ? 1 : 0; }
+    if (!want) return;
+    const size_t bytes = r->N_allocated*sizeof(struct reb_particle);
+    if (s->pinned_ptr==(void*)r->particles && s->pinned_bytes==bytes) return;
+    if (s->pinned_ptr){ rebcu_host_unregister(s->pinned_ptr); s->pinned_ptr = NULL; s->pinned_bytes = 0; }
+    if (r->particles && bytes >= (8u<<20) && rebcu_host_register(r->particles, bytes)==0){
+        s->pinned_ptr = r->particles; s->pinned_bytes = bytes;
+    }
+}
+
 int shim_to_device(struct reb_simulation* r, struct shim_state* s){
+    shim_pin(r, s);
     /* Only resident mode trusts the device copy across calls; the default mode re-uploads every time. */
     if (shim_resident_mode() && s->device_valid && !r->did_modify_particles && s->uploaded_from==r->particles && s->uploaded_N==r->N) return 0;
     int err = rebcu_upload(s->h, (const rebcu_particle*)r->particles, r->N);

@@ -26,6 +26,8 @@ struct shim_state {
     int host_stale;              /* r->particles is behind the device copy (resident mode, is_synchronized==0) */
     struct reb_particle* uploaded_from;
     size_t uploaded_N;
+    void* pinned_ptr;            /* r->particles as registered with cudaHostRegister (REBOUND_B200_PIN=1) */
+    size_t pinned_bytes;
 };
 
 /* Returns the per-simulation state (creating the rebcu handle on first use); NULL + reb_simulation_error

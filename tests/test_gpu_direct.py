@@ -184,3 +184,45 @@ def test_strict_math_selftest(eng):
     r = eng.selftest_math(n, seed=12345)
     assert r["sqrt_mismatch"] == 0 and r["div_mismatch"] == 0
     assert r["sqrt_flagged"] < 1e-3 * n and r["div_flagged"] < 1e-3 * n
+
+
+@pytest.mark.parametrize("n_test,steps", [((1 << 18) + 77, 5), ((1 << 19), 3)])
+@pytest.mark.parametrize("grav", [abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED])
+def test_planetesimal_host_pipeline_bitwise(eng, n_test, steps, grav):
+    """rebcu_steps_host on a large test-particle problem takes the chunk-pipelined path (copies overlapped
+    with kernels, massive-body history replayed per chunk); it must equal the oracle bit for bit, leave the
+    device state resident, and agree with the plain resident path."""
+    p = ics.planetesimal_disk(n_test, seed=21)
+    cfg = ics.planetesimal_config(gravity=grav)
+    want, cw, _ = checkers.oracle().steps(cfg, p, steps)
+    q, c = p.copy(), cfg.copy()
+    eng.steps_host(c, q, steps)
+    assert c.t == cw.t and c.dt_last_done == cw.dt_last_done
+    assert bits_equal(q, want)
+    assert bits_equal(eng.download(), want)          # device copy is the final state too
+    c2 = cfg.copy()
+    eng.upload(p.copy())
+    eng.steps(c2, steps)
+    assert bits_equal(eng.download(), want)
+
+
+@pytest.mark.parametrize("mode", [abi.MODE_STRICT, abi.MODE_FAST])
+def test_planetesimal_single_steps_equal_multistep_launch(eng, mode):
+    """One step per call (tp_leapfrog_kernel, one launch per step) and n steps per call (massive-body history +
+    tp_multistep_kernel, two launches in total) execute the same operation sequence per particle."""
+    p = ics.planetesimal_disk(3000, seed=31)
+    cfg = ics.planetesimal_config(mode=mode)
+    eng.upload(p.copy())
+    c1 = cfg.copy()
+    for _ in range(6):
+        eng.steps(c1, 1)
+    a = eng.download().copy()
+    eng.upload(p.copy())
+    c2 = cfg.copy()
+    eng.steps(c2, 6)
+    b = eng.download().copy()
+    assert c1.t == c2.t
+    assert bits_equal(a, b)
+    if mode == abi.MODE_STRICT:
+        want, _, _ = checkers.oracle().steps(cfg, p, 6)
+        assert bits_equal(a, want)

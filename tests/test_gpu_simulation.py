@@ -1,0 +1,96 @@
+"""The Python mirror of the reference's Simulation interface for the hot path (rebound_b200/simulation.py):
+attribute names and string enums as in rebound/simulation.py, add / steps / integrate / synchronize, and
+the reference's error texts."""
+import numpy as np
+import pytest
+
+import checkers
+from checkers import bits_equal
+from rebound_b200 import abi, ics
+from rebound_b200.simulation import ReboundCudaError, Simulation
+
+pytestmark = pytest.mark.gpu
+
+
+def test_simulation_mirror_plummer_leapfrog():
+    p = ics.plummer(1500, seed=3)
+    cfg = ics.plummer_config(1500)
+    sim = Simulation()
+    sim.integrator = "leapfrog"
+    sim.gravity = "basic"
+    sim.G = cfg.G
+    sim.dt = cfg.dt
+    sim.softening = cfg.softening
+    sim.add(p)
+    assert sim.N == 1500
+    sim.steps(4)
+    want, cw, _ = checkers.oracle().steps(cfg, p, 4)
+    assert bits_equal(sim.particles, want)
+    assert sim.t == cw.t and sim.steps_done == 4
+    # particles modified on the host between steps (did_modify_particles protocol)
+    q = sim.particles
+    q["vx"] += 0.125
+    sim.did_modify_particles()
+    sim.steps(2)
+    w2 = want.copy()
+    w2["vx"] += 0.125
+    want2, _, _ = checkers.oracle().steps(cw, w2, 2)
+    assert bits_equal(sim.particles, want2)
+    sim.close()
+
+
+def test_simulation_mirror_integrate_and_enums():
+    sim = Simulation()
+    with pytest.raises(ValueError):
+        sim.gravity = "nonsense"
+    sim.gravity = "tree"
+    sim.boundary = "open"
+    sim.collision = "none"
+    sim.integrator = "leapfrog"
+    sim.root_size = 10.2
+    sim.opening_angle2 = 0.25
+    sim.softening = 0.02
+    sim.dt = 3e-2
+    p = ics.selfgravity_disc(2000, seed=5)
+    sim.add(p)
+    sim.integrate(0.1)            # 4 whole steps of 0.03
+    cfg = ics.selfgravity_disc_config()
+    want, cw, _ = checkers.oracle().steps(cfg, p, 4)
+    assert sim.N == len(want)
+    assert bits_equal(sim.particles, want)
+    assert sim.t == cw.t
+    cells = sim.tree()
+    assert len(cells) == len(checkers.oracle().tree_dump(cw, checkers.oracle().boundary_check(cw, want)[0]))
+    sim.close()
+
+
+def test_simulation_mirror_errors_use_reference_text():
+    sim = Simulation()
+    sim.gravity = "tree"
+    sim.integrator = "leapfrog"
+    p = ics.selfgravity_disc(10, seed=5)
+    sim.add(p)
+    with pytest.raises(ReboundCudaError) as e:
+        sim.steps(1)            # root_size not set
+    assert e.value.msg == "Set root_size to a finite value to use a tree based gravity or collision solver."
+    sim.root_size = 10.2
+    q = sim.particles
+    q["x"][3], q["y"][3], q["z"][3] = q["x"][2], q["y"][2], q["z"][2]
+    sim.did_modify_particles()
+    with pytest.raises(ReboundCudaError) as e:
+        sim.update_acceleration()
+    assert e.value.msg == "Cannot add two particles with the same coordinates to the tree."
+    sim.close()
+
+
+def test_simulation_mirror_collision_search_shearing_sheet():
+    p = ics.shearing_sheet(root_size=30.0, seed=9)
+    cfg = ics.shearing_sheet_config(root_size=30.0, t=55.5)
+    sim = Simulation()
+    for name, _ in abi.Config._fields_:
+        setattr(sim, name, getattr(cfg, name))
+    sim.add(p)
+    got = sim.collision_search()
+    want = checkers.oracle().collision_search(cfg, p)
+    assert checkers.collisions_equal(got, want)
+    sim.close()
