@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-INNER_STEPS = {"c2": 100, "c1": 100, "c1fast": 100, "c2fast": 100}
+INNER_STEPS = {"c2": 100, "c1": 100, "c1fast": 100, "c2fast": 100, "c3": 1, "c4": 1}
 
 
 def workload(name, rank=0):
@@ -146,8 +146,99 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def run_sharded(args):
+    """BASELINE.json configs[2] / configs[3] (`--workload c3|c4`): ONE problem sharded over the ranks in
+    contiguous target blocks (strong scaling), positions all-gathered over NCCL between drift and force
+    (rebound_b200/distributed.py).  c3: Plummer sphere, REB_GRAVITY_COMPENSATED direct summation;
+    c4: self-gravitating disc, REB_GRAVITY_TREE theta^2=0.25, open boundary.  `--n-log2` scales N."""
+    import torch
+    import torch.distributed as dist
+
+    from rebound_b200 import abi, distributed as D, ics
+    from rebound_b200.simulation import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    if args.workload == "c3":
+        n = 1 << (args.n_log2 or 22)
+        p = ics.plummer(n, seed=42)
+        cfg = ics.plummer_config(n, gravity=abi.GRAVITY_COMPENSATED)
+        units_per_step = float(n) * n - n
+        metric, unit = "pairwise interactions/s (direct)", "interactions/s"
+        desc = f"C3 Plummer sphere N=2^{int(np.log2(n))}, REB_GRAVITY_COMPENSATED direct summation, leapfrog"
+    else:
+        n = 1 << (args.n_log2 or 24)
+        p = ics.selfgravity_disc(n - 1, seed=42)
+        cfg = ics.selfgravity_disc_config()
+        units_per_step = float(n)
+        metric, unit = "particle-steps/s (tree)", "particle-steps/s"
+        desc = f"C4 self-gravitating disc N=2^{int(np.log2(n))}, REB_GRAVITY_TREE opening_angle2=0.25, leapfrog, open boundary"
+    if args.mode == "fast":
+        cfg.mode = abi.MODE_FAST
+    inner = args.inner or 1
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = Engine(local_rank, stream.cuda_stream)
+    eng.upload(np.ascontiguousarray(p))
+    if world > 1:
+        D.attach(eng, dev)
+    c = cfg.copy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.steps(c, inner)
+    barrier()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        eng.steps(c, inner)
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = units_per_step * inner * args.steps / (ms_total * 1e-3)
+    eng.timing_enable(True)
+    eng.timing_reset()
+    eng.steps(c, inner)
+    tim = eng.timing_read()
+    eng.timing_enable(False)
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "inner_steps_per_step": inner, "N_total": int(n),
+                       "mode": "strict (bit-identical to the reference)" if cfg.mode == 0 else "fast",
+                       "sharding": "contiguous target blocks per rank, NCCL all-gather of x,y,z between drift and force",
+                       "l2": "inputs larger than L2" if n >= (1 << 22) else "L2 not flushed (state fits L2)"},
+            "clocks": clocks, "gpu_launches": int(eng.launch_count - launches0),
+            "kernel_ms_per_step_rank0": {k: v["ms"] for k, v in tim.items() if v["launches"]},
+            "e2e": None, "roofline": None, "cpu_baseline": None,
+        }))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--n-log2", type=int, default=0, help="log2 of N for the sharded workloads c3/c4")
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -161,6 +252,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.workload in ("c3", "c4"):
+        run_sharded(args)
         return
 
     import torch
