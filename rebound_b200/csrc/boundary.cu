@@ -8,7 +8,7 @@
 // particle.c:360-369), N_active is decremented once per removed active particle.
 // Bound: HBM (48 B/particle for the wrap; the compaction only runs when something left the box).
 #include "engine.cuh"
-#include <cub/device/device_scan.cuh>
+#include "primitives.cuh"
 #include <math.h>
 
 namespace {
@@ -104,8 +104,7 @@ int boundary_check(rebcu_handle* h, rebcu_config* c) {
         h->compact_flag = h->compact_pos = nullptr; h->compact_buf = nullptr; h->compact_tmp = nullptr; h->compact_cap = 0;
         CU_TRY(h, cudaMalloc(&h->compact_flag, h->cap * sizeof(uint32_t)));
         CU_TRY(h, cudaMalloc(&h->compact_pos, h->cap * sizeof(uint32_t)));
-        size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->compact_flag, h->compact_pos, (int)h->cap, h->stream);
+        const size_t tmp = prim::scan_scratch_words(h->cap) * sizeof(uint32_t);
         h->compact_tmp_bytes = tmp;
         CU_TRY(h, cudaMalloc(&h->compact_tmp, tmp));
         h->compact_cap = h->cap;
@@ -127,8 +126,7 @@ int boundary_check(rebcu_handle* h, rebcu_config* c) {
     if (!h->compact_buf) CU_TRY(h, cudaMalloc(&h->compact_buf, h->cap * F_COUNT * sizeof(double)));
     {
         LaunchScope ls(h, TC_BOUNDARY, 2);
-        size_t tmp = h->compact_tmp_bytes;
-        cub::DeviceScan::ExclusiveSum(h->compact_tmp, tmp, h->compact_flag, h->compact_pos, (int)N, h->stream);
+        prim::exclusive_scan_u32(h->stream, h->compact_flag, h->compact_pos, N, (uint32_t*)h->compact_tmp);
         compact_kernel<<<div_up(N, 256), 256, 0, h->stream>>>((const uint64_t*)h->soa, (uint64_t*)h->compact_buf, h->cap,
                                                             h->compact_flag, h->compact_pos, N);
     }

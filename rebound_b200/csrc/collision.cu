@@ -14,7 +14,7 @@
 // r->map / N_targets subsets (used by MERCURIUS/TRACE) are not part of this path.
 // Bound: DIRECT FP64 pipe (N^2 predicates); TREE L2/HBM latency on the cell arrays.
 #include "engine.cuh"
-#include <cub/device/device_scan.cuh>
+#include "primitives.cuh"
 
 namespace {
 
@@ -171,8 +171,7 @@ int ensure_lists(rebcu_handle* h, uint64_t n_counts) {
         const uint64_t cap = n_counts + n_counts / 8 + 1024;
         CU_TRY(h, cudaMalloc(&h->col_count, cap * sizeof(uint32_t)));
         CU_TRY(h, cudaMalloc(&h->col_off, cap * sizeof(uint32_t)));
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, h->col_count, (uint32_t*)h->col_off, (int)cap, h->stream);
+        const size_t tb = prim::scan_scratch_words(cap) * sizeof(uint32_t);
         CU_TRY(h, cudaMalloc(&h->col_scan_tmp, tb));
         h->col_scan_tmp_bytes = tb;
         h->col_cap_n = cap;
@@ -183,8 +182,7 @@ int ensure_lists(rebcu_handle* h, uint64_t n_counts) {
 // scan the counts (n_counts entries + a zero sentinel) and fetch the total
 int scan_counts(rebcu_handle* h, uint64_t n_counts, uint64_t* total) {
     CU_TRY(h, cudaMemsetAsync(h->col_count + n_counts, 0, sizeof(uint32_t), h->stream));
-    size_t tb = h->col_scan_tmp_bytes;
-    cub::DeviceScan::ExclusiveSum(h->col_scan_tmp, tb, h->col_count, (uint32_t*)h->col_off, (int)n_counts + 1, h->stream);
+    prim::exclusive_scan_u32(h->stream, h->col_count, (uint32_t*)h->col_off, n_counts + 1, (uint32_t*)h->col_scan_tmp);
     uint32_t* pin = (uint32_t*)h->pinned;
     CU_TRY(h, cudaMemcpyAsync(pin, (uint32_t*)h->col_off + n_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));

@@ -13,7 +13,7 @@
 //                (centre = parent centre +- w/4, tree.c:99-102, which rounds when root_size is not a
 //                power of two) -- octant bit 1 = low side, so ascending key order = the reference's
 //                depth-first octant order.  64-bit key = root box | 3 bits per level.
-//   2. sort      stable LSD radix sort of (key, index) [cub::DeviceRadixSort as the staging sorter].
+//   2. sort      stable LSD radix sort of (key, index), hand-written (primitives.cuh).
 //   3. ties      particles agreeing in all key levels are ordered (and duplicates detected,
 //                tree.c:119-123) by continuing the exact descent pairwise.
 //   4. lcp       common path length of sorted neighbours; cells opened at sorted position k are the
@@ -30,8 +30,7 @@
 // cells ~1.5/particle x 80 B out); the walk is FP64-pipe / L2-latency bound.
 #include "engine.cuh"
 #include "strict_math.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "primitives.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -512,27 +511,26 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
         if ((err = ensure(h, &T.cell_cnt, cap + 1))) return err;
         if ((err = ensure(h, &T.shard_list, cap))) return err;
         if (!T.flags) { if ((err = ensure(h, &T.flags, 8))) return err; }
-        size_t sb = 0, cb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sb, T.keys, T.keys_sorted, T.perm_in, T.perm, (int)cap, 0, 64, h->stream);
-        cub::DeviceScan::ExclusiveSum(nullptr, cb, T.cell_cnt, T.cell_off, (int)cap + 1, h->stream);
+        // radix-sort histogram (256 bins per 2048-element tile) and scan scratch (tile sums)
+        const size_t hist_words = prim::radix_hist_words(cap);
+        const size_t scan_words = prim::scan_scratch_words(hist_words > cap + 1 ? hist_words : cap + 1);
         cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); T.sort_tmp = T.scan_tmp = nullptr;
-        CU_TRY(h, cudaMalloc(&T.sort_tmp, sb)); T.sort_tmp_bytes = sb;
-        CU_TRY(h, cudaMalloc(&T.scan_tmp, cb)); T.scan_tmp_bytes = cb;
+        CU_TRY(h, cudaMalloc(&T.sort_tmp, hist_words * sizeof(uint32_t))); T.sort_tmp_bytes = hist_words * sizeof(uint32_t);
+        CU_TRY(h, cudaMalloc(&T.scan_tmp, scan_words * sizeof(uint32_t))); T.scan_tmp_bytes = scan_words * sizeof(uint32_t);
         T.cap_n = cap;
     }
     const double *x = h->f(F_X), *y = h->f(F_Y), *z = h->f(F_Z), *m = h->f(F_M);
     {
-        LaunchScope ls(h, TC_TREEBUILD, 6);
+        LaunchScope ls(h, TC_TREEBUILD, 8);
         CU_TRY(h, cudaMemsetAsync(T.flags, 0x7f, 8 * sizeof(int), h->stream));   // 0x7f7f7f7f: "no error"
         key_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(P, x, y, z, T.keys, T.perm_in, T.flags);
-        size_t sb = T.sort_tmp_bytes;
-        cub::DeviceRadixSort::SortPairs(T.sort_tmp, sb, T.keys, T.keys_sorted, T.perm_in, T.perm, (int)n, 0, P.rbits + 3 * P.L0, h->stream);
+        h->launches += prim::radix_sort_pairs(h->stream, T.keys, T.perm_in, T.keys_sorted, T.perm, n, P.rbits + 3 * P.L0,
+                                              (uint32_t*)T.sort_tmp, (uint32_t*)T.scan_tmp);
         tie_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(P, T.keys_sorted, T.perm, x, y, z, T.flags);
         lcp_kernel<<<div_up(n + 1, 256), 256, 0, h->stream>>>(P, T.keys_sorted, T.perm, x, y, z, T.lcp, T.flags);
         count_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.lcp, T.cell_cnt);
         CU_TRY(h, cudaMemsetAsync(T.cell_cnt + n, 0, sizeof(uint32_t), h->stream));
-        size_t cb = T.scan_tmp_bytes;
-        cub::DeviceScan::ExclusiveSum(T.scan_tmp, cb, T.cell_cnt, T.cell_off, (int)n + 1, h->stream);
+        prim::exclusive_scan_u32(h->stream, T.cell_cnt, T.cell_off, n + 1, (uint32_t*)T.scan_tmp);
     }
     CU_TRY(h, cudaGetLastError());
     // cell count and error flags back to the host
@@ -617,8 +615,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
         uint32_t* flag = T.cell_cnt; uint32_t* pos = T.cell_off;      // reuse (build is finished)
         LaunchScope ls(h, TC_TREEWALK, 3);
         shard_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.perm, (uint32_t)b, (uint32_t)e, flag);
-        size_t cb = T.scan_tmp_bytes;
-        cub::DeviceScan::ExclusiveSum(T.scan_tmp, cb, flag, pos, (int)n, h->stream);
+        prim::exclusive_scan_u32(h->stream, flag, pos, n, (uint32_t*)T.scan_tmp);
         shard_list_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, flag, pos, T.shard_list);
         a.list = T.shard_list; a.n_work = e - b;
     }
