@@ -13,7 +13,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.exists(os.path.join(DROPIN, "driver_dropin")),
                                  reason="rebound_b200/_dropin not built (needs the reference sources at build time)")]
 
-SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8)]
+SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8), ("sheet", 25, 400)]
 
 
 def run(binary, scen, n, steps, tmp_path, env=None):
@@ -26,7 +26,7 @@ def run(binary, scen, n, steps, tmp_path, env=None):
     return np.fromfile(out, dtype=np.float64).view(np.uint64)
 
 
-@pytest.mark.parametrize("scen,n,steps", SCENARIOS, ids=[s[0] for s in SCENARIOS])
+@pytest.mark.parametrize("scen,n,steps", SCENARIOS, ids=[f"{s[0]}-{s[1]}-{s[2]}" for s in SCENARIOS])
 @pytest.mark.parametrize("resident", ["0", "1"], ids=["host_authoritative", "resident"])
 def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
     ref = run("driver_ref", scen, n, steps, tmp_path)

@@ -280,3 +280,19 @@ def test_disc_2pow20_full_size_bitwise(eng):
     assert -internal["pt"][0] == m                                                          # root counts everything
     assert np.all(cells["skip"] > np.arange(len(cells))) and cells["skip"][0] == len(cells)
     assert abs(cells["m"][0] - p["m"].sum()) < 1e-12
+
+
+def test_empty_and_tiny_inputs(eng):
+    """N = 0 and N = 1 through every entry point (the reference's loops simply do nothing)."""
+    for n in (0, 1):
+        p = abi.particles(n)
+        if n:
+            p["x"], p["m"], p["r"] = 0.3, 1.0, 0.1
+        for cfg in (ics.plummer_config(8), ics.plummer_config(8, gravity=abi.GRAVITY_COMPENSATED),
+                    ics.selfgravity_disc_config(collision=abi.COLLISION_TREE),
+                    ics.shearing_sheet_config(root_size=10.0), abi.default_config(collision=abi.COLLISION_DIRECT, root_size=5.0)):
+            q, c = p.copy(), cfg.copy()
+            m = eng.steps_host(c, q, 2)
+            want, cw, _ = checkers.oracle().steps(cfg, p, 2)
+            assert m == len(want) == n and bits_equal(q[:m], want) and c.t == cw.t
+            assert len(eng.collision_search_host(cfg.copy(), p.copy())) == 0
