@@ -101,16 +101,24 @@ struct TreeColArgs {
     double r2nd;
 };
 
-template <bool FILL>
+// One traversal per projectile.  Pass 0 counts the hits and parks the first COL_SLOTS of them (target, ghost
+// box, root box packed in 8 bytes) in a per-projectile slot row; after the scan, tree_slots_kernel turns the
+// parked hits into list entries without touching the tree again.  Only projectiles with more than COL_SLOTS
+// hits (rare) walk a second time (pass 1) to write their entries directly.
+constexpr int COL_SLOTS = 6;
+
+template <int PASS>
 __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColArgs a, uint32_t* __restrict__ count,
-                                                             const uint32_t* __restrict__ off, rebcu_collision* __restrict__ out) {
+                                                             const uint32_t* __restrict__ off, rebcu_collision* __restrict__ out,
+                                                             uint64_t* __restrict__ slots) {
     const uint32_t k = blockIdx.x * 128 + threadIdx.x;
     if (k >= a.n) return;
     const uint32_t i = a.perm[k];            // key order => neighbouring lanes walk neighbouring paths
+    if (PASS == 1 && count[i] <= COL_SLOTS) return;
     const double r1 = P.r[i];
     const double reach = s_add(r1, a.r2nd);
     uint32_t found = 0;
-    const uint64_t base = FILL ? off[i] : 0;
+    const uint64_t base = (PASS == 1) ? off[i] : 0;
     const int ngb = a.ghosts->n;
     for (int g = 0; g < ngb; g++) {
         const rebcu_vec6d gb = a.ghosts->gb[g];
@@ -122,7 +130,9 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
                 if ((uint32_t)mt.x != i) {
                     const double4 q = ld256(a.pos + c);              // leaf: the particle's own position
                     if (hit(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x)) {
-                        if (FILL) emit(out, base + found, i, (uint32_t)mt.x, gb, (uint64_t)mt.w);
+                        if (PASS == 1) emit(out, base + found, i, (uint32_t)mt.x, gb, (uint64_t)mt.w);
+                        else if (found < COL_SLOTS)
+                            slots[(uint64_t)i * COL_SLOTS + found] = (uint64_t)(uint32_t)mt.x | ((uint64_t)g << 32) | ((uint64_t)mt.w << 40);
                         found++;
                     }
                 }
@@ -136,7 +146,28 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
             }
         }
     }
-    if (!FILL) count[i] = found;
+    if (PASS == 0) count[i] = found;
+}
+
+// list entries of the projectiles whose hits all fit their slot row; flags[0] is set if some projectile overflowed
+__global__ void __launch_bounds__(256) tree_slots_kernel(uint32_t n, const uint32_t* __restrict__ count, const uint32_t* __restrict__ off,
+                                                         const uint64_t* __restrict__ slots, const GhostShifts* ghosts,
+                                                         rebcu_collision* __restrict__ out) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cnt = count[i];
+    if (cnt == 0 || cnt > COL_SLOTS) return;
+    const uint64_t base = off[i];
+    for (uint32_t q = 0; q < cnt; q++) {
+        const uint64_t e = slots[(uint64_t)i * COL_SLOTS + q];
+        emit(out, base + q, i, (uint32_t)e, ghosts->gb[(e >> 32) & 0xff], e >> 40);
+    }
+}
+
+__global__ void __launch_bounds__(256) overflow_flag_kernel(uint32_t n, const uint32_t* __restrict__ count, unsigned long long* flag) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const bool over = i < n && count[i] > COL_SLOTS;
+    if (__any_sync(0xffffffffu, over) && (threadIdx.x & 31) == 0) atomicAdd(flag, 1ull);
 }
 
 // Radius of the second largest particle (reb_simulation_two_largest_particles, simulation.c:718-799).
@@ -243,15 +274,28 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         CU_TRY(h, cudaMemcpyAsync(pin, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         a.r2nd = pin[0];
+        if (h->col_slots_cap < n) {
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(h->col_slots); h->col_slots = nullptr;
+            const uint64_t cap = n + n / 8 + 1024;
+            CU_TRY(h, cudaMalloc(&h->col_slots, cap * COL_SLOTS * sizeof(uint64_t)));
+            h->col_slots_cap = cap;
+        }
+        CU_TRY(h, cudaMemsetAsync(h->counters + 4, 0, sizeof(unsigned long long), h->stream));
         {
-            LaunchScope ls(h, TC_COLLISION);
-            tree_collision_kernel<false><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr);
+            LaunchScope ls(h, TC_COLLISION, 2);
+            tree_collision_kernel<0><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
+            overflow_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>((uint32_t)n, h->col_count, h->counters + 4);
         }
         CU_TRY(h, cudaGetLastError());
-        if ((err = scan_counts(h, n, &total))) return err;
+        CU_TRY(h, cudaMemcpyAsync(h->pinned + 16, h->counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        if ((err = scan_counts(h, n, &total))) return err;          // synchronises the stream
         if (total) {
-            LaunchScope ls(h, TC_COLLISION);
-            tree_collision_kernel<true><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, nullptr, (const uint32_t*)h->col_off, h->col_list);
+            LaunchScope ls(h, TC_COLLISION, 2);
+            tree_slots_kernel<<<div_up(n, 256), 256, 0, h->stream>>>((uint32_t)n, h->col_count, (const uint32_t*)h->col_off, h->col_slots,
+                                                                   h->ghosts_dev, h->col_list);
+            if (h->pinned[16])       // some projectile has more hits than slots: those walk again and write directly
+                tree_collision_kernel<1><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
         }
     }
     CU_TRY(h, cudaGetLastError());

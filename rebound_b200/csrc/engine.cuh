@@ -82,6 +82,7 @@ struct rebcu_handle {
     uint32_t* col_count = nullptr; uint32_t* col_off = nullptr; uint64_t col_cap_n = 0;
     rebcu_collision* col_list = nullptr; uint64_t col_cap = 0; uint64_t col_n = 0;
     void* col_scan_tmp = nullptr; size_t col_scan_tmp_bytes = 0;
+    uint64_t* col_slots = nullptr; uint64_t col_slots_cap = 0;   // parked hits of the single-traversal tree search
     // small device scratch
     double* scratch = nullptr;            // 64 doubles
     unsigned long long* counters = nullptr; // 16 counters
