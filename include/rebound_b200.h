@@ -52,7 +52,8 @@ typedef struct rebcu_collision {
 } rebcu_collision;
 
 /* Enum values are the reference's (src/rebound.h:372-393). */
-enum { REBCU_COLLISION_NONE = 0, REBCU_COLLISION_DIRECT = 1, REBCU_COLLISION_TREE = 2 };
+enum { REBCU_COLLISION_NONE = 0, REBCU_COLLISION_DIRECT = 1, REBCU_COLLISION_TREE = 2,
+       REBCU_COLLISION_LINE = 4, REBCU_COLLISION_LINETREE = 5 };
 enum { REBCU_BOUNDARY_NONE = 0, REBCU_BOUNDARY_OPEN = 1, REBCU_BOUNDARY_PERIODIC = 2, REBCU_BOUNDARY_SHEAR = 3 };
 enum { REBCU_GRAVITY_NONE = 0, REBCU_GRAVITY_BASIC = 1, REBCU_GRAVITY_COMPENSATED = 2, REBCU_GRAVITY_TREE = 3 };
 enum { REBCU_IGNORE_TERMS_NONE = 0, REBCU_IGNORE_TERMS_BETWEEN_0_AND_1 = 1, REBCU_IGNORE_TERMS_INVOLVING_0 = 2 };

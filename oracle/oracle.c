@@ -580,6 +580,25 @@ static int overlapping_and_approaching(const rebcu_vec6d* s, double r1, const re
     return 1;
 }
 
+/* Straight-line trajectories over the last step come closer than the sum of the radii
+ * (collision.c:155-177 for LINE, :513-535 for LINETREE; same arithmetic). */
+static int trajectories_overlap(const rebcu_vec6d* s, double r1, const rebcu_particle* q, double dt_last_done){
+    const double dx1 = s->x - q->x, dy1 = s->y - q->y, dz1 = s->z - q->z;
+    const double r1sq = (dx1*dx1 + dy1*dy1 + dz1*dz1);
+    const double dvx1 = s->vx - q->vx, dvy1 = s->vy - q->vy, dvz1 = s->vz - q->vz;
+    const double dx2 = dx1 - dt_last_done*dvx1, dy2 = dy1 - dt_last_done*dvy1, dz2 = dz1 - dt_last_done*dvz1;
+    const double r2sq = (dx2*dx2 + dy2*dy2 + dz2*dz2);
+    const double t_closest = (dx1*dvx1 + dy1*dvy1 + dz1*dvz1)/(dvx1*dvx1 + dvy1*dvy1 + dvz1*dvz1);
+    double rmin2 = (r1sq > r2sq) ? r2sq : r1sq;                      /* MIN(r1,r2), collision.c:43 */
+    if (t_closest/dt_last_done>=0. && t_closest/dt_last_done<=1.){
+        const double dx3 = dx1 - t_closest*dvx1, dy3 = dy1 - t_closest*dvy1, dz3 = dz1 - t_closest*dvz1;
+        const double r3sq = (dx3*dx3 + dy3*dy3 + dz3*dz3);
+        rmin2 = (rmin2 > r3sq) ? r3sq : rmin2;
+    }
+    const double rsum = r1 + q->r;
+    return !(rmin2 > rsum*rsum);
+}
+
 /* Radius of the second largest particle, first-index-wins on ties (simulation.c:782-798). */
 static double second_largest_radius(const rebcu_particle* p, uint64_t N){
     double l1=-1.0, l2=-1.0; int have2 = 0; int have1 = 0;
@@ -631,6 +650,55 @@ static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint
                         const double dx = s.x - n->x, dy = s.y - n->y, dz = s.z - n->z;
                         const double r2 = dx*dx + dy*dy + dz*dz;
                         const double rp = p[i].r + r2nd + 0.86602540378443*n->w;   /* collision.c:492 */
+                        k = (r2 < rp*rp) ? k+1 : (size_t)n->skip;
+                    }
+                }
+            }
+        }
+        free(cells);
+        return 0;
+    }
+    if (c->collision==REBCU_COLLISION_LINE){
+        /* ghost box outermost, then i, then j > i (collision.c:132-194) */
+        for (int gx=-gx1; gx<=gx1; gx++) for (int gy=-gy1; gy<=gy1; gy++) for (int gz=-gz1; gz<=gz1; gz++){
+            const rebcu_vec6d gb = ghostbox(c, gx, gy, gz);
+            for (uint64_t i=0;i<N;i++){
+                rebcu_vec6d s = gb;
+                s.x += p[i].x; s.y += p[i].y; s.z += p[i].z; s.vx += p[i].vx; s.vy += p[i].vy; s.vz += p[i].vz;
+                for (uint64_t j=i+1;j<N;j++)
+                    if (trajectories_overlap(&s, p[i].r, &p[j], c->dt_last_done)) clist_push(out, i, j, gb, 0);
+            }
+        }
+        return 0;
+    }
+    if (c->collision==REBCU_COLLISION_LINETREE){
+        /* collision.c:270-331 with the descent of :506-568 */
+        double vmax2 = 0.;
+        for (uint64_t i=0;i<N;i++){
+            const double v2 = p[i].vx*p[i].vx + p[i].vy*p[i].vy + p[i].vz*p[i].vz;
+            vmax2 = (vmax2 > v2) ? vmax2 : v2;                         /* MAX(vmax2, v2), collision.c:44 */
+        }
+        const double maxdrift = c->dt_last_done*sqrt(vmax2);
+        rebcu_treecell* cells; size_t n_cells;
+        int err = build_flat(c, p, N, &cells, &n_cells);
+        if (err) return err;
+        for (uint64_t i=0;i<N;i++){
+            const double reach = p[i].r + c->dt_last_done*sqrt(p[i].vx*p[i].vx + p[i].vy*p[i].vy + p[i].vz*p[i].vz);
+            for (int gx=-gx1; gx<=gx1; gx++) for (int gy=-gy1; gy<=gy1; gy++) for (int gz=-gz1; gz<=gz1; gz++){
+                const rebcu_vec6d gb = ghostbox(c, gx, gy, gz);
+                rebcu_vec6d s = gb;
+                s.x += p[i].x; s.y += p[i].y; s.z += p[i].z; s.vx += p[i].vx; s.vy += p[i].vy; s.vz += p[i].vz;
+                size_t k = 0;
+                while (k<n_cells){
+                    const rebcu_treecell* n = &cells[k];
+                    if (n->pt>=0){
+                        if ((uint64_t)n->pt!=i && trajectories_overlap(&s, p[i].r, &p[n->pt], c->dt_last_done))
+                            clist_push(out, i, (uint64_t)n->pt, gb, (uint64_t)n->rootbox);
+                        k = n->skip;
+                    }else{
+                        const double dx = s.x - n->x, dy = s.y - n->y, dz = s.z - n->z;
+                        const double r2 = dx*dx + dy*dy + dz*dz;
+                        const double rp = reach + maxdrift + 0.86602540378443*n->w;   /* collision.c:557 */
                         k = (r2 < rp*rp) ? k+1 : (size_t)n->skip;
                     }
                 }

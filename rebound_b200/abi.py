@@ -33,6 +33,7 @@ TREECELL_DTYPE = np.dtype(
 assert TREECELL_DTYPE.itemsize == 80
 
 COLLISION_NONE, COLLISION_DIRECT, COLLISION_TREE = 0, 1, 2
+COLLISION_LINE, COLLISION_LINETREE = 4, 5
 BOUNDARY_NONE, BOUNDARY_OPEN, BOUNDARY_PERIODIC, BOUNDARY_SHEAR = 0, 1, 2, 3
 GRAVITY_NONE, GRAVITY_BASIC, GRAVITY_COMPENSATED, GRAVITY_TREE = 0, 1, 2, 3
 IGNORE_TERMS_NONE, IGNORE_TERMS_BETWEEN_0_AND_1, IGNORE_TERMS_INVOLVING_0 = 0, 1, 2

@@ -15,6 +15,7 @@
 // Bound: DIRECT FP64 pipe (N^2 predicates); TREE L2/HBM latency on the cell arrays.
 #include "engine.cuh"
 #include "primitives.cuh"
+#include <math.h>
 
 namespace {
 
@@ -43,6 +44,28 @@ __device__ __forceinline__ bool hit(const rebcu_vec6d& s, double r1, double x2, 
     return true;
 }
 
+// LINE / LINETREE test: the straight-line trajectories over the last step come closer than r1 + r2
+// (collision.c:155-177, :513-535).  MIN is the reference's macro ((a) > (b) ? (b) : (a)), collision.c:43.
+__device__ __forceinline__ bool hit_line(const rebcu_vec6d& s, double r1, double x2, double y2, double z2, double r2p,
+                                         const ColSoa& P, uint32_t j, double dt) {
+    const double dx1 = s_sub(s.x, x2), dy1 = s_sub(s.y, y2), dz1 = s_sub(s.z, z2);
+    const double r1sq = s_add(s_add(s_mul(dx1, dx1), s_mul(dy1, dy1)), s_mul(dz1, dz1));
+    const double dvx = s_sub(s.vx, P.vx[j]), dvy = s_sub(s.vy, P.vy[j]), dvz = s_sub(s.vz, P.vz[j]);
+    const double dx2 = s_sub(dx1, s_mul(dt, dvx)), dy2 = s_sub(dy1, s_mul(dt, dvy)), dz2 = s_sub(dz1, s_mul(dt, dvz));
+    const double r2sq = s_add(s_add(s_mul(dx2, dx2), s_mul(dy2, dy2)), s_mul(dz2, dz2));
+    const double tc = s_div(s_add(s_add(s_mul(dx1, dvx), s_mul(dy1, dvy)), s_mul(dz1, dvz)),
+                            s_add(s_add(s_mul(dvx, dvx), s_mul(dvy, dvy)), s_mul(dvz, dvz)));
+    double rmin2 = (r1sq > r2sq) ? r2sq : r1sq;
+    const double frac = s_div(tc, dt);
+    if (frac >= 0. && frac <= 1.) {
+        const double dx3 = s_sub(dx1, s_mul(tc, dvx)), dy3 = s_sub(dy1, s_mul(tc, dvy)), dz3 = s_sub(dz1, s_mul(tc, dvz));
+        const double r3sq = s_add(s_add(s_mul(dx3, dx3), s_mul(dy3, dy3)), s_mul(dz3, dz3));
+        rmin2 = (rmin2 > r3sq) ? r3sq : rmin2;
+    }
+    const double rsum = s_add(r1, r2p);
+    return !(rmin2 > s_mul(rsum, rsum));
+}
+
 __device__ __forceinline__ rebcu_vec6d shifted(const rebcu_vec6d& gb, const ColSoa& P, uint32_t i) {
     rebcu_vec6d s;
     s.x = s_add(gb.x, P.x[i]); s.y = s_add(gb.y, P.y[i]); s.z = s_add(gb.z, P.z[i]);
@@ -58,10 +81,11 @@ __device__ __forceinline__ void emit(rebcu_collision* out, uint64_t at, uint32_t
 
 // ---- DIRECT ------------------------------------------------------------------------------------
 // grid.y = ghost box, thread = projectile, targets tiled through shared memory.
-template <bool FILL>
+// LINE: pairs j > i only, straight-line test over the last step (collision.c:152-189).
+template <bool FILL, bool LINE>
 __global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_t n, const GhostShifts* ghosts,
                                                                uint32_t* __restrict__ count, const uint32_t* __restrict__ off,
-                                                               rebcu_collision* __restrict__ out) {
+                                                               rebcu_collision* __restrict__ out, double dt_last_done) {
     __shared__ double4 tile[128];
     const uint32_t g = blockIdx.y;
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
@@ -81,9 +105,9 @@ __global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_
         if (valid) {
             for (int jj = 0; jj < jn; jj++) {
                 const uint32_t j = t0 + jj;
-                if (j == i) continue;
+                if (LINE ? (j <= i) : (j == i)) continue;
                 const double4 q = tile[jj];
-                if (hit(s, r1, q.x, q.y, q.z, q.w, P, j)) {
+                if (LINE ? hit_line(s, r1, q.x, q.y, q.z, q.w, P, j, dt_last_done) : hit(s, r1, q.x, q.y, q.z, q.w, P, j)) {
                     if (FILL) emit(out, base + found, i, j, gb, 0);
                     found++;
                 }
@@ -98,7 +122,8 @@ struct TreeColArgs {
     const double4* pos; const double4* geo; const int4* meta; uint32_t n_cells;
     const uint32_t* perm; uint32_t n;
     const GhostShifts* ghosts;
-    double r2nd;
+    double r2nd;          // TREE: radius of the second largest particle; LINETREE: maxdrift = dt_last_done*sqrt(max v^2)
+    double dt_last_done;
 };
 
 // One traversal per projectile.  Pass 0 counts the hits and parks the first COL_SLOTS of them (target, ghost
@@ -107,7 +132,7 @@ struct TreeColArgs {
 // hits (rare) walk a second time (pass 1) to write their entries directly.
 constexpr int COL_SLOTS = 6;
 
-template <int PASS>
+template <int PASS, bool LINE>
 __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColArgs a, uint32_t* __restrict__ count,
                                                              const uint32_t* __restrict__ off, rebcu_collision* __restrict__ out,
                                                              uint64_t* __restrict__ slots) {
@@ -116,7 +141,12 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
     const uint32_t i = a.perm[k];            // key order => neighbouring lanes walk neighbouring paths
     if (PASS == 1 && count[i] <= COL_SLOTS) return;
     const double r1 = P.r[i];
-    const double reach = s_add(r1, a.r2nd);
+    double reach;
+    if (LINE) {   // p1_r_plus_dtv + maxdrift (collision.c:302, 557)
+        const double vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
+        const double v = s_sqrt(s_add(s_add(s_mul(vx, vx), s_mul(vy, vy)), s_mul(vz, vz)));
+        reach = s_add(s_add(r1, s_mul(a.dt_last_done, v)), a.r2nd);
+    } else reach = s_add(r1, a.r2nd);                 // collision.c:492
     uint32_t found = 0;
     const uint64_t base = (PASS == 1) ? off[i] : 0;
     const int ngb = a.ghosts->n;
@@ -129,7 +159,8 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
             if (mt.x >= 0) {
                 if ((uint32_t)mt.x != i) {
                     const double4 q = ld256(a.pos + c);              // leaf: the particle's own position
-                    if (hit(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x)) {
+                    if (LINE ? hit_line(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x, a.dt_last_done)
+                             : hit(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x)) {
                         if (PASS == 1) emit(out, base + found, i, (uint32_t)mt.x, gb, (uint64_t)mt.w);
                         else if (found < COL_SLOTS)
                             slots[(uint64_t)i * COL_SLOTS + found] = (uint64_t)(uint32_t)mt.x | ((uint64_t)g << 32) | ((uint64_t)mt.w << 40);
@@ -194,6 +225,24 @@ __global__ void __launch_bounds__(1024) second_largest_kernel(const double* __re
     if (threadIdx.x == 0) out[0] = (n >= 2) ? s2[0] : 0.0;
 }
 
+// max over particles of vx^2+vy^2+vz^2 (collision.c:273-277)
+__global__ void __launch_bounds__(1024) vmax2_kernel(ColSoa P, uint32_t n, double* out) {
+    __shared__ double sm[1024];
+    double m = 0.;
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+        const double vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
+        const double v2 = s_add(s_add(s_mul(vx, vx), s_mul(vy, vy)), s_mul(vz, vz));
+        m = (m > v2) ? m : v2;
+    }
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { const double a = sm[threadIdx.x], b = sm[threadIdx.x + w]; sm[threadIdx.x] = (a > b) ? a : b; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
 int ensure_lists(rebcu_handle* h, uint64_t n_counts) {
     if (h->col_cap_n < n_counts + 1) {
         CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -233,8 +282,11 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
     h->col_n = 0;
     const uint64_t n = h->N;
     if (c->collision == REBCU_COLLISION_NONE || n == 0) return REBCU_OK;
-    if (c->collision != REBCU_COLLISION_DIRECT && c->collision != REBCU_COLLISION_TREE)
+    const bool direct = c->collision == REBCU_COLLISION_DIRECT || c->collision == REBCU_COLLISION_LINE;
+    const bool line = c->collision == REBCU_COLLISION_LINE || c->collision == REBCU_COLLISION_LINETREE;
+    if (!direct && c->collision != REBCU_COLLISION_TREE && c->collision != REBCU_COLLISION_LINETREE)
         return rebcu_fail(h, REBCU_ERR_ARG, "Collision routine not implemented.");
+    if (h->world > 1) return rebcu_fail(h, REBCU_ERR_ARG, "collision search while sharded over several GPUs is not implemented");
     if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "collision search supports N < 2^31");
     // only the innermost ring of ghost boxes (collision.c:67-69, 214-216)
     GhostShifts g;
@@ -243,20 +295,22 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
     int err;
     ColSoa P = col_soa(h);
     uint64_t total = 0;
-    if (c->collision == REBCU_COLLISION_DIRECT) {
+    if (direct) {
         if ((err = engine_upload_ghosts(h, &g))) return err;
         const uint64_t n_counts = (uint64_t)g.n * n;
         if ((err = ensure_lists(h, n_counts))) return err;
         dim3 grid(div_up(n, 128), g.n);
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            direct_collision_kernel<false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, h->col_count, nullptr, nullptr);
+            if (line) direct_collision_kernel<false, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, h->col_count, nullptr, nullptr, c->dt_last_done);
+            else direct_collision_kernel<false, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, h->col_count, nullptr, nullptr, 0.);
         }
         CU_TRY(h, cudaGetLastError());
         if ((err = scan_counts(h, n_counts, &total))) return err;
         if (total) {
             LaunchScope ls(h, TC_COLLISION);
-            direct_collision_kernel<true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list);
+            if (line) direct_collision_kernel<true, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, c->dt_last_done);
+            else direct_collision_kernel<true, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, 0.);
         }
     } else {
         if ((err = tree_build(h, c))) return err;                       // collision.c:200
@@ -268,12 +322,14 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         a.perm = T.perm; a.n = (uint32_t)n; a.ghosts = h->ghosts_dev;
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            second_largest_kernel<<<1, 1024, 0, h->stream>>>(P.r, (uint32_t)n, h->scratch);
+            if (line) vmax2_kernel<<<1, 1024, 0, h->stream>>>(P, (uint32_t)n, h->scratch);
+            else second_largest_kernel<<<1, 1024, 0, h->stream>>>(P.r, (uint32_t)n, h->scratch);
         }
         double* pin = (double*)(h->pinned + 8);
         CU_TRY(h, cudaMemcpyAsync(pin, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
-        a.r2nd = pin[0];
+        a.r2nd = line ? c->dt_last_done * sqrt(pin[0]) : pin[0];      // collision.c:278 / :222-225
+        a.dt_last_done = c->dt_last_done;
         if (h->col_slots_cap < n) {
             CU_TRY(h, cudaStreamSynchronize(h->stream));
             cudaFree(h->col_slots); h->col_slots = nullptr;
@@ -284,7 +340,8 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         CU_TRY(h, cudaMemsetAsync(h->counters + 4, 0, sizeof(unsigned long long), h->stream));
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            tree_collision_kernel<0><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
+            if (line) tree_collision_kernel<0, true><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
+            else tree_collision_kernel<0, false><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
             overflow_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>((uint32_t)n, h->col_count, h->counters + 4);
         }
         CU_TRY(h, cudaGetLastError());
@@ -294,8 +351,10 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
             LaunchScope ls(h, TC_COLLISION, 2);
             tree_slots_kernel<<<div_up(n, 256), 256, 0, h->stream>>>((uint32_t)n, h->col_count, (const uint32_t*)h->col_off, h->col_slots,
                                                                    h->ghosts_dev, h->col_list);
-            if (h->pinned[16])       // some projectile has more hits than slots: those walk again and write directly
-                tree_collision_kernel<1><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
+            if (h->pinned[16]) {     // some projectile has more hits than slots: those walk again and write directly
+                if (line) tree_collision_kernel<1, true><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
+                else tree_collision_kernel<1, false><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
+            }
         }
     }
     CU_TRY(h, cudaGetLastError());

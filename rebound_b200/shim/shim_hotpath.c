@@ -103,7 +103,8 @@ void reb_boundary_check(struct reb_simulation* r){
 
 /* ---- collisions ---------------------------------------------------------------------------- */
 void reb_collision_search(struct reb_simulation* const r){
-    const int gpu_mode = (r->collision==REB_COLLISION_DIRECT || r->collision==REB_COLLISION_TREE)
+    const int gpu_mode = (r->collision==REB_COLLISION_DIRECT || r->collision==REB_COLLISION_TREE
+                          || r->collision==REB_COLLISION_LINE || r->collision==REB_COLLISION_LINETREE)
                        && r->map==NULL && r->N_targets==SIZE_MAX;
     struct shim_state* s = shim_get(r);
     if (!s) return;

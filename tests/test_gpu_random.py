@@ -38,12 +38,13 @@ def test_random_tree_cells_and_gravity(d):
 
 
 @SET
-@given(cfg_st, st.sampled_from([abi.COLLISION_DIRECT, abi.COLLISION_TREE]))
-def test_random_collision_lists(d, col):
-    c, p = make(d, collision=col)
+@given(cfg_st, st.sampled_from([abi.COLLISION_DIRECT, abi.COLLISION_TREE, abi.COLLISION_LINE, abi.COLLISION_LINETREE]),
+       st.sampled_from([0.0, 0.05, -0.2]))
+def test_random_collision_lists(d, col, dtl):
+    c, p = make(d, collision=col, dt_last_done=dtl)
     got = eng().collision_search_host(c.copy(), np.ascontiguousarray(p))
     want = checkers.oracle().collision_search(c, p)
-    assert collisions_equal(got, want, with_ri=(col == abi.COLLISION_TREE))
+    assert collisions_equal(got, want, with_ri=(col in (abi.COLLISION_TREE, abi.COLLISION_LINETREE)))
 
 
 @SET

@@ -296,3 +296,13 @@ def test_empty_and_tiny_inputs(eng):
             want, cw, _ = checkers.oracle().steps(cfg, p, 2)
             assert m == len(want) == n and bits_equal(q[:m], want) and c.t == cw.t
             assert len(eng.collision_search_host(cfg.copy(), p.copy())) == 0
+
+
+def test_line_and_linetree_collision_lists_bitwise(eng):
+    """REB_COLLISION_LINE / LINETREE on the GPU against the oracle (same cases as the oracle-vs-reference pin)."""
+    from test_oracle_vs_reference import LINE_CASES
+    for name, cfg, p in LINE_CASES:
+        want = checkers.oracle().collision_search(cfg, p)
+        got = eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p))
+        assert len(want) > 0 and len(got) == len(want), name
+        assert collisions_equal(got, want, with_ri=(cfg.collision == abi.COLLISION_LINETREE)), name

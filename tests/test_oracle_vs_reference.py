@@ -214,3 +214,35 @@ def test_energy():
     p = ics.plummer(200, seed=1)
     cfg = ics.plummer_config(200)
     assert checkers.reference().energy(cfg, p) == checkers.oracle().energy(cfg, p)
+
+
+def line_cases():
+    """REB_COLLISION_LINE / LINETREE (collision.c:125-196, 270-331): trajectories over the last step."""
+    rng = np.random.default_rng(3)
+    n = 400
+    q = abi.particles(n)
+    for f in ("x", "y", "z"):
+        q[f] = rng.uniform(-4.9, 4.9, n)
+    for f in ("vx", "vy", "vz"):
+        q[f] = rng.normal(0, 3, n)
+    q["r"] = rng.uniform(0.02, 0.2, n)
+    q["m"] = 1.0
+    for col in (abi.COLLISION_LINE, abi.COLLISION_LINETREE):
+        yield f"open_c{col}", abi.default_config(collision=col, root_size=10.0, boundary=abi.BOUNDARY_OPEN, dt_last_done=0.05), q
+        yield f"per_c{col}", abi.default_config(collision=col, root_size=10.0, boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=1,
+                                                N_ghost_y=1, N_ghost_z=1, dt_last_done=0.03), q
+        yield f"2root_negdt_c{col}", abi.default_config(collision=col, root_size=5.0, N_root_x=2, N_root_y=2, N_root_z=2,
+                                                        boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=2, N_ghost_y=1, dt_last_done=-0.02), q
+        yield f"sheet_c{col}", ics.shearing_sheet_config(root_size=40.0, t=55.5, collision=col, dt_last_done=30.0), \
+            ics.shearing_sheet(root_size=40.0, seed=5)
+
+
+LINE_CASES = list(line_cases())
+
+
+@pytest.mark.parametrize("name,cfg,p", LINE_CASES, ids=[c[0] for c in LINE_CASES])
+def test_line_collision_list_bitwise(name, cfg, p):
+    ref = checkers.reference().collision_search(cfg, p)
+    orc = checkers.oracle().collision_search(cfg, p)
+    assert len(ref) > 0
+    assert checkers.collisions_equal(ref, orc, with_ri=(cfg.collision == abi.COLLISION_LINETREE))
