@@ -215,6 +215,10 @@ int rebcu_timing_reset(rebcu_handle* h);
  * n_samples pseudo-random operand pairs: result4 = {sqrt mismatches, divide mismatches (both must be 0),
  * sqrt / divide operands of the ordinary families that were sent to the generic path}. */
 int rebcu_selftest_math(rebcu_handle* h, uint64_t n_samples, uint64_t seed, uint64_t* result4);
+/* Device self-tests of the hand-written primitives behind the tree build (csrc/primitives.cuh): a stable LSD
+ * radix sort of host (key, value) pairs by the low `bits` key bits, and an exclusive scan, both in place. */
+int rebcu_selftest_sort(rebcu_handle* h, uint64_t* keys, uint32_t* vals, uint64_t n, int bits);
+int rebcu_selftest_scan(rebcu_handle* h, uint32_t* values, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -180,6 +180,8 @@ PRODUCT_SIGNATURES = {
     "timing_read": (C.c_int, [_P, _DBLP, _U64P, C.c_int]),
     "timing_reset": (C.c_int, [_P]),
     "selftest_math": (C.c_int, [_P, C.c_uint64, C.c_uint64, _U64P]),
+    "selftest_sort": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
+    "selftest_scan": (C.c_int, [_P, _P, C.c_uint64]),
 }
 
 

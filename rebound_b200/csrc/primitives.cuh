@@ -110,7 +110,7 @@ constexpr int RS_ITEMS = 8;                         // elements per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048 elements per CTA (33 KB of static shared memory)
 constexpr int RS_BINS = 256;
 
-static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift,
+static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift, uint32_t mask,
                                                                 uint32_t* __restrict__ hist, uint32_t n_tiles) {
     __shared__ uint32_t bins[RS_BINS];
     bins[threadIdx.x] = 0;
@@ -119,7 +119,7 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uin
 #pragma unroll 4
     for (int k = 0; k < RS_ITEMS; k++) {
         const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&bins[(keys[i] >> shift) & 0xff], 1u);
+        if (i < n) atomicAdd(&bins[(uint32_t)(keys[i] >> shift) & mask], 1u);
     }
     __syncthreads();
     hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = bins[threadIdx.x];
@@ -127,7 +127,7 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uin
 
 static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                                   uint64_t n, int shift, const uint32_t* __restrict__ bucket_start,
+                                                                   uint64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ bucket_start,
                                                                    uint32_t n_tiles) {
     __shared__ uint32_t warp_cnt[RS_WARPS][RS_BINS];     // running per-warp digit counters, then per-warp exclusive offsets
     __shared__ uint32_t digit_start[RS_BINS];            // start of each digit run inside the reordered tile
@@ -148,7 +148,7 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const 
         const bool ok = i < n;
         key[k] = ok ? keys_in[i] : ~0ull;
         val[k] = ok ? vals_in[i] : 0u;
-        const uint32_t d = ok ? (uint32_t)((key[k] >> shift) & 0xff) : 0x100u;   // 0x100: padding, matches nothing real
+        const uint32_t d = ok ? ((uint32_t)(key[k] >> shift) & mask) : 0x100u;   // 0x100: padding, matches nothing real
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
@@ -178,7 +178,7 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const 
     for (int k = 0; k < RS_ITEMS; k++) {
         const uint64_t i = warp_base + (uint64_t)k * 32 + lane;
         if (i < n) {
-            const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+            const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
             const uint32_t pos = digit_start[d] + warp_cnt[w][d] + rank[k];
             s_keys[pos] = key[k];
             s_vals[pos] = val[k];
@@ -188,7 +188,7 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const 
     // write the digit runs to their global buckets: consecutive threads -> consecutive addresses inside a run
     for (uint32_t pos = threadIdx.x; pos < tile_total; pos += RS_THREADS) {
         const uint64_t kk = s_keys[pos];
-        const uint32_t d = (uint32_t)((kk >> shift) & 0xff);
+        const uint32_t d = (uint32_t)(kk >> shift) & mask;
         const uint64_t dst = (uint64_t)digit_global[d] + (pos - digit_start[d]);
         keys_out[dst] = kk;
         vals_out[dst] = s_vals[pos];
@@ -222,9 +222,11 @@ inline int radix_sort_pairs(cudaStream_t s, uint64_t* keys_in, uint32_t* vals_in
     int launches = 0;
     for (int p = 0; p < passes; p++) {
         const int shift = 8 * p;
-        radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(ka, n, shift, hist, n_tiles);
+        const int rem = bits - shift;                               // the last digit may be narrower than 8 bits
+        const uint32_t mask = rem >= 8 ? 0xffu : ((1u << rem) - 1u);
+        radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(ka, n, shift, mask, hist, n_tiles);
         exclusive_scan_u32(s, hist, hist, (uint64_t)RS_BINS * n_tiles, scan_tmp);
-        radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, hist, n_tiles);
+        radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, mask, hist, n_tiles);
         launches += 5;
         uint64_t* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;

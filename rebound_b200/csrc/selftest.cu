@@ -3,6 +3,7 @@
 // out-of-range flag (and that the flag is raised rarely on ordinary operands).
 #include "engine.cuh"
 #include "strict_math.cuh"
+#include "primitives.cuh"
 
 namespace {
 
@@ -40,6 +41,48 @@ __global__ void math_selftest_kernel(uint64_t n, uint64_t seed, unsigned long lo
 }
 
 }  // namespace
+
+// Sorts caller-provided (key, value) pairs by the low `bits` key bits with the hand-written radix sort of
+// primitives.cuh (the tree build's sorter) so that tests can compare it with a host stable sort.
+extern "C" int rebcu_selftest_sort(rebcu_handle* h, uint64_t* keys, uint32_t* vals, uint64_t n, int bits) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (n == 0) return REBCU_OK;
+    uint64_t *k0 = nullptr, *k1 = nullptr; uint32_t *v0 = nullptr, *v1 = nullptr, *hist = nullptr, *tmp = nullptr;
+    const size_t hw = prim::radix_hist_words(n), sw = prim::scan_scratch_words(hw);
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&k0, n * 8)) || (e = cudaMalloc(&k1, n * 8)) || (e = cudaMalloc(&v0, n * 4)) || (e = cudaMalloc(&v1, n * 4)) ||
+        (e = cudaMalloc(&hist, hw * 4)) || (e = cudaMalloc(&tmp, sw * 4))) {
+        cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(hist); cudaFree(tmp);
+        return rebcu_cuda_fail(h, e, "selftest_sort allocation");
+    }
+    cudaMemcpyAsync(k0, keys, n * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(v0, vals, n * 4, cudaMemcpyHostToDevice, h->stream);
+    h->launches += prim::radix_sort_pairs(h->stream, k0, v0, k1, v1, n, bits, hist, tmp);
+    cudaMemcpyAsync(keys, k1, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(vals, v1, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(hist); cudaFree(tmp);
+    if (e != cudaSuccess) return rebcu_cuda_fail(h, e, "selftest_sort");
+    return REBCU_OK;
+}
+
+// Exclusive scan of caller-provided counts with the hand-written scan of primitives.cuh.
+extern "C" int rebcu_selftest_scan(rebcu_handle* h, uint32_t* values, uint64_t n) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (n == 0) return REBCU_OK;
+    uint32_t *d = nullptr, *tmp = nullptr;
+    CU_TRY(h, cudaMalloc(&d, n * 4));
+    cudaError_t e = cudaMalloc(&tmp, prim::scan_scratch_words(n) * 4);
+    if (e != cudaSuccess) { cudaFree(d); return rebcu_cuda_fail(h, e, "selftest_scan allocation"); }
+    cudaMemcpyAsync(d, values, n * 4, cudaMemcpyHostToDevice, h->stream);
+    prim::exclusive_scan_u32(h->stream, d, d, n, tmp);
+    h->launches += 3;
+    cudaMemcpyAsync(values, d, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    cudaFree(d); cudaFree(tmp);
+    if (e != cudaSuccess) return rebcu_cuda_fail(h, e, "selftest_scan");
+    return REBCU_OK;
+}
 
 extern "C" int rebcu_selftest_math(rebcu_handle* h, uint64_t n_samples, uint64_t seed, uint64_t* result4) {
     CU_TRY(h, cudaSetDevice(h->device));

@@ -187,6 +187,15 @@ class Engine:
         self._check(self.f["selftest_math"](self.h, n_samples, seed, out))
         return {"sqrt_mismatch": int(out[0]), "div_mismatch": int(out[1]), "sqrt_flagged": int(out[2]), "div_flagged": int(out[3])}
 
+    def selftest_sort(self, keys, vals, bits=64):
+        """Sorts (keys uint64, vals uint32) in place on the device with the tree build's radix sort."""
+        assert keys.dtype == np.uint64 and vals.dtype == np.uint32 and len(keys) == len(vals)
+        self._check(self.f["selftest_sort"](self.h, abi.as_ptr(keys), abi.as_ptr(vals), len(keys), bits))
+
+    def selftest_scan(self, values):
+        assert values.dtype == np.uint32
+        self._check(self.f["selftest_scan"](self.h, abi.as_ptr(values), len(values)))
+
     def timing_enable(self, on=True):
         self._check(self.f["timing_enable"](self.h, 1 if on else 0))
 
