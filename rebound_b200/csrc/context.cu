@@ -72,6 +72,7 @@ void rebcu_destroy(rebcu_handle* h) {
     cudaFree(h->tp_hist);
     for (int k = 0; k < AUX_STREAMS; k++) if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
     for (int k = 0; k < 3; k++) if (h->aux_ev[k]) cudaEventDestroy(h->aux_ev[k]);
+    for (int k = 0; k < 3 * PIPE_RANGES; k++) if (h->pipe_ev[k]) cudaEventDestroy(h->pipe_ev[k]);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->ghost_ring) cudaFreeHost(h->ghost_ring);
     for (int i = 0; i < GHOST_RING; i++) if (h->ghost_ring_ev[i]) cudaEventDestroy(h->ghost_ring_ev[i]);
@@ -233,22 +234,25 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(uint64_t* __restrict
 }
 
 // Range versions on an arbitrary stream, for the chunk-pipelined host-buffer path (integrate.cu).
-// b must be a multiple of PACK_THREADS.
-int engine_upload_range(rebcu_handle* h, cudaStream_t s, const rebcu_particle* particles, uint64_t b, uint64_t e) {
+// b must be a multiple of PACK_THREADS.  The copy runs on s_copy, the AoS<->SoA kernel on s_kernel, chained by
+// `ev`: a copy stream then carries nothing but back-to-back DMA transfers and never waits for an SM to free up.
+int engine_upload_range(rebcu_handle* h, cudaStream_t s_copy, cudaEvent_t ev, cudaStream_t s_kernel, const rebcu_particle* particles, uint64_t b, uint64_t e) {
     if (e <= b) return REBCU_OK;
-    CU_TRY(h, cudaMemcpyAsync(h->aos + b, particles + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(h->aos + b, particles + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyHostToDevice, s_copy));
+    if (s_copy != s_kernel) { CU_TRY(h, cudaEventRecord(ev, s_copy)); CU_TRY(h, cudaStreamWaitEvent(s_kernel, ev, 0)); }
     h->launches++;
-    unpack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s>>>((const uint64_t*)(h->aos + b), (uint64_t*)h->soa + b, h->cap, e - b);
+    unpack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s_kernel>>>((const uint64_t*)(h->aos + b), (uint64_t*)h->soa + b, h->cap, e - b);
     CU_TRY(h, cudaGetLastError());
     return REBCU_OK;
 }
 
-int engine_download_range(rebcu_handle* h, cudaStream_t s, rebcu_particle* particles, uint64_t b, uint64_t e) {
+int engine_download_range(rebcu_handle* h, cudaStream_t s_kernel, cudaEvent_t ev, cudaStream_t s_copy, rebcu_particle* particles, uint64_t b, uint64_t e) {
     if (e <= b) return REBCU_OK;
     h->launches++;
-    pack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s>>>((uint64_t*)(h->aos + b), (const uint64_t*)h->soa + b, h->cap, e - b);
+    pack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s_kernel>>>((uint64_t*)(h->aos + b), (const uint64_t*)h->soa + b, h->cap, e - b);
     CU_TRY(h, cudaGetLastError());
-    CU_TRY(h, cudaMemcpyAsync(particles + b, h->aos + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyDeviceToHost, s));
+    if (s_copy != s_kernel) { CU_TRY(h, cudaEventRecord(ev, s_kernel)); CU_TRY(h, cudaStreamWaitEvent(s_copy, ev, 0)); }
+    CU_TRY(h, cudaMemcpyAsync(particles + b, h->aos + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyDeviceToHost, s_copy));
     return REBCU_OK;
 }
 

@@ -22,7 +22,8 @@ enum { TC_DIRECT = 0, TC_KICKDRIFT, TC_TREEBUILD, TC_TREEWALK, TC_COLLISION, TC_
 
 #define REBCU_MAX_GHOST 729   // (2*4+1)^3
 #define GHOST_RING 8
-#define AUX_STREAMS 4
+#define AUX_STREAMS 6
+#define PIPE_RANGES 130
 
 struct GhostShifts {          // ghost-box offsets, computed on the host exactly as src/boundary.c:145-201
     int n;
@@ -92,6 +93,7 @@ struct rebcu_handle {
     int tp_phase = 0;
     cudaStream_t aux[AUX_STREAMS] = {};         // copy/compute overlap streams of the chunk-pipelined host path
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ev[3 * PIPE_RANGES] = {};  // per range: [3i] upload done, [3i+1] kernels done, [3i+2] download done (trace)
     double* tp_hist = nullptr; uint64_t tp_hist_cap = 0;   // per-step snapshots of the massive bodies
     void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)
     void* exchange_user = nullptr;
@@ -133,8 +135,8 @@ int sei_step(rebcu_handle* h, rebcu_config* c);
 // configuration is not eligible (caller falls back to upload / steps / download), 0 on success, <0 on error.
 int tp_steps_resident(rebcu_handle* h, rebcu_config* c, uint64_t n_steps);
 int tp_steps_host_pipelined(rebcu_handle* h, rebcu_config* c, rebcu_particle* particles, uint64_t N, uint64_t n_steps);
-int engine_upload_range(rebcu_handle* h, cudaStream_t s, const rebcu_particle* particles, uint64_t b, uint64_t e);
-int engine_download_range(rebcu_handle* h, cudaStream_t s, rebcu_particle* particles, uint64_t b, uint64_t e);
+int engine_upload_range(rebcu_handle* h, cudaStream_t s_copy, cudaEvent_t ev, cudaStream_t s_kernel, const rebcu_particle* particles, uint64_t b, uint64_t e);
+int engine_download_range(rebcu_handle* h, cudaStream_t s_kernel, cudaEvent_t ev, cudaStream_t s_copy, rebcu_particle* particles, uint64_t b, uint64_t e);
 int boundary_check(rebcu_handle* h, rebcu_config* c);
 int tree_build(rebcu_handle* h, const rebcu_config* c);
 int tree_gravity(rebcu_handle* h, rebcu_config* c);

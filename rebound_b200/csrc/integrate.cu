@@ -10,6 +10,8 @@
 #include "engine.cuh"
 #include "strict_math.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace {
 
@@ -270,6 +272,93 @@ __global__ void __launch_bounds__(TP_MAX_ACTIVE) tp_history_kernel(const TpMulti
     }
 }
 
+// Pair-parallel variant for Na <= TP_PAIR_MAX: thread (i,j) evaluates the pair prefactor and separation,
+// thread i then accumulates its row in ascending j with exactly the operations of tp_force_strict /
+// tp_force_fast, so the bits equal tp_history_kernel's while the ~300-cycle sqrt/divide chains of one step
+// run side by side instead of back to back (the history is on the critical path of every call).
+constexpr int TP_PAIR_MAX = 16;
+
+template <bool FAST, bool KAHAN>
+__global__ void __launch_bounds__(TP_PAIR_MAX * TP_PAIR_MAX) tp_history_pair_kernel(const TpMultiArgs a) {
+    __shared__ double4 src[TP_PAIR_MAX];
+    __shared__ double4 term[TP_PAIR_MAX * TP_PAIR_MAX];      // (p, dx, dy, dz) of pair (i,j)
+    const int t = threadIdx.x, Na = a.Na;
+    const bool live = t < Na;                                 // owner of body t
+    const int pi = t / Na, pj = t - pi * Na;
+    const bool pair = t < Na * Na && pi != pj;
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, m = 0, ax = 0, ay = 0, az = 0;
+    if (live) { x = a.s.x[t]; y = a.s.y[t]; z = a.s.z[t]; vx = a.s.vx[t]; vy = a.s.vy[t]; vz = a.s.vz[t]; m = a.s.m[t]; }
+    const double negG = -a.G;
+    for (uint64_t st = 0; st < a.n_steps; st++) {
+        if (live) {
+            double* hs = a.hist + st * 7 * Na;
+            hs[0 * Na + t] = x; hs[1 * Na + t] = y; hs[2 * Na + t] = z; hs[3 * Na + t] = vx; hs[4 * Na + t] = vy; hs[5 * Na + t] = vz; hs[6 * Na + t] = m;
+            if (st == 0) { x = s_add(x, s_mul(a.d0, vx)); y = s_add(y, s_mul(a.d0, vy)); z = s_add(z, s_mul(a.d0, vz)); }
+            src[t] = make_double4(x, y, z, m);
+        }
+        __syncthreads();
+        if (pair) {
+            const double4 si = src[pi], sj = src[pj];
+            double xi = si.x, yi = si.y, zi = si.z;
+            if (!KAHAN) { xi = s_add(a.gbx, xi); yi = s_add(a.gby, yi); zi = s_add(a.gbz, zi); }
+            double p, dx, dy, dz;
+            if (FAST) {
+                dx = xi - sj.x; dy = yi - sj.y; dz = zi - sj.z;
+                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
+                const double ri = rsqrt(r2);
+                p = negG * sj.w * (ri * ri * ri);
+            } else {
+                dx = s_sub(xi, sj.x); dy = s_sub(yi, sj.y); dz = s_sub(zi, sj.z);
+                const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);
+                const bool w = a.windowed && strict_window_key(r2) < STRICT_WINDOW_LIMIT;
+                const double r = w ? fsqrt_rn_w(r2) : s_sqrt(r2);
+                if (!KAHAN) {
+                    const double b = s_mul(s_mul(r, r), r);
+                    p = s_mul(w ? fdiv_rn_w(negG, b) : s_div(negG, b), sj.w);
+                } else {
+                    const double b = s_mul(r2, r);
+                    p = s_mul(-(w ? fdiv_rn_w(a.G, b) : s_div(a.G, b)), sj.w);
+                }
+            }
+            term[t] = make_double4(p, dx, dy, dz);
+        }
+        __syncthreads();
+        if (live) {
+            double cx = 0, cy = 0, cz = 0;
+            ax = ay = az = 0;
+            for (int j = 0; j < Na; j++) {
+                if (j == t) continue;
+                const double4 q = term[t * Na + j];
+                if (FAST) {
+                    if (!KAHAN) { ax = fma(q.x, q.y, ax); ay = fma(q.x, q.z, ay); az = fma(q.x, q.w, az); }
+                    else {
+                        double yy, tt;
+                        yy = fma(q.x, q.y, -cx); tt = ax + yy; cx = (tt - ax) - yy; ax = tt;
+                        yy = fma(q.x, q.z, -cy); tt = ay + yy; cy = (tt - ay) - yy; ay = tt;
+                        yy = fma(q.x, q.w, -cz); tt = az + yy; cz = (tt - az) - yy; az = tt;
+                    }
+                } else if (!KAHAN) {
+                    ax = s_add(ax, s_mul(q.x, q.y)); ay = s_add(ay, s_mul(q.x, q.z)); az = s_add(az, s_mul(q.x, q.w));
+                } else {
+                    double yy, tt;
+                    yy = s_sub(s_mul(q.x, q.y), cx); tt = s_add(ax, yy); cx = s_sub(s_sub(tt, ax), yy); ax = tt;
+                    yy = s_sub(s_mul(q.x, q.z), cy); tt = s_add(ay, yy); cy = s_sub(s_sub(tt, ay), yy); ay = tt;
+                    yy = s_sub(s_mul(q.x, q.w), cz); tt = s_add(az, yy); cz = s_sub(s_sub(tt, az), yy); az = tt;
+                }
+            }
+            vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
+            x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));
+            if (st + 1 < a.n_steps) { x = s_add(x, s_mul(a.d2, vx)); y = s_add(y, s_mul(a.d2, vy)); z = s_add(z, s_mul(a.d2, vz)); }
+        }
+    }
+    if (live) {
+        double* hs = a.hist + a.n_steps * 7 * Na;
+        hs[0 * Na + t] = x; hs[1 * Na + t] = y; hs[2 * Na + t] = z; hs[3 * Na + t] = vx; hs[4 * Na + t] = vy; hs[5 * Na + t] = vz; hs[6 * Na + t] = m;
+        a.s.x[t] = x; a.s.y[t] = y; a.s.z[t] = z; a.s.vx[t] = vx; a.s.vy[t] = vy; a.s.vz[t] = vz;
+        a.s.ax[t] = ax; a.s.ay[t] = ay; a.s.az[t] = az;
+    }
+}
+
 // Test particles i in [max(i_begin, Na), i_end): all steps in one launch, massive bodies replayed from hist.
 template <bool FAST, bool KAHAN>
 __global__ void __launch_bounds__(TP_BLOCK) tp_multistep_kernel(const TpMultiArgs a) {
@@ -443,6 +532,12 @@ static TpMultiArgs tp_multi_args(rebcu_handle* h, const rebcu_config* c, uint64_
     return a;
 }
 static void tp_launch_history(const TpMultiArgs& a, cudaStream_t s) {
+    if (a.Na <= TP_PAIR_MAX) {
+        const int nt = ((max(a.Na * a.Na, 32) + 31) / 32) * 32;
+        if (a.fast) { if (a.kahan) tp_history_pair_kernel<true, true><<<1, nt, 0, s>>>(a); else tp_history_pair_kernel<true, false><<<1, nt, 0, s>>>(a); }
+        else { if (a.kahan) tp_history_pair_kernel<false, true><<<1, nt, 0, s>>>(a); else tp_history_pair_kernel<false, false><<<1, nt, 0, s>>>(a); }
+        return;
+    }
     if (a.fast) { if (a.kahan) tp_history_kernel<true, true><<<1, TP_MAX_ACTIVE, 0, s>>>(a); else tp_history_kernel<true, false><<<1, TP_MAX_ACTIVE, 0, s>>>(a); }
     else { if (a.kahan) tp_history_kernel<false, true><<<1, TP_MAX_ACTIVE, 0, s>>>(a); else tp_history_kernel<false, false><<<1, TP_MAX_ACTIVE, 0, s>>>(a); }
 }
@@ -521,31 +616,62 @@ int tp_steps_host_pipelined(rebcu_handle* h, rebcu_config* c, rebcu_particle* pa
     CU_TRY(h, cudaEventRecord(h->aux_ev[0], h->stream));
     for (int k = 0; k < AUX_STREAMS; k++) CU_TRY(h, cudaStreamWaitEvent(h->aux[k], h->aux_ev[0], 0));
 
+    // Three-stage pipeline: aux[0] carries nothing but the H2D copies, aux[1] nothing but the D2H copies, and
+    // aux[2..] the kernels (AoS->SoA, all steps, SoA->AoS) round-robin, chained by per-range events -- so both
+    // DMA engines stream back to back (measured 2.3 ms for 112 MB each way, full duplex) and kernels of
+    // neighbouring ranges overlap to fill each other's tail waves.
     // range 0 = the first 256 particles (holds the massive bodies): their history starts as early as possible
-    const int n_chunks = 16;
+    int n_chunks = 24;
+    if (const char* e = getenv("REBOUND_B200_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= PIPE_RANGES - 2) n_chunks = v; }
     const uint64_t head = 256;
     uint64_t cs = (N - head + n_chunks - 1) / n_chunks;
     cs = ((cs + 255) / 256) * 256;
+    cudaStream_t s_up = h->aux[0], s_down = h->aux[1];
+    const bool trace = getenv("REBOUND_B200_PIPE_TRACE") != nullptr;     // prints a per-range timeline to stderr
+    cudaEvent_t ev_t0 = nullptr;
+    if (trace) { CU_TRY(h, cudaEventCreate(&ev_t0)); CU_TRY(h, cudaEventRecord(ev_t0, s_up)); }
     int idx = 0;
     for (uint64_t b = 0; b < N; idx++) {
+        if (idx >= PIPE_RANGES) return rebcu_fail(h, REBCU_ERR_ARG, "pipelined host path: too many ranges");
         const uint64_t e = (idx == 0) ? head : ((b + cs < N) ? b + cs : N);
-        cudaStream_t s = h->aux[idx % AUX_STREAMS];
-        if ((err = engine_upload_range(h, s, particles, b, e))) return err;
+        cudaEvent_t& ev_up = h->pipe_ev[3 * idx];
+        cudaEvent_t& ev_k = h->pipe_ev[3 * idx + 1];
+        cudaEvent_t& ev_dn = h->pipe_ev[3 * idx + 2];
+        const unsigned evf = trace ? cudaEventDefault : cudaEventDisableTiming;
+        if (trace && ev_up) { cudaEventDestroy(ev_up); cudaEventDestroy(ev_k); ev_up = ev_k = nullptr; }
+        if (!ev_up) CU_TRY(h, cudaEventCreateWithFlags(&ev_up, evf));
+        if (!ev_k) CU_TRY(h, cudaEventCreateWithFlags(&ev_k, evf));
+        if (trace && !ev_dn) CU_TRY(h, cudaEventCreateWithFlags(&ev_dn, evf));
+        cudaStream_t s = h->aux[2 + idx % (AUX_STREAMS - 2)];
+        if ((err = engine_upload_range(h, s_up, ev_up, s, particles, b, e))) return err;
         if (idx == 0) {
             h->launches++;
             tp_launch_history(a, s);
             CU_TRY(h, cudaEventRecord(h->aux_ev[1], s));
-        } else if (idx < AUX_STREAMS) {
-            CU_TRY(h, cudaStreamWaitEvent(s, h->aux_ev[1], 0));      // history complete (stream 0 is ordered anyway)
+        } else {
+            CU_TRY(h, cudaStreamWaitEvent(s, h->aux_ev[1], 0));      // massive-body history complete
         }
         a.i_begin = b; a.i_end = e;
         h->launches++;
         tp_launch_multistep(a, s);
         CU_TRY(h, cudaGetLastError());
-        if ((err = engine_download_range(h, s, particles, b, e))) return err;
+        if ((err = engine_download_range(h, s, ev_k, s_down, particles, b, e))) return err;
+        if (trace) CU_TRY(h, cudaEventRecord(ev_dn, s_down));
         b = e;
     }
     for (int k = 0; k < AUX_STREAMS; k++) CU_TRY(h, cudaStreamSynchronize(h->aux[k]));
+    if (trace) {
+        for (int i = 0; i < idx; i++) {
+            float tu = 0, tk = 0, td = 0;
+            cudaEventElapsedTime(&tu, ev_t0, h->pipe_ev[3 * i]);
+            cudaEventElapsedTime(&tk, ev_t0, h->pipe_ev[3 * i + 1]);
+            cudaEventElapsedTime(&td, ev_t0, h->pipe_ev[3 * i + 2]);
+            fprintf(stderr, "[pipe] range %2d  upload done %.3f  kernels done %.3f  download done %.3f ms\n", i, tu, tk, td);
+            cudaEventDestroy(h->pipe_ev[3 * i]); cudaEventDestroy(h->pipe_ev[3 * i + 1]); cudaEventDestroy(h->pipe_ev[3 * i + 2]);
+            h->pipe_ev[3 * i] = h->pipe_ev[3 * i + 1] = h->pipe_ev[3 * i + 2] = nullptr;
+        }
+        cudaEventDestroy(ev_t0);
+    }
     for (uint64_t st = 0; st < n_steps; st++) { c->t += drift[0]; c->t += drift[1]; }
     c->dt_last_done = c->dt;
     return REBCU_OK;
