@@ -142,8 +142,8 @@ int rebcu_download(rebcu_handle* h, rebcu_particle* particles, uint64_t N);
 /* Only ax,ay,az are written back (what a gravity routine produces). */
 int rebcu_download_acc(rebcu_handle* h, rebcu_particle* particles, uint64_t N);
 uint64_t rebcu_N(const rebcu_handle* h);
-/* Device pointer of one resident SoA field (0..10 = x,y,z,vx,vy,vz,ax,ay,az,m,r), for
- * torch.distributed plumbing; length rebcu_N(h) doubles. */
+/* Device pointer of one resident SoA field (0..10 = x,y,z,vx,vy,vz,ax,ay,az,m,r as doubles;
+ * 11..13 = name, ap, sim as 64-bit words), for torch.distributed plumbing; length rebcu_N(h). */
 void* rebcu_device_field(rebcu_handle* h, int field);
 
 /* ---- resident hot path ------------------------------------------------------------------- */
@@ -200,7 +200,25 @@ int rebcu_set_shard(rebcu_handle* h, int rank, int world);
  * reference's MPI build calls reb_communication_mpi_distribute_particles, gravity.c:58-61): the caller
  * all-gathers the x,y,z fields of the other ranks' blocks (torch.distributed / NCCL on this stream). */
 int rebcu_set_exchange_callback(rebcu_handle* h, void (*cb)(void* user), void* user);
+/* Which fields the engine needs gathered by the exchange callback it is calling right now:
+ *   POSITIONS   x,y,z                  between drift and force (every step)
+ *   VELOCITIES  vx,vy,vz in addition   before a collision search (the overlap test reads the target's
+ *                                      velocity, src/collision.c:101-106)
+ *   ALL         all 14 fields          before an open-boundary compaction: particles change owner when
+ *                                      indices shift (reb_simulation_remove_particle, src/particle.c:313-352)
+ * Outside a callback the value is POSITIONS. */
+#define REBCU_EXCHANGE_POSITIONS 1
+#define REBCU_EXCHANGE_VELOCITIES 2
+#define REBCU_EXCHANGE_ALL 4
+int rebcu_exchange_request(const rebcu_handle* h);
 void rebcu_shard_range(const rebcu_handle* h, uint64_t* begin, uint64_t* end);
+/* Sharded collision search: each rank searches for the projectiles of its own block against ALL particles
+ * (replicated positions / tree), so its list is the reference's serial list restricted to those
+ * projectiles.  The serial order is ghost box, projectile, target for DIRECT/LINE (src/collision.c:64-124)
+ * and projectile-major for TREE/LINETREE (:197-269); the complete list is therefore, segment by segment,
+ * the concatenation over ranks.  counts[s] = number of local entries in segment s (one segment per ghost
+ * box of the innermost ring for DIRECT/LINE, a single segment otherwise). */
+int rebcu_collisions_segments(rebcu_handle* h, uint64_t* counts, uint64_t cap, uint64_t* n_segments);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* Number of kernels this handle launched since creation (bench.py's gpu_launches). */

@@ -39,6 +39,8 @@ GRAVITY_NONE, GRAVITY_BASIC, GRAVITY_COMPENSATED, GRAVITY_TREE = 0, 1, 2, 3
 IGNORE_TERMS_NONE, IGNORE_TERMS_BETWEEN_0_AND_1, IGNORE_TERMS_INVOLVING_0 = 0, 1, 2
 INTEGRATOR_NONE, INTEGRATOR_LEAPFROG, INTEGRATOR_SEI = 0, 1, 2
 MODE_STRICT, MODE_FAST = 0, 1
+EXCHANGE_POSITIONS, EXCHANGE_VELOCITIES, EXCHANGE_ALL = 1, 2, 4
+N_FIELDS = 14  # x y z vx vy vz ax ay az m r name ap sim
 
 ERRORS = {
     -1: "CUDA",
@@ -174,6 +176,8 @@ PRODUCT_SIGNATURES = {
     "set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "shard_range": (None, [_P, _U64P, _U64P]),
     "set_exchange_callback": (C.c_int, [_P, _P, _P]),
+    "exchange_request": (C.c_int, [_P]),
+    "collisions_segments": (C.c_int, [_P, _U64P, C.c_uint64, _U64P]),
     "set_collision_callback": (C.c_int, [_P, _P, _P]),
     "launch_count": (C.c_uint64, [_P]),
     "timing_enable": (C.c_int, [_P, C.c_int]),

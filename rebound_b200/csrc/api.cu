@@ -80,16 +80,10 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
         int err = integrator_step(h, cfg, carried, carry_out, last);
         if (err) return err;
         carried = carry_out;
-        const uint64_t n_before = h->N;
         if (h->world > 1 && cfg->boundary == REBCU_BOUNDARY_OPEN) {
             // every rank must see every particle's final position to agree on what left the box
-            if (h->exchange) h->exchange(h->exchange_user);
-            const int rank = h->rank, world = h->world;
-            h->rank = 0; h->world = 1;
-            err = boundary_check(h, cfg);
-            h->rank = rank; h->world = world;
-            if (!err && h->N != n_before)
-                err = rebcu_fail(h, REBCU_ERR_ARG, "open-boundary removal while sharded over several GPUs needs a full-state exchange (not implemented)");
+            engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
+            err = boundary_check_full(h, cfg);
         } else {
             err = boundary_check(h, cfg);
         }

@@ -122,6 +122,15 @@ int boundary_check(rebcu_handle* h, rebcu_config* c) {
     const uint64_t removed = h->pinned[0];
     uint64_t removed_active = h->pinned[1];
     if (removed == 0) return REBCU_OK;
+    if (h->full_check_world > 1) {
+        // Sharded: every rank found the same particles outside (positions are replicated), but it only owns the
+        // velocities / accelerations / tags of its own block, and the compaction moves particles across block
+        // borders.  Gather every field from its owner first; all ranks then compact identical arrays.
+        if (!h->exchange) return rebcu_fail(h, REBCU_ERR_ARG, "open-boundary removal while sharded over several GPUs needs the exchange callback");
+        h->rank = h->full_check_rank; h->world = h->full_check_world;
+        engine_exchange(h, REBCU_EXCHANGE_ALL);
+        h->rank = 0; h->world = 1;
+    }
     // order-preserving compaction into a second SoA block, then swap
     if (!h->compact_buf) CU_TRY(h, cudaMalloc(&h->compact_buf, h->cap * F_COUNT * sizeof(double)));
     {
@@ -140,4 +149,16 @@ int boundary_check(rebcu_handle* h, rebcu_config* c) {
         c->N_active -= removed_active;
     }
     return REBCU_OK;
+}
+
+// Sharded runs: every rank checks EVERY particle (the positions are replicated after the exchange), so that
+// wraps and removals are applied identically everywhere.
+int boundary_check_full(rebcu_handle* h, rebcu_config* c) {
+    const int rank = h->rank, world = h->world;
+    h->full_check_rank = rank; h->full_check_world = world;
+    h->rank = 0; h->world = 1;
+    const int err = boundary_check(h, c);
+    h->rank = rank; h->world = world;
+    h->full_check_world = 0;
+    return err;
 }

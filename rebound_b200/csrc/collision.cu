@@ -83,19 +83,20 @@ __device__ __forceinline__ void emit(rebcu_collision* out, uint64_t at, uint32_t
 // grid.y = ghost box, thread = projectile, targets tiled through shared memory.
 // LINE: pairs j > i only, straight-line test over the last step (collision.c:152-189).
 template <bool FILL, bool LINE>
-__global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_t n, const GhostShifts* ghosts,
+__global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_t n, uint32_t ib, uint32_t nloc, const GhostShifts* ghosts,
                                                                uint32_t* __restrict__ count, const uint32_t* __restrict__ off,
                                                                rebcu_collision* __restrict__ out, double dt_last_done) {
     __shared__ double4 tile[128];
     const uint32_t g = blockIdx.y;
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    const bool valid = i < n;
+    const uint32_t il = blockIdx.x * 128 + threadIdx.x;       // projectiles [ib, ib+nloc): this rank's block
+    const uint32_t i = ib + il;
+    const bool valid = il < nloc;
     const rebcu_vec6d gb = ghosts->gb[g];
     rebcu_vec6d s = gb;
     double r1 = 0;
     if (valid) { s = shifted(gb, P, i); r1 = P.r[i]; }
     uint32_t found = 0;
-    const uint64_t base = (FILL && valid) ? off[(uint64_t)g * n + i] : 0;
+    const uint64_t base = (FILL && valid) ? off[(uint64_t)g * nloc + il] : 0;
     for (uint32_t t0 = 0; t0 < n; t0 += 128) {
         __syncthreads();
         const uint32_t j0 = t0 + threadIdx.x;
@@ -114,13 +115,14 @@ __global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_
             }
         }
     }
-    if (!FILL && valid) count[(uint64_t)g * n + i] = found;
+    if (!FILL && valid) count[(uint64_t)g * nloc + il] = found;
 }
 
 // ---- TREE ---------------------------------------------------------------------------------------
 struct TreeColArgs {
     const double4* pos; const double4* geo; const int4* meta; uint32_t n_cells;
     const uint32_t* perm; uint32_t n;
+    const uint32_t* list; uint32_t n_work;       // sharded: work item t -> sorted position list[t] (else t)
     const GhostShifts* ghosts;
     double r2nd;          // TREE: radius of the second largest particle; LINETREE: maxdrift = dt_last_done*sqrt(max v^2)
     double dt_last_done;
@@ -136,9 +138,9 @@ template <int PASS, bool LINE>
 __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColArgs a, uint32_t* __restrict__ count,
                                                              const uint32_t* __restrict__ off, rebcu_collision* __restrict__ out,
                                                              uint64_t* __restrict__ slots) {
-    const uint32_t k = blockIdx.x * 128 + threadIdx.x;
-    if (k >= a.n) return;
-    const uint32_t i = a.perm[k];            // key order => neighbouring lanes walk neighbouring paths
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= a.n_work) return;
+    const uint32_t i = a.perm[a.list ? a.list[t] : t];     // key order => neighbouring lanes walk neighbouring paths
     if (PASS == 1 && count[i] <= COL_SLOTS) return;
     const double r1 = P.r[i];
     double reach;
@@ -279,14 +281,17 @@ int scan_counts(rebcu_handle* h, uint64_t n_counts, uint64_t* total) {
 }  // namespace
 
 int collision_search(rebcu_handle* h, const rebcu_config* c) {
-    h->col_n = 0;
+    h->col_n = 0; h->col_seg_n = 0; h->col_seg_stride = 0;
     const uint64_t n = h->N;
     if (c->collision == REBCU_COLLISION_NONE || n == 0) return REBCU_OK;
     const bool direct = c->collision == REBCU_COLLISION_DIRECT || c->collision == REBCU_COLLISION_LINE;
     const bool line = c->collision == REBCU_COLLISION_LINE || c->collision == REBCU_COLLISION_LINETREE;
     if (!direct && c->collision != REBCU_COLLISION_TREE && c->collision != REBCU_COLLISION_LINETREE)
         return rebcu_fail(h, REBCU_ERR_ARG, "Collision routine not implemented.");
-    if (h->world > 1) return rebcu_fail(h, REBCU_ERR_ARG, "collision search while sharded over several GPUs is not implemented");
+    // Sharded: the overlap tests read the target's velocity, which only its owner has kept current.
+    if (h->world > 1) engine_exchange(h, REBCU_EXCHANGE_POSITIONS | REBCU_EXCHANGE_VELOCITIES);
+    uint64_t ib, ie; engine_shard(h, &ib, &ie);
+    const uint64_t nloc = ie - ib;
     if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "collision search supports N < 2^31");
     // only the innermost ring of ghost boxes (collision.c:67-69, 214-216)
     GhostShifts g;
@@ -297,20 +302,22 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
     uint64_t total = 0;
     if (direct) {
         if ((err = engine_upload_ghosts(h, &g))) return err;
-        const uint64_t n_counts = (uint64_t)g.n * n;
+        const uint64_t n_counts = (uint64_t)g.n * nloc;
+        h->col_seg_n = g.n; h->col_seg_stride = nloc;
+        if (nloc == 0) return REBCU_OK;
         if ((err = ensure_lists(h, n_counts))) return err;
-        dim3 grid(div_up(n, 128), g.n);
+        dim3 grid(div_up(nloc, 128), g.n);
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            if (line) direct_collision_kernel<false, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, h->col_count, nullptr, nullptr, c->dt_last_done);
-            else direct_collision_kernel<false, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, h->col_count, nullptr, nullptr, 0.);
+            if (line) direct_collision_kernel<false, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, h->col_count, nullptr, nullptr, c->dt_last_done);
+            else direct_collision_kernel<false, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, h->col_count, nullptr, nullptr, 0.);
         }
         CU_TRY(h, cudaGetLastError());
         if ((err = scan_counts(h, n_counts, &total))) return err;
         if (total) {
             LaunchScope ls(h, TC_COLLISION);
-            if (line) direct_collision_kernel<true, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, c->dt_last_done);
-            else direct_collision_kernel<true, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, 0.);
+            if (line) direct_collision_kernel<true, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, c->dt_last_done);
+            else direct_collision_kernel<true, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, 0.);
         }
     } else {
         if ((err = tree_build(h, c))) return err;                       // collision.c:200
@@ -320,6 +327,14 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         TreeColArgs a;
         a.pos = T.walk_pos; a.geo = T.walk_geo; a.meta = (const int4*)T.walk_meta; a.n_cells = (uint32_t)T.n_cells;
         a.perm = T.perm; a.n = (uint32_t)n; a.ghosts = h->ghosts_dev;
+        a.list = nullptr; a.n_work = (uint32_t)n;
+        h->col_seg_n = 1; h->col_seg_stride = n;
+        if (h->world > 1) {
+            uint64_t nw = 0;
+            if ((err = tree_shard_list(h, &a.list, &nw))) return err;
+            a.n_work = (uint32_t)nw;
+            CU_TRY(h, cudaMemsetAsync(h->col_count, 0, n * sizeof(uint32_t), h->stream));   // the other ranks' projectiles
+        }
         {
             LaunchScope ls(h, TC_COLLISION, 2);
             if (line) vmax2_kernel<<<1, 1024, 0, h->stream>>>(P, (uint32_t)n, h->scratch);
@@ -340,8 +355,8 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         CU_TRY(h, cudaMemsetAsync(h->counters + 4, 0, sizeof(unsigned long long), h->stream));
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            if (line) tree_collision_kernel<0, true><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
-            else tree_collision_kernel<0, false><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
+            if (line) tree_collision_kernel<0, true><<<div_up(max(a.n_work, 1u), 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
+            else tree_collision_kernel<0, false><<<div_up(max(a.n_work, 1u), 128), 128, 0, h->stream>>>(P, a, h->col_count, nullptr, nullptr, h->col_slots);
             overflow_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>((uint32_t)n, h->col_count, h->counters + 4);
         }
         CU_TRY(h, cudaGetLastError());
@@ -352,12 +367,28 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
             tree_slots_kernel<<<div_up(n, 256), 256, 0, h->stream>>>((uint32_t)n, h->col_count, (const uint32_t*)h->col_off, h->col_slots,
                                                                    h->ghosts_dev, h->col_list);
             if (h->pinned[16]) {     // some projectile has more hits than slots: those walk again and write directly
-                if (line) tree_collision_kernel<1, true><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
-                else tree_collision_kernel<1, false><<<div_up(n, 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
+                if (line) tree_collision_kernel<1, true><<<div_up(max(a.n_work, 1u), 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
+                else tree_collision_kernel<1, false><<<div_up(max(a.n_work, 1u), 128), 128, 0, h->stream>>>(P, a, h->col_count, (const uint32_t*)h->col_off, h->col_list, nullptr);
             }
         }
     }
     CU_TRY(h, cudaGetLastError());
     h->col_n = total;
+    return REBCU_OK;
+}
+
+extern "C" int rebcu_collisions_segments(rebcu_handle* h, uint64_t* counts, uint64_t cap, uint64_t* n_segments) {
+    *n_segments = h->col_seg_n;
+    if (h->col_seg_n == 0) return REBCU_OK;
+    if (cap < h->col_seg_n) return rebcu_fail(h, REBCU_ERR_CAPACITY, "segment buffer too small");
+    if (h->col_seg_n == 1) { counts[0] = h->col_n; return REBCU_OK; }
+    if (h->col_n == 0) { for (uint64_t s = 0; s < h->col_seg_n; s++) counts[s] = 0; return REBCU_OK; }
+    // DIRECT / LINE: entry offsets are the scanned counts, ghost box major: segment s starts at off[s * stride]
+    CU_TRY(h, cudaSetDevice(h->device));
+    uint32_t* pin = (uint32_t*)h->pinned;       // 32 words of 8 bytes >= 28 offsets
+    for (uint64_t s = 0; s <= h->col_seg_n; s++)
+        CU_TRY(h, cudaMemcpyAsync(pin + s, (const uint32_t*)h->col_off + s * h->col_seg_stride, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (uint64_t s = 0; s < h->col_seg_n; s++) counts[s] = pin[s + 1] - pin[s];
     return REBCU_OK;
 }

@@ -104,6 +104,8 @@ void* rebcu_device_field(rebcu_handle* h, int field) {
     return (void*)h->f(field);
 }
 
+int rebcu_exchange_request(const rebcu_handle* h) { return h->exchange_need; }
+
 uint64_t rebcu_launch_count(const rebcu_handle* h) { return h->launches; }
 
 int rebcu_timing_enable(rebcu_handle* h, int on) { h->timing = on != 0; return REBCU_OK; }
@@ -234,6 +236,14 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(uint64_t* __restrict
 }
 
 // Range versions on an arbitrary stream, for the chunk-pipelined host-buffer path (integrate.cu).
+// Runs the caller's exchange callback with the set of fields it has to gather (rebcu_exchange_request).
+void engine_exchange(rebcu_handle* h, int need) {
+    if (!h->exchange) return;
+    h->exchange_need = need;
+    h->exchange(h->exchange_user);
+    h->exchange_need = REBCU_EXCHANGE_POSITIONS;
+}
+
 // b must be a multiple of PACK_THREADS.  The copy runs on s_copy, the AoS<->SoA kernel on s_kernel, chained by
 // `ev`: a copy stream then carries nothing but back-to-back DMA transfers and never waits for an SM to free up.
 int engine_upload_range(rebcu_handle* h, cudaStream_t s_copy, cudaEvent_t ev, cudaStream_t s_kernel, const rebcu_particle* particles, uint64_t b, uint64_t e) {

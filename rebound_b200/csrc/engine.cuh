@@ -97,6 +97,9 @@ struct rebcu_handle {
     double* tp_hist = nullptr; uint64_t tp_hist_cap = 0;   // per-step snapshots of the massive bodies
     void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)
     void* exchange_user = nullptr;
+    int exchange_need = REBCU_EXCHANGE_POSITIONS;   // what the running exchange callback must gather
+    int full_check_rank = 0, full_check_world = 0;  // real shard while a full-range boundary check runs (else world 0)
+    uint64_t col_seg_n = 0, col_seg_stride = 0;     // local collision list: segments (ghost boxes) x projectiles per segment
     int (*collision_hook)(void*) = nullptr;   // called after each step's collision search (host resolve)
     void* collision_hook_user = nullptr;
     // pinned staging for small host<->device exchanges
@@ -124,6 +127,9 @@ struct LaunchScope {
 
 // internal entry points (one per translation unit)
 int engine_reserve(rebcu_handle* h, uint64_t n);
+void engine_exchange(rebcu_handle* h, int need);
+int boundary_check_full(rebcu_handle* h, rebcu_config* c);
+int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work);
 void engine_ghost_shifts(const rebcu_config* c, int gx, int gy, int gz, GhostShifts* out);
 int engine_upload_ghosts(rebcu_handle* h, const GhostShifts* g);
 int direct_gravity(rebcu_handle* h, const rebcu_config* c);

@@ -503,7 +503,7 @@ int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry
             drift_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(s, drift[0], b, e);
         }
         c->t += drift[k];
-        if (h->exchange) h->exchange(h->exchange_user);
+        engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
         int err = update_acceleration(h, c);
         if (err) return err;
         engine_shard(h, &b, &e);   // N may shrink (tree gravity + open boundary)
@@ -697,7 +697,7 @@ int sei_step(rebcu_handle* h, rebcu_config* c) {
         sei_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(soa_of(h), k, 0, b, e);
     }
     c->t += c->dt / 2.;
-    if (h->exchange) h->exchange(h->exchange_user);
+    engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
     int err = update_acceleration(h, c);
     if (err) return err;
     engine_shard(h, &b, &e);

@@ -578,17 +578,28 @@ int tree_export(rebcu_handle* h) {
     return REBCU_OK;
 }
 
+// Sorted positions (indices into perm) of the particles this rank owns, in key order.  Valid until the next build.
+int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work) {
+    TreeBuffers& T = h->tree;
+    const uint64_t n = h->N;
+    uint64_t b, e; engine_shard(h, &b, &e);
+    uint32_t* flag = T.cell_cnt; uint32_t* pos = T.cell_off;      // reuse (build is finished)
+    {
+        LaunchScope ls(h, TC_TREEWALK, 3);
+        shard_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.perm, (uint32_t)b, (uint32_t)e, flag);
+        prim::exclusive_scan_u32(h->stream, flag, pos, n, (uint32_t*)T.scan_tmp);
+        shard_list_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, flag, pos, T.shard_list);
+    }
+    CU_TRY(h, cudaGetLastError());
+    *list = T.shard_list; *n_work = e - b;
+    return REBCU_OK;
+}
+
 int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     // gravity.c:56.  Every rank holds all positions at this point (they were exchanged after the drift), and
     // the replicated tree needs all of them wrapped, so the check covers the full range on every rank.
-    const int rank = h->rank, world = h->world;
-    const uint64_t n_before = h->N;
-    h->rank = 0; h->world = 1;
-    int err = boundary_check(h, c);
-    h->rank = rank; h->world = world;
+    int err = boundary_check_full(h, c);
     if (err) return err;
-    if (world > 1 && h->N != n_before)
-        return rebcu_fail(h, REBCU_ERR_ARG, "open-boundary removal while sharded over several GPUs needs a full-state exchange (not implemented)");
     err = tree_build(h, c);                               // gravity.c:63-71
     if (err) return err;
     const uint64_t n = h->N;
@@ -611,13 +622,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     for (int d = 0; d < W_TABLE; d++) { a.w2[d] = w * w; w = w / 2.; }
     if (h->world > 1) {
         // walk only the particles of this rank's index block, visited in key order
-        uint64_t b, e; engine_shard(h, &b, &e);
-        uint32_t* flag = T.cell_cnt; uint32_t* pos = T.cell_off;      // reuse (build is finished)
-        LaunchScope ls(h, TC_TREEWALK, 3);
-        shard_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.perm, (uint32_t)b, (uint32_t)e, flag);
-        prim::exclusive_scan_u32(h->stream, flag, pos, n, (uint32_t*)T.scan_tmp);
-        shard_list_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, flag, pos, T.shard_list);
-        a.list = T.shard_list; a.n_work = e - b;
+        if ((err = tree_shard_list(h, &a.list, &a.n_work))) return err;
     }
     if (a.n_work) {
         LaunchScope ls(h, TC_TREEWALK);

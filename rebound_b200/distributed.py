@@ -6,12 +6,18 @@ drift and the force evaluation every rank needs the other blocks' new positions:
 exchange step of the path -- an all-gather of x, y, z (24 B per particle), the role the reference's MPI
 build gives to reb_communication_mpi_distribute_* (src/communication_mpi.c:109-181, 354-438).
 The engine calls back into `BlockExchange.__call__` at exactly that point (rebcu_set_exchange_callback).
+Two rarer events widen the exchange (rebcu_exchange_request): a collision search also needs the other
+blocks' velocities, and an open-boundary removal needs every field, because the compaction shifts particles
+across block borders.  The collision lists themselves are merged on the host (`gather_collisions`).
 
 Everything here is plumbing on torch tensors; it runs on CPU tensors with the gloo backend as well, which
 is how tests/test_distributed_cpu.py covers it without a GPU.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import abi
 
 
 def shard_range(n, rank, world):
@@ -22,12 +28,22 @@ def shard_range(n, rank, world):
 class _DevicePtr:
     """Zero-copy torch view of a device array owned by the engine (CUDA array interface v2)."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def device_view(ptr, n, device):
-    return torch.as_tensor(_DevicePtr(ptr, n), device=device)
+def device_view(ptr, n, device, typestr="<f8"):
+    return torch.as_tensor(_DevicePtr(ptr, n, typestr), device=device)
+
+
+def exchange_fields(request):
+    """Field indices (rebcu_device_field) the exchange callback has to gather for a rebcu_exchange_request mask."""
+    if request & abi.EXCHANGE_ALL:
+        return list(range(abi.N_FIELDS))
+    fields = [0, 1, 2]
+    if request & abi.EXCHANGE_VELOCITIES:
+        fields += [3, 4, 5]
+    return fields
 
 
 class BlockExchange:
@@ -75,9 +91,12 @@ def attach(engine, device, group=None):
         # of an explicit stream to Engine) so that NCCL orders behind the drift kernel.  Views are rebuilt
         # per call: the engine may swap its SoA block (open-boundary compaction) or change N.
         n = engine.N
-        fields = [device_view(engine.device_field(k), n, device) for k in range(3)]      # x, y, z
+        ks = exchange_fields(engine.exchange_request)       # x, y, z unless a collision search / removal asks for more
+        # 64-bit integer views: a byte-exact transport also for the tag fields (name, ap, sim)
+        fields = [device_view(engine.device_field(k), n, device, "<i8") for k in ks]
         BlockExchange(fields, group)()
         state["calls"] += 1
+        state["fields"] = state.get("fields", 0) + len(ks)
 
     engine.set_exchange_callback(exchange)
     return state
@@ -89,3 +108,50 @@ def gather_owned(engine, device, group=None):
     n = engine.N
     fields = [device_view(engine.device_field(k), n, device) for k in range(9)]
     BlockExchange(fields, group)()
+
+
+def merge_collision_segments(lists, segments):
+    """The complete list in the reference's serial order from per-rank lists (rebcu_collisions_segments):
+    segment by segment (ghost box major for DIRECT/LINE, a single segment for TREE/LINETREE), ranks in
+    order inside a segment (projectile blocks are contiguous and ascending in rank)."""
+    n_seg = max((len(s) for s in segments), default=0)
+    starts = [np.concatenate([[0], np.cumsum(s)]).astype(np.int64) if len(s) else np.zeros(1, np.int64) for s in segments]
+    parts = []
+    for g in range(n_seg):
+        for r, lst in enumerate(lists):
+            if g < len(segments[r]) and segments[r][g]:
+                parts.append(lst[starts[r][g]:starts[r][g + 1]])
+    if not parts:
+        return np.zeros(0, dtype=abi.COLLISION_DTYPE)
+    return np.concatenate(parts)
+
+
+def gather_collisions(engine, device, group=None):
+    """After a sharded collision search (rebcu_collision_search / rebcu_steps): every rank receives the
+    complete collision list in the reference's serial order.  `device` is the tensor device used for the
+    transport ("cuda:k" with NCCL, "cpu" with gloo)."""
+    world = dist.get_world_size(group)
+    local = engine.collisions_fetch()
+    seg = engine.collisions_segments()
+    n_seg = torch.tensor([len(seg)], dtype=torch.int64, device=device)
+    dist.all_reduce(n_seg, op=dist.ReduceOp.MAX, group=group)
+    n_seg = int(n_seg.item())
+    mine = torch.zeros(n_seg + 1, dtype=torch.int64)
+    mine[: len(seg)] = torch.tensor(seg, dtype=torch.int64)
+    mine[n_seg] = len(local)
+    mine = mine.to(device)
+    counts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(counts, mine, group=group)
+    counts = [c.cpu().numpy() for c in counts]
+    longest = max(int(c[n_seg]) for c in counts)
+    if longest == 0:
+        return np.zeros(0, dtype=abi.COLLISION_DTYPE)
+    size = abi.COLLISION_DTYPE.itemsize
+    buf = torch.zeros(longest * size, dtype=torch.uint8)
+    if len(local):
+        buf[: len(local) * size] = torch.from_numpy(local.view(np.uint8).reshape(-1).copy())
+    buf = buf.to(device)
+    bufs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    lists = [b.cpu().numpy()[: int(c[n_seg]) * size].view(abi.COLLISION_DTYPE) for b, c in zip(bufs, counts)]
+    return merge_collision_segments(lists, [list(map(int, c[:n_seg])) for c in counts])

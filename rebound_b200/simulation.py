@@ -172,6 +172,18 @@ class Engine:
         self._keep.append(cb)
         self._check(self.f["set_exchange_callback"](self.h, C.cast(cb, C.c_void_p) if cb else None, None))
 
+    @property
+    def exchange_request(self):
+        """Bit mask of abi.EXCHANGE_*: what the exchange callback running right now has to gather."""
+        return int(self.f["exchange_request"](self.h))
+
+    def collisions_segments(self):
+        """Entries per segment of the local collision list (rebcu_collisions_segments)."""
+        counts = (C.c_uint64 * 32)()
+        n = C.c_uint64(0)
+        self._check(self.f["collisions_segments"](self.h, counts, 32, C.byref(n)))
+        return [int(counts[i]) for i in range(n.value)]
+
     def set_collision_callback(self, fn):
         cb = COLLISION_CB(lambda _u: int(fn() or 0)) if fn else None
         self._keep.append(cb)
