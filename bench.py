@@ -354,13 +354,17 @@ def main():
         # tp_multistep_kernel: ONE launch advances every test particle through all `inner` steps with x,v in
         # registers: 48 B read + 72 B written per particle per launch (x,v in; x,v,a out), DESIGN.md section 3.
         steps_in_launch = inner
-        alg_bytes = 120.0 * n
+        # 96 B per particle-step (x,v in; x,v out) x the particle-steps one launch processes.
+        alg_bytes = 96.0 * n * inner
         roof = {"bound": "hbm", "kernel": "tp_multistep_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "unit": "GB/s", "peak_source": peak_src,
+                "traffic": 67.76e6,          # dram__bytes_read + write per launch, ncu --set full (profiles/r01_ms_ncu.txt)
+                "algorithmic_bytes_per_launch": alg_bytes, "resident_state_bytes_per_launch": 120.0 * n,
                 "limiting_resource": "fp64 pipe",
-                "note": f"one launch = {inner} leapfrog steps of all particles held in registers, so HBM traffic is 120 B per "
-                        "particle per launch by construction and the kernel is bound by the FP64 pipe (strict IEEE sqrt+divide: "
-                        "36 DP instructions per interaction); see fp64.pipe_frac"}
+                "note": f"algorithmic bytes = 96 B per particle-step (SURVEY 8d) x N x {inner} steps per launch; the kernel keeps "
+                        "x,v in registers across all steps of the launch, so the DRAM traffic it really causes is 120 B per particle "
+                        "per LAUNCH (`traffic`, far below the algorithmic bytes) and what bounds it is the FP64 pipe (strict IEEE "
+                        "sqrt+divide: 36 DP instructions per interaction), see fp64.pipe_frac / fp64.frac_of_measured_peak"}
     else:
         flops = 20.0 * inter                 # 20 flop per interaction
         roof = {"bound": "hbm", "kernel": "direct_strict_kernel", "achieved": 32.0 * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -372,11 +376,15 @@ def main():
     # FP64 pipe view: interactions/s of the kernel alone x 20 flop against 148 SM x 64 DFMA/clk x 2 x clock
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    fp64_measured = eng.measure_fp64_peak()          # DFMA microbenchmark on this box, TFLOP/s
     k_inter_per_s = inter * steps_in_launch / (k_ms * 1e-3)
     dp_per_inter = 36.0 if cfg.mode == 0 else 22.0      # FP64-pipe instructions per interaction (SASS count)
     roof["fp64"] = {"achieved_tflops": 20.0 * k_inter_per_s / 1e12, "peak_tflops": fp64_peak,
                     "peak_source": "148 SM x 64 DFMA/clk x 2 flop x sampled SM clock (nominal)",
                     "frac": 20.0 * k_inter_per_s / 1e12 / fp64_peak,
+                    "measured_peak_tflops": fp64_measured,
+                    "frac_of_measured_peak": 20.0 * k_inter_per_s / 1e12 / fp64_measured,
+                    "pipe_frac_of_measured_peak": k_inter_per_s * dp_per_inter * 2.0 / 1e12 / fp64_measured,
                     "pipe_frac": k_inter_per_s * dp_per_inter / (148 * 64 * sm_mhz * 1e6),
                     "pipe_frac_note": "issued FP64-pipe instructions per lane-slot: interactions/s x DP instructions per "
                                       "interaction / (148 SM x 64 lanes x clock); 20 flop/interaction is BASELINE.md's algorithmic count"}

@@ -220,7 +220,22 @@ void rebcu_shard_range(const rebcu_handle* h, uint64_t* begin, uint64_t* end);
  * box of the innermost ring for DIRECT/LINE, a single segment otherwise). */
 int rebcu_collisions_segments(rebcu_handle* h, uint64_t* counts, uint64_t cap, uint64_t* n_segments);
 
+/* ---- diagnostics on the resident state ----------------------------------------- */
+/* reb_simulation_energy, src/tools.c:108-162: out3 = {kinetic, potential, kinetic + potential}
+ * (r->energy_offset is host state and is not added).  Uses cfg->G, N_active, testparticle_type.
+ * The reference sums into one scalar in index order; this is a compensated parallel sum: equal to
+ * ~1e-13 relative, not bit for bit. */
+int rebcu_energy(rebcu_handle* h, const rebcu_config* cfg, double* out3);
+/* reb_simulation_com, src/tools.c:376-408: out10 = {m, x, y, z, vx, vy, vz, ax, ay, az} of the centre of
+ * mass (plain sums if the total mass is not positive). */
+int rebcu_com(rebcu_handle* h, double* out10);
+/* reb_simulation_angular_momentum, src/tools.c:164-174. */
+int rebcu_angular_momentum(rebcu_handle* h, double* out3);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
+/* Sustained FP64 FMA rate of the device in TFLOP/s (2 flop per DFMA), timed with CUDA events: the
+ * measured peak bench.py reports the FP64-bound kernels against. */
+int rebcu_measure_fp64_peak(rebcu_handle* h, double* tflops);
 /* Number of kernels this handle launched since creation (bench.py's gpu_launches). */
 uint64_t rebcu_launch_count(const rebcu_handle* h);
 /* Device time in ms (CUDA events on the handle's stream) accumulated per kernel class since the

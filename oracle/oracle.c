@@ -815,6 +815,32 @@ double orc_energy(rebcu_config* c, rebcu_particle* p, uint64_t N){
     return ek + ep;
 }
 
+/* reb_simulation_com / reb_particle_com_of_pair, tools.c:376-408: out = {m,x,y,z,vx,vy,vz,ax,ay,az} */
+void orc_com(rebcu_config* c, rebcu_particle* p, uint64_t N, double* out){
+    (void)c;
+    double m=0., q[9]={0.};
+    for (uint64_t i=0;i<N;i++){
+        const double v[9] = {p[i].x,p[i].y,p[i].z,p[i].vx,p[i].vy,p[i].vz,p[i].ax,p[i].ay,p[i].az};
+        for (int k=0;k<9;k++) q[k] = q[k]*m + v[k]*p[i].m;
+        m += p[i].m;
+        if (m>0.) for (int k=0;k<9;k++) q[k] /= m;
+    }
+    out[0] = m;
+    for (int k=0;k<9;k++) out[1+k] = q[k];
+}
+
+/* reb_simulation_angular_momentum, tools.c:164-174 */
+void orc_angular_momentum(rebcu_config* c, rebcu_particle* p, uint64_t N, double* out){
+    (void)c;
+    double lx=0., ly=0., lz=0.;
+    for (uint64_t i=0;i<N;i++){
+        lx += p[i].m*(p[i].y*p[i].vz - p[i].z*p[i].vy);
+        ly += p[i].m*(p[i].z*p[i].vx - p[i].x*p[i].vz);
+        lz += p[i].m*(p[i].x*p[i].vy - p[i].y*p[i].vx);
+    }
+    out[0]=lx; out[1]=ly; out[2]=lz;
+}
+
 int orc_openmp_threads(void){
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

@@ -247,6 +247,23 @@ double refh_energy(rebcu_config* c, rebcu_particle* p, uint64_t N){
     return e;
 }
 
+/* reb_simulation_com (tools.c:410): out = {m,x,y,z,vx,vy,vz,ax,ay,az}. */
+void refh_com(rebcu_config* c, rebcu_particle* p, uint64_t N, double* out){
+    struct reb_simulation* r = make_sim(c, p, N);
+    struct reb_particle com = reb_simulation_com(r);
+    out[0]=com.m; out[1]=com.x; out[2]=com.y; out[3]=com.z; out[4]=com.vx; out[5]=com.vy; out[6]=com.vz;
+    out[7]=com.ax; out[8]=com.ay; out[9]=com.az;
+    reb_simulation_free(r);
+}
+
+/* reb_simulation_angular_momentum (tools.c:164). */
+void refh_angular_momentum(rebcu_config* c, rebcu_particle* p, uint64_t N, double* out){
+    struct reb_simulation* r = make_sim(c, p, N);
+    struct reb_vec3d L = reb_simulation_angular_momentum(r);
+    out[0]=L.x; out[1]=L.y; out[2]=L.z;
+    reb_simulation_free(r);
+}
+
 static size_t dump_cell(const struct reb_treecell* node, int depth, int rootbox,
                         rebcu_treecell* out, uint64_t cap, size_t idx){
     size_t me = idx;

@@ -139,6 +139,8 @@ CHECKER_SIGNATURES = {
     "collision_search": (C.c_int, [_CFG, _P, C.c_uint64, _P, C.c_uint64, _U64P]),
     "steps": (C.c_int, [_CFG, _P, _U64P, C.c_uint64, C.c_int, C.c_double, _DBLP]),
     "energy": (C.c_double, [_CFG, _P, C.c_uint64]),
+    "com": (None, [_CFG, _P, C.c_uint64, _DBLP]),
+    "angular_momentum": (None, [_CFG, _P, C.c_uint64, _DBLP]),
     "tree_dump": (C.c_int, [_CFG, _P, C.c_uint64, _P, C.c_uint64, _U64P]),
     "last_error": (C.c_char_p, []),
     "openmp_threads": (C.c_int, []),
@@ -179,6 +181,10 @@ PRODUCT_SIGNATURES = {
     "exchange_request": (C.c_int, [_P]),
     "collisions_segments": (C.c_int, [_P, _U64P, C.c_uint64, _U64P]),
     "set_collision_callback": (C.c_int, [_P, _P, _P]),
+    "energy": (C.c_int, [_P, _CFG, _DBLP]),
+    "com": (C.c_int, [_P, _DBLP]),
+    "angular_momentum": (C.c_int, [_P, _DBLP]),
+    "measure_fp64_peak": (C.c_int, [_P, _DBLP]),
     "launch_count": (C.c_uint64, [_P]),
     "timing_enable": (C.c_int, [_P, C.c_int]),
     "timing_read": (C.c_int, [_P, _DBLP, _U64P, C.c_int]),

@@ -189,6 +189,29 @@ class Engine:
         self._keep.append(cb)
         self._check(self.f["set_collision_callback"](self.h, C.cast(cb, C.c_void_p) if cb else None, None))
 
+    # diagnostics on the resident state
+    def energy(self, cfg):
+        """(kinetic, potential, total) -- reb_simulation_energy without energy_offset."""
+        out = (C.c_double * 3)()
+        self._check(self.f["energy"](self.h, C.byref(cfg), out))
+        return out[0], out[1], out[2]
+
+    def com(self):
+        """Centre of mass as a dict m, x, y, z, vx, vy, vz, ax, ay, az (reb_simulation_com)."""
+        out = (C.c_double * 10)()
+        self._check(self.f["com"](self.h, out))
+        return dict(zip(("m", "x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az"), out))
+
+    def angular_momentum(self):
+        out = (C.c_double * 3)()
+        self._check(self.f["angular_momentum"](self.h, out))
+        return out[0], out[1], out[2]
+
+    def measure_fp64_peak(self):
+        out = C.c_double(0)
+        self._check(self.f["measure_fp64_peak"](self.h, C.byref(out)))
+        return out.value
+
     # instrumentation
     @property
     def launch_count(self):
@@ -340,6 +363,21 @@ class Simulation:
     def collision_search(self):
         self._to_device()
         return self._engine.collision_search(self._cfg)
+
+    def energy(self):
+        """reb_simulation_energy (src/tools.c:108-162), evaluated on the device."""
+        self._to_device()
+        return self._engine.energy(self._cfg)[2]
+
+    def com(self):
+        """reb_simulation_com (src/tools.c:401-408), evaluated on the device."""
+        self._to_device()
+        return self._engine.com()
+
+    def angular_momentum(self):
+        """reb_simulation_angular_momentum (src/tools.c:164-174), evaluated on the device."""
+        self._to_device()
+        return self._engine.angular_momentum()
 
     def tree(self):
         self._to_device()

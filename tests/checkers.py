@@ -87,6 +87,18 @@ class Checker:
         c = cfg.copy()
         return self.f["energy"](C.byref(c), abi.as_ptr(p), len(p))
 
+    def com(self, cfg, p):
+        p = p.copy()
+        out = (C.c_double * 10)()
+        self.f["com"](C.byref(cfg.copy()), abi.as_ptr(p), len(p), out)
+        return dict(zip(("m", "x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az"), out))
+
+    def angular_momentum(self, cfg, p):
+        p = p.copy()
+        out = (C.c_double * 3)()
+        self.f["angular_momentum"](C.byref(cfg.copy()), abi.as_ptr(p), len(p), out)
+        return out[0], out[1], out[2]
+
     def tree_dump(self, cfg, p):
         p = p.copy()
         c = cfg.copy()

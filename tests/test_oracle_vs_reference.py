@@ -246,3 +246,13 @@ def test_line_collision_list_bitwise(name, cfg, p):
     orc = checkers.oracle().collision_search(cfg, p)
     assert len(ref) > 0
     assert checkers.collisions_equal(ref, orc, with_ri=(cfg.collision == abi.COLLISION_LINETREE))
+
+
+def test_com_and_angular_momentum():
+    """reb_simulation_com / reb_simulation_angular_momentum (src/tools.c:164-174, 376-408)."""
+    for p, cfg in ((ics.plummer(777, seed=3), ics.plummer_config(777)),
+                   (ics.planetesimal_disk(300, seed=4), ics.planetesimal_config())):
+        p = p.copy()
+        p["ax"] = np.linspace(-1, 1, len(p))
+        assert checkers.reference().com(cfg, p) == checkers.oracle().com(cfg, p)
+        assert checkers.reference().angular_momentum(cfg, p) == checkers.oracle().angular_momentum(cfg, p)
