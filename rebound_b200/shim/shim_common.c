@@ -32,6 +32,14 @@ struct shim_state* shim_get(struct reb_simulation* r){
     return s;
 }
 
+struct shim_state* shim_find(struct reb_simulation* r){
+    pthread_mutex_lock(&table_lock);
+    struct shim_state* s = NULL;
+    for (int i=0;i<table_n;i++) if (table[i].r==r){ s = &table[i]; break; }
+    pthread_mutex_unlock(&table_lock);
+    return s;
+}
+
 void shim_forget(struct reb_simulation* r){
     pthread_mutex_lock(&table_lock);
     for (int i=0;i<table_n;i++) if (table[i].r==r){

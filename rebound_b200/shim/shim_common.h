@@ -33,6 +33,8 @@ struct shim_state {
 /* Returns the per-simulation state (creating the rebcu handle on first use); NULL + reb_simulation_error
  * if no CUDA device is usable -- there is no CPU fallback for the replaced functions. */
 struct shim_state* shim_get(struct reb_simulation* r);
+/* The state if this simulation has one, else NULL (never creates a handle, never raises). */
+struct shim_state* shim_find(struct reb_simulation* r);
 void shim_forget(struct reb_simulation* r);
 
 /* 1 if REBOUND_B200_RESIDENT=1: the leapfrog / SEI steps keep particles in HBM between steps and set

@@ -22,6 +22,17 @@ static double restitution_bridges(const struct reb_simulation* const r, double v
 static int heartbeat_calls = 0;
 static void heartbeat(struct reb_simulation* r){ (void)r; heartbeat_calls++; }
 
+/* "archive" scenario: diagnostics read in the middle of a run, while a resident simulation is unsynchronised */
+static double mid_energy = 0., mid_com_x = 0., mid_Lz = 0.;
+static void heartbeat_mid(struct reb_simulation* r){
+    heartbeat_calls++;
+    if (r->steps_done==3){
+        mid_energy = reb_simulation_energy(r);
+        mid_com_x = reb_simulation_com(r).x;
+        mid_Lz = reb_simulation_angular_momentum(r).z;
+    }
+}
+
 int main(int argc, char** argv){
     if (argc<3){ fprintf(stderr, "usage: %s scenario outfile [N] [steps]\n", argv[0]); return 2; }
     const char* scen = argv[1];
@@ -29,7 +40,8 @@ int main(int argc, char** argv){
     int steps = argc>4 ? atoi(argv[4]) : 5;
     struct reb_simulation* r = reb_simulation_create();
     r->rand_seed = 42;
-    if (strcmp(scen, "plummer")==0 || strcmp(scen, "plummer_comp")==0){
+    char sa_file[4096] = {0};
+    if (strcmp(scen, "plummer")==0 || strcmp(scen, "plummer_comp")==0 || strcmp(scen, "archive")==0){
         /* examples/selfgravity_plummer/problem.c */
         double M=1, R=1, E=3./64.*M_PI*M*M/R, r0=16./(3.*M_PI)*R;
         double t0 = r->G*pow(M,5./2.)*pow(4.*E,-3./2.)*(double)N/log(0.4*(double)N);
@@ -39,6 +51,13 @@ int main(int argc, char** argv){
         reb_simulation_add_plummer(r, N, M, R);
         reb_simulation_move_to_com(r);
         r->heartbeat = heartbeat;
+        if (strcmp(scen, "archive")==0){
+            /* Simulationarchive snapshot every 2 steps, written from inside reb_simulation_steps */
+            snprintf(sa_file, sizeof(sa_file), "%s.sa", argv[2]);
+            remove(sa_file);
+            reb_simulation_save_to_file_step(r, sa_file, 2);
+            r->heartbeat = heartbeat_mid;
+        }
     }else if (strcmp(scen, "testparticles")==0){
         reb_simulation_set_integrator(r, "leapfrog");
         r->dt = 1e-2;
@@ -96,6 +115,19 @@ int main(int argc, char** argv){
     double hdr[6] = {(double)r->N, r->t, (double)r->collisions_log_n, r->collisions_plog, (double)r->status, (double)heartbeat_calls};
     fwrite(hdr, sizeof(double), 6, f);
     for (size_t i=0;i<r->N;i++) fwrite(&r->particles[i], sizeof(double), 11, f);
+    if (sa_file[0]){
+        /* restart from the snapshot taken after 2 steps and run to the same step count: must land on the same bits
+         * (python_tests/test_simulationarchive.py:610-630) */
+        struct reb_simulation* r2 = reb_simulation_create_from_file(sa_file, 1);
+        if (!r2) return 4;
+        const double restart_steps_done = (double)r2->steps_done;
+        reb_simulation_steps(r2, (size_t)steps - (size_t)r2->steps_done);
+        double tail[6] = {(double)r2->N, r2->t, restart_steps_done, mid_energy, mid_com_x, mid_Lz};
+        fwrite(tail, sizeof(double), 6, f);
+        for (size_t i=0;i<r2->N;i++) fwrite(&r2->particles[i], sizeof(double), 11, f);
+        reb_simulation_free(r2);
+        remove(sa_file);
+    }
     fclose(f);
     printf("%s N=%zu t=%.17g collisions=%lld\n", scen, r->N, r->t, (long long)r->collisions_log_n);
     reb_simulation_free(r);

@@ -33,3 +33,19 @@ def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
     got = run("driver_dropin", scen, n, steps, tmp_path, env={"REBOUND_B200_RESIDENT": resident})
     assert len(ref) == len(got)
     assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("resident", ["0", "1"], ids=["host_authoritative", "resident"])
+def test_dropin_archive_restart_and_midrun_diagnostics(resident, tmp_path):
+    """Simulationarchive snapshots written from inside reb_simulation_steps, and energy / COM /
+    angular momentum read from a heartbeat, see the current particles also while a resident simulation is
+    unsynchronised; restarting from a snapshot lands on the same bits as the uninterrupted run."""
+    n, steps = 800, 7
+    ref = run("driver_ref", "archive", n, steps, tmp_path)
+    got = run("driver_dropin", "archive", n, steps, tmp_path, env={"REBOUND_B200_RESIDENT": resident})
+    assert len(ref) == len(got) == 2 * (6 + 11 * n)
+    assert np.array_equal(ref, got)
+    direct, restart = got[6:6 + 11 * n], got[12 + 11 * n:]
+    assert np.array_equal(direct, restart)
+    tail = got[6 + 11 * n:12 + 11 * n].view(np.float64)
+    assert tail[0] == n and tail[2] == 2.0 and tail[3] != 0.0       # restarted from the snapshot after 2 steps
