@@ -306,3 +306,30 @@ def test_line_and_linetree_collision_lists_bitwise(eng):
         got = eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p))
         assert len(want) > 0 and len(got) == len(want), name
         assert collisions_equal(got, want, with_ri=(cfg.collision == abi.COLLISION_LINETREE)), name
+
+
+def _pair_keys(col):
+    """(p1, p2, ghost shift) of every entry as sortable rows."""
+    k = np.stack([col["p1"].astype(np.float64), col["p2"].astype(np.float64), col["gb_x"], col["gb_y"], col["gb_vy"]], axis=1)
+    return k[np.lexsort(k.T[::-1])]
+
+
+def test_sheet_full_size_tree_and_direct_searches_agree(eng):
+    """Config C5 recipe at N ~ 2^18 (beyond what the CPU oracle does in seconds): a size-independent property --
+    the tree search and the all-pairs search report the same set of (p1, p2, ghost box) entries, every entry
+    appears in both directions unless a ghost shift separates them, and the lists are reproducible."""
+    root = 1327.5                       # 2x2 root boxes of this size hold ~2^18 particles (ics.shearing_sheet)
+    p = ics.shearing_sheet(root_size=root, seed=3)
+    assert 200_000 < len(p) < 330_000
+    cfg_t = ics.shearing_sheet_config(root_size=root, t=12.5)
+    cfg_d = ics.shearing_sheet_config(root_size=root, t=12.5, collision=abi.COLLISION_DIRECT)
+    tree = eng.collision_search_host(cfg_t.copy(), p.copy())
+    direct = eng.collision_search_host(cfg_d.copy(), p.copy())
+    assert len(tree) == len(direct) > 1000
+    assert np.array_equal(_pair_keys(tree), _pair_keys(direct))
+    again = eng.collision_search_host(cfg_t.copy(), p.copy())
+    assert tree.tobytes() == again.tobytes()
+    # inside the main box (zero shift) overlap is symmetric: (i, j) present <=> (j, i) present
+    main = tree[(tree["gb_x"] == 0) & (tree["gb_y"] == 0)]
+    fwd = set(zip(main["p1"].tolist(), main["p2"].tolist()))
+    assert all((j, i) in fwd for i, j in fwd)
