@@ -18,6 +18,7 @@
 // Bound: FP64 pipe.  HBM traffic is 32 B read per source per CTA tile + 24 B written per particle.
 #include "engine.cuh"
 #include "strict_math.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -227,6 +228,120 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
     }
 }
 
+// Strict kernel for MID-SIZE problems (too few particles to give every scheduler several warps with one
+// thread per particle: C1, N = 16384, is 512 warps for 592 schedulers).  A CTA still owns 32 particles (lane =
+// particle in every warp) but spreads the sources of a tile over SPLIT_W-1 producer warps: producer w evaluates
+// the pair prefactor and the products p*dx, p*dy, p*dz for its SPLIT_T sources -- all of the sqrt/divide work -- and
+// parks them in shared memory; warp 0 then adds the parked products to the running sums in ascending source
+// order, exactly the additions (or Kahan updates) of the one-thread-per-particle kernel.  Only the 3 (12) adds per
+// term are sequential, the other ~33 FP64 instructions run on 7x more warps; the bits do not change.
+// SPLIT_W warps per CTA: 1 adder + SPLIT_W-1 producers; SPLIT_T sources per producer per tile (advanced in lock step)
+template <bool KAHAN, int SPLIT_W, int SPLIT_T>
+__global__ void __launch_bounds__(32 * SPLIT_W) direct_strict_split_kernel(const DirectArgs a) {
+    constexpr int SPLIT_TJ = (SPLIT_W - 1) * SPLIT_T;
+    __shared__ double term[2][SPLIT_TJ][3][32];
+    __shared__ double4 src[2][SPLIT_TJ];
+    __shared__ unsigned wflag[SPLIT_W][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t i0 = a.i_begin + (uint64_t)blockIdx.x * 32;
+    const uint64_t i = i0 + lane;
+    const bool valid = i < a.i_end;
+    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;
+    uint64_t ns = 0, skip0 = NO_SKIP, skip1 = NO_SKIP;
+    double pxi = 0, pyi = 0, pzi = 0;
+    if (valid) {
+        source_set(a, i, ns, skip0, skip1);
+        pxi = a.x[i]; pyi = a.y[i]; pzi = a.z[i];
+    }
+    double sx = 0, sy = 0, sz = 0, cx = 0, cy = 0, cz = 0;
+    unsigned wmax = 0;
+    const double negG = -a.G;
+    const uint64_t n_tiles = (ns_blk + SPLIT_TJ - 1) / SPLIT_TJ;
+    const int ngb = a.use_ghosts ? a.ghosts->n : 1;
+    for (int g = 0; g < ngb; g++) {
+        double xi = pxi, yi = pyi, zi = pzi;
+        if (a.use_ghosts) {
+            xi = s_add(a.ghosts->gb[g].x, pxi);
+            yi = s_add(a.ghosts->gb[g].y, pyi);
+            zi = s_add(a.ghosts->gb[g].z, pzi);
+        }
+        __syncthreads();                         // the previous ghost box is fully consumed
+        for (int jj = threadIdx.x; jj < SPLIT_TJ; jj += 32 * SPLIT_W) {
+            const uint64_t j = jj;
+            src[0][jj] = (j < ns_blk) ? make_double4(a.x[j], a.y[j], a.z[j], a.m[j]) : make_double4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        // iteration k: producers evaluate tile k into buffer k&1, the adder consumes tile k-1, warp 0 stages the
+        // sources of tile k+1; one barrier per iteration
+        for (uint64_t k = 0; k <= n_tiles; k++) {
+            const int b = (int)(k & 1);
+            if (w > 0) {
+                if (k < n_tiles) {
+                    const int j0 = (w - 1) * SPLIT_T;
+                    double dx[SPLIT_T], dy[SPLIT_T], dz[SPLIT_T], r2[SPLIT_T], r[SPLIT_T], bb[SPLIT_T], q[SPLIT_T], m[SPLIT_T];
+#pragma unroll
+                    for (int u = 0; u < SPLIT_T; u++) {
+                        const double4 sj = src[b][j0 + u];
+                        dx[u] = s_sub(xi, sj.x); dy[u] = s_sub(yi, sj.y); dz[u] = s_sub(zi, sj.z); m[u] = sj.w;
+                    }
+#pragma unroll
+                    for (int u = 0; u < SPLIT_T; u++) r2[u] = s_add(s_add(s_add(s_mul(dx[u], dx[u]), s_mul(dy[u], dy[u])), s_mul(dz[u], dz[u])), a.soft2);
+#pragma unroll
+                    for (int u = 0; u < SPLIT_T; u++) {
+                        const uint64_t j = k * SPLIT_TJ + j0 + u;
+                        if ((j < ns) & (j != skip0) & (j != skip1)) wmax = max(wmax, strict_window_key(r2[u]));
+                    }
+                    fsqrt_rn_w_vec<SPLIT_T>(r2, r);
+#pragma unroll
+                    for (int u = 0; u < SPLIT_T; u++) bb[u] = KAHAN ? s_mul(r2[u], r[u]) : s_mul(s_mul(r[u], r[u]), r[u]);
+                    fdiv_rn_w_vec<SPLIT_T>(KAHAN ? a.G : negG, bb, q);
+#pragma unroll
+                    for (int u = 0; u < SPLIT_T; u++) {
+                        const double p = KAHAN ? s_mul(-q[u], m[u]) : s_mul(q[u], m[u]);
+                        term[b][j0 + u][0][lane] = s_mul(p, dx[u]);
+                        term[b][j0 + u][1][lane] = s_mul(p, dy[u]);
+                        term[b][j0 + u][2][lane] = s_mul(p, dz[u]);
+                    }
+                }
+            } else {
+                if (k + 1 < n_tiles) {
+                    for (int jj = lane; jj < SPLIT_TJ; jj += 32) {
+                        const uint64_t j = (k + 1) * SPLIT_TJ + jj;
+                        src[b ^ 1][jj] = (j < ns_blk) ? make_double4(a.x[j], a.y[j], a.z[j], a.m[j]) : make_double4(0, 0, 0, 0);
+                    }
+                }
+                if (k >= 1) {
+                    const uint64_t t0 = (k - 1) * SPLIT_TJ;
+#pragma unroll 4
+                    for (int jj = 0; jj < SPLIT_TJ; jj++) {
+                        const uint64_t j = t0 + jj;
+                        if (!((j < ns) & (j != skip0) & (j != skip1))) continue;
+                        const double tx = term[b ^ 1][jj][0][lane], ty = term[b ^ 1][jj][1][lane], tz = term[b ^ 1][jj][2][lane];
+                        if (!KAHAN) {
+                            sx = s_add(sx, tx); sy = s_add(sy, ty); sz = s_add(sz, tz);
+                        } else {
+                            double y, t;
+                            y = s_sub(tx, cx); t = s_add(sx, y); cx = s_sub(s_sub(t, sx), y); sx = t;
+                            y = s_sub(ty, cy); t = s_add(sy, y); cy = s_sub(s_sub(t, sy), y); sy = t;
+                            y = s_sub(tz, cz); t = s_add(sz, y); cz = s_sub(s_sub(t, sz), y); sz = t;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    wflag[w][lane] = wmax;
+    __syncthreads();
+    if (w == 0 && valid) {
+        unsigned wm = 0;
+#pragma unroll
+        for (int q = 1; q < SPLIT_W; q++) wm = max(wm, wflag[q][lane]);
+        if (wm >= STRICT_WINDOW_LIMIT) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, sx, sy, sz);
+        a.ax[i] = sx; a.ay[i] = sy; a.az[i] = sz;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FAST
 // ------------------------------------------------------------------------------------------------
@@ -310,6 +425,19 @@ __global__ void zero3_kernel(double* ax, double* ay, double* az, uint64_t b, uin
 template <bool KAHAN>
 void launch_strict(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
     // Spread small problems over all 148 SMs: one warp per CTA until there are >= 2 CTAs per SM.
+    // Mid-size problems: too few particles to keep the FP64 pipe busy with one thread per particle, so the sources
+    // of a tile are spread over producer warps (direct_strict_split_kernel).  Measured on B200, Plummer sphere,
+    // split vs one-thread-per-particle: BASIC N=1024 0.036 vs 0.114 ms, 4096 0.13 vs 0.44, 16384 1.04 vs 1.75,
+    // 32768 3.58 vs 4.26, 49152 8.2 vs 7.2 (crossover); COMPENSATED 16384 1.67 vs 2.11, 24576 4.1 vs 2.6 (the
+    // Kahan update makes the adder's dependent chain four times longer, so it crosses over earlier).
+    const uint64_t split_max = KAHAN ? 20480 : 40960;
+    if (a.windowed && a.Na >= 256 && n_i < split_max) {
+        // 1 adder + 3 producer warps, 8 sources per producer in lock step: fastest of the (W, T) shapes that fit
+        // 48 KB of static shared memory (N = 16384: (4,8) 1.06 ms, (4,4) 1.11, (8,4) 1.18, (6,6) 1.33, (12,2) 1.47,
+        // (8,2) 1.84)
+        direct_strict_split_kernel<KAHAN, 4, 8><<<div_up(n_i, 32), 128, 0, h->stream>>>(a);
+        return;
+    }
     if (n_i >= 148ull * 128 * 2) direct_strict_kernel<KAHAN, 128, 1><<<div_up(n_i, 128), 128, 0, h->stream>>>(a);
     else if (n_i >= 148ull * 64 * 2) direct_strict_kernel<KAHAN, 64, 2><<<div_up(n_i, 64), 64, 0, h->stream>>>(a);
     else direct_strict_kernel<KAHAN, 32, 4><<<div_up(n_i, 32), 32, 0, h->stream>>>(a);

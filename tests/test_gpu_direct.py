@@ -47,6 +47,16 @@ def direct_cases():
     for terms in (1, 2):
         for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
             yield f"ignore{terms}_g{grav}", ics.plummer_config(1000, gravity_ignore_terms=terms, gravity=grav), p
+    # N_active in the range of the producer/adder split kernel (256 <= N_active, N < 40960): ragged source
+    # ranges per particle (type 1: actives see everybody, test particles see the actives only)
+    pa = ics.plummer(2500, seed=6)
+    for typ in (0, 1):
+        for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
+            yield f"nactive700_t{typ}_g{grav}", ics.plummer_config(2500, N_active=700, testparticle_type=typ, gravity=grav), pa
+    yield "nactive700_ignore2", ics.plummer_config(2500, N_active=700, testparticle_type=1, gravity_ignore_terms=2), pa
+    yield "n257", ics.plummer_config(257), ics.plummer(257, seed=7)
+    yield "n40959", ics.plummer_config(40959), ics.plummer(40959, seed=8)
+    yield "n40961", ics.plummer_config(40961), ics.plummer(40961, seed=8)
     q = ics.planetesimal_disk(50, seed=4)
     q["m"][1:] = 1e-6
     yield "nactive1_ignore1", ics.planetesimal_config(N_active=1, testparticle_type=1, gravity_ignore_terms=1), q
