@@ -61,7 +61,9 @@ static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_s
     r->OMEGAZ = c.OMEGAZ;
     r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
     s->host_stale = 1;
-    if (shim_resident_mode()){
+    /* run_heartbeat (src/simulation.c:240-274) scans r->particles after every step when an exit distance is set:
+     * such simulations are kept host-current even in resident mode */
+    if (shim_resident_mode() && !r->exit_max_distance && !r->exit_min_distance){
         r->N = rebcu_N(s->h);            /* tree gravity + open boundary may have removed particles */
         s->uploaded_N = r->N;
         r->is_synchronized = 0;
