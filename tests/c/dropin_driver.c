@@ -10,6 +10,7 @@
 #include <string.h>
 #include <math.h>
 #include "rebound.h"
+#include "integrator_leapfrog.h"
 
 static double restitution_bridges(const struct reb_simulation* const r, double v){
     (void)r;                                   /* examples/shearing_sheet/problem.c:96-103 */
@@ -105,6 +106,63 @@ int main(int argc, char** argv){
             pt.r = radius; pt.m = 400.*4./3.*M_PI*radius*radius*radius;
             reb_simulation_add(r, pt);
             mass += pt.m;
+        }
+    }else if (strncmp(scen, "lf", 2)==0 && strlen(scen)==3){
+        /* higher-order leapfrog (integrator_leapfrog.c:101-208): lf4, lf6, lf8 */
+        double M=1, R=1, E=3./64.*M_PI*M*M/R, r0=16./(3.*M_PI)*R;
+        double t0 = r->G*pow(M,5./2.)*pow(4.*E,-3./2.)*(double)N/log(0.4*(double)N);
+        reb_simulation_set_integrator(r, "leapfrog");
+        ((struct reb_integrator_leapfrog_state*)r->integrator.state)->order = (unsigned int)(scen[2]-'0');
+        r->dt = 2e-4*t0; r->softening = 0.01*r0;
+        reb_simulation_add_plummer(r, N, M, R);
+    }else if (strcmp(scen, "tp0")==0){
+        /* examples/solar_system_with_testparticles: massless planetesimals, testparticle_type 0 */
+        reb_simulation_set_integrator(r, "leapfrog");
+        r->dt = 1e-2;
+        struct reb_particle star = {0}; star.m = 1; reb_simulation_add(r, star);
+        for (int i=1;i<10;i++) reb_simulation_add_fmt(r, "m a", 1e-4*i, (double)i);
+        r->N_active = 10; r->testparticle_type = 0;
+        for (int i=0;i<N;i++) reb_simulation_add_fmt(r, "a e omega f", reb_random_uniform(r,0.4,20.), reb_random_uniform(r,0.01,0.2),
+                                                     reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,2.*M_PI));
+    }else if (strcmp(scen, "merge")==0 || strcmp(scen, "line")==0){
+        /* a cold cloud of big particles: DIRECT search + merging (collision.c:64-124, 674-737), or the LINE search
+         * with hard-sphere bounces (collision.c:125-196) */
+        reb_simulation_set_integrator(r, "leapfrog");
+        r->gravity = REB_GRAVITY_BASIC; r->dt = 2e-2; r->softening = 0.01;
+        if (strcmp(scen, "merge")==0){ r->collision = REB_COLLISION_DIRECT; r->collision_resolve = reb_collision_resolve_merge; }
+        else { r->collision = REB_COLLISION_LINE; r->collision_resolve = reb_collision_resolve_hardsphere; }
+        for (int i=0;i<N;i++){
+            struct reb_particle pt = {0};
+            pt.x = reb_random_uniform(r,-1.,1.); pt.y = reb_random_uniform(r,-1.,1.); pt.z = reb_random_uniform(r,-1.,1.);
+            pt.vx = reb_random_normal(r, 0.05); pt.vy = reb_random_normal(r, 0.05); pt.vz = reb_random_normal(r, 0.05);
+            pt.m = 1./(double)N; pt.r = 0.4*pow((double)N, -1./3.)*reb_random_uniform(r, 0.5, 1.);
+            reb_simulation_add(r, pt);
+        }
+    }else if (strcmp(scen, "periodic")==0){
+        /* tree gravity in a periodic box with one ring of ghost boxes, 2x2x1 root boxes */
+        reb_simulation_set_integrator(r, "leapfrog");
+        r->gravity = REB_GRAVITY_TREE; r->boundary = REB_BOUNDARY_PERIODIC; r->opening_angle2 = 0.3;
+        r->softening = 0.05; r->dt = 5e-2;
+        r->root_size = 4.; r->N_root_x = 2; r->N_root_y = 2; r->N_root_z = 1;
+        r->N_ghost_x = 1; r->N_ghost_y = 1; r->N_ghost_z = 1;
+        for (int i=0;i<N;i++){
+            struct reb_particle pt = {0};
+            pt.x = reb_random_uniform(r,-4.,4.); pt.y = reb_random_uniform(r,-4.,4.); pt.z = reb_random_uniform(r,-2.,2.);
+            pt.vx = reb_random_normal(r, 1.); pt.vy = reb_random_normal(r, 1.); pt.vz = reb_random_normal(r, 1.);
+            pt.m = 1./(double)N;
+            reb_simulation_add(r, pt);
+        }
+    }else if (strcmp(scen, "open_direct")==0){
+        /* direct gravity in an open box: fast particles leave and are removed (boundary.c:44-77) */
+        reb_simulation_set_integrator(r, "leapfrog");
+        r->gravity = REB_GRAVITY_BASIC; r->boundary = REB_BOUNDARY_OPEN; r->softening = 0.05; r->dt = 5e-2;
+        r->root_size = 6.;
+        for (int i=0;i<N;i++){
+            struct reb_particle pt = {0};
+            pt.x = reb_random_uniform(r,-2.,2.); pt.y = reb_random_uniform(r,-2.,2.); pt.z = reb_random_uniform(r,-2.,2.);
+            pt.vx = reb_random_normal(r, 3.); pt.vy = reb_random_normal(r, 3.); pt.vz = reb_random_normal(r, 3.);
+            pt.m = 1./(double)N;
+            reb_simulation_add(r, pt);
         }
     }else{ fprintf(stderr, "unknown scenario %s\n", scen); return 2; }
 

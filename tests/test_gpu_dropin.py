@@ -13,7 +13,9 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.exists(os.path.join(DROPIN, "driver_dropin")),
                                  reason="rebound_b200/_dropin not built (needs the reference sources at build time)")]
 
-SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8), ("sheet", 25, 400)]
+SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8), ("sheet", 25, 400),
+             ("lf4", 700, 3), ("lf6", 700, 3), ("lf8", 700, 2), ("tp0", 3000, 6), ("merge", 400, 30), ("line", 400, 30),
+             ("periodic", 1500, 6), ("open_direct", 1200, 12)]
 
 
 def run(binary, scen, n, steps, tmp_path, env=None):
