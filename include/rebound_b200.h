@@ -141,6 +141,10 @@ int rebcu_upload(rebcu_handle* h, const rebcu_particle* particles, uint64_t N);
 int rebcu_download(rebcu_handle* h, rebcu_particle* particles, uint64_t N);
 /* Only ax,ay,az are written back (what a gravity routine produces). */
 int rebcu_download_acc(rebcu_handle* h, rebcu_particle* particles, uint64_t N);
+/* The Kahan compensation terms of the last REB_GRAVITY_COMPENSATED force evaluation, laid out as the
+ * reference's r->gravity_cs (struct reb_vec3d[N], src/gravity.c:293-306): IAS15 reads them
+ * (src/integrator_ias15.c:337-343).  Bit-identical in STRICT mode. */
+int rebcu_download_gravity_cs(rebcu_handle* h, double* out_xyz, uint64_t N);
 uint64_t rebcu_N(const rebcu_handle* h);
 /* Device pointer of one resident SoA field (0..10 = x,y,z,vx,vy,vz,ax,ay,az,m,r as doubles;
  * 11..13 = name, ap, sim as 64-bit words), for torch.distributed plumbing; length rebcu_N(h). */

@@ -101,7 +101,7 @@ static void gravity_basic(const rebcu_config* c, rebcu_particle* p, uint64_t N){
     free(gbs);
 }
 
-static void gravity_compensated(const rebcu_config* c, rebcu_particle* p, uint64_t N){
+static void gravity_compensated(const rebcu_config* c, rebcu_particle* p, uint64_t N, double* cs_out){
     const double G = c->G;
     const double soft2 = c->softening*c->softening;
 #pragma omp parallel for schedule(dynamic,64)
@@ -125,6 +125,7 @@ static void gravity_compensated(const rebcu_config* c, rebcu_particle* p, uint64
             }
         }
         p[i].ax = s[0]; p[i].ay = s[1]; p[i].az = s[2];
+        if (cs_out){ cs_out[3*i] = e[0]; cs_out[3*i+1] = e[1]; cs_out[3*i+2] = e[2]; }   /* r->gravity_cs[i] */
     }
 }
 
@@ -412,7 +413,7 @@ static int update_acceleration(rebcu_config* c, rebcu_particle* p, uint64_t* Np)
             for (uint64_t i=0;i<*Np;i++){ p[i].ax=0; p[i].ay=0; p[i].az=0; }
             return 0;
         case REBCU_GRAVITY_BASIC: gravity_basic(c, p, *Np); return 0;
-        case REBCU_GRAVITY_COMPENSATED: gravity_compensated(c, p, *Np); return 0;
+        case REBCU_GRAVITY_COMPENSATED: gravity_compensated(c, p, *Np, NULL); return 0;
         case REBCU_GRAVITY_TREE: return gravity_tree(c, p, Np);
         default: return orc_fail(REBCU_ERR_ARG, "Gravity calculation not yet implemented.");
     }
@@ -421,6 +422,14 @@ static int update_acceleration(rebcu_config* c, rebcu_particle* p, uint64_t* Np)
 int orc_gravity(rebcu_config* c, rebcu_particle* p, uint64_t* N){
     orc_errbuf[0]=0;
     return update_acceleration(c, p, N);
+}
+
+/* Force evaluation that also returns r->gravity_cs (3 doubles per particle); COMPENSATED only. */
+int orc_gravity_cs(rebcu_config* c, rebcu_particle* p, uint64_t* N, double* cs_out){
+    orc_errbuf[0]=0;
+    if (c->gravity!=REBCU_GRAVITY_COMPENSATED){ snprintf(orc_errbuf, sizeof(orc_errbuf), "gravity_cs needs REB_GRAVITY_COMPENSATED"); return -2; }
+    gravity_compensated(c, p, *N, cs_out);
+    return 0;
 }
 
 int orc_gravity_timed(rebcu_config* c, rebcu_particle* p, uint64_t* N, int n_evals, double* sec){

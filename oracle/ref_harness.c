@@ -127,6 +127,17 @@ int refh_gravity(rebcu_config* c, rebcu_particle* p, uint64_t* N){
     return err;
 }
 
+/* Force evaluation that also returns r->gravity_cs (src/gravity.c:293-306), 3 doubles per particle. */
+int refh_gravity_cs(rebcu_config* c, rebcu_particle* p, uint64_t* N, double* cs_out){
+    struct reb_simulation* r = make_sim(c, p, *N);
+    reb_simulation_update_acceleration(r);
+    int err = collect_error(r);
+    if (!err && r->gravity_cs) memcpy(cs_out, r->gravity_cs, r->N*sizeof(struct reb_vec3d));
+    copy_back(r, c, p, N);
+    reb_simulation_free(r);
+    return err;
+}
+
 /* Repeats the force evaluation n times (timing); returns seconds per evaluation in *sec. */
 int refh_gravity_timed(rebcu_config* c, rebcu_particle* p, uint64_t* N, int n_evals, double* sec){
     struct reb_simulation* r = make_sim(c, p, *N);

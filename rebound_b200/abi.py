@@ -134,6 +134,7 @@ _DBLP = C.POINTER(C.c_double)
 CHECKER_SIGNATURES = {
     "gravity": (C.c_int, [_CFG, _P, _U64P]),
     "gravity_timed": (C.c_int, [_CFG, _P, _U64P, C.c_int, _DBLP]),
+    "gravity_cs": (C.c_int, [_CFG, _P, _U64P, _DBLP]),
     "boundary_check": (C.c_int, [_CFG, _P, _U64P]),
     "integrator_step": (C.c_int, [_CFG, _P, _U64P]),
     "collision_search": (C.c_int, [_CFG, _P, C.c_uint64, _P, C.c_uint64, _U64P]),
@@ -161,6 +162,7 @@ PRODUCT_SIGNATURES = {
     "upload": (C.c_int, [_P, _P, C.c_uint64]),
     "download": (C.c_int, [_P, _P, C.c_uint64]),
     "download_acc": (C.c_int, [_P, _P, C.c_uint64]),
+    "download_gravity_cs": (C.c_int, [_P, _DBLP, C.c_uint64]),
     "N": (C.c_uint64, [_P]),
     "device_field": (_P, [_P, C.c_int]),
     "update_acceleration": (C.c_int, [_P, _CFG]),

@@ -34,6 +34,7 @@ struct DirectArgs {
     const GhostShifts* ghosts;   // device
     int use_ghosts;              // 0: compensated (no shift at all, gravity.c:315-317)
     int windowed;                // G inside the window of the branch-free sqrt/divide (strict_math.cuh)
+    double* csx; double* csy; double* csz;   // COMPENSATED: final Kahan compensation per particle (r->gravity_cs, gravity.c:297), else null
 };
 
 // Per-particle source range and the (at most two) excluded source indices.
@@ -52,9 +53,10 @@ __device__ __forceinline__ void source_set(const DirectArgs& a, uint64_t i, uint
 // particles whose branch-free pass met an operand outside the fast range of fsqrt_rn / fdiv_rn.
 template <bool KAHAN>
 __device__ __forceinline__ void direct_slow(const DirectArgs& a, uint64_t i, uint64_t ns, uint64_t skip0, uint64_t skip1,
-                                         double pxi, double pyi, double pzi, double& sx, double& sy, double& sz) {
+                                         double pxi, double pyi, double pzi, double& sx, double& sy, double& sz,
+                                         double& cx, double& cy, double& cz) {
     sx = sy = sz = 0;
-    double cx = 0, cy = 0, cz = 0;
+    cx = cy = cz = 0;
     const double negG = -a.G;
     const int ngb = a.use_ghosts ? a.ghosts->n : 1;
     for (int g = 0; g < ngb; g++) {
@@ -223,8 +225,9 @@ __global__ void __launch_bounds__(BLOCK) direct_strict_kernel(const DirectArgs a
         __syncthreads();
     }
     if (valid) {
-        if (A.wmax >= STRICT_WINDOW_LIMIT) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, A.sx, A.sy, A.sz);
+        if (A.wmax >= STRICT_WINDOW_LIMIT) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, A.sx, A.sy, A.sz, A.cx, A.cy, A.cz);
         a.ax[i] = A.sx; a.ay[i] = A.sy; a.az[i] = A.sz;
+        if (KAHAN && a.csx) { a.csx[i] = A.cx; a.csy[i] = A.cy; a.csz[i] = A.cz; }
     }
 }
 
@@ -337,8 +340,9 @@ __global__ void __launch_bounds__(32 * SPLIT_W) direct_strict_split_kernel(const
         unsigned wm = 0;
 #pragma unroll
         for (int q = 1; q < SPLIT_W; q++) wm = max(wm, wflag[q][lane]);
-        if (wm >= STRICT_WINDOW_LIMIT) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, sx, sy, sz);
+        if (wm >= STRICT_WINDOW_LIMIT) direct_slow<KAHAN>(a, i, ns, skip0, skip1, pxi, pyi, pzi, sx, sy, sz, cx, cy, cz);
         a.ax[i] = sx; a.ay[i] = sy; a.az[i] = sz;
+        if (KAHAN && a.csx) { a.csx[i] = cx; a.csy[i] = cy; a.csz[i] = cz; }
     }
 }
 
@@ -413,7 +417,10 @@ __global__ void __launch_bounds__(32 * W) direct_fast_kernel(const DirectArgs a)
             v = red[k][1][lane]; t = ty + v; bb = t - ty; ey += (ty - (t - bb)) + (v - bb) - red[k][4][lane]; ty = t;
             v = red[k][2][lane]; t = tz + v; bb = t - tz; ez += (tz - (t - bb)) + (v - bb) - red[k][5][lane]; tz = t;
         }
-        a.ax[i] = tx + ex; a.ay[i] = ty + ey; a.az[i] = tz + ez;
+        const double fx = tx + ex, fy = ty + ey, fz = tz + ez;
+        a.ax[i] = fx; a.ay[i] = fy; a.az[i] = fz;
+        // what the last addition lost, in the sign convention of a Kahan compensation (true sum = a - cs)
+        if (KAHAN && a.csx) { a.csx[i] = (fx - tx) - ex; a.csy[i] = (fy - ty) - ey; a.csz[i] = (fz - tz) - ez; }
     }
 }
 
@@ -488,6 +495,18 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
         int err = engine_upload_ghosts(h, &g);
         if (err) return err;
     }
+    a.csx = a.csy = a.csz = nullptr;
+    h->gravity_cs_valid = false;
+    if (kahan) {
+        if (h->gravity_cs_cap < h->cap) {
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(h->gravity_cs); h->gravity_cs = nullptr; h->gravity_cs_cap = 0;
+            CU_TRY(h, cudaMalloc(&h->gravity_cs, 3 * h->cap * sizeof(double)));
+            h->gravity_cs_cap = h->cap;
+        }
+        a.csx = h->gravity_cs; a.csy = h->gravity_cs + h->gravity_cs_cap; a.csz = h->gravity_cs + 2 * h->gravity_cs_cap;
+        h->gravity_cs_valid = true;
+    }
     const uint64_t n_i = a.i_end - a.i_begin;
     if (n_i == 0) return REBCU_OK;
     {
@@ -496,5 +515,31 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
         else { if (kahan) launch_strict<true>(h, a, n_i); else launch_strict<false>(h, a, n_i); }
     }
     CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) interleave3_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                          double* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) { out[3 * i] = x[i]; out[3 * i + 1] = y[i]; out[3 * i + 2] = z[i]; }
+}
+}  // namespace
+
+// r->gravity_cs of the last COMPENSATED force evaluation as struct reb_vec3d[N] (x,y,z interleaved).
+extern "C" int rebcu_download_gravity_cs(rebcu_handle* h, double* out_xyz, uint64_t N) {
+    if (!h->resident || !h->gravity_cs_valid) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no compensation terms: the last force evaluation was not REB_GRAVITY_COMPENSATED");
+    if (N < h->N) return rebcu_fail(h, REBCU_ERR_CAPACITY, "gravity_cs buffer too small");
+    if (h->N == 0) return REBCU_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    double* stage = (double*)h->aos;            // AoS staging block: 112 B per particle >= 24 B needed
+    {
+        LaunchScope ls(h, TC_PACK);
+        interleave3_kernel<<<div_up(h->N, 256), 256, 0, h->stream>>>(h->gravity_cs, h->gravity_cs + h->gravity_cs_cap,
+                                                                     h->gravity_cs + 2 * h->gravity_cs_cap, stage, h->N);
+    }
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(out_xyz, stage, 3 * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return REBCU_OK;
 }

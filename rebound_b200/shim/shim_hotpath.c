@@ -50,6 +50,15 @@ static void gravity_gpu(struct reb_simulation* r){
         r->did_modify_particles = 1;
     }
     r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
+    if (r->gravity==REB_GRAVITY_COMPENSATED && r->N>0){
+        /* r->gravity_cs is public state of the compensated routine (gravity.c:293-306); IAS15 reads it
+         * (integrator_ias15.c:337-343) */
+        if (r->N_allocated_gravity_cs<r->N){
+            r->gravity_cs = realloc(r->gravity_cs, r->N*sizeof(struct reb_vec3d));
+            r->N_allocated_gravity_cs = r->N;
+        }
+        shim_report(r, s, rebcu_download_gravity_cs(s->h, (double*)r->gravity_cs, r->N));
+    }
 }
 
 void reb_gravity_basic_calculate_acceleration(struct reb_simulation* r){ gravity_gpu(r); }

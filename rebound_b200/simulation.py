@@ -98,6 +98,13 @@ class Engine:
     def synchronize(self):
         self._check(self.f["synchronize"](self.h))
 
+    def download_gravity_cs(self):
+        """r->gravity_cs of the last COMPENSATED force evaluation, shape (N, 3)."""
+        n = self.N
+        out = np.zeros((max(n, 1), 3), dtype=np.float64)
+        self._check(self.f["download_gravity_cs"](self.h, out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return out[:n]
+
     def device_field(self, field):
         return self.f["device_field"](self.h, field)
 

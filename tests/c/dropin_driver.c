@@ -115,6 +115,16 @@ int main(int argc, char** argv){
         ((struct reb_integrator_leapfrog_state*)r->integrator.state)->order = (unsigned int)(scen[2]-'0');
         r->dt = 2e-4*t0; r->softening = 0.01*r0;
         reb_simulation_add_plummer(r, N, M, R);
+    }else if (strncmp(scen, "ias15", 5)==0 || strcmp(scen, "whfast")==0){
+        /* integrators outside the GPU hot path that call reb_simulation_update_acceleration: IAS15 with
+         * BASIC or COMPENSATED gravity (reads r->gravity_cs, integrator_ias15.c:337-343), WHFast (Jacobi terms stay on
+         * the reference path, the rest goes through reb_gravity_basic with gravity_ignore_terms) */
+        struct reb_particle star = {0}; star.m = 1; reb_simulation_add(r, star);
+        for (int i=0;i<N;i++) reb_simulation_add_fmt(r, "m a e omega f inc", 1e-6, reb_random_uniform(r,1.,30.), reb_random_uniform(r,0.0,0.1),
+                                                     reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,0.05));
+        reb_simulation_move_to_com(r);
+        if (strcmp(scen, "whfast")==0){ reb_simulation_set_integrator(r, "whfast"); r->dt = 0.05; }
+        else { reb_simulation_set_integrator(r, "ias15"); r->dt = 0.01; if (strcmp(scen, "ias15_comp")==0) r->gravity = REB_GRAVITY_COMPENSATED; }
     }else if (strcmp(scen, "tp0")==0){
         /* examples/solar_system_with_testparticles: massless planetesimals, testparticle_type 0 */
         reb_simulation_set_integrator(r, "leapfrog");

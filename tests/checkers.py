@@ -40,6 +40,15 @@ class Checker:
         self._check(self.f["gravity"](C.byref(c), abi.as_ptr(p), C.byref(n)))
         return p[: n.value], c
 
+    def gravity_cs(self, cfg, p):
+        """(particles, r->gravity_cs as (N,3)) after one COMPENSATED force evaluation."""
+        p = p.copy()
+        c = cfg.copy()
+        n = C.c_uint64(len(p))
+        cs = np.zeros((max(len(p), 1), 3), dtype=np.float64)
+        self._check(self.f["gravity_cs"](C.byref(c), abi.as_ptr(p), C.byref(n), cs.ctypes.data_as(C.POINTER(C.c_double))))
+        return p[: n.value], cs[: n.value]
+
     def gravity_timed(self, cfg, p, n_evals=1):
         p = p.copy()
         c = cfg.copy()

@@ -236,3 +236,31 @@ def test_planetesimal_single_steps_equal_multistep_launch(eng, mode):
     if mode == abi.MODE_STRICT:
         want, _, _ = checkers.oracle().steps(cfg, p, 6)
         assert bits_equal(a, want)
+
+
+@pytest.mark.parametrize("n", [100, 1000, 20000, 30000])
+def test_compensation_terms_bitwise(eng, n):
+    """r->gravity_cs (the running Kahan compensation, src/gravity.c:297-341; read by IAS15) through every strict
+    compensated kernel: one thread per particle (n < 256, n >= 20480) and the producer/adder split kernel."""
+    p = ics.plummer(n, seed=12)
+    cfg = ics.plummer_config(n, gravity=abi.GRAVITY_COMPENSATED)
+    want_p, want_cs = checkers.oracle().gravity_cs(cfg, p)
+    eng.upload(np.ascontiguousarray(p))
+    eng.update_acceleration(cfg.copy())
+    got_cs = eng.download_gravity_cs()
+    assert bits_equal(eng.download(), want_p)
+    assert np.array_equal(got_cs.view(np.uint64), want_cs.view(np.uint64))
+    # FAST mode: the corrected sum a - cs agrees with the strict one to the tolerance of the mode
+    c = cfg.copy()
+    c.mode = abi.MODE_FAST
+    eng.update_acceleration(c)
+    cs_fast = eng.download_gravity_cs()
+    assert np.all(np.isfinite(cs_fast)) and np.max(np.abs(cs_fast)) <= 1e-12 * np.max(np.abs(want_p["ax"]))
+
+
+def test_compensation_terms_need_a_compensated_evaluation(eng):
+    p = ics.plummer(64, seed=1)
+    eng.upload(np.ascontiguousarray(p))
+    eng.update_acceleration(ics.plummer_config(64))
+    with pytest.raises(Exception):
+        eng.download_gravity_cs()

@@ -15,7 +15,7 @@ pytestmark = [pytest.mark.gpu,
 
 SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8), ("sheet", 25, 400),
              ("lf4", 700, 3), ("lf6", 700, 3), ("lf8", 700, 2), ("tp0", 3000, 6), ("merge", 400, 30), ("line", 400, 30),
-             ("periodic", 1500, 6), ("open_direct", 1200, 12)]
+             ("periodic", 1500, 6), ("open_direct", 1200, 12), ("ias15", 300, 3), ("ias15_comp", 300, 3), ("whfast", 300, 10)]
 
 
 def run(binary, scen, n, steps, tmp_path, env=None):

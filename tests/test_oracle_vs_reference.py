@@ -256,3 +256,20 @@ def test_com_and_angular_momentum():
         p["ax"] = np.linspace(-1, 1, len(p))
         assert checkers.reference().com(cfg, p) == checkers.oracle().com(cfg, p)
         assert checkers.reference().angular_momentum(cfg, p) == checkers.oracle().angular_momentum(cfg, p)
+
+
+def test_gravity_cs_compensation_terms():
+    """r->gravity_cs after reb_gravity_compensated_calculate_acceleration (src/gravity.c:293-414), which IAS15 reads."""
+    cases = [(ics.plummer(300, seed=3), ics.plummer_config(300, gravity=abi.GRAVITY_COMPENSATED)),
+             (ics.plummer(300, seed=3), ics.plummer_config(300, gravity=abi.GRAVITY_COMPENSATED, gravity_ignore_terms=1)),
+             (ics.plummer(300, seed=3), ics.plummer_config(300, gravity=abi.GRAVITY_COMPENSATED, gravity_ignore_terms=2))]
+    for typ in (0, 1):
+        q = ics.planetesimal_disk(200, seed=4)
+        q["m"][10:] = 1e-9
+        cases.append((q, ics.planetesimal_config(testparticle_type=typ, gravity=abi.GRAVITY_COMPENSATED)))
+    for p, cfg in cases:
+        pr, cr = checkers.reference().gravity_cs(cfg, p)
+        po, co = checkers.oracle().gravity_cs(cfg, p)
+        assert bits_equal(po, pr)
+        assert np.array_equal(co.view(np.uint64), cr.view(np.uint64))
+        assert np.any(co != 0.0)
