@@ -115,14 +115,17 @@ void reb_collision_search(struct reb_simulation* const r){
     const int gpu_mode = (r->collision==REB_COLLISION_DIRECT || r->collision==REB_COLLISION_TREE
                           || r->collision==REB_COLLISION_LINE || r->collision==REB_COLLISION_LINETREE)
                        && r->map==NULL && r->N_targets==SIZE_MAX;
-    struct shim_state* s = shim_get(r);
-    if (!s) return;
+    if (r->collision==REB_COLLISION_NONE) return;               /* collision.c:52 switch: nothing to do */
     if (!gpu_mode){
-        if (shim_to_host(r, s)) return;
+        /* outside the GPU path (r->map / N_targets subsets of MERCURIUS and TRACE, unknown modes): the reference's
+         * routine on host data; a simulation that never used the GPU does not get a device context for this */
+        struct shim_state* s0 = shim_find(r);
+        if (s0){ if (shim_to_host(r, s0)) return; s0->device_valid = 0; }
         reb_collision_search_cpuref(r);
-        s->device_valid = 0;
         return;
     }
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
     r->N_collisions = 0;
     rebcu_config c;
     shim_fill_config(r, &c);

@@ -43,7 +43,7 @@ static int device_step_possible(const struct reb_simulation* r){
 
 static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_simulation*, void*), void* state){
     if (!device_step_possible(r)){
-        struct shim_state* s = shim_get(r);
+        struct shim_state* s = shim_find(r);
         if (s){ if (shim_to_host(r, s)) return; s->device_valid = 0; }
         host_step(r, state);
         return;
