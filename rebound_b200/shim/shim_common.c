@@ -50,9 +50,23 @@ void shim_forget(struct reb_simulation* r){
     pthread_mutex_unlock(&table_lock);
 }
 
-int shim_resident_mode(void){
-    const char* env = getenv("REBOUND_B200_RESIDENT");
-    return env && env[0]=='1';
+int shim_residency(void){
+    static int mode = -1;
+    if (mode<0){
+        const char* env = getenv("REBOUND_B200_RESIDENT");
+        mode = (env && env[0]=='0') ? SHIM_HOST_AUTHORITATIVE : (env && env[0]=='1') ? SHIM_RESIDENT : SHIM_AUTO;
+    }
+    return mode;
+}
+
+int shim_resident(const struct reb_simulation* r){
+    const int mode = shim_residency();
+    if (mode!=SHIM_AUTO) return mode==SHIM_RESIDENT;
+    /* Between the steps of reb_simulation_steps / reb_simulation_integrate only these can look at r->particles
+     * (run_heartbeat and reb_simulation_step, src/simulation.c:240-274, 514-603); without them nobody sees the host
+     * copy before the reb_simulation_synchronize that ends the call (:455, :511). */
+    return !r->heartbeat && !r->pre_timestep_modifications && !r->post_timestep_modifications
+        && !r->exit_max_distance && !r->exit_min_distance && !r->display_data && !r->server_data;
 }
 
 void shim_fill_config(const struct reb_simulation* r, rebcu_config* c){
@@ -105,8 +119,8 @@ static void shim_pin(struct reb_simulation* r, struct shim_state* s){
 
 int shim_to_device(struct reb_simulation* r, struct shim_state* s){
     shim_pin(r, s);
-    /* Only resident mode trusts the device copy across calls; the default mode re-uploads every time. */
-    if (shim_resident_mode() && s->device_valid && !r->did_modify_particles && s->uploaded_from==r->particles && s->uploaded_N==r->N) return 0;
+    /* Only a resident simulation trusts the device copy across calls; otherwise every call uploads. */
+    if (shim_resident(r) && s->device_valid && !r->did_modify_particles && s->uploaded_from==r->particles && s->uploaded_N==r->N) return 0;
     int err = rebcu_upload(s->h, (const rebcu_particle*)r->particles, r->N);
     if (err) return shim_report(r, s, err);
     s->uploaded_from = r->particles; s->uploaded_N = r->N;

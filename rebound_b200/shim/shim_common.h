@@ -37,9 +37,17 @@ struct shim_state* shim_get(struct reb_simulation* r);
 struct shim_state* shim_find(struct reb_simulation* r);
 void shim_forget(struct reb_simulation* r);
 
-/* 1 if REBOUND_B200_RESIDENT=1: the leapfrog / SEI steps keep particles in HBM between steps and set
- * r->is_synchronized = 0 (the protocol WHFast uses, src/simulation.c:633-637). */
-int shim_resident_mode(void);
+/* Residency of the particle state between the steps of one reb_simulation_steps / _integrate call:
+ *   REBOUND_B200_RESIDENT=0  host-authoritative: every replaced call uploads r->particles and writes the result back
+ *   REBOUND_B200_RESIDENT=1  resident: particles stay in HBM, r->is_synchronized = 0 until reb_simulation_synchronize
+ *                            (the protocol WHFast uses, src/simulation.c:633-637); the caller flags host edits with
+ *                            r->did_modify_particles
+ *   unset (default)          automatic: resident inside a call as long as no callback or exit check can observe
+ *                            r->particles between its steps; the device copy is dropped at the synchronize that ends the
+ *                            call, so host edits between calls need no flag */
+enum { SHIM_HOST_AUTHORITATIVE = 0, SHIM_RESIDENT = 1, SHIM_AUTO = 2 };
+int shim_residency(void);
+int shim_resident(const struct reb_simulation* r);
 
 void shim_fill_config(const struct reb_simulation* r, rebcu_config* c);
 /* Forwards a rebcu error to reb_simulation_error (src/simulation.c:82-86); returns err. */

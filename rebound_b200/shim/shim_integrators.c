@@ -63,7 +63,7 @@ static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_s
     s->host_stale = 1;
     /* run_heartbeat (src/simulation.c:240-274) scans r->particles after every step when an exit distance is set:
      * such simulations are kept host-current even in resident mode */
-    if (shim_resident_mode() && !r->exit_max_distance && !r->exit_min_distance){
+    if (shim_resident(r) && !r->exit_max_distance && !r->exit_min_distance){
         r->N = rebcu_N(s->h);            /* tree gravity + open boundary may have removed particles */
         s->uploaded_N = r->N;
         r->is_synchronized = 0;
@@ -74,10 +74,12 @@ static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_s
 
 static void synchronize(struct reb_simulation* r, void* state){
     (void)state;
-    struct shim_state* s = shim_get(r);
-    if (!s) return;
+    struct shim_state* s = shim_find(r);
+    if (!s){ r->is_synchronized = 1; return; }
     if (shim_to_host(r, s)) return;
     r->is_synchronized = 1;
+    /* automatic residency: the call is over, the host copy is the truth again (it may be edited without any flag) */
+    if (shim_residency()==SHIM_AUTO) s->device_valid = 0;
 }
 
 static void leapfrog_step(struct reb_simulation* r, void* state){ device_step(r, reb_integrator_leapfrog_step, state); }

@@ -42,7 +42,7 @@ int main(int argc, char** argv){
     struct reb_simulation* r = reb_simulation_create();
     r->rand_seed = 42;
     char sa_file[4096] = {0};
-    if (strcmp(scen, "plummer")==0 || strcmp(scen, "plummer_comp")==0 || strcmp(scen, "archive")==0){
+    if (strcmp(scen, "plummer")==0 || strcmp(scen, "plummer_comp")==0 || strcmp(scen, "archive")==0 || strcmp(scen, "edit")==0){
         /* examples/selfgravity_plummer/problem.c */
         double M=1, R=1, E=3./64.*M_PI*M*M/R, r0=16./(3.*M_PI)*R;
         double t0 = r->G*pow(M,5./2.)*pow(4.*E,-3./2.)*(double)N/log(0.4*(double)N);
@@ -52,6 +52,7 @@ int main(int argc, char** argv){
         reb_simulation_add_plummer(r, N, M, R);
         reb_simulation_move_to_com(r);
         r->heartbeat = heartbeat;
+        if (strcmp(scen, "edit")==0) r->heartbeat = NULL;      /* nothing observes the particles between steps */
         if (strcmp(scen, "archive")==0){
             /* Simulationarchive snapshot every 2 steps, written from inside reb_simulation_steps */
             snprintf(sa_file, sizeof(sa_file), "%s.sa", argv[2]);
@@ -177,6 +178,11 @@ int main(int argc, char** argv){
     }else{ fprintf(stderr, "unknown scenario %s\n", scen); return 2; }
 
     reb_simulation_steps(r, steps);
+    if (strcmp(scen, "edit")==0){
+        /* plain host edits between two calls, without r->did_modify_particles: legal with the reference's leapfrog */
+        for (size_t i=0;i<r->N;i+=7){ r->particles[i].vx += 0.125; r->particles[i].y *= 1.5; }
+        reb_simulation_steps(r, steps);
+    }
 
     FILE* f = fopen(argv[2], "wb");
     if (!f) return 3;

@@ -29,7 +29,7 @@ def run(binary, scen, n, steps, tmp_path, env=None):
 
 
 @pytest.mark.parametrize("scen,n,steps", SCENARIOS, ids=[f"{s[0]}-{s[1]}-{s[2]}" for s in SCENARIOS])
-@pytest.mark.parametrize("resident", ["0", "1"], ids=["host_authoritative", "resident"])
+@pytest.mark.parametrize("resident", ["0", "1", ""], ids=["host_authoritative", "resident", "auto"])
 def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
     ref = run("driver_ref", scen, n, steps, tmp_path)
     got = run("driver_dropin", scen, n, steps, tmp_path, env={"REBOUND_B200_RESIDENT": resident})
@@ -37,7 +37,7 @@ def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
     assert np.array_equal(ref, got)
 
 
-@pytest.mark.parametrize("resident", ["0", "1"], ids=["host_authoritative", "resident"])
+@pytest.mark.parametrize("resident", ["0", "1", ""], ids=["host_authoritative", "resident", "auto"])
 def test_dropin_archive_restart_and_midrun_diagnostics(resident, tmp_path):
     """Simulationarchive snapshots written from inside reb_simulation_steps, and energy / COM /
     angular momentum read from a heartbeat, see the current particles also while a resident simulation is
@@ -51,3 +51,13 @@ def test_dropin_archive_restart_and_midrun_diagnostics(resident, tmp_path):
     assert np.array_equal(direct, restart)
     tail = got[6 + 11 * n:12 + 11 * n].view(np.float64)
     assert tail[0] == n and tail[2] == 2.0 and tail[3] != 0.0       # restarted from the snapshot after 2 steps
+
+
+@pytest.mark.parametrize("resident", ["0", ""], ids=["host_authoritative", "auto"])
+def test_dropin_host_edits_between_calls_need_no_flag(resident, tmp_path):
+    """Particles edited in r->particles between two reb_simulation_steps calls without setting
+    r->did_modify_particles (legal with the reference's leapfrog, which keeps no state) are picked up: automatic
+    residency drops the device copy at the synchronize that ends every call."""
+    ref = run("driver_ref", "edit", 900, 4, tmp_path)
+    got = run("driver_dropin", "edit", 900, 4, tmp_path, env={"REBOUND_B200_RESIDENT": resident})
+    assert np.array_equal(ref, got)
