@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include "rebound.h"
 #include "integrator_leapfrog.h"
 
@@ -133,8 +134,11 @@ int main(int argc, char** argv){
         struct reb_particle star = {0}; star.m = 1; reb_simulation_add(r, star);
         for (int i=1;i<10;i++) reb_simulation_add_fmt(r, "m a", 1e-4*i, (double)i);
         r->N_active = 10; r->testparticle_type = 0;
-        for (int i=0;i<N;i++) reb_simulation_add_fmt(r, "a e omega f", reb_random_uniform(r,0.4,20.), reb_random_uniform(r,0.01,0.2),
-                                                     reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,2.*M_PI));
+        for (int i=0;i<N;i++){      /* explicit primary: reb_simulation_add_fmt would recompute the centre of mass per particle */
+            const double a = reb_random_uniform(r,0.4,20.), e = reb_random_uniform(r,0.01,0.2);
+            const double omega = reb_random_uniform(r,0.,2.*M_PI), f = reb_random_uniform(r,0.,2.*M_PI);
+            reb_simulation_add(r, reb_particle_from_orbit(r->G, r->particles[0], 0., a, e, 0., 0., omega, f));
+        }
     }else if (strcmp(scen, "merge")==0 || strcmp(scen, "line")==0){
         /* a cold cloud of big particles: DIRECT search + merging (collision.c:64-124, 674-737), or the LINE search
          * with hard-sphere bounces (collision.c:125-196) */
@@ -177,7 +181,11 @@ int main(int argc, char** argv){
         }
     }else{ fprintf(stderr, "unknown scenario %s\n", scen); return 2; }
 
+    struct timespec t_begin, t_end;
+    if (getenv("DRIVER_WARMUP")) reb_simulation_steps(r, 1);      /* timing runs: CUDA context + first upload outside the clock */
+    clock_gettime(CLOCK_MONOTONIC, &t_begin);
     reb_simulation_steps(r, steps);
+    clock_gettime(CLOCK_MONOTONIC, &t_end);
     if (strcmp(scen, "edit")==0){
         /* plain host edits between two calls, without r->did_modify_particles: legal with the reference's leapfrog */
         for (size_t i=0;i<r->N;i+=7){ r->particles[i].vx += 0.125; r->particles[i].y *= 1.5; }
@@ -203,7 +211,8 @@ int main(int argc, char** argv){
         remove(sa_file);
     }
     fclose(f);
-    printf("%s N=%zu t=%.17g collisions=%lld\n", scen, r->N, r->t, (long long)r->collisions_log_n);
+    printf("%s N=%zu t=%.17g collisions=%lld steps_call_seconds=%.6f\n", scen, r->N, r->t, (long long)r->collisions_log_n,
+           (t_end.tv_sec-t_begin.tv_sec) + 1e-9*(t_end.tv_nsec-t_begin.tv_nsec));
     reb_simulation_free(r);
     return 0;
 }
