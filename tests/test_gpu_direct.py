@@ -264,3 +264,22 @@ def test_compensation_terms_need_a_compensated_evaluation(eng):
     eng.update_acceleration(ics.plummer_config(64))
     with pytest.raises(Exception):
         eng.download_gravity_cs()
+
+
+@pytest.mark.parametrize("grav", [abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED])
+@pytest.mark.parametrize("n", [40, 600])
+def test_coincident_particles_give_nan_where_the_reference_does(eng, grav, n):
+    """Two particles at the same coordinates with zero softening: -G/0 * 0 = NaN in the reference's loop
+    (gravity.c:222-230).  The GPU produces NaN for exactly the same particles and components (NaN sign/payload is
+    the one thing not compared: x86 SSE returns the negative 'indefinite' NaN, the GPU the positive canonical one);
+    everything finite stays bit-identical."""
+    p = ics.plummer(n, seed=21)
+    p["x"][7], p["y"][7], p["z"][7] = p["x"][3], p["y"][3], p["z"][3]
+    cfg = ics.plummer_config(n, gravity=grav, softening=0.0)
+    want, _ = checkers.oracle().gravity(cfg, p)
+    got, _ = gpu_gravity(eng, cfg, p)
+    for f in ("ax", "ay", "az"):
+        assert np.array_equal(np.isnan(got[f]), np.isnan(want[f])), f
+        ok = ~np.isnan(want[f])
+        assert np.array_equal(got[f][ok].view(np.uint64), want[f][ok].view(np.uint64)), f
+    assert np.isnan(want["ax"][3]) and np.isnan(want["ax"][7]) and not np.isnan(want["ax"][0])
