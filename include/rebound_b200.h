@@ -89,6 +89,8 @@ typedef struct rebcu_config {
     int32_t integrator;
     int32_t leapfrog_order;       /* struct reb_integrator_leapfrog_state.order (integrator_leapfrog.h:30-32) */
     int32_t mode;                 /* REBCU_MODE_* */
+    int32_t quadrupole;           /* 1: the reference was compiled with -DQUADRUPOLE (src/tree.c:148-198, 293-303):
+                                   * tree cells carry the mass quadrupole tensor and accepted cells apply it */
 } rebcu_config;
 
 /* One cell of the octree in depth-first pre-order (octants ascending), the order in which the

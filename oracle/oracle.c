@@ -188,6 +188,7 @@ static void boundary_check(rebcu_config* c, rebcu_particle* p, uint64_t* Np){
 /* ------------------------------------------------------------------------------------------ */
 typedef struct ocell {
     double x,y,z,w,m,mx,my,mz;
+    double q[6];        /* mxx mxy mxz myy myz mzz: only with -DQUADRUPOLE (tree.h:43-50) */
     int pt;
     int rootbox;
     int kid[8];
@@ -296,14 +297,15 @@ static int tree_build(otree* t, const rebcu_config* c, const rebcu_particle* p, 
 }
 
 /* Post-order mass / centre of mass, children combined in octant order (tree.c:156-206). */
-static void tree_moments(otree* t, const rebcu_particle* p, int id){
+static void tree_moments(otree* t, const rebcu_particle* p, int id, int quadrupole){
     ocell* n = &t->c[id];
+    for (int k=0;k<6;k++) n->q[k] = 0.;                      /* tree.c:148-155 */
     if (n->pt < 0){
         double m=0., mx=0., my=0., mz=0.;
         for (int o=0;o<8;o++){
             const int k = t->c[id].kid[o];
             if (!k) continue;
-            tree_moments(t, p, k);
+            tree_moments(t, p, k, quadrupole);
             const ocell* d = &t->c[k];
             const double dm = d->m;
             mx += d->mx*dm; my += d->my*dm; mz += d->mz*dm; m += dm;
@@ -311,16 +313,33 @@ static void tree_moments(otree* t, const rebcu_particle* p, int id){
         n = &t->c[id];
         if (m>0){ mx /= m; my /= m; mz /= m; }
         n->m = m; n->mx = mx; n->my = my; n->mz = mz;
+        if (quadrupole){                                      /* tree.c:180-197, Hernquist 1987 */
+            for (int o=0;o<8;o++){
+                const int k = n->kid[o];
+                if (!k) continue;
+                const ocell* d = &t->c[k];
+                const double d_m = d->m;
+                const double qx = d->mx - n->mx, qy = d->my - n->my, qz = d->mz - n->mz;
+                const double qr2 = qx*qx + qy*qy + qz*qz;
+                n->q[0] += d->q[0] + d_m*(3.*qx*qx - qr2);
+                n->q[1] += d->q[1] + d_m*3.*qx*qy;
+                n->q[2] += d->q[2] + d_m*3.*qx*qz;
+                n->q[3] += d->q[3] + d_m*(3.*qy*qy - qr2);
+                n->q[4] += d->q[4] + d_m*3.*qy*qz;
+            }
+            n->q[5] = -n->q[0] -n->q[3];
+        }
     }else{
         n->m = p[n->pt].m; n->mx = p[n->pt].x; n->my = p[n->pt].y; n->mz = p[n->pt].z;
     }
 }
 
 /* Flatten to depth-first pre-order with skip links. */
-static size_t tree_flatten(const otree* t, int id, int depth, rebcu_treecell* out, size_t cap, size_t idx){
+static size_t tree_flatten(const otree* t, int id, int depth, rebcu_treecell* out, size_t cap, size_t idx, double* quad){
     const size_t me = idx++;
     const ocell* n = &t->c[id];
-    for (int o=0;o<8;o++) if (n->kid[o]) idx = tree_flatten(t, n->kid[o], depth+1, out, cap, idx);
+    for (int o=0;o<8;o++) if (n->kid[o]) idx = tree_flatten(t, n->kid[o], depth+1, out, cap, idx, quad);
+    if (me<cap && quad) for (int k=0;k<6;k++) quad[6*me+k] = n->q[k];
     if (me<cap){
         rebcu_treecell* q = &out[me];
         q->x=n->x; q->y=n->y; q->z=n->z; q->w=n->w; q->m=n->m; q->mx=n->mx; q->my=n->my; q->mz=n->mz;
@@ -332,22 +351,30 @@ static size_t tree_flatten(const otree* t, int id, int depth, rebcu_treecell* ou
 static void tree_free(otree* t){ free(t->c); free(t->root); memset(t,0,sizeof(*t)); }
 
 /* Builds the flattened tree (with moments) for the given particles. */
-static int build_flat(const rebcu_config* c, const rebcu_particle* p, uint64_t N,
-                      rebcu_treecell** cells, size_t* n_cells){
+static int build_flat_q(const rebcu_config* c, const rebcu_particle* p, uint64_t N,
+                        rebcu_treecell** cells, size_t* n_cells, double** quad_out){
     otree t;
     int err = tree_build(&t, c, p, N);
+    if (quad_out) *quad_out = NULL;
     if (err){ tree_free(&t); *cells = NULL; *n_cells = 0; return err; }
     size_t total = t.n - 1;
     rebcu_treecell* out = malloc(sizeof(rebcu_treecell)*(total?total:1));
+    double* quad = (quad_out && c->quadrupole) ? malloc(sizeof(double)*6*(total?total:1)) : NULL;
     size_t idx = 0;
     for (int rb=0; rb<t.n_root; rb++){
         if (!t.root[rb]) continue;
-        tree_moments(&t, p, t.root[rb]);
-        idx = tree_flatten(&t, t.root[rb], 0, out, total, idx);
+        tree_moments(&t, p, t.root[rb], c->quadrupole);
+        idx = tree_flatten(&t, t.root[rb], 0, out, total, idx, quad);
     }
     tree_free(&t);
     *cells = out; *n_cells = idx;
+    if (quad_out) *quad_out = quad;
     return 0;
+}
+
+static int build_flat(const rebcu_config* c, const rebcu_particle* p, uint64_t N,
+                      rebcu_treecell** cells, size_t* n_cells){
+    return build_flat_q(c, p, N, cells, n_cells, NULL);
 }
 
 int orc_tree_dump(rebcu_config* c, rebcu_particle* p, uint64_t N,
@@ -364,7 +391,7 @@ int orc_tree_dump(rebcu_config* c, rebcu_particle* p, uint64_t N,
 
 /* Barnes-Hut walk over the pre-order array: gravity.c:84-99 and tree.c:275-328.
  * A cell is opened iff  w*w > opening_angle2 * r2  (tree.c:284); the distance uses the unsoftened r2. */
-static void tree_walk_one(const rebcu_config* c, const rebcu_treecell* cells, size_t n_cells,
+static void tree_walk_one(const rebcu_config* c, const rebcu_treecell* cells, size_t n_cells, const double* quad,
                           int self, double px, double py, double pz, double* a){
     const double G = c->G, soft2 = c->softening*c->softening, th2 = c->opening_angle2;
     size_t k = 0;
@@ -377,7 +404,21 @@ static void tree_walk_one(const rebcu_config* c, const rebcu_treecell* cells, si
         }else if (n->pt == self){ k = n->skip; continue; }
         const double rr = sqrt(r2 + soft2);
         const double pre = -G/(rr*rr*rr)*n->m;
-        a[0] += pre*dx; a[1] += pre*dy; a[2] += pre*dz;
+        if (quad && n->pt < 0){                               /* tree.c:293-303 */
+            const double* q = quad + 6*k;                     /* mxx mxy mxz myy myz mzz */
+            double qpre = G/(rr*rr*rr*rr*rr);
+            a[0] += qpre*(dx*q[0] + dy*q[1] + dz*q[2]);
+            a[1] += qpre*(dx*q[1] + dy*q[3] + dz*q[4]);
+            a[2] += qpre*(dx*q[2] + dy*q[4] + dz*q[5]);
+            double mrr = dx*dx*q[0] + dy*dy*q[3] + dz*dz*q[5]
+                       + 2.*dx*dy*q[1] + 2.*dx*dz*q[2] + 2.*dy*dz*q[4];
+            qpre *= -5.0/(2.0*rr*rr)*mrr;
+            a[0] += (qpre + pre) * dx;
+            a[1] += (qpre + pre) * dy;
+            a[2] += (qpre + pre) * dz;
+        }else{
+            a[0] += pre*dx; a[1] += pre*dy; a[2] += pre*dz;
+        }
         k = n->skip;
     }
 }
@@ -385,8 +426,8 @@ static void tree_walk_one(const rebcu_config* c, const rebcu_treecell* cells, si
 static int gravity_tree(rebcu_config* c, rebcu_particle* p, uint64_t* Np){
     boundary_check(c, p, Np);                                   /* gravity.c:56 */
     const uint64_t N = *Np;
-    rebcu_treecell* cells; size_t n_cells;
-    int err = build_flat(c, p, N, &cells, &n_cells);
+    rebcu_treecell* cells; size_t n_cells; double* quad = NULL;
+    int err = build_flat_q(c, p, N, &cells, &n_cells, &quad);
     if (err) return err;
     const int ngb = (2*c->N_ghost_x+1)*(2*c->N_ghost_y+1)*(2*c->N_ghost_z+1);
     rebcu_vec6d* gbs = malloc(sizeof(rebcu_vec6d)*ngb);
@@ -399,10 +440,10 @@ static int gravity_tree(rebcu_config* c, rebcu_particle* p, uint64_t* Np){
     for (uint64_t i=0;i<N;i++){
         double a[3] = {0.,0.,0.};
         for (int g=0; g<ngb; g++)
-            tree_walk_one(c, cells, n_cells, (int)i, gbs[g].x+p[i].x, gbs[g].y+p[i].y, gbs[g].z+p[i].z, a);
+            tree_walk_one(c, cells, n_cells, quad, (int)i, gbs[g].x+p[i].x, gbs[g].y+p[i].y, gbs[g].z+p[i].z, a);
         p[i].ax=a[0]; p[i].ay=a[1]; p[i].az=a[2];
     }
-    free(gbs); free(cells);
+    free(gbs); free(cells); free(quad);
     return 0;
 }
 

@@ -84,6 +84,7 @@ class Config(C.Structure):
         ("integrator", C.c_int32),
         ("leapfrog_order", C.c_int32),
         ("mode", C.c_int32),
+        ("quadrupole", C.c_int32),
     ]
 
     def copy(self):

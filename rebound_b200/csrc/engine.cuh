@@ -49,6 +49,8 @@ struct TreeBuffers {
     double4* walk_geo = nullptr;   // [cap_cells] (x,y,z,w) packed for the collision walk
     int2* walk_meta = nullptr;     // [cap_cells] int4 (pt, skip, depth, rootbox)
     int2* walk_meta2 = nullptr;    // [cap_cells] (leaf: pt >= 0 | internal: -(depth+1), skip): all the gravity walk needs
+    double* quad = nullptr; uint64_t quad_cap = 0;   // [6][quad_cap] mxx mxy mxz myy myz mzz (QUADRUPOLE builds only)
+    bool has_quad = false;         // the current tree carries quadrupole moments
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
     uint64_t n_cells = 0;

@@ -181,6 +181,8 @@ struct CellArrays {
     int32_t* parent;
     uint32_t* ready; // children still missing
     int2* meta2;     // (leaf: pt | internal: -(depth+1), skip) -- the 8 bytes the gravity walk reads per visit
+    double* quad;    // null, or mxx mxy mxz myy myz mzz as six arrays of quad_stride cells (QUADRUPOLE, tree.c:148-198)
+    uint64_t quad_stride;
 };
 
 // Emits the cells opened at sorted position k (geometry, pt, skip, depth, rootbox; leaf moments).
@@ -272,6 +274,25 @@ __global__ void __launch_bounds__(256) moment_kernel(uint64_t n_cells, CellArray
         if (mm > 0) { mx = s_div(mx, mm); my = s_div(my, mm); mz = s_div(mz, mm); }
         volatile double4* o = (volatile double4*)&C.pos[c];
         o->x = mx; o->y = my; o->z = mz; o->w = mm;
+        if (C.quad) {
+            // tree.c:180-197 (Hernquist 1987): children in octant order, each term  d.mxx + d_m*(3*qx*qx - qr2)  etc.
+            volatile double* Q = C.quad;
+            const uint64_t S = C.quad_stride;
+            double mxx = 0., mxy = 0., mxz = 0., myy = 0., myz = 0.;
+            for (int ch = c + 1; ch < end; ch = C.meta[ch].y) {
+                const volatile double4* q = (const volatile double4*)&C.pos[ch];
+                const double dm = q->w;
+                const double qx = s_sub(q->x, mx), qy = s_sub(q->y, my), qz = s_sub(q->z, mz);
+                const double qr2 = s_add(s_add(s_mul(qx, qx), s_mul(qy, qy)), s_mul(qz, qz));
+                mxx = s_add(mxx, s_add(Q[0 * S + ch], s_mul(dm, s_sub(s_mul(s_mul(3., qx), qx), qr2))));
+                mxy = s_add(mxy, s_add(Q[1 * S + ch], s_mul(s_mul(s_mul(dm, 3.), qx), qy)));
+                mxz = s_add(mxz, s_add(Q[2 * S + ch], s_mul(s_mul(s_mul(dm, 3.), qx), qz)));
+                myy = s_add(myy, s_add(Q[3 * S + ch], s_mul(dm, s_sub(s_mul(s_mul(3., qy), qy), qr2))));
+                myz = s_add(myz, s_add(Q[4 * S + ch], s_mul(s_mul(s_mul(dm, 3.), qy), qz)));
+            }
+            Q[0 * S + c] = mxx; Q[1 * S + c] = mxy; Q[2 * S + c] = mxz; Q[3 * S + c] = myy; Q[4 * S + c] = myz;
+            Q[5 * S + c] = s_sub(-mxx, myy);            // node->mzz = -node->mxx - node->myy
+        }
         c = C.parent[c];
     }
 }
@@ -306,6 +327,7 @@ struct WalkArgs {
     double w2[W_TABLE];      // squared cell width by depth
     double root_size;
     int windowed;            // G inside the window of the branch-free sqrt/divide (strict_math.cuh)
+    const double* quad; uint64_t quad_stride;     // QUADRUPOLE builds: six arrays mxx mxy mxz myy myz mzz, else null
 };
 
 // MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
@@ -371,6 +393,83 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
     unsigned wkey = STRICT_WINDOW_LIMIT;
     if (FAST || a.windowed) wkey = walk_one<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
     if (!FAST && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
+    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+}
+
+// Walk of a QUADRUPOLE build (tree.c:286-304): accepted internal cells add the quadrupole correction, in two
+// separate additions per component exactly as the reference does; leaves are monopoles.  Generic IEEE sqrt and
+// divide (three divisions per accepted cell), one thread per particle.
+template <bool FAST>
+__global__ void __launch_bounds__(128) walk_quad_kernel(const WalkArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (t >= a.n_work) return;
+    const uint64_t k = a.list ? a.list[t] : t;
+    const uint32_t self = a.perm[k];
+    const double px = a.x[self], py = a.y[self], pz = a.z[self];
+    double sx = 0., sy = 0., sz = 0.;
+    const double negG = -a.G;
+    const int ngb = a.ghosts->n;
+    const int n_cells = (int)a.n_cells;
+    const uint64_t S = a.quad_stride;
+    for (int g = 0; g < ngb; g++) {
+        const double gx = s_add(a.ghosts->gb[g].x, px), gy = s_add(a.ghosts->gb[g].y, py), gz = s_add(a.ghosts->gb[g].z, pz);
+        int c = 0;
+        while (c < n_cells) {
+            const double4 q = ld_pos256(a.pos + c);
+            const int2 mt = a.meta2[c];
+            const double dx = s_sub(gx, q.x), dy = s_sub(gy, q.y), dz = s_sub(gz, q.z);
+            const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+            const bool internal = mt.x < 0;
+            if (internal) {
+                const int depth = -mt.x - 1;
+                double w2;
+                if (depth < W_TABLE) w2 = a.w2[depth];
+                else { double w = a.root_size; for (int d = 0; d < depth; d++) w = s_div(w, 2.); w2 = s_mul(w, w); }
+                if (w2 > s_mul(a.theta2, r2)) { c++; continue; }
+            } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }
+            if (FAST) {
+                const double ri = rsqrt(r2 + a.soft2);
+                const double ri2 = ri * ri, ri3 = ri2 * ri;
+                const double prefact = negG * q.w * ri3;
+                if (internal) {
+                    const double mxx = a.quad[0 * S + c], mxy = a.quad[1 * S + c], mxz = a.quad[2 * S + c];
+                    const double myy = a.quad[3 * S + c], myz = a.quad[4 * S + c], mzz = a.quad[5 * S + c];
+                    double qp = a.G * ri3 * ri2;
+                    sx += qp * (dx * mxx + dy * mxy + dz * mxz);
+                    sy += qp * (dx * mxy + dy * myy + dz * myz);
+                    sz += qp * (dx * mxz + dy * myz + dz * mzz);
+                    const double mrr = dx * dx * mxx + dy * dy * myy + dz * dz * mzz + 2. * dx * dy * mxy + 2. * dx * dz * mxz + 2. * dy * dz * myz;
+                    qp *= -2.5 * ri2 * mrr;
+                    sx += (qp + prefact) * dx; sy += (qp + prefact) * dy; sz += (qp + prefact) * dz;
+                } else { sx = fma(prefact, dx, sx); sy = fma(prefact, dy, sy); sz = fma(prefact, dz, sz); }
+            } else {
+                const double r = s_sqrt(s_add(r2, a.soft2));
+                const double r3 = s_mul(s_mul(r, r), r);
+                const double prefact = s_mul(s_div(negG, r3), q.w);                         // tree.c:292
+                if (internal) {
+                    const double mxx = a.quad[0 * S + c], mxy = a.quad[1 * S + c], mxz = a.quad[2 * S + c];
+                    const double myy = a.quad[3 * S + c], myz = a.quad[4 * S + c], mzz = a.quad[5 * S + c];
+                    double qp = s_div(a.G, s_mul(s_mul(r3, r), r));                          // G/(_r*_r*_r*_r*_r), tree.c:294
+                    sx = s_add(sx, s_mul(qp, s_add(s_add(s_mul(dx, mxx), s_mul(dy, mxy)), s_mul(dz, mxz))));
+                    sy = s_add(sy, s_mul(qp, s_add(s_add(s_mul(dx, mxy), s_mul(dy, myy)), s_mul(dz, myz))));
+                    sz = s_add(sz, s_mul(qp, s_add(s_add(s_mul(dx, mxz), s_mul(dy, myz)), s_mul(dz, mzz))));
+                    // mrr = dx*dx*mxx + dy*dy*myy + dz*dz*mzz + 2.*dx*dy*mxy + 2.*dx*dz*mxz + 2.*dy*dz*myz   (tree.c:298-299)
+                    double mrr = s_mul(s_mul(dx, dx), mxx);
+                    mrr = s_add(mrr, s_mul(s_mul(dy, dy), myy));
+                    mrr = s_add(mrr, s_mul(s_mul(dz, dz), mzz));
+                    mrr = s_add(mrr, s_mul(s_mul(s_mul(2., dx), dy), mxy));
+                    mrr = s_add(mrr, s_mul(s_mul(s_mul(2., dx), dz), mxz));
+                    mrr = s_add(mrr, s_mul(s_mul(s_mul(2., dy), dz), myz));
+                    qp = s_mul(qp, s_mul(s_div(-5.0, s_mul(s_mul(2.0, r), r)), mrr));        // qprefact *= -5.0/(2.0*_r*_r)*mrr
+                    const double f = s_add(qp, prefact);
+                    sx = s_add(sx, s_mul(f, dx)); sy = s_add(sy, s_mul(f, dy)); sz = s_add(sz, s_mul(f, dz));
+                } else {
+                    sx = s_add(sx, s_mul(prefact, dx)); sy = s_add(sy, s_mul(prefact, dy)); sz = s_add(sz, s_mul(prefact, dz));
+                }
+            }
+            c = mt.y;
+        }
+    }
     a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
 }
 
@@ -467,7 +566,7 @@ void tree_free(rebcu_handle* h) {
     cudaFree(T.keys); cudaFree(T.keys_sorted); cudaFree(T.perm); cudaFree(T.perm_in); cudaFree(T.lcp);
     cudaFree(T.cell_off); cudaFree(T.cell_cnt); cudaFree(T.cells); cudaFree(T.parent); cudaFree(T.ready);
     cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
-    cudaFree(T.shard_list);
+    cudaFree(T.shard_list); cudaFree(T.quad);
     T = TreeBuffers();
 }
 
@@ -554,7 +653,19 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
         cudaFree(T.cells); T.cells = nullptr;
         T.cap_cells = cap;
     }
-    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2};
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2, nullptr, 0};
+    T.has_quad = false;
+    if (c->quadrupole) {
+        if (T.quad_cap < T.cap_cells) {
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(T.quad); T.quad = nullptr; T.quad_cap = 0;
+            CU_TRY(h, cudaMalloc(&T.quad, 6 * T.cap_cells * sizeof(double)));
+            T.quad_cap = T.cap_cells;
+        }
+        CU_TRY(h, cudaMemsetAsync(T.quad, 0, 6 * T.quad_cap * sizeof(double), h->stream));     // leaves: tree.c:148-155
+        C.quad = T.quad; C.quad_stride = T.quad_cap;
+        T.has_quad = true;
+    }
     {
         LaunchScope ls(h, TC_TREEBUILD, 3);
         emit_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(P, T.keys_sorted, T.perm, T.lcp, T.cell_off, x, y, z, m, C);
@@ -572,7 +683,7 @@ int tree_export(rebcu_handle* h) {
     TreeBuffers& T = h->tree;
     if (T.n_cells == 0) return REBCU_OK;
     if (!T.cells) CU_TRY(h, cudaMalloc(&T.cells, T.cap_cells * sizeof(rebcu_treecell)));
-    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2};
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2, nullptr, 0};
     export_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, C, T.cells);
     CU_TRY(h, cudaGetLastError());
     return REBCU_OK;
@@ -612,6 +723,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     WalkArgs a;
     a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
     a.perm = T.perm; a.list = nullptr; a.n_work = n;
+    a.quad = nullptr; a.quad_stride = 0;
     a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
     a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
     a.ghosts = h->ghosts_dev;
@@ -632,7 +744,11 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
         // Default: per-thread; REBOUND_B200_WALK=coop selects the cooperative kernel.
         static const bool per_thread = [] { const char* e = getenv("REBOUND_B200_WALK"); return !(e && strcmp(e, "coop") == 0); }();
         const unsigned int nb = div_up(a.n_work, 128);
-        if (per_thread) {
+        if (T.has_quad) {
+            a.quad = T.quad; a.quad_stride = T.quad_cap;
+            if (c->mode == REBCU_MODE_FAST) walk_quad_kernel<true><<<nb, 128, 0, h->stream>>>(a);
+            else walk_quad_kernel<false><<<nb, 128, 0, h->stream>>>(a);
+        } else if (per_thread) {
             if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_kernel<false><<<nb, 128, 0, h->stream>>>(a);
         } else {

@@ -75,6 +75,9 @@ void shim_fill_config(const struct reb_simulation* r, rebcu_config* c){
     c->OMEGA = r->OMEGA; c->OMEGAZ = r->OMEGAZ;
     c->dt = r->dt; c->dt_last_done = r->dt_last_done;
     c->opening_angle2 = r->opening_angle2;
+#ifdef QUADRUPOLE
+    c->quadrupole = 1;           /* the reference sources of this build carry the quadrupole option (tree.h:43-50) */
+#endif
     c->root_size = r->root_size;
     c->N_active = (r->N_active==SIZE_MAX)?REBCU_SIZE_MAX:(uint64_t)r->N_active;
     c->testparticle_type = r->testparticle_type;

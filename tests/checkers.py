@@ -144,12 +144,14 @@ def oracle():
     return _cache["oracle"]
 
 
-def reference(openmp=False):
+def reference(openmp=False, quadrupole=False):
     """The unmodified reference, or None if oracle/_ref has not been built (it is built in the
-    authoring container, where /root/reference exists, and travels to the GPU box as a binary)."""
-    key = "ref_omp" if openmp else "ref"
+    authoring container, where /root/reference exists, and travels to the GPU box as a binary).
+    quadrupole=True: the serial build compiled with -DQUADRUPOLE."""
+    key = "ref_quad" if quadrupole else ("ref_omp" if openmp else "ref")
     if key not in _cache:
-        path = os.path.join(ORACLE_DIR, "_ref", "libref_harness_omp.so" if openmp else "libref_harness.so")
+        name = "libref_harness_quad.so" if quadrupole else ("libref_harness_omp.so" if openmp else "libref_harness.so")
+        path = os.path.join(ORACLE_DIR, "_ref", name)
         _cache[key] = Checker(path, "refh_", "reference") if os.path.exists(path) else None
     return _cache[key]
 

@@ -333,3 +333,43 @@ def test_sheet_full_size_tree_and_direct_searches_agree(eng):
     main = tree[(tree["gb_x"] == 0) & (tree["gb_y"] == 0)]
     fwd = set(zip(main["p1"].tolist(), main["p2"].tolist()))
     assert all((j, i) in fwd for i, j in fwd)
+
+
+def _box_particles(n, half, seed):
+    rng = np.random.default_rng(seed)
+    p = abi.particles(n)
+    for f in ("x", "y", "z"):
+        p[f] = rng.uniform(-half, half, n)
+    p["m"] = rng.uniform(0.5, 1.5, n) / n
+    return p
+
+
+def quadrupole_cases():
+    yield "disc", ics.selfgravity_disc_config(collision=abi.COLLISION_NONE), ics.selfgravity_disc(6000, seed=3)
+    yield "sheet_ghosts", ics.shearing_sheet_config(root_size=30.0, t=3.3, collision=abi.COLLISION_NONE), ics.shearing_sheet(root_size=30.0, seed=4)
+    yield "plummer_wide", ics.plummer_config(800, gravity=abi.GRAVITY_TREE, root_size=200.0, opening_angle2=1.0), ics.plummer(800, seed=5)
+    yield "two_root_boxes", abi.default_config(gravity=abi.GRAVITY_TREE, root_size=5.0, N_root_x=2, N_root_y=2, N_root_z=2,
+                                                opening_angle2=0.7, softening=0.01), _box_particles(900, 4.9, seed=6)
+
+
+QUAD_CASES = list(quadrupole_cases())
+
+
+@pytest.mark.parametrize("name,cfg,p", QUAD_CASES, ids=[c[0] for c in QUAD_CASES])
+def test_quadrupole_tree_gravity_bitwise(eng, name, cfg, p):
+    """cfg.quadrupole = 1 (a reference compiled with -DQUADRUPOLE, src/tree.c:148-198, 293-303): the oracle is pinned
+    against that build in tests/test_oracle_vs_reference.py; STRICT accelerations are bit-identical, FAST within 1e-11."""
+    cq = cfg.copy()
+    cq.quadrupole = 1
+    want, _ = checkers.oracle().gravity(cq, p)
+    q = p.copy()
+    n = eng.gravity_host(cq.copy(), q)
+    assert n == len(want) and bits_equal(q[:n], want)
+    mono = p.copy()
+    eng.gravity_host(cfg.copy(), mono)
+    assert not bits_equal(mono[:n], want)                    # the option is really on
+    cf = cq.copy()
+    cf.mode = abi.MODE_FAST
+    f = p.copy()
+    eng.gravity_host(cf, f)
+    assert max_rel_acc_error(f[:n], want) <= 1e-11

@@ -273,3 +273,28 @@ def test_gravity_cs_compensation_terms():
         assert bits_equal(po, pr)
         assert np.array_equal(co.view(np.uint64), cr.view(np.uint64))
         assert np.any(co != 0.0)
+
+
+def test_quadrupole_tree_gravity():
+    """-DQUADRUPOLE build of the reference (src/tree.c:148-198 moments, :293-303 force) against the oracle with
+    cfg.quadrupole = 1; and the option really changes the result."""
+    ref = checkers.reference(quadrupole=True)
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_harness_quad.so not built")
+    cases = [(ics.selfgravity_disc(2000, seed=3), ics.selfgravity_disc_config(collision=abi.COLLISION_NONE)),
+             (ics.shearing_sheet(root_size=30.0, seed=4), ics.shearing_sheet_config(root_size=30.0, t=3.3, collision=abi.COLLISION_NONE)),
+             (ics.plummer(500, seed=5), ics.plummer_config(500, gravity=abi.GRAVITY_TREE, root_size=200.0, opening_angle2=1.0))]
+    for p, cfg in cases:
+        cq = cfg.copy()
+        cq.quadrupole = 1
+        want, _ = ref.gravity(cq, p)
+        got, _ = checkers.oracle().gravity(cq, p)
+        assert bits_equal(got, want)
+        mono, _ = checkers.oracle().gravity(cfg, p)
+        assert not bits_equal(got, mono)
+        # the quadrupole moves the tree force towards the direct sum
+        if cfg.N_ghost_x == 0:
+            cd = cfg.copy()
+            cd.gravity = abi.GRAVITY_BASIC
+            direct, _ = checkers.oracle().gravity(cd, p)
+            assert checkers.max_rel_acc_error(got, direct) < checkers.max_rel_acc_error(mono, direct)
