@@ -428,7 +428,8 @@ def main():
         chk.set_threads(os.cpu_count() or 1)
         chk.steps(cfg, p, 1)                  # thread pool start-up, page faults
         _, _, aux = chk.steps(cfg, p, 2)
-        n_cpu = max(1, min(inner, int(15.0 / max(aux["seconds"] / 2, 1e-6))))
+        # about 10 s of CPU work on the full-size workload (more steps, never fewer particles)
+        n_cpu = max(1, min(50 * inner, int(10.0 / max(aux["seconds"] / 2, 1e-6))))
         _, _, aux = chk.steps(cfg, p, n_cpu)
         cpu = {"value": inter * n_cpu / aux["seconds"], "unit": "interactions/s", "cores": chk.threads(), "kind": kind,
                "sample": f"reb_simulation_steps(r,{n_cpu}) on the full workload ({aux['seconds']:.1f} s)"}
