@@ -424,6 +424,193 @@ __global__ void __launch_bounds__(32 * W) direct_fast_kernel(const DirectArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Active rows of testparticle_type 1: a handful of massive particles that feel EVERY particle.
+// ------------------------------------------------------------------------------------------------
+// With one thread per target such a row is a serial loop over N sources (137 ms per evaluation at N_active = 10,
+// N = 2^20: slower than the reference's CPU).  STRICT: the terms p*dx, p*dy, p*dz of all (row, source) pairs are
+// evaluated by one thread per SOURCE (all the sqrt/divide work, fully parallel) into a term buffer, then one warp
+// per row adds them in ascending source order -- the same additions as direct_strict_kernel, so the same bits; what
+// remains serial is one dependent add (four with Kahan) per source.  FAST: per-CTA partial sums, fixed-order final sum.
+constexpr int ROW_MAX = 256;
+
+struct RowArgs {
+    DirectArgs a;
+    uint64_t row0; int n_rows;          // rows [row0, row0 + n_rows), all < N_active
+    uint64_t j0, j1;                    // source chunk of this launch
+    double* terms; uint64_t chunk_cap;  // [n_rows][3][chunk_cap]
+    double* state;                      // [n_rows][6] running sx sy sz cx cy cz between chunks
+    double gbx, gby, gbz;               // ghost box (0,0,0) shift, added as the reference does (BASIC only)
+    int first, last;                    // first / last chunk
+};
+
+template <bool KAHAN>
+__global__ void __launch_bounds__(128) row_terms_kernel(const RowArgs R) {
+    __shared__ double4 rows[ROW_MAX];
+    const DirectArgs& a = R.a;
+    for (int r = threadIdx.x; r < R.n_rows; r += 128) {
+        const uint64_t i = R.row0 + r;
+        double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+        if (a.use_ghosts) { xi = s_add(R.gbx, xi); yi = s_add(R.gby, yi); zi = s_add(R.gbz, zi); }
+        rows[r] = make_double4(xi, yi, zi, 0.);
+    }
+    __syncthreads();
+    const uint64_t j = R.j0 + (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= R.j1) return;
+    const double xj = a.x[j], yj = a.y[j], zj = a.z[j], mj = a.m[j];
+    const double negG = -a.G;
+    const uint64_t col = j - R.j0;
+    for (int r = 0; r < R.n_rows; r++) {
+        const double4 ri = rows[r];
+        const double dx = s_sub(ri.x, xj), dy = s_sub(ri.y, yj), dz = s_sub(ri.z, zj);
+        const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);
+        const unsigned key = strict_window_key(r2);
+        double p;
+        if (a.windowed && key < STRICT_WINDOW_LIMIT) {
+            const double d = fsqrt_rn_w(r2);
+            p = KAHAN ? s_mul(-fdiv_rn_w(a.G, s_mul(r2, d)), mj) : s_mul(fdiv_rn_w(negG, s_mul(s_mul(d, d), d)), mj);
+        } else {
+            const double d = s_sqrt(r2);          // correctly rounded either way: no recomputation needed
+            p = KAHAN ? s_mul(-s_div(a.G, s_mul(r2, d)), mj) : s_mul(s_div(negG, s_mul(s_mul(d, d), d)), mj);
+        }
+        double* t = R.terms + (uint64_t)r * 3 * R.chunk_cap + col;
+        t[0] = s_mul(p, dx); t[R.chunk_cap] = s_mul(p, dy); t[2 * R.chunk_cap] = s_mul(p, dz);
+    }
+}
+
+// Ordered sums.  Lane (row, component): one warp carries the 30 chains of 10 rows in lock step, so one DADD
+// instruction per source advances all of them; each lane streams its own term array, 16 terms per batch, the next
+// batch already in flight while the current one is added.
+constexpr int ROWS_PER_WARP = 10;
+constexpr int ROW_BATCH = 16;
+
+template <bool KAHAN>
+__global__ void __launch_bounds__(32) row_sum_kernel(const RowArgs R) {
+    const DirectArgs& a = R.a;
+    const int lane = threadIdx.x;
+    const int rl = lane / 3, c = lane - 3 * rl;
+    const int r = blockIdx.x * ROWS_PER_WARP + rl;
+    if (rl >= ROWS_PER_WARP || r >= R.n_rows) return;
+    const uint64_t i = R.row0 + r;
+    uint64_t ns, skip0, skip1;
+    source_set(a, i, ns, skip0, skip1);
+    double s = 0, e = 0;
+    if (!R.first) { s = R.state[(uint64_t)r * 6 + c]; e = R.state[(uint64_t)r * 6 + 3 + c]; }
+    const double* t = R.terms + ((uint64_t)r * 3 + c) * R.chunk_cap;
+    const uint64_t cnt = R.j1 - R.j0;
+    // four register buffers: three batches (48 terms) are in flight while one is added, which covers the L2 latency
+    // at one dependent add per ~16 cycles
+    double B0[ROW_BATCH], B1[ROW_BATCH], B2[ROW_BATCH], B3[ROW_BATCH];
+    auto fetch = [&](double (&buf)[ROW_BATCH], uint64_t b) {
+        if (b >= cnt) return;
+#pragma unroll
+        for (int u = 0; u < ROW_BATCH; u += 2) {
+            // chunk_cap is a multiple of 1024 doubles and b of 16: 16-byte aligned, and a batch never leaves the row
+            const double2 v = *reinterpret_cast<const double2*>(t + b + u);
+            buf[u] = v.x; buf[u + 1] = v.y;
+        }
+    };
+    auto consume = [&](const double (&buf)[ROW_BATCH], uint64_t b) {
+        if (b >= cnt) return;
+        const uint64_t jb = R.j0 + b, je = jb + ROW_BATCH;
+        const bool clean = (b + ROW_BATCH <= cnt) && (je <= ns) && (skip0 < jb || skip0 >= je) && (skip1 < jb || skip1 >= je);
+        if (clean) {
+#pragma unroll
+            for (int u = 0; u < ROW_BATCH; u++) {
+                if (!KAHAN) s = s_add(s, buf[u]);
+                else { const double y = s_sub(buf[u], e), w = s_add(s, y); e = s_sub(s_sub(w, s), y); s = w; }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < ROW_BATCH; u++) {
+                const uint64_t j = jb + u;
+                if ((b + u < cnt) & (j < ns) & (j != skip0) & (j != skip1)) {
+                    if (!KAHAN) s = s_add(s, buf[u]);
+                    else { const double y = s_sub(buf[u], e), w = s_add(s, y); e = s_sub(s_sub(w, s), y); s = w; }
+                }
+            }
+        }
+    };
+    fetch(B0, 0); fetch(B1, ROW_BATCH); fetch(B2, 2 * ROW_BATCH);
+    for (uint64_t b = 0; b < cnt; b += 4 * ROW_BATCH) {
+        fetch(B3, b + 3 * ROW_BATCH); consume(B0, b);
+        fetch(B0, b + 4 * ROW_BATCH); consume(B1, b + ROW_BATCH);
+        fetch(B1, b + 5 * ROW_BATCH); consume(B2, b + 2 * ROW_BATCH);
+        fetch(B2, b + 6 * ROW_BATCH); consume(B3, b + 3 * ROW_BATCH);
+    }
+    if (R.last) {
+        double* out = (c == 0) ? a.ax : (c == 1) ? a.ay : a.az;
+        out[i] = s;
+        if (KAHAN && a.csx) { double* cs = (c == 0) ? a.csx : (c == 1) ? a.csy : a.csz; cs[i] = e; }
+    } else {
+        R.state[(uint64_t)r * 6 + c] = s; R.state[(uint64_t)r * 6 + 3 + c] = e;
+    }
+}
+
+// FAST: CTA b owns sources [j0 + 1024 b, +1024); for every row each thread sums its 8 sources, the CTA reduces in a
+// fixed order and writes one partial per (row, CTA); row_fast_final_kernel adds the partials in CTA order.
+template <bool KAHAN>
+__global__ void __launch_bounds__(128) row_fast_kernel(const RowArgs R, double* __restrict__ partial, unsigned n_cta) {
+    __shared__ double4 rows[ROW_MAX];
+    __shared__ double red[4][3];
+    const DirectArgs& a = R.a;
+    for (int r = threadIdx.x; r < R.n_rows; r += 128) {
+        const uint64_t i = R.row0 + r;
+        double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+        if (a.use_ghosts) { xi += R.gbx; yi += R.gby; zi += R.gbz; }
+        rows[r] = make_double4(xi, yi, zi, 0.);
+    }
+    double4 src[8];
+    uint64_t jj[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        jj[k] = R.j0 + (uint64_t)blockIdx.x * 1024 + (uint64_t)k * 128 + threadIdx.x;
+        src[k] = (jj[k] < R.j1) ? make_double4(a.x[jj[k]], a.y[jj[k]], a.z[jj[k]], -a.G * a.m[jj[k]]) : make_double4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int r = 0; r < R.n_rows; r++) {
+        const uint64_t i = R.row0 + r;
+        uint64_t ns, skip0, skip1;
+        source_set(a, i, ns, skip0, skip1);
+        const double4 ri = rows[r];
+        double px = 0, py = 0, pz = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double dx = ri.x - src[k].x, dy = ri.y - src[k].y, dz = ri.z - src[k].z;
+            const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
+            const double q = rsqrt(r2);
+            const bool ok = (jj[k] < R.j1) & (jj[k] < ns) & (jj[k] != skip0) & (jj[k] != skip1);
+            const double p = ok ? src[k].w * (q * q * q) : 0.0;
+            px = fma(p, dx, px); py = fma(p, dy, py); pz = fma(p, dz, pz);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            px += __shfl_down_sync(0xffffffffu, px, o); py += __shfl_down_sync(0xffffffffu, py, o); pz += __shfl_down_sync(0xffffffffu, pz, o);
+        }
+        __syncthreads();
+        if (lane == 0) { red[w][0] = px; red[w][1] = py; red[w][2] = pz; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            const int c = threadIdx.x;
+            partial[((uint64_t)r * 3 + c) * n_cta + blockIdx.x] = ((red[0][c] + red[1][c]) + red[2][c]) + red[3][c];
+        }
+    }
+}
+
+template <bool KAHAN>
+__global__ void __launch_bounds__(128) row_fast_final_kernel(const RowArgs R, const double* __restrict__ partial, unsigned n_cta) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= R.n_rows * 3) return;
+    const int r = t / 3, c = t - 3 * r;
+    const double* p = partial + (uint64_t)t * n_cta;
+    double s = 0, e = 0;
+    for (unsigned k = 0; k < n_cta; k++) { const double y = p[k] - e, u = s + y; e = (u - s) - y; s = u; }
+    const uint64_t i = R.row0 + r;
+    double* out = (c == 0) ? R.a.ax : (c == 1) ? R.a.ay : R.a.az;
+    out[i] = s;
+    if (KAHAN && R.a.csx) { double* cs = (c == 0) ? R.a.csx : (c == 1) ? R.a.csy : R.a.csz; cs[i] = e; }
+}
+
 __global__ void zero3_kernel(double* ax, double* ay, double* az, uint64_t b, uint64_t e) {
     const uint64_t i = b + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e) { ax[i] = 0; ay[i] = 0; az[i] = 0; }
@@ -489,11 +676,14 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
     const bool kahan = c->gravity == REBCU_GRAVITY_COMPENSATED;
     a.use_ghosts = kahan ? 0 : 1;
     a.windowed = strict_window_ok(c->G) ? 1 : 0;
+    int ghosts_n = 1;
+    rebcu_vec6d gb0 = {0, 0, 0, 0, 0, 0};
     if (!kahan) {
         GhostShifts g;
         engine_ghost_shifts(c, c->N_ghost_x, c->N_ghost_y, c->N_ghost_z, &g);
         int err = engine_upload_ghosts(h, &g);
         if (err) return err;
+        ghosts_n = g.n; gb0 = g.gb[0];
     }
     a.csx = a.csy = a.csz = nullptr;
     h->gravity_cs_valid = false;
@@ -506,6 +696,48 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
         }
         a.csx = h->gravity_cs; a.csy = h->gravity_cs + h->gravity_cs_cap; a.csz = h->gravity_cs + 2 * h->gravity_cs_cap;
         h->gravity_cs_valid = true;
+    }
+    // testparticle_type 1 with few massive particles among many: the massive rows see all N sources and go through
+    // the row path; the regular kernels then only handle the test particles (sources = the massive ones).
+    if (a.type && a.Na < N && a.Na >= 1 && a.Na <= (uint64_t)ROW_MAX && N >= 4096 && (kahan || ghosts_n == 1)) {
+        const uint64_t r0 = a.i_begin, r1 = a.i_end < a.Na ? a.i_end : a.Na;
+        if (r1 > r0) {
+            RowArgs R;
+            R.a = a; R.row0 = r0; R.n_rows = (int)(r1 - r0);
+            R.gbx = gb0.x; R.gby = gb0.y; R.gbz = gb0.z;
+            const bool fast = c->mode == REBCU_MODE_FAST;
+            // chunk of sources per pass: the term buffer (24 B per row and source) stays L2 resident (<= 48 MB), so the
+            // ordered sum reads it back at L2 latency
+            uint64_t chunk = (48ull << 20) / (8ull * 3 * (uint64_t)R.n_rows);
+            if (const char* e = getenv("REBOUND_B200_ROWCHUNK")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) chunk = v; }   // tests: force several chunks
+            chunk = (chunk / 1024) * 1024;
+            if (chunk > N) chunk = ((N + 1023) / 1024) * 1024;
+            const uint64_t need = (fast ? (uint64_t)R.n_rows * 3 * ((N + 1023) / 1024) : (uint64_t)R.n_rows * 3 * chunk) + 64;
+            if (h->row_cap < need + 6 * ROW_MAX) {
+                CU_TRY(h, cudaStreamSynchronize(h->stream));
+                cudaFree(h->row_buf); h->row_buf = nullptr; h->row_cap = 0;
+                CU_TRY(h, cudaMalloc(&h->row_buf, (need + 6 * ROW_MAX) * sizeof(double)));
+                h->row_cap = need + 6 * ROW_MAX;
+            }
+            R.state = h->row_buf; R.terms = h->row_buf + 6 * ROW_MAX; R.chunk_cap = chunk;
+            if (fast) {
+                const unsigned n_cta = (unsigned)((N + 1023) / 1024);
+                R.j0 = 0; R.j1 = N; R.first = R.last = 1;
+                LaunchScope ls(h, TC_DIRECT, 2);
+                if (kahan) { row_fast_kernel<true><<<n_cta, 128, 0, h->stream>>>(R, R.terms, n_cta); row_fast_final_kernel<true><<<div_up(R.n_rows * 3, 128), 128, 0, h->stream>>>(R, R.terms, n_cta); }
+                else { row_fast_kernel<false><<<n_cta, 128, 0, h->stream>>>(R, R.terms, n_cta); row_fast_final_kernel<false><<<div_up(R.n_rows * 3, 128), 128, 0, h->stream>>>(R, R.terms, n_cta); }
+            } else {
+                for (uint64_t j0 = 0; j0 < N; j0 += chunk) {
+                    R.j0 = j0; R.j1 = (j0 + chunk < N) ? j0 + chunk : N;
+                    R.first = (j0 == 0); R.last = (R.j1 == N);
+                    LaunchScope ls(h, TC_DIRECT, 2);
+                    if (kahan) { row_terms_kernel<true><<<div_up(R.j1 - R.j0, 128), 128, 0, h->stream>>>(R); row_sum_kernel<true><<<div_up(R.n_rows, ROWS_PER_WARP), 32, 0, h->stream>>>(R); }
+                    else { row_terms_kernel<false><<<div_up(R.j1 - R.j0, 128), 128, 0, h->stream>>>(R); row_sum_kernel<false><<<div_up(R.n_rows, ROWS_PER_WARP), 32, 0, h->stream>>>(R); }
+                }
+            }
+            CU_TRY(h, cudaGetLastError());
+        }
+        if (a.i_begin < a.Na) a.i_begin = a.Na < a.i_end ? a.Na : a.i_end;
     }
     const uint64_t n_i = a.i_end - a.i_begin;
     if (n_i == 0) return REBCU_OK;

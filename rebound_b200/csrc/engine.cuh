@@ -97,6 +97,7 @@ struct rebcu_handle {
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ev[3 * PIPE_RANGES] = {};  // per range: [3i] upload done, [3i+1] kernels done, [3i+2] download done (trace)
     double* gravity_cs = nullptr; uint64_t gravity_cs_cap = 0; bool gravity_cs_valid = false;   // r->gravity_cs of the last COMPENSATED evaluation: x[cap], y[cap], z[cap]
+    double* row_buf = nullptr; uint64_t row_cap = 0;        // state + term buffer of the massive-row path (testparticle_type 1)
     double* diag_partial = nullptr; uint64_t diag_cap = 0;  // per-block partial sums of the diagnostics
     double* tp_hist = nullptr; uint64_t tp_hist_cap = 0;   // per-step snapshots of the massive bodies
     void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)

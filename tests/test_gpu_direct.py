@@ -2,6 +2,8 @@
 (oracle/oracle.c, pinned bitwise to the reference in test_oracle_vs_reference.py).
 
 STRICT mode must be bit-identical; FAST mode within 1e-12 relative (BASELINE.json north_star)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,7 @@ from rebound_b200 import abi, ics
 from rebound_b200.simulation import Engine, ReboundCudaError
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 ACC = ("ax", "ay", "az")
 
@@ -283,3 +286,58 @@ def test_coincident_particles_give_nan_where_the_reference_does(eng, grav, n):
         ok = ~np.isnan(want[f])
         assert np.array_equal(got[f][ok].view(np.uint64), want[f][ok].view(np.uint64)), f
     assert np.isnan(want["ax"][3]) and np.isnan(want["ax"][7]) and not np.isnan(want["ax"][0])
+
+
+def _type1_case(n, n_active, seed):
+    q = ics.planetesimal_disk(n, seed=seed)
+    q["m"][10:] = 1e-9
+    if n_active > 10:                      # promote some planetesimals to (light) massive bodies
+        q["m"][10:n_active] = 3e-7
+    return q
+
+
+@pytest.mark.parametrize("grav", [abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED])
+@pytest.mark.parametrize("n,n_active,terms", [(6000, 10, 0), (6000, 10, 1), (6000, 10, 2), (5000, 200, 0), (9000, 256, 0)])
+def test_type1_massive_rows_bitwise(eng, grav, n, n_active, terms):
+    """testparticle_type 1 with few massive particles among many (N >= 4096, N_active <= 256): the massive rows go
+    through the term-buffer + ordered-sum kernels; accelerations (and the Kahan compensation) stay bit-identical,
+    FAST stays within 1e-12."""
+    p = _type1_case(n, n_active, seed=31)
+    cfg = ics.planetesimal_config(testparticle_type=1, gravity=grav, N_active=n_active, gravity_ignore_terms=terms)
+    want, _ = checkers.oracle().gravity(cfg, p)
+    got, _ = gpu_gravity(eng, cfg, p)
+    assert bits_equal(got, want)
+    if grav == abi.GRAVITY_COMPENSATED:
+        _, want_cs = checkers.oracle().gravity_cs(cfg, p)
+        eng.upload(np.ascontiguousarray(p))
+        eng.update_acceleration(cfg.copy())
+        assert np.array_equal(eng.download_gravity_cs().view(np.uint64), want_cs.view(np.uint64))
+    c = cfg.copy()
+    c.mode = abi.MODE_FAST
+    fast, _ = gpu_gravity(eng, c, p)
+    assert max_rel_acc_error(fast, want) <= 1e-12
+
+
+def test_type1_massive_rows_in_several_source_chunks(tmp_path):
+    """The term buffer is filled and consumed chunk by chunk (REBOUND_B200_ROWCHUNK forces small chunks here); the
+    running sums carry over between chunks."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import checkers
+        from rebound_b200 import abi, ics
+        from rebound_b200.simulation import Engine
+        import test_gpu_direct as T
+        eng = Engine(0)
+        for grav in (abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED):
+            p = T._type1_case(7000, 10, seed=33)
+            cfg = ics.planetesimal_config(testparticle_type=1, gravity=grav)
+            want, _ = checkers.oracle().gravity(cfg, p)
+            got, _ = T.gpu_gravity(eng, cfg, p)
+            assert checkers.bits_equal(got, want)
+        print("CHUNKS OK")
+    """ % (ROOT, os.path.join(ROOT, "tests")))
+    env = dict(os.environ, REBOUND_B200_ROWCHUNK="2048")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "CHUNKS OK" in r.stdout, r.stderr

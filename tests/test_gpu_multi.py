@@ -111,6 +111,11 @@ def make_case(case):
         q = ics.planetesimal_disk(2000, seed=5)
         q["m"][10:] = 1e-9
         return q, ics.planetesimal_config(testparticle_type=1), 2
+    if case == "testp_type1_rows":
+        # N >= 4096: the massive rows take the term-buffer path on the rank that owns them
+        q = ics.planetesimal_disk(6000, seed=8)
+        q["m"][10:] = 1e-9
+        return q, ics.planetesimal_config(testparticle_type=1), 2
     if case == "disc_tree":
         return ics.selfgravity_disc(3000, seed=6), ics.selfgravity_disc_config(boundary=abi.BOUNDARY_NONE), 2
     if case in ("open_basic", "open_tree"):
@@ -176,7 +181,7 @@ def test_two_gpu_sharded_collision_search_bitwise(case, tmp_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("case", ["plummer_basic", "plummer_comp", "testp_type1", "disc_tree"])
+@pytest.mark.parametrize("case", ["plummer_basic", "plummer_comp", "testp_type1", "testp_type1_rows", "disc_tree"])
 def test_two_gpu_sharded_steps_bitwise(case, tmp_path):
     import torch.multiprocessing as mp
 
