@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_reference_layout():
     assert abi.PARTICLE_DTYPE.itemsize == 112      # struct reb_particle, rebound.h:86-104
     assert abi.COLLISION_DTYPE.itemsize == 72      # struct reb_collision, rebound.h:144-149
-    assert C.sizeof(abi.Config) == 9 * 8 + 8 + 14 * 4
+    assert C.sizeof(abi.Config) == 144             # 9 doubles + uint64 + 15 int32, padded to 8 bytes (rebcu_config)
 
 
 def test_no_cpu_fallback():
