@@ -197,6 +197,32 @@ int rebcu_collision_search_host(rebcu_handle* h, const rebcu_config* cfg,
 int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N,
                      uint64_t n_steps);
 
+/* ---- device-side hard-sphere resolve (NOT bit-identical, see csrc/resolve.cu) ---- */
+/* reb_collision_resolve_hardsphere (src/collision.c:573-665) applied on the device to the list of the last
+ * collision search, in the reference's shuffled order (rand_r, collision.c:337-342) with the sequential semantics of
+ * its loop (collision.c:351-404).  The rotation uses the device's atan2/sin/cos and the restitution law its pow, so
+ * velocities agree with the reference to a few ulp per resolved collision, not bit for bit -- which is why the
+ * drop-in librebound keeps resolving on the host.  Restitution laws (the reference takes a user callback,
+ * rebound.h:403-409; a device needs a closed form):
+ *   CONSTANT   eps = a
+ *   POWERLAW   eps = clamp(a * pow(fabs(v) * b, c), lo, hi)     e.g. Bridges et al. 1984: a=0.32, b=100, c=-0.234, [0,1] */
+#define REBCU_RESTITUTION_CONSTANT 0
+#define REBCU_RESTITUTION_POWERLAW 1
+typedef struct rebcu_restitution {
+    int32_t kind;
+    int32_t pad_;
+    double a, b, c, lo, hi;
+} rebcu_restitution;
+/* enable != 0: rebcu_steps resolves every step's list on the device instead of calling the collision callback.
+ * restitution NULL = perfectly elastic (the reference's default when coefficient_of_restitution is NULL).
+ * rand_seed = r->rand_seed.  Resets the statistics below. */
+int rebcu_set_device_resolve(rebcu_handle* h, int enable, const rebcu_restitution* restitution,
+                             double minimum_collision_velocity, unsigned int rand_seed);
+/* Resolve the list left by the last rebcu_collision_search now (what rebcu_steps does per step when enabled). */
+int rebcu_collision_resolve(rebcu_handle* h, const rebcu_config* cfg);
+/* r->collisions_plog, r->collisions_log_n, r->rand_seed as the device resolver advanced them; rounds of the last call. */
+int rebcu_collision_stats(const rebcu_handle* h, double* plog, uint64_t* log_n, unsigned int* rand_seed, int* rounds_last);
+
 /* ---- multi-GPU sharding ------------------------------------------------------- */
 /* Rank `rank` of `world` owns the contiguous i-block [N*rank/world, N*(rank+1)/world): the direct
  * and tree force kernels and kick/drift touch only that block; positions of the other blocks are

@@ -56,6 +56,16 @@ ERRORS = {
 }
 
 
+class Restitution(C.Structure):
+    """rebcu_restitution: closed-form restitution law for the device-side resolver."""
+
+    _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double),
+                ("lo", C.c_double), ("hi", C.c_double)]
+
+
+RESTITUTION_CONSTANT, RESTITUTION_POWERLAW = 0, 1
+
+
 class Config(C.Structure):
     """rebcu_config: the scalar fields of struct reb_simulation the hot path reads."""
 
@@ -178,6 +188,9 @@ PRODUCT_SIGNATURES = {
     "gravity_host": (C.c_int, [_P, _CFG, _P, _U64P]),
     "collision_search_host": (C.c_int, [_P, _CFG, _P, C.c_uint64, _P, C.c_uint64, _U64P]),
     "steps_host": (C.c_int, [_P, _CFG, _P, _U64P, C.c_uint64]),
+    "set_device_resolve": (C.c_int, [_P, C.c_int, C.POINTER(Restitution), C.c_double, C.c_uint]),
+    "collision_resolve": (C.c_int, [_P, _CFG]),
+    "collision_stats": (C.c_int, [_P, _DBLP, _U64P, C.POINTER(C.c_uint), C.POINTER(C.c_int)]),
     "set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "shard_range": (None, [_P, _U64P, _U64P]),
     "set_exchange_callback": (C.c_int, [_P, _P, _P]),

@@ -91,7 +91,10 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
         if (cfg->collision != REBCU_COLLISION_NONE) {
             err = collision_search(h, cfg);
             if (err) return err;
-            if (h->collision_hook) {
+            if (h->resolve_on) {
+                err = collision_resolve_device(h, cfg);
+                if (err) return err;
+            } else if (h->collision_hook) {
                 err = h->collision_hook(h->collision_hook_user);
                 if (err) return err;
             }

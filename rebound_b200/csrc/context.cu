@@ -72,6 +72,7 @@ void rebcu_destroy(rebcu_handle* h) {
     cudaFree(h->tp_hist);
     cudaFree(h->diag_partial);
     cudaFree(h->row_buf);
+    cudaFree(h->resolve_buf);
     cudaFree(h->gravity_cs);
     for (int k = 0; k < AUX_STREAMS; k++) if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
     for (int k = 0; k < 3; k++) if (h->aux_ev[k]) cudaEventDestroy(h->aux_ev[k]);

@@ -97,6 +97,10 @@ struct rebcu_handle {
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ev[3 * PIPE_RANGES] = {};  // per range: [3i] upload done, [3i+1] kernels done, [3i+2] download done (trace)
     double* gravity_cs = nullptr; uint64_t gravity_cs_cap = 0; bool gravity_cs_valid = false;   // r->gravity_cs of the last COMPENSATED evaluation: x[cap], y[cap], z[cap]
+    // device-side hard-sphere resolve (resolve.cu)
+    bool resolve_on = false; rebcu_restitution resolve_rest = {0, 0, 1.0, 0, 0, 0, 1}; double resolve_min_v = 0;
+    unsigned int resolve_seed = 0; double resolve_plog = 0; uint64_t resolve_log_n = 0; int resolve_rounds = 0;
+    uint32_t* resolve_buf = nullptr; uint64_t resolve_cap = 0;
     double* row_buf = nullptr; uint64_t row_cap = 0;        // state + term buffer of the massive-row path (testparticle_type 1)
     double* diag_partial = nullptr; uint64_t diag_cap = 0;  // per-block partial sums of the diagnostics
     double* tp_hist = nullptr; uint64_t tp_hist_cap = 0;   // per-step snapshots of the massive bodies
@@ -134,6 +138,7 @@ struct LaunchScope {
 int engine_reserve(rebcu_handle* h, uint64_t n);
 void engine_exchange(rebcu_handle* h, int need);
 int boundary_check_full(rebcu_handle* h, rebcu_config* c);
+int collision_resolve_device(rebcu_handle* h, const rebcu_config* c);
 int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work);
 void engine_ghost_shifts(const rebcu_config* c, int gx, int gy, int gz, GhostShifts* out);
 int engine_upload_ghosts(rebcu_handle* h, const GhostShifts* g);

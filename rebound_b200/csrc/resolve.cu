@@ -1,0 +1,234 @@
+// resolve.cu -- hard-sphere collision resolve on the device, for callers of the C ABI that
+// accept a documented relaxation of the parity bar.
+//
+// What the reference does (src/collision.c:336-404, 573-665): shuffle the list with rand_r, then walk it IN ORDER,
+// each collision reading and changing the velocities of its two particles -- so a collision sees the outcome of
+// every earlier collision that involves one of its particles.
+//
+// Here the same order is kept with conflict-free rounds: in a round every pending collision that is the earliest
+// pending one of BOTH its particles is resolved (no two such collisions share a particle, and everything that had to
+// happen before them already has); the globally earliest pending collision always qualifies, so the rounds terminate.
+// The result is the one of the sequential loop up to the arithmetic inside a single resolve.
+//
+// The relaxation: the resolver rotates with atan2 / sin / cos and restitution laws use pow.  CUDA's libm does not
+// return glibc's bits for these (and glibc picks FMA / non-FMA variants per CPU), so velocities after a resolved
+// collision agree with the reference to a few ulp, not bit for bit; collisions_plog is a compensated parallel sum.
+// The drop-in librebound therefore keeps resolving on the host with the reference's own functions; this entry point is
+// for resident simulations driven through the C ABI (rebcu_set_device_resolve), where it removes the per-step
+// download + serial host loop (C5: ~7e5 list entries per step).
+#include "engine.cuh"
+#include <stdlib.h>
+#include <math.h>
+#include <vector>
+
+namespace {
+
+constexpr uint32_t NONE = 0xffffffffu;
+
+struct ResolveArgs {
+    double *x, *y, *z, *vx, *vy, *vz;
+    const double *m, *r;
+    const rebcu_collision* list;
+    const uint32_t* order;        // processing position k -> list index (the rand_r shuffle)
+    uint32_t n;
+    uint32_t* first;              // per particle: earliest pending processing position
+    uint8_t* done;                // per processing position
+    double* plog_term;            // per processing position
+    unsigned long long* counters; // [0] pending after this round, [1] resolved (collisions_log_n)
+    rebcu_restitution rest;
+    double min_v;
+};
+
+__global__ void __launch_bounds__(256) claim_kernel(ResolveArgs A) {
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= A.n || A.done[k]) return;
+    const rebcu_collision c = A.list[A.order[k]];
+    atomicMin(&A.first[c.p1], k);
+    atomicMin(&A.first[c.p2], k);
+}
+
+__device__ __forceinline__ double restitution(const rebcu_restitution& R, double v) {
+    if (R.kind == REBCU_RESTITUTION_CONSTANT) return R.a;
+    double eps = R.a * pow(fabs(v) * R.b, R.c);      // e.g. Bridges et al.: 0.32*pow(fabs(v)*100., -0.234)
+    if (eps > R.hi) eps = R.hi;
+    if (eps < R.lo) eps = R.lo;
+    return eps;
+}
+
+// reb_collision_resolve_hardsphere, src/collision.c:573-665 (same expressions, device libm)
+__global__ void __launch_bounds__(256) resolve_kernel(ResolveArgs A) {
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= A.n || A.done[k]) return;
+    const rebcu_collision c = A.list[A.order[k]];
+    const uint32_t p1 = (uint32_t)c.p1, p2 = (uint32_t)c.p2;
+    if (A.first[p1] != k || A.first[p2] != k) { atomicAdd(&A.counters[0], 1ull); return; }     // an earlier collision is pending
+    A.done[k] = 1;
+    double term = 0.;
+    const double x21 = A.x[p1] + c.gb.x - A.x[p2];
+    const double y21 = A.y[p1] + c.gb.y - A.y[p2];
+    const double z21 = A.z[p1] + c.gb.z - A.z[p2];
+    const double r1 = A.r[p1], r2 = A.r[p2], m1 = A.m[p1], m2 = A.m[p2];
+    const double rp = r1 + r2;
+    const double v1x = A.vx[p1], v1y = A.vy[p1], v1z = A.vz[p1];
+    const double v2x = A.vx[p2], v2y = A.vy[p2], v2z = A.vz[p2];
+    const double oldvyouter = (x21 > 0) ? v1y : v2y;
+    bool act = !(rp * rp < x21 * x21 + y21 * y21 + z21 * z21);
+    const double vx21 = v1x + c.gb.vx - v2x;
+    const double vy21 = v1y + c.gb.vy - v2y;
+    const double vz21 = v1z + c.gb.vz - v2z;
+    if (act && vx21 * x21 + vy21 * y21 + vz21 * z21 > 0) act = false;        // not approaching
+    if (act) {
+        const double theta = atan2(z21, y21);
+        const double stheta = sin(theta), ctheta = cos(theta);
+        const double vy21n = ctheta * vy21 + stheta * vz21;
+        const double y21n = ctheta * y21 + stheta * z21;
+        const double phi = atan2(y21n, x21);
+        const double cphi = cos(phi), sphi = sin(phi);
+        const double vx21nn = cphi * vx21 + sphi * vy21n;
+        const double eps = restitution(A.rest, vx21nn);
+        double dvx2 = -(1.0 + eps) * vx21nn;
+        const double minr = (r1 > r2) ? r2 : r1;
+        const double maxr = (r1 < r2) ? r2 : r1;
+        double mindv = minr * A.min_v;
+        const double rr = sqrt(x21 * x21 + y21 * y21 + z21 * z21);
+        mindv *= 1. - (rr - maxr) / minr;
+        if (mindv > maxr * A.min_v) mindv = maxr * A.min_v;
+        if (dvx2 < mindv) dvx2 = mindv;
+        const double dvx2n = cphi * dvx2;
+        const double dvy2n = sphi * dvx2;
+        const double dvy2nn = ctheta * dvy2n;
+        const double dvz2nn = stheta * dvy2n;
+        const double p2pf = m1 / (m1 + m2);
+        const double n2x = v2x - p2pf * dvx2n, n2y = v2y - p2pf * dvy2nn, n2z = v2z - p2pf * dvz2nn;
+        const double p1pf = m2 / (m1 + m2);
+        const double n1x = v1x + p1pf * dvx2n, n1y = v1y + p1pf * dvy2nn, n1z = v1z + p1pf * dvz2nn;
+        A.vx[p2] = n2x; A.vy[p2] = n2y; A.vz[p2] = n2z;
+        A.vx[p1] = n1x; A.vy[p1] = n1y; A.vz[p1] = n1z;
+        term = (x21 > 0) ? -fabs(x21) * (oldvyouter - n1y) * m1 : -fabs(x21) * (oldvyouter - n2y) * m2;
+        atomicAdd(&A.counters[1], 1ull);
+    }
+    A.plog_term[k] = term;
+}
+
+// the particles of still pending collisions get a fresh "earliest" slot for the next round
+__global__ void __launch_bounds__(256) release_kernel(ResolveArgs A) {
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= A.n) return;
+    const rebcu_collision c = A.list[A.order[k]];
+    A.first[c.p1] = NONE;
+    A.first[c.p2] = NONE;
+}
+
+__global__ void __launch_bounds__(256) plog_partial_kernel(const double* __restrict__ t, uint32_t n, double* __restrict__ partial) {
+    __shared__ double sm[8];
+    double s = 0, e = 0;
+    for (uint32_t k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) { const double y = t[k] - e, u = s + y; e = (u - s) - y; s = u; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double v = 0; for (int w = 0; w < 8; w++) v += sm[w]; partial[blockIdx.x] = v; }
+}
+
+}  // namespace
+
+// Resolves the list the last collision search left on the device.  Returns the number of rounds in *rounds (may be null).
+int collision_resolve_device(rebcu_handle* h, const rebcu_config* c) {
+    (void)c;
+    const uint64_t n = h->col_n;
+    if (n == 0) return REBCU_OK;
+    if (n >= NONE) return rebcu_fail(h, REBCU_ERR_ARG, "device resolve supports fewer than 2^32 list entries");
+    // the rand_r shuffle of the reference, applied to the processing order (collision.c:337-342)
+    std::vector<uint32_t> order(n);
+    for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t j = (uint64_t)rand_r(&h->resolve_seed) % n;
+        const uint32_t t = order[i]; order[i] = order[j]; order[j] = t;
+    }
+    const uint64_t words = n /*order*/ + h->cap /*first*/ + (n + 3) / 4 /*done*/ + 2 * n /*plog terms*/ + 2 * 1024 /*partials*/ + 64;
+    if (h->resolve_cap < words) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->resolve_buf); h->resolve_buf = nullptr; h->resolve_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->resolve_buf, (words + words / 4) * sizeof(uint32_t)));
+        h->resolve_cap = words + words / 4;
+    }
+    uint32_t* base = h->resolve_buf;
+    ResolveArgs A;
+    A.plog_term = (double*)base;                       // 8-byte aligned first
+    double* partial = A.plog_term + n;
+    A.order = base + 2 * n + 2 * 1024;
+    A.first = (uint32_t*)A.order + n;
+    A.done = (uint8_t*)(A.first + h->cap);
+    A.x = h->f(F_X); A.y = h->f(F_Y); A.z = h->f(F_Z); A.vx = h->f(F_VX); A.vy = h->f(F_VY); A.vz = h->f(F_VZ);
+    A.m = h->f(F_M); A.r = h->f(F_R);
+    A.list = h->col_list; A.n = (uint32_t)n;
+    A.counters = h->counters + 8;
+    A.rest = h->resolve_rest; A.min_v = h->resolve_min_v;
+    CU_TRY(h, cudaMemcpyAsync((void*)A.order, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemsetAsync(A.first, 0xff, h->cap * sizeof(uint32_t), h->stream));
+    CU_TRY(h, cudaMemsetAsync(A.done, 0, n, h->stream));
+    CU_TRY(h, cudaMemsetAsync(A.counters, 0, 2 * sizeof(unsigned long long), h->stream));
+    const unsigned nb = div_up(n, 256);
+    unsigned long long* pin = h->pinned + 20;
+    int rounds = 0;
+    for (;;) {
+        {
+            LaunchScope ls(h, TC_COLLISION, 3);
+            claim_kernel<<<nb, 256, 0, h->stream>>>(A);
+            resolve_kernel<<<nb, 256, 0, h->stream>>>(A);
+            release_kernel<<<nb, 256, 0, h->stream>>>(A);
+        }
+        rounds++;
+        CU_TRY(h, cudaMemcpyAsync(pin, A.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemsetAsync(A.counters, 0, sizeof(unsigned long long), h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if (pin[0] == 0) break;
+        if (rounds > 100000) return rebcu_fail(h, REBCU_ERR_CUDA, "device resolve did not terminate");
+    }
+    h->resolve_log_n += pin[1];
+    h->resolve_rounds = rounds;
+    // collisions_plog: compensated parallel sum of the per-collision terms
+    const unsigned pb = nb < 1024 ? nb : 1024;
+    {
+        LaunchScope ls(h, TC_COLLISION);
+        plog_partial_kernel<<<pb, 256, 0, h->stream>>>(A.plog_term, A.n, partial);
+    }
+    CU_TRY(h, cudaGetLastError());
+    std::vector<double> part(pb);
+    CU_TRY(h, cudaMemcpyAsync(part.data(), partial, pb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    double s = 0, e = 0;
+    for (unsigned k = 0; k < pb; k++) { const double y = part[k] - e, u = s + y; e = (u - s) - y; s = u; }
+    h->resolve_plog += s;
+    h->col_n = 0;                                       // consumed
+    return REBCU_OK;
+}
+
+extern "C" {
+
+int rebcu_set_device_resolve(rebcu_handle* h, int enable, const rebcu_restitution* restitution, double minimum_collision_velocity,
+                             unsigned int rand_seed) {
+    h->resolve_on = enable != 0;
+    if (restitution) h->resolve_rest = *restitution;
+    else { h->resolve_rest.kind = REBCU_RESTITUTION_CONSTANT; h->resolve_rest.a = 1.0; h->resolve_rest.b = h->resolve_rest.c = 0; h->resolve_rest.lo = 0; h->resolve_rest.hi = 1; }
+    h->resolve_min_v = minimum_collision_velocity;
+    h->resolve_seed = rand_seed;
+    h->resolve_plog = 0; h->resolve_log_n = 0; h->resolve_rounds = 0;
+    return REBCU_OK;
+}
+
+int rebcu_collision_resolve(rebcu_handle* h, const rebcu_config* cfg) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (h->world > 1) return rebcu_fail(h, REBCU_ERR_ARG, "device resolve while sharded over several GPUs is not implemented");
+    return collision_resolve_device(h, cfg);
+}
+
+int rebcu_collision_stats(const rebcu_handle* h, double* plog, uint64_t* log_n, unsigned int* rand_seed, int* rounds_last) {
+    if (plog) *plog = h->resolve_plog;
+    if (log_n) *log_n = h->resolve_log_n;
+    if (rand_seed) *rand_seed = h->resolve_seed;
+    if (rounds_last) *rounds_last = h->resolve_rounds;
+    return REBCU_OK;
+}
+
+}  // extern "C"

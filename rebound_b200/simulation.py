@@ -165,6 +165,28 @@ class Engine:
             return self.collision_search_host(cfg, p, cap=n.value)
         return out[: n.value]
 
+    # device-side hard-sphere resolve (not bit-identical: see csrc/resolve.cu)
+    def set_device_resolve(self, enable=True, restitution=None, minimum_collision_velocity=0.0, rand_seed=0):
+        """restitution: None (elastic), a float (constant), or (a, b, c, lo, hi) for eps = clamp(a*pow(|v|*b, c), lo, hi)."""
+        rest = None
+        if restitution is not None:
+            rest = abi.Restitution()
+            if isinstance(restitution, (int, float)):
+                rest.kind, rest.a, rest.lo, rest.hi = abi.RESTITUTION_CONSTANT, float(restitution), 0.0, 1.0
+            else:
+                rest.kind = abi.RESTITUTION_POWERLAW
+                rest.a, rest.b, rest.c, rest.lo, rest.hi = (float(v) for v in restitution)
+        self._check(self.f["set_device_resolve"](self.h, 1 if enable else 0, C.byref(rest) if rest is not None else None,
+                                                 float(minimum_collision_velocity), int(rand_seed)))
+
+    def collision_resolve(self, cfg):
+        self._check(self.f["collision_resolve"](self.h, C.byref(cfg)))
+
+    def collision_stats(self):
+        plog, n, seed, rounds = C.c_double(0), C.c_uint64(0), C.c_uint(0), C.c_int(0)
+        self._check(self.f["collision_stats"](self.h, C.byref(plog), C.byref(n), C.byref(seed), C.byref(rounds)))
+        return {"collisions_plog": plog.value, "collisions_log_n": int(n.value), "rand_seed": int(seed.value), "rounds": int(rounds.value)}
+
     # sharding
     def set_shard(self, rank, world):
         self._check(self.f["set_shard"](self.h, rank, world))

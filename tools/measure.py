@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel-class device timings of the other BASELINE.json configurations (not the bench line).
-usage: python tools/measure.py [c1|c1fast|c3s|c4_20|c4_22|c4_24|c5_18|c5_20 ...]"""
+usage: python tools/measure.py [c1|c1fast|c3s|c4_20|c4_22|c4_24|c5_18|c5_20|c5r_20 ...]
+(c5r_N: C5 with the device-side hard-sphere resolve, Bridges restitution)"""
 import json
 import os
 import sys
@@ -51,6 +52,10 @@ def main():
         p, cfg, steps, inter = case(name)
         eng.upload(np.ascontiguousarray(p))
         c = cfg.copy()
+        device_resolve = name.startswith("c5r")
+        if device_resolve:
+            eng.set_device_resolve(True, restitution=(0.32, 100.0, -0.234, 0.0, 1.0),
+                                   minimum_collision_velocity=1.0 * ics.SHEET_OMEGA * 0.001, rand_seed=42)
         eng.steps(c, 1)
         eng.synchronize()
         eng.timing_enable(True)
@@ -67,7 +72,10 @@ def main():
                "launches_per_step": {k: v["launches"] / steps for k, v in tim.items() if v["launches"]}}
         if inter:
             out["interactions_per_s"] = inter * steps / wall
-        if cfg.collision:
+        if device_resolve:
+            out["resolve"] = eng.collision_stats()
+            eng.set_device_resolve(False)
+        elif cfg.collision:
             out["collisions_last_step"] = int(len(eng.collisions_fetch()))
         print(json.dumps(out), flush=True)
     eng.close()
