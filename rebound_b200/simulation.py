@@ -393,6 +393,16 @@ class Simulation:
         self._to_device()
         return self._engine.collision_search(self._cfg)
 
+    def set_device_resolve(self, enable=True, restitution=None, minimum_collision_velocity=0.0, rand_seed=0):
+        """Hard-sphere resolve on the device after every step's collision search (Engine.set_device_resolve); the
+        counterpart of `sim.collision_resolve = "hardsphere"` for a resident simulation.  Not bit-identical."""
+        self._engine.set_device_resolve(enable, restitution, minimum_collision_velocity, rand_seed)
+
+    @property
+    def collision_stats(self):
+        """collisions_plog / collisions_log_n as advanced by the device resolver."""
+        return self._engine.collision_stats()
+
     def energy(self):
         """reb_simulation_energy (src/tools.c:108-162), evaluated on the device."""
         self._to_device()
