@@ -1,5 +1,7 @@
 """Randomised (hypothesis, derandomised) GPU parity through the C ABI against the oracle: the same strategy as
 tests/test_oracle_random.py (random N, boxes, ghost rings, root-box grids, modes, test-particle settings)."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -11,7 +13,9 @@ from rebound_b200.simulation import Engine
 from test_oracle_random import cfg_st, make
 
 pytestmark = pytest.mark.gpu
-SET = settings(max_examples=50, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+# REBOUND_B200_FUZZ=<n>: a longer, non-derandomised campaign (default: 50 fixed examples per test)
+_N = int(os.environ.get("REBOUND_B200_FUZZ", "50"))
+SET = settings(max_examples=_N, deadline=None, derandomize=(_N == 50), suppress_health_check=list(HealthCheck))
 
 _eng = None
 
@@ -24,9 +28,9 @@ def eng():
 
 
 @SET
-@given(cfg_st)
-def test_random_tree_cells_and_gravity(d):
-    c, p = make(d, gravity=abi.GRAVITY_TREE)
+@given(cfg_st, st.integers(0, 1))
+def test_random_tree_cells_and_gravity(d, quad):
+    c, p = make(d, gravity=abi.GRAVITY_TREE, quadrupole=quad)
     pb, cb = checkers.oracle().boundary_check(c, p)
     e = eng()
     e.upload(np.ascontiguousarray(pb))

@@ -93,3 +93,16 @@ def test_random_full_steps(d, integ):
     b, cb, xb = checkers.oracle().steps(c, p, 3, resolve=1)
     assert len(a) == len(b) and bits_equal(a, b)
     assert ca.t == cb.t and xa["collisions_log_n"] == xb["collisions_log_n"] and xa["collisions_plog"] == xb["collisions_plog"]
+
+
+@SET
+@given(cfg_st)
+def test_random_quadrupole_gravity(d):
+    """cfg.quadrupole = 1 against the reference compiled with -DQUADRUPOLE (src/tree.c:148-198, 293-303)."""
+    ref = checkers.reference(quadrupole=True)
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_harness_quad.so not built")
+    c, p = make(d, gravity=abi.GRAVITY_TREE, quadrupole=1)
+    a, _ = ref.gravity(c, p)
+    b, _ = checkers.oracle().gravity(c, p)
+    assert len(a) == len(b) and bits_equal(a, b)

@@ -1,3 +1,5 @@
+"""Prints the per-range timeline of the chunk-pipelined host path (rebcu_steps_host on C2): REBOUND_B200_PIPE_TRACE=1.
+usage: [REBOUND_B200_CHUNKS=n] python tools/pipe_trace.py"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, ".")
 from rebound_b200 import ics, abi
