@@ -94,3 +94,47 @@ def test_simulation_mirror_collision_search_shearing_sheet():
     want = checkers.oracle().collision_search(cfg, p)
     assert checkers.collisions_equal(got, want)
     sim.close()
+
+
+def test_independent_simulations_in_parallel_threads():
+    """SURVEY 8b threading: several simulations may be stepped from different threads (ctypes releases the GIL);
+    every handle owns its stream and buffers, so concurrent runs give the bits of the serial runs."""
+    import threading
+
+    from rebound_b200.simulation import Engine
+
+    cases = [(ics.plummer(3000, seed=1), ics.plummer_config(3000), 6),
+             (ics.selfgravity_disc(4000, seed=2), ics.selfgravity_disc_config(collision=abi.COLLISION_NONE), 5),
+             (ics.shearing_sheet(root_size=40.0, seed=3), ics.shearing_sheet_config(root_size=40.0), 8),
+             (ics.planetesimal_disk(5000, seed=4), ics.planetesimal_config(), 12)]
+    serial = []
+    for p, cfg, steps in cases:
+        e = Engine(0)
+        q = p.copy()
+        n = e.steps_host(cfg.copy(), q, steps)
+        serial.append(q[:n].tobytes())
+        e.close()
+    results = [None] * len(cases)
+    errors = []
+
+    def work(k):
+        try:
+            p, cfg, steps = cases[k]
+            e = Engine(0)
+            out = None
+            for _ in range(5):                      # repeat to give the threads time to overlap
+                q = p.copy()
+                n = e.steps_host(cfg.copy(), q, steps)
+                out = q[:n].tobytes()
+            e.close()
+            results[k] = out
+        except Exception as exc:                    # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    assert results == serial
