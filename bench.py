@@ -56,18 +56,48 @@ def workload(name, rank=0):
     return p, cfg, inter, desc
 
 
+def _nvml_handle(gpu_index):
+    """NVML handle of the CUDA device `gpu_index` of this process (honours a numeric CUDA_VISIBLE_DEVICES)."""
+    import pynvml
+
+    pynvml.nvmlInit()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    idx = gpu_index
+    try:
+        ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+        if ids:
+            idx = ids[gpu_index]
+    except ValueError:
+        pass
+    return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples the SM clock and the clock event (throttle) reasons of one GPU DURING the timed region: NVML every
+    2 ms from a thread (the timed region of the default run is ~30 ms); falls back to an nvidia-smi loop."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []          # (sm_mhz, reasons bit mask)
+        self.max_mhz = None
+        self.stop_flag = False
 
     def start(self):
+        try:
+            self.nvml, self.handle = _nvml_handle(self.gpu)
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,11 +106,30 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), int(reasons_fn(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = [s for s, _ in self.samples]
+            mask = 0
+            for _, m in self.samples:
+                mask |= m
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, bit in self.BITS.items() if mask & bit), "samples": len(sm), "source": "nvml, 2 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -100,7 +149,33 @@ class ClockSampler:
                 if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """One process per GPU: run on the cores next to this GPU so that the pinned host buffers (first touch) and the
+    copy threads are local to its PCIe root; without it 8 ranks push their host traffic through one socket."""
+    try:
+        nvml, handle = _nvml_handle(gpu_index)
+        bus = nvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:            # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def cpu_reference_checker():
@@ -266,6 +341,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    numa_cpus = None
+    if world > 1:
+        numa_cpus = bind_to_gpu_numa_node(local_rank)      # before anything allocates host memory or starts threads
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -442,7 +520,8 @@ def main():
             "config": {"workload": desc, "inner_steps_per_step": inner, "N_per_gpu": int(n),
                        "mode": "strict (bit-identical to the reference)" if cfg.mode == 0 else "fast",
                        "l2": "flushed between timed steps (256 MiB fill), untimed",
-                       "sharding": "test particles sharded per rank, massive bodies replicated, no collective"},
+                       "sharding": "test particles sharded per rank, massive bodies replicated, no collective",
+                       "host_affinity": (f"each rank bound to the {numa_cpus} cores local to its GPU" if numa_cpus else "unbound")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": int(n * 112), "d2h_bytes_per_step": int(n * 112)},
             "gpu_launches": int(launches),
