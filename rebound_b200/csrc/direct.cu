@@ -438,7 +438,7 @@ struct RowArgs {
     DirectArgs a;
     uint64_t row0; int n_rows;          // rows [row0, row0 + n_rows), all < N_active
     uint64_t j0, j1;                    // source chunk of this launch
-    double* terms; uint64_t chunk_cap;  // [n_rows][3][chunk_cap]
+    double* terms; uint64_t chunk_cap;  // [chunk_cap/2 source pairs][n_rows][3][2]
     double* state;                      // [n_rows][6] running sx sy sz cx cy cz between chunks
     double gbx, gby, gbz;               // ghost box (0,0,0) shift, added as the reference does (BASIC only)
     int first, last;                    // first / last chunk
@@ -473,16 +473,18 @@ __global__ void __launch_bounds__(128) row_terms_kernel(const RowArgs R) {
             const double d = s_sqrt(r2);          // correctly rounded either way: no recomputation needed
             p = KAHAN ? s_mul(-s_div(a.G, s_mul(r2, d)), mj) : s_mul(s_div(negG, s_mul(s_mul(d, d), d)), mj);
         }
-        double* t = R.terms + (uint64_t)r * 3 * R.chunk_cap + col;
-        t[0] = s_mul(p, dx); t[R.chunk_cap] = s_mul(p, dy); t[2 * R.chunk_cap] = s_mul(p, dz);
+        // [source pair][row][component][2]: the two sources of a pair are adjacent, so the ordered sum moves 16 bytes
+        // per chain and pair, and the chains of a pair are contiguous (a warp-wide access touches four cache lines)
+        double* t = R.terms + ((col >> 1) * (uint64_t)(3 * R.n_rows) + 3 * r) * 2 + (col & 1);
+        t[0] = s_mul(p, dx); t[2] = s_mul(p, dy); t[4] = s_mul(p, dz);
     }
 }
 
 // Ordered sums.  Lane (row, component): one warp carries the 30 chains of 10 rows in lock step, so one DADD
-// instruction per source advances all of them; each lane streams its own term array, 16 terms per batch, the next
-// batch already in flight while the current one is added.
+// instruction per source advances all of them.
 constexpr int ROWS_PER_WARP = 10;
 constexpr int ROW_BATCH = 16;
+constexpr int ROW_STAGES = 8;
 
 template <bool KAHAN>
 __global__ void __launch_bounds__(32) row_sum_kernel(const RowArgs R) {
@@ -496,47 +498,54 @@ __global__ void __launch_bounds__(32) row_sum_kernel(const RowArgs R) {
     source_set(a, i, ns, skip0, skip1);
     double s = 0, e = 0;
     if (!R.first) { s = R.state[(uint64_t)r * 6 + c]; e = R.state[(uint64_t)r * 6 + 3 + c]; }
-    const double* t = R.terms + ((uint64_t)r * 3 + c) * R.chunk_cap;
+    const uint64_t S = (uint64_t)3 * R.n_rows;
+    const double* t = R.terms + ((uint64_t)r * 3 + c) * 2;       // + (source / 2) * 2S + (source & 1)
     const uint64_t cnt = R.j1 - R.j0;
-    // four register buffers: three batches (48 terms) are in flight while one is added, which covers the L2 latency
-    // at one dependent add per ~16 cycles
-    double B0[ROW_BATCH], B1[ROW_BATCH], B2[ROW_BATCH], B3[ROW_BATCH];
-    auto fetch = [&](double (&buf)[ROW_BATCH], uint64_t b) {
-        if (b >= cnt) return;
+    // The chain is one dependent add per source; everything else must stay off its critical path.  The terms of one
+    // source are contiguous over the chains, so a warp-wide 8-byte access touches two cache lines; they are streamed
+    // into a shared-memory ring with cp.async (no registers held while in flight): ROW_STAGES-1 batches of 16 sources
+    // are under way while one batch is added, which covers the L2 round trip (~700 cycles) of a single warp.
+    __shared__ double2 ring[ROW_STAGES][ROW_BATCH / 2][32];
+    const uint64_t n_batches = (cnt + ROW_BATCH - 1) / ROW_BATCH;
+    auto issue = [&](uint64_t bt) {
+        if (bt < n_batches) {
+            const double* src = t + bt * ROW_BATCH * S;          // (bt*ROW_BATCH/2) pairs * 2S doubles; the buffer is padded
+            const int st = (int)(bt % ROW_STAGES);
 #pragma unroll
-        for (int u = 0; u < ROW_BATCH; u += 2) {
-            // chunk_cap is a multiple of 1024 doubles and b of 16: 16-byte aligned, and a batch never leaves the row
-            const double2 v = *reinterpret_cast<const double2*>(t + b + u);
-            buf[u] = v.x; buf[u + 1] = v.y;
+            for (int u = 0; u < ROW_BATCH / 2; u++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[st][u][lane]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (uint64_t)u * 2 * S) : "memory");
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto consume = [&](const double (&buf)[ROW_BATCH], uint64_t b) {
-        if (b >= cnt) return;
-        const uint64_t jb = R.j0 + b, je = jb + ROW_BATCH;
-        const bool clean = (b + ROW_BATCH <= cnt) && (je <= ns) && (skip0 < jb || skip0 >= je) && (skip1 < jb || skip1 >= je);
+    for (uint64_t bt = 0; bt + 1 < ROW_STAGES; bt++) issue(bt);
+    for (uint64_t bt = 0; bt < n_batches; bt++) {
+        issue(bt + ROW_STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ROW_STAGES - 1) : "memory");
+        const int st = (int)(bt % ROW_STAGES);
+        const uint64_t b0 = bt * ROW_BATCH;
+        const uint64_t jb = R.j0 + b0, je = jb + ROW_BATCH;
+        const bool clean = (b0 + ROW_BATCH <= cnt) && (je <= ns) && (skip0 < jb || skip0 >= je) && (skip1 < jb || skip1 >= je);
+        double v[ROW_BATCH];
+#pragma unroll
+        for (int u = 0; u < ROW_BATCH / 2; u++) { const double2 w2 = ring[st][u][lane]; v[2 * u] = w2.x; v[2 * u + 1] = w2.y; }
         if (clean) {
 #pragma unroll
             for (int u = 0; u < ROW_BATCH; u++) {
-                if (!KAHAN) s = s_add(s, buf[u]);
-                else { const double y = s_sub(buf[u], e), w = s_add(s, y); e = s_sub(s_sub(w, s), y); s = w; }
+                if (!KAHAN) s = s_add(s, v[u]);
+                else { const double y = s_sub(v[u], e), w = s_add(s, y); e = s_sub(s_sub(w, s), y); s = w; }
             }
         } else {
 #pragma unroll
             for (int u = 0; u < ROW_BATCH; u++) {
                 const uint64_t j = jb + u;
-                if ((b + u < cnt) & (j < ns) & (j != skip0) & (j != skip1)) {
-                    if (!KAHAN) s = s_add(s, buf[u]);
-                    else { const double y = s_sub(buf[u], e), w = s_add(s, y); e = s_sub(s_sub(w, s), y); s = w; }
+                if ((b0 + u < cnt) & (j < ns) & (j != skip0) & (j != skip1)) {
+                    if (!KAHAN) s = s_add(s, v[u]);
+                    else { const double y = s_sub(v[u], e), w = s_add(s, y); e = s_sub(s_sub(w, s), y); s = w; }
                 }
             }
         }
-    };
-    fetch(B0, 0); fetch(B1, ROW_BATCH); fetch(B2, 2 * ROW_BATCH);
-    for (uint64_t b = 0; b < cnt; b += 4 * ROW_BATCH) {
-        fetch(B3, b + 3 * ROW_BATCH); consume(B0, b);
-        fetch(B0, b + 4 * ROW_BATCH); consume(B1, b + ROW_BATCH);
-        fetch(B1, b + 5 * ROW_BATCH); consume(B2, b + 2 * ROW_BATCH);
-        fetch(B2, b + 6 * ROW_BATCH); consume(B3, b + 3 * ROW_BATCH);
     }
     if (R.last) {
         double* out = (c == 0) ? a.ax : (c == 1) ? a.ay : a.az;
@@ -712,7 +721,7 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
             if (const char* e = getenv("REBOUND_B200_ROWCHUNK")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) chunk = v; }   // tests: force several chunks
             chunk = (chunk / 1024) * 1024;
             if (chunk > N) chunk = ((N + 1023) / 1024) * 1024;
-            const uint64_t need = (fast ? (uint64_t)R.n_rows * 3 * ((N + 1023) / 1024) : (uint64_t)R.n_rows * 3 * chunk) + 64;
+            const uint64_t need = (fast ? (uint64_t)R.n_rows * 3 * ((N + 1023) / 1024) : (uint64_t)R.n_rows * 3 * (chunk + 64)) + 64;
             if (h->row_cap < need + 6 * ROW_MAX) {
                 CU_TRY(h, cudaStreamSynchronize(h->stream));
                 cudaFree(h->row_buf); h->row_buf = nullptr; h->row_cap = 0;
