@@ -708,13 +708,17 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
     }
     // testparticle_type 1 with few massive particles among many: the massive rows see all N sources and go through
     // the row path; the regular kernels then only handle the test particles (sources = the massive ones).
-    if (a.type && a.Na < N && a.Na >= 1 && a.Na <= (uint64_t)ROW_MAX && N >= 4096 && (kahan || ghosts_n == 1)) {
-        const uint64_t r0 = a.i_begin, r1 = a.i_end < a.Na ? a.i_end : a.Na;
-        if (r1 > r0) {
+    const bool fast_mode = c->mode == REBCU_MODE_FAST;
+    // (FAST: any number of massive rows up to 8192, in tiles of ROW_MAX rows; STRICT: up to ROW_MAX rows, more go to the
+    // split kernel below)
+    if (a.type && a.Na < N && a.Na >= 1 && a.Na <= (uint64_t)(fast_mode ? 8192 : ROW_MAX) && N >= 4096 && (kahan || ghosts_n == 1)) {
+        const uint64_t rows_begin = a.i_begin, rows_end = a.i_end < a.Na ? a.i_end : a.Na;
+        for (uint64_t r0 = rows_begin; r0 < rows_end; r0 += ROW_MAX) {
+            const uint64_t r1 = (r0 + ROW_MAX < rows_end) ? r0 + ROW_MAX : rows_end;
             RowArgs R;
             R.a = a; R.row0 = r0; R.n_rows = (int)(r1 - r0);
             R.gbx = gb0.x; R.gby = gb0.y; R.gbz = gb0.z;
-            const bool fast = c->mode == REBCU_MODE_FAST;
+            const bool fast = fast_mode;
             // chunk of sources per pass: the term buffer (24 B per row and source) stays L2 resident (<= 48 MB), so the
             // ordered sum reads it back at L2 latency
             uint64_t chunk = (48ull << 20) / (8ull * 3 * (uint64_t)R.n_rows);
@@ -747,6 +751,19 @@ int direct_gravity(rebcu_handle* h, const rebcu_config* c) {
             CU_TRY(h, cudaGetLastError());
         }
         if (a.i_begin < a.Na) a.i_begin = a.Na < a.i_end ? a.Na : a.i_end;
+    } else if (a.type && a.Na < N && N >= 4096 && a.i_begin < a.Na && c->mode != REBCU_MODE_FAST && a.windowed) {
+        // More massive rows than the row path takes: each still sees all N sources, which one thread per target would
+        // walk serially.  The producer/adder split kernel spreads a row block's sources over three producer warps and
+        // leaves one dependent add per source on the adder (same bits); the test particles follow separately.
+        DirectArgs ar = a;
+        ar.i_end = a.i_end < a.Na ? a.i_end : a.Na;
+        {
+            LaunchScope ls(h, TC_DIRECT);
+            if (kahan) direct_strict_split_kernel<true, 4, 8><<<div_up(ar.i_end - ar.i_begin, 32), 128, 0, h->stream>>>(ar);
+            else direct_strict_split_kernel<false, 4, 8><<<div_up(ar.i_end - ar.i_begin, 32), 128, 0, h->stream>>>(ar);
+        }
+        CU_TRY(h, cudaGetLastError());
+        a.i_begin = ar.i_end;
     }
     const uint64_t n_i = a.i_end - a.i_begin;
     if (n_i == 0) return REBCU_OK;

@@ -297,10 +297,11 @@ def _type1_case(n, n_active, seed):
 
 
 @pytest.mark.parametrize("grav", [abi.GRAVITY_BASIC, abi.GRAVITY_COMPENSATED])
-@pytest.mark.parametrize("n,n_active,terms", [(6000, 10, 0), (6000, 10, 1), (6000, 10, 2), (5000, 200, 0), (9000, 256, 0)])
+@pytest.mark.parametrize("n,n_active,terms", [(6000, 10, 0), (6000, 10, 1), (6000, 10, 2), (5000, 200, 0), (9000, 256, 0),
+                                              (7000, 300, 0), (7000, 1000, 2), (6000, 600, 1)])
 def test_type1_massive_rows_bitwise(eng, grav, n, n_active, terms):
-    """testparticle_type 1 with few massive particles among many (N >= 4096, N_active <= 256): the massive rows go
-    through the term-buffer + ordered-sum kernels; accelerations (and the Kahan compensation) stay bit-identical,
+    """testparticle_type 1 with few massive particles among many (N >= 4096): up to 256 massive rows go through the
+    term-buffer + ordered-sum kernels, more of them through the producer/adder split kernel; accelerations (and the Kahan compensation) stay bit-identical,
     FAST stays within 1e-12."""
     p = _type1_case(n, n_active, seed=31)
     cfg = ics.planetesimal_config(testparticle_type=1, gravity=grav, N_active=n_active, gravity_ignore_terms=terms)
