@@ -167,6 +167,13 @@ int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg);
  * The shuffle and the resolve loop (collision.c:336-404) stay with the caller. */
 int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg,
                            rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+/* r->map / r->N_map / r->N_targets for the following searches (src/rebound.h:257-258,344; read at
+ * src/collision.c:53-58; MERCURIUS and TRACE set them around their encounter steps,
+ * integrator_mercurius.c:429, integrator_trace.c:820,1047,1093).  map == NULL: every particle is a
+ * projectile; N_targets == REBCU_SIZE_MAX: as many targets as projectiles.  As in the reference, DIRECT
+ * sends projectile and target slots through the map, LINE ignores N_targets, and TREE / LINETREE only cut
+ * the projectile loop to the first N_map particles.  The map is copied; (NULL, 0, REBCU_SIZE_MAX) resets. */
+int rebcu_set_collision_subset(rebcu_handle* h, const uint64_t* map, uint64_t N_map, uint64_t N_targets);
 /* reb_simulation_steps for a simulation without host callbacks (src/simulation.c:504-603):
  * n x { integrator step; boundary check; collision search }.  With cfg->collision != NONE the
  * collision list of the LAST step is left on the device (rebcu_collisions_fetch). */
@@ -263,6 +270,12 @@ int rebcu_energy(rebcu_handle* h, const rebcu_config* cfg, double* out3);
 int rebcu_com(rebcu_handle* h, double* out10);
 /* reb_simulation_angular_momentum, src/tools.c:164-174. */
 int rebcu_angular_momentum(rebcu_handle* h, double* out3);
+
+/* The exit conditions run_heartbeat tests after every step (src/simulation.c:242-272): *escape = some particle
+ * is farther than exit_max_distance from the origin (r->status = REB_STATUS_ESCAPE), *encounter = some pair is
+ * closer than exit_min_distance (REB_STATUS_ENCOUNTER).  A distance of 0 switches its check off, as in the
+ * reference.  Pure predicates in the reference's expression order: exact. */
+int rebcu_exit_check(rebcu_handle* h, double exit_max_distance, double exit_min_distance, int* escape, int* encounter);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* Sustained FP64 FMA rate of the device in TFLOP/s (2 flop per DFMA), timed with CUDA events: the

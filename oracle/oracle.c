@@ -659,7 +659,14 @@ static double second_largest_radius(const rebcu_particle* p, uint64_t N){
     return have2 ? l2 : 0.;
 }
 
-static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint64_t N, clist* out){
+/* map / N_map / N_targets: r->map, r->N_map, r->N_targets (collision.c:53-58).  map==NULL: all N particles are
+ * projectiles; N_targets==REBCU_SIZE_MAX: as many targets as projectiles.  DIRECT maps projectile and target
+ * slots (:78,93) and skips equal SLOTS (:92); LINE maps both sides but ignores N_targets (:140,153); the tree
+ * modes only cut the projectile loop to the first N_projectiles particles, unmapped (:229,:286). */
+static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint64_t N,
+                            const uint64_t* map, uint64_t N_map, uint64_t N_targets_in, clist* out){
+    const uint64_t NP = map ? N_map : N;
+    const uint64_t NT = N_targets_in!=REBCU_SIZE_MAX ? N_targets_in : NP;
     const int gx1 = c->N_ghost_x>1?1:c->N_ghost_x;
     const int gy1 = c->N_ghost_y>1?1:c->N_ghost_y;
     const int gz1 = c->N_ghost_z>1?1:c->N_ghost_z;
@@ -667,12 +674,14 @@ static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint
         /* ghost box outermost, then projectile, then target (collision.c:70-121) */
         for (int gx=-gx1; gx<=gx1; gx++) for (int gy=-gy1; gy<=gy1; gy++) for (int gz=-gz1; gz<=gz1; gz++){
             const rebcu_vec6d gb = ghostbox(c, gx, gy, gz);
-            for (uint64_t i=0;i<N;i++){
+            for (uint64_t i=0;i<NP;i++){
+                const uint64_t ip = map ? map[i] : i;
                 rebcu_vec6d s = gb;
-                s.x += p[i].x; s.y += p[i].y; s.z += p[i].z; s.vx += p[i].vx; s.vy += p[i].vy; s.vz += p[i].vz;
-                for (uint64_t j=0;j<N;j++){
+                s.x += p[ip].x; s.y += p[ip].y; s.z += p[ip].z; s.vx += p[ip].vx; s.vy += p[ip].vy; s.vz += p[ip].vz;
+                for (uint64_t j=0;j<NT;j++){
                     if (i==j) continue;
-                    if (overlapping_and_approaching(&s, p[i].r, &p[j])) clist_push(out, i, j, gb, 0);
+                    const uint64_t jp = map ? map[j] : j;
+                    if (overlapping_and_approaching(&s, p[ip].r, &p[jp])) clist_push(out, ip, jp, gb, 0);
                 }
             }
         }
@@ -684,7 +693,7 @@ static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint
         int err = build_flat(c, p, N, &cells, &n_cells);
         if (err) return err;
         const double r2nd = second_largest_radius(p, N);
-        for (uint64_t i=0;i<N;i++){
+        for (uint64_t i=0;i<NP;i++){
             for (int gx=-gx1; gx<=gx1; gx++) for (int gy=-gy1; gy<=gy1; gy++) for (int gz=-gz1; gz<=gz1; gz++){
                 const rebcu_vec6d gb = ghostbox(c, gx, gy, gz);
                 rebcu_vec6d s = gb;
@@ -712,11 +721,14 @@ static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint
         /* ghost box outermost, then i, then j > i (collision.c:132-194) */
         for (int gx=-gx1; gx<=gx1; gx++) for (int gy=-gy1; gy<=gy1; gy++) for (int gz=-gz1; gz<=gz1; gz++){
             const rebcu_vec6d gb = ghostbox(c, gx, gy, gz);
-            for (uint64_t i=0;i<N;i++){
+            for (uint64_t i=0;i<NP;i++){
+                const uint64_t ip = map ? map[i] : i;
                 rebcu_vec6d s = gb;
-                s.x += p[i].x; s.y += p[i].y; s.z += p[i].z; s.vx += p[i].vx; s.vy += p[i].vy; s.vz += p[i].vz;
-                for (uint64_t j=i+1;j<N;j++)
-                    if (trajectories_overlap(&s, p[i].r, &p[j], c->dt_last_done)) clist_push(out, i, j, gb, 0);
+                s.x += p[ip].x; s.y += p[ip].y; s.z += p[ip].z; s.vx += p[ip].vx; s.vy += p[ip].vy; s.vz += p[ip].vz;
+                for (uint64_t j=i+1;j<NP;j++){
+                    const uint64_t jp = map ? map[j] : j;
+                    if (trajectories_overlap(&s, p[ip].r, &p[jp], c->dt_last_done)) clist_push(out, ip, jp, gb, 0);
+                }
             }
         }
         return 0;
@@ -724,7 +736,7 @@ static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint
     if (c->collision==REBCU_COLLISION_LINETREE){
         /* collision.c:270-331 with the descent of :506-568 */
         double vmax2 = 0.;
-        for (uint64_t i=0;i<N;i++){
+        for (uint64_t i=0;i<NP;i++){
             const double v2 = p[i].vx*p[i].vx + p[i].vy*p[i].vy + p[i].vz*p[i].vz;
             vmax2 = (vmax2 > v2) ? vmax2 : v2;                         /* MAX(vmax2, v2), collision.c:44 */
         }
@@ -732,7 +744,7 @@ static int collision_search(const rebcu_config* c, const rebcu_particle* p, uint
         rebcu_treecell* cells; size_t n_cells;
         int err = build_flat(c, p, N, &cells, &n_cells);
         if (err) return err;
-        for (uint64_t i=0;i<N;i++){
+        for (uint64_t i=0;i<NP;i++){
             const double reach = p[i].r + c->dt_last_done*sqrt(p[i].vx*p[i].vx + p[i].vy*p[i].vy + p[i].vz*p[i].vz);
             for (int gx=-gx1; gx<=gx1; gx++) for (int gy=-gy1; gy<=gy1; gy++) for (int gz=-gz1; gz<=gz1; gz++){
                 const rebcu_vec6d gb = ghostbox(c, gx, gy, gz);
@@ -764,7 +776,21 @@ int orc_collision_search(rebcu_config* c, rebcu_particle* p, uint64_t N,
                          rebcu_collision* out, uint64_t cap, uint64_t* n_found){
     orc_errbuf[0]=0;
     clist l = {0,0,0};
-    int err = collision_search(c, p, N, &l);
+    int err = collision_search(c, p, N, NULL, 0, REBCU_SIZE_MAX, &l);
+    *n_found = l.n;
+    if (out && l.n) memcpy(out, l.v, sizeof(rebcu_collision)*(l.n<cap?l.n:cap));
+    free(l.v);
+    return err;
+}
+
+/* The same search restricted by r->map / r->N_map / r->N_targets (what MERCURIUS and TRACE set around their
+ * encounter steps, integrator_mercurius.c:429, integrator_trace.c:820). */
+int orc_collision_search_subset(rebcu_config* c, rebcu_particle* p, uint64_t N,
+                                const uint64_t* map, uint64_t N_map, uint64_t N_targets,
+                                rebcu_collision* out, uint64_t cap, uint64_t* n_found){
+    orc_errbuf[0]=0;
+    clist l = {0,0,0};
+    int err = collision_search(c, p, N, map, N_map, N_targets, &l);
     *n_found = l.n;
     if (out && l.n) memcpy(out, l.v, sizeof(rebcu_collision)*(l.n<cap?l.n:cap));
     free(l.v);
@@ -838,7 +864,7 @@ int orc_steps(rebcu_config* c, rebcu_particle* p, uint64_t* N, uint64_t n_steps,
         boundary_check(c, p, N);
         if (c->collision!=REBCU_COLLISION_NONE){
             clist l = {0,0,0};
-            err = collision_search(c, p, *N, &l);
+            err = collision_search(c, p, *N, NULL, 0, REBCU_SIZE_MAX, &l);
             for (size_t i=0;i<l.n;i++){             /* collision.c:337-342 */
                 size_t j = rand_r(&seed)%l.n;
                 rebcu_collision t = l.v[i]; l.v[i] = l.v[j]; l.v[j] = t;
@@ -889,6 +915,29 @@ void orc_angular_momentum(rebcu_config* c, rebcu_particle* p, uint64_t N, double
         lz += p[i].m*(p[i].x*p[i].vy - p[i].y*p[i].vx);
     }
     out[0]=lx; out[1]=ly; out[2]=lz;
+}
+
+/* Exit conditions of run_heartbeat (src/simulation.c:242-272): returns the status the reference ends up with,
+ * 4 = REB_STATUS_ESCAPE, 3 = REB_STATUS_ENCOUNTER (tested second, so it wins), 0 = neither. */
+int orc_exit_check(rebcu_config* c, rebcu_particle* p, uint64_t N, double exit_max_distance, double exit_min_distance){
+    (void)c;
+    int status = 0;
+    if (exit_max_distance){
+        const double max2 = exit_max_distance*exit_max_distance;
+        for (uint64_t i=0;i<N;i++){
+            const double r2 = p[i].x*p[i].x + p[i].y*p[i].y + p[i].z*p[i].z;
+            if (r2>max2) status = 4;
+        }
+    }
+    if (exit_min_distance){
+        const double min2 = exit_min_distance*exit_min_distance;
+        for (uint64_t i=0;i<N;i++) for (uint64_t j=0;j<i;j++){
+            const double x = p[i].x-p[j].x, y = p[i].y-p[j].y, z = p[i].z-p[j].z;
+            const double r2 = x*x + y*y + z*z;
+            if (r2<min2) status = 3;
+        }
+    }
+    return status;
 }
 
 int orc_openmp_threads(void){

@@ -229,6 +229,27 @@ int refh_collision_search(rebcu_config* c, rebcu_particle* p, uint64_t N,
     return err;
 }
 
+/* reb_collision_search with r->map / r->N_map / r->N_targets set (rebound.h:257-258,344). */
+int refh_collision_search_subset(rebcu_config* c, rebcu_particle* p, uint64_t N,
+                                 const uint64_t* map, uint64_t N_map, uint64_t N_targets,
+                                 rebcu_collision* out, uint64_t cap, uint64_t* n_found){
+    struct reb_simulation* r = make_sim(c, p, N);
+    install_resolve(r, 0, 0.);
+    r->map = (size_t*)map;                 /* not owned by the simulation (rebound.h:258) */
+    r->N_map = map ? (size_t)N_map : 0;
+    r->N_targets = (size_t)N_targets;
+    unsigned int seed0 = r->rand_seed;
+    reb_collision_search(r);
+    int err = collect_error(r);
+    unshuffle(r->collisions, r->N_collisions, seed0);
+    *n_found = r->N_collisions;
+    size_t ncopy = r->N_collisions < cap ? r->N_collisions : cap;
+    if (out && ncopy) memcpy(out, r->collisions, ncopy*sizeof(struct reb_collision));
+    r->map = NULL;
+    reb_simulation_free(r);
+    return err;
+}
+
 /* reb_simulation_steps (simulation.c:504).  aux[0] <- collisions_log_n, aux[1] <- collisions_plog,
  * aux[2] <- wall seconds spent in reb_simulation_steps. */
 int refh_steps(rebcu_config* c, rebcu_particle* p, uint64_t* N, uint64_t n_steps,
@@ -248,6 +269,21 @@ int refh_steps(rebcu_config* c, rebcu_particle* p, uint64_t* N, uint64_t n_steps
     copy_back(r, c, p, N);
     reb_simulation_free(r);
     return err;
+}
+
+/* The exit checks of run_heartbeat (simulation.c:242-272; static): reb_simulation_integrate runs the heartbeat once
+ * before its loop (:392) and leaves as soon as the status is non-negative, so integrating to the current time
+ * evaluates exactly those checks.  Returns r->status (4 escape, 3 encounter, 0 = REB_STATUS_SUCCESS: neither). */
+int refh_exit_check(rebcu_config* c, rebcu_particle* p, uint64_t N, double exit_max_distance, double exit_min_distance){
+    struct reb_simulation* r = make_sim(c, p, N);
+    r->exit_max_distance = exit_max_distance;
+    r->exit_min_distance = exit_min_distance;
+    r->integrator.callbacks.step = NULL;        /* should a step run after all, it does nothing */
+    r->gravity = REB_GRAVITY_NONE; r->collision = REB_COLLISION_NONE; r->boundary = REB_BOUNDARY_NONE;
+    r->exact_finish_time = 1;
+    int status = (int)reb_simulation_integrate(r, r->t);
+    reb_simulation_free(r);
+    return status;
 }
 
 /* reb_simulation_energy (tools.c:108). */

@@ -149,7 +149,9 @@ CHECKER_SIGNATURES = {
     "boundary_check": (C.c_int, [_CFG, _P, _U64P]),
     "integrator_step": (C.c_int, [_CFG, _P, _U64P]),
     "collision_search": (C.c_int, [_CFG, _P, C.c_uint64, _P, C.c_uint64, _U64P]),
+    "collision_search_subset": (C.c_int, [_CFG, _P, C.c_uint64, _P, C.c_uint64, C.c_uint64, _P, C.c_uint64, _U64P]),
     "steps": (C.c_int, [_CFG, _P, _U64P, C.c_uint64, C.c_int, C.c_double, _DBLP]),
+    "exit_check": (C.c_int, [_CFG, _P, C.c_uint64, C.c_double, C.c_double]),
     "energy": (C.c_double, [_CFG, _P, C.c_uint64]),
     "com": (None, [_CFG, _P, C.c_uint64, _DBLP]),
     "angular_momentum": (None, [_CFG, _P, C.c_uint64, _DBLP]),
@@ -182,6 +184,7 @@ PRODUCT_SIGNATURES = {
     "collision_search": (C.c_int, [_P, _CFG, _P, C.c_uint64, _U64P]),
     "steps": (C.c_int, [_P, _CFG, C.c_uint64]),
     "collisions_fetch": (C.c_int, [_P, _P, C.c_uint64, _U64P]),
+    "set_collision_subset": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64]),
     "tree_build": (C.c_int, [_P, _CFG]),
     "tree_cell_count": (C.c_uint64, [_P]),
     "tree_fetch": (C.c_int, [_P, _P, C.c_uint64]),
@@ -200,6 +203,7 @@ PRODUCT_SIGNATURES = {
     "energy": (C.c_int, [_P, _CFG, _DBLP]),
     "com": (C.c_int, [_P, _DBLP]),
     "angular_momentum": (C.c_int, [_P, _DBLP]),
+    "exit_check": (C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "measure_fp64_peak": (C.c_int, [_P, _DBLP]),
     "launch_count": (C.c_uint64, [_P]),
     "timing_enable": (C.c_int, [_P, C.c_int]),

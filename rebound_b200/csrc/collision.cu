@@ -11,11 +11,14 @@
 // order-dependent resolve loop (collision.c:336-404), which stay on the host.
 // All predicates use strictly rounded arithmetic in the reference's expression order, so the pair set is
 // bit-exact.  `ri` is written for TREE only (the reference leaves it uninitialised in DIRECT).
-// r->map / N_targets subsets (used by MERCURIUS/TRACE) are not part of this path.
+// r->map / r->N_map / r->N_targets subsets (collision.c:53-58; set by MERCURIUS/TRACE around encounter steps):
+//   rebcu_set_collision_subset.  DIRECT maps projectile and target SLOTS through the map and skips equal slots,
+//   LINE maps both sides and ignores N_targets, the tree modes only cut the projectile loop (as the reference does).
 // Bound: DIRECT FP64 pipe (N^2 predicates); TREE L2/HBM latency on the cell arrays.
 #include "engine.cuh"
 #include "primitives.cuh"
 #include <math.h>
+#include <vector>
 
 namespace {
 
@@ -82,25 +85,41 @@ __device__ __forceinline__ void emit(rebcu_collision* out, uint64_t at, uint32_t
 // ---- DIRECT ------------------------------------------------------------------------------------
 // grid.y = ghost box, thread = projectile, targets tiled through shared memory.
 // LINE: pairs j > i only, straight-line test over the last step (collision.c:152-189).
+// A subset search (collision.c:53-58) runs over SLOTS: projectile slot i and target slot j stand for the particles
+// map[i], map[j] (the slot itself without a map); only equal slots are skipped (:92), so a map that lists a
+// particle twice reports it against itself, as the reference does.
+struct DirectColArgs {
+    const uint32_t* map;      // nullptr: slot == particle
+    uint32_t n_targ;          // target slots [0, n_targ)   (LINE: [0, n_proj), collision.c:153)
+    uint32_t ib, nloc;        // this rank's block of projectile slots
+};
+
 template <bool FILL, bool LINE>
-__global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_t n, uint32_t ib, uint32_t nloc, const GhostShifts* ghosts,
+__global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, DirectColArgs a, const GhostShifts* ghosts,
                                                                uint32_t* __restrict__ count, const uint32_t* __restrict__ off,
                                                                rebcu_collision* __restrict__ out, double dt_last_done) {
     __shared__ double4 tile[128];
+    __shared__ uint32_t tile_p[128];
     const uint32_t g = blockIdx.y;
-    const uint32_t il = blockIdx.x * 128 + threadIdx.x;       // projectiles [ib, ib+nloc): this rank's block
-    const uint32_t i = ib + il;
-    const bool valid = il < nloc;
+    const uint32_t il = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t i = a.ib + il;                              // projectile slot
+    const bool valid = il < a.nloc;
+    const uint32_t n = a.n_targ;
     const rebcu_vec6d gb = ghosts->gb[g];
     rebcu_vec6d s = gb;
     double r1 = 0;
-    if (valid) { s = shifted(gb, P, i); r1 = P.r[i]; }
+    uint32_t ip = 0;
+    if (valid) { ip = a.map ? a.map[i] : i; s = shifted(gb, P, ip); r1 = P.r[ip]; }
     uint32_t found = 0;
-    const uint64_t base = (FILL && valid) ? off[(uint64_t)g * nloc + il] : 0;
+    const uint64_t base = (FILL && valid) ? off[(uint64_t)g * a.nloc + il] : 0;
     for (uint32_t t0 = 0; t0 < n; t0 += 128) {
         __syncthreads();
         const uint32_t j0 = t0 + threadIdx.x;
-        tile[threadIdx.x] = (j0 < n) ? make_double4(P.x[j0], P.y[j0], P.z[j0], P.r[j0]) : make_double4(0, 0, 0, 0);
+        if (j0 < n) {
+            const uint32_t jp = a.map ? a.map[j0] : j0;
+            tile[threadIdx.x] = make_double4(P.x[jp], P.y[jp], P.z[jp], P.r[jp]);
+            tile_p[threadIdx.x] = jp;
+        }
         __syncthreads();
         const int jn = min(128u, n - t0);
         if (valid) {
@@ -108,14 +127,15 @@ __global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, uint32_
                 const uint32_t j = t0 + jj;
                 if (LINE ? (j <= i) : (j == i)) continue;
                 const double4 q = tile[jj];
-                if (LINE ? hit_line(s, r1, q.x, q.y, q.z, q.w, P, j, dt_last_done) : hit(s, r1, q.x, q.y, q.z, q.w, P, j)) {
-                    if (FILL) emit(out, base + found, i, j, gb, 0);
+                const uint32_t jp = tile_p[jj];
+                if (LINE ? hit_line(s, r1, q.x, q.y, q.z, q.w, P, jp, dt_last_done) : hit(s, r1, q.x, q.y, q.z, q.w, P, jp)) {
+                    if (FILL) emit(out, base + found, ip, jp, gb, 0);
                     found++;
                 }
             }
         }
     }
-    if (!FILL && valid) count[(uint64_t)g * nloc + il] = found;
+    if (!FILL && valid) count[(uint64_t)g * a.nloc + il] = found;
 }
 
 // ---- TREE ---------------------------------------------------------------------------------------
@@ -123,6 +143,7 @@ struct TreeColArgs {
     const double4* pos; const double4* geo; const int4* meta; uint32_t n_cells;
     const uint32_t* perm; uint32_t n;
     const uint32_t* list; uint32_t n_work;       // sharded: work item t -> sorted position list[t] (else t)
+    uint32_t n_proj;                             // only particles [0, n_proj) are projectiles (collision.c:229,:286 with r->map set)
     const GhostShifts* ghosts;
     double r2nd;          // TREE: radius of the second largest particle; LINETREE: maxdrift = dt_last_done*sqrt(max v^2)
     double dt_last_done;
@@ -141,6 +162,7 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
     const uint32_t t = blockIdx.x * 128 + threadIdx.x;
     if (t >= a.n_work) return;
     const uint32_t i = a.perm[a.list ? a.list[t] : t];     // key order => neighbouring lanes walk neighbouring paths
+    if (i >= a.n_proj) { if (PASS == 0) count[i] = 0; return; }
     if (PASS == 1 && count[i] <= COL_SLOTS) return;
     const double r1 = P.r[i];
     double reach;
@@ -290,9 +312,18 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         return rebcu_fail(h, REBCU_ERR_ARG, "Collision routine not implemented.");
     // Sharded: the overlap tests read the target's velocity, which only its owner has kept current.
     if (h->world > 1) engine_exchange(h, REBCU_EXCHANGE_POSITIONS | REBCU_EXCHANGE_VELOCITIES);
-    uint64_t ib, ie; engine_shard(h, &ib, &ie);
-    const uint64_t nloc = ie - ib;
     if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "collision search supports N < 2^31");
+    // r->map / r->N_map / r->N_targets (collision.c:53-58)
+    const uint32_t* map = h->col_map_on ? h->col_map : nullptr;
+    const uint64_t n_proj = h->col_map_on ? h->col_map_n : n;
+    const uint64_t n_targ = h->col_targets != REBCU_SIZE_MAX ? h->col_targets : n_proj;
+    if (h->col_map_on && h->col_map_n && h->col_map_max >= n) return rebcu_fail(h, REBCU_ERR_ARG, "collision subset: map entry >= N");
+    if (n_targ > n_proj) return rebcu_fail(h, REBCU_ERR_ARG, "collision subset: N_targets exceeds the number of projectiles");
+    if (!direct && n_proj > n) return rebcu_fail(h, REBCU_ERR_ARG, "collision subset: N_map exceeds N in a tree search");
+    // this rank's block of projectile slots (the i-block of the force kernels when there is no subset)
+    const uint64_t n_slots = direct ? n_proj : n;
+    const uint64_t ib = n_slots * (uint64_t)h->rank / (uint64_t)h->world, ie = n_slots * (uint64_t)(h->rank + 1) / (uint64_t)h->world;
+    const uint64_t nloc = ie - ib;
     // only the innermost ring of ghost boxes (collision.c:67-69, 214-216)
     GhostShifts g;
     engine_ghost_shifts(c, c->N_ghost_x > 1 ? 1 : c->N_ghost_x, c->N_ghost_y > 1 ? 1 : c->N_ghost_y,
@@ -307,17 +338,18 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         if (nloc == 0) return REBCU_OK;
         if ((err = ensure_lists(h, n_counts))) return err;
         dim3 grid(div_up(nloc, 128), g.n);
+        const DirectColArgs da{map, (uint32_t)(line ? n_proj : n_targ), (uint32_t)ib, (uint32_t)nloc};
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            if (line) direct_collision_kernel<false, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, h->col_count, nullptr, nullptr, c->dt_last_done);
-            else direct_collision_kernel<false, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, h->col_count, nullptr, nullptr, 0.);
+            if (line) direct_collision_kernel<false, true><<<grid, 128, 0, h->stream>>>(P, da, h->ghosts_dev, h->col_count, nullptr, nullptr, c->dt_last_done);
+            else direct_collision_kernel<false, false><<<grid, 128, 0, h->stream>>>(P, da, h->ghosts_dev, h->col_count, nullptr, nullptr, 0.);
         }
         CU_TRY(h, cudaGetLastError());
         if ((err = scan_counts(h, n_counts, &total))) return err;
         if (total) {
             LaunchScope ls(h, TC_COLLISION);
-            if (line) direct_collision_kernel<true, true><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, c->dt_last_done);
-            else direct_collision_kernel<true, false><<<grid, 128, 0, h->stream>>>(P, (uint32_t)n, (uint32_t)ib, (uint32_t)nloc, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, 0.);
+            if (line) direct_collision_kernel<true, true><<<grid, 128, 0, h->stream>>>(P, da, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, c->dt_last_done);
+            else direct_collision_kernel<true, false><<<grid, 128, 0, h->stream>>>(P, da, h->ghosts_dev, nullptr, (const uint32_t*)h->col_off, h->col_list, 0.);
         }
     } else {
         if ((err = tree_build(h, c))) return err;                       // collision.c:200
@@ -327,7 +359,7 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         TreeColArgs a;
         a.pos = T.walk_pos; a.geo = T.walk_geo; a.meta = (const int4*)T.walk_meta; a.n_cells = (uint32_t)T.n_cells;
         a.perm = T.perm; a.n = (uint32_t)n; a.ghosts = h->ghosts_dev;
-        a.list = nullptr; a.n_work = (uint32_t)n;
+        a.list = nullptr; a.n_work = (uint32_t)n; a.n_proj = (uint32_t)n_proj;
         h->col_seg_n = 1; h->col_seg_stride = n;
         if (h->world > 1) {
             uint64_t nw = 0;
@@ -337,7 +369,7 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         }
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            if (line) vmax2_kernel<<<1, 1024, 0, h->stream>>>(P, (uint32_t)n, h->scratch);
+            if (line) vmax2_kernel<<<1, 1024, 0, h->stream>>>(P, (uint32_t)n_proj, h->scratch);      // collision.c:273-277
             else second_largest_kernel<<<1, 1024, 0, h->stream>>>(P.r, (uint32_t)n, h->scratch);
         }
         double* pin = (double*)(h->pinned + 8);
@@ -374,6 +406,34 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
     }
     CU_TRY(h, cudaGetLastError());
     h->col_n = total;
+    return REBCU_OK;
+}
+
+// r->map / r->N_map / r->N_targets of the next searches (src/rebound.h:257-258,344; collision.c:53-58).
+extern "C" int rebcu_set_collision_subset(rebcu_handle* h, const uint64_t* map, uint64_t N_map, uint64_t N_targets) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->col_targets = N_targets;
+    h->col_map_on = map != nullptr;
+    h->col_map_n = map ? N_map : 0;
+    h->col_map_max = 0;
+    if (!map || N_map == 0) return REBCU_OK;
+    if (N_map >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "collision subset supports N_map < 2^31");
+    std::vector<uint32_t> m32(N_map);
+    for (uint64_t i = 0; i < N_map; i++) {
+        if (map[i] >= (1ull << 31)) { h->col_map_on = false; h->col_map_n = 0; return rebcu_fail(h, REBCU_ERR_ARG, "collision subset: map entry >= 2^31"); }
+        m32[i] = (uint32_t)map[i];
+        if (map[i] > h->col_map_max) h->col_map_max = map[i];
+    }
+    if (h->col_map_cap < N_map) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->col_map); h->col_map = nullptr; h->col_map_cap = 0;
+        const uint64_t cap = N_map + N_map / 4 + 256;
+        CU_TRY(h, cudaMalloc(&h->col_map, cap * sizeof(uint32_t)));
+        h->col_map_cap = cap;
+    }
+    // pageable source: the copy is staged before the call returns, so m32 may go out of scope
+    CU_TRY(h, cudaMemcpyAsync(h->col_map, m32.data(), N_map * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return REBCU_OK;
 }
 

@@ -67,7 +67,7 @@ void rebcu_destroy(rebcu_handle* h) {
     cudaStreamSynchronize(h->stream);
     tree_free(h);
     cudaFree(h->soa); cudaFree(h->aos); cudaFree(h->ghosts_dev); cudaFree(h->scratch); cudaFree(h->counters); cudaFree(h->scratch_big);
-    cudaFree(h->col_count); cudaFree(h->col_off); cudaFree(h->col_list); cudaFree(h->col_scan_tmp); cudaFree(h->col_slots);
+    cudaFree(h->col_count); cudaFree(h->col_off); cudaFree(h->col_list); cudaFree(h->col_scan_tmp); cudaFree(h->col_slots); cudaFree(h->col_map);
     cudaFree(h->compact_tmp); cudaFree(h->compact_buf); cudaFree(h->compact_flag); cudaFree(h->compact_pos);
     cudaFree(h->tp_hist);
     cudaFree(h->diag_partial);

@@ -3,6 +3,7 @@
 //   reb_simulation_energy            src/tools.c:108-162   (kinetic over N_interact, potential over i<N_active, j>i)
 //   reb_simulation_com               src/tools.c:401-408, 376-399 (mass-weighted means of x, v, a)
 //   reb_simulation_angular_momentum  src/tools.c:164-174
+//   exit_max_distance / exit_min_distance scans of run_heartbeat  src/simulation.c:242-272  (exact: flags only)
 // The reference accumulates each of these in ONE scalar in index order; a parallel sum cannot reproduce that
 // rounding sequence, so these are the only entry points of the library that are not bit-identical: they agree
 // with the reference to ~1e-13 relative (tests state 1e-12) and are deterministic run to run (fixed partial
@@ -145,9 +146,73 @@ int moments(rebcu_handle* h, uint64_t n_interact, double* out14) {
     return REBCU_OK;
 }
 
+// ---- exit conditions of run_heartbeat (simulation.c:242-272): pure predicates, strictly rounded, exact --------
+// flags[0] = some particle has x^2+y^2+z^2 > max2 (:250-253)
+__global__ void __launch_bounds__(256) escape_kernel(DiagSoa P, uint64_t n, double max2, unsigned int* __restrict__ flags) {
+    bool any = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const double x = P.x[i], y = P.y[i], z = P.z[i];
+        any |= s_add(s_add(s_mul(x, x), s_mul(y, y)), s_mul(z, z)) > max2;
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) flags[0] = 1u;
+}
+
+// flags[1] = some pair j < i has |x_i - x_j|^2 < min2 (:262-269).  Block (bx, by): particles i of tile bx against
+// the j tiles by, by + gridDim.y, ... <= bx, staged in shared memory.
+__global__ void __launch_bounds__(128) encounter_kernel(DiagSoa P, uint64_t n, double min2, unsigned int* __restrict__ flags) {
+    __shared__ double sx[128], sy[128], sz[128];
+    const uint64_t i = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    const bool valid = i < n;
+    const double xi = valid ? P.x[i] : 0., yi = valid ? P.y[i] : 0., zi = valid ? P.z[i] : 0.;
+    bool any = false;
+    for (uint64_t t = blockIdx.y; t <= blockIdx.x; t += gridDim.y) {
+        const uint64_t j0 = t * 128 + threadIdx.x;
+        __syncthreads();
+        if (j0 < n) { sx[threadIdx.x] = P.x[j0]; sy[threadIdx.x] = P.y[j0]; sz[threadIdx.x] = P.z[j0]; }
+        __syncthreads();
+        if (!valid) continue;
+        const uint64_t jb = t * 128;
+        const int jn = (int)min((uint64_t)128, i > jb ? i - jb : 0);        // j < i only
+        for (int jj = 0; jj < jn; jj++) {
+            const double x = s_sub(xi, sx[jj]), y = s_sub(yi, sy[jj]), z = s_sub(zi, sz[jj]);
+            any |= s_add(s_add(s_mul(x, x), s_mul(y, y)), s_mul(z, z)) < min2;
+        }
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) flags[1] = 1u;
+}
+
 }  // namespace
 
 extern "C" {
+
+// The exit checks run_heartbeat makes after every step (src/simulation.c:242-272).
+int rebcu_exit_check(rebcu_handle* h, double exit_max_distance, double exit_min_distance, int* escape, int* encounter) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    *escape = 0; *encounter = 0;
+    const uint64_t n = h->N;
+    // the reference tests the distances for truth (`if (r->exit_max_distance)`): zero switches a check off
+    if (n == 0 || (!exit_max_distance && !exit_min_distance)) return REBCU_OK;
+    if (h->world > 1) engine_exchange(h, REBCU_EXCHANGE_POSITIONS);     // every rank scans all particles
+    unsigned int* flags = (unsigned int*)(h->counters + 12);
+    CU_TRY(h, cudaMemsetAsync(flags, 0, 2 * sizeof(unsigned int), h->stream));
+    if (exit_max_distance) {
+        LaunchScope ls(h, TC_BOUNDARY);
+        escape_kernel<<<min(div_up(n, 256), 148u * 8u), 256, 0, h->stream>>>(diag_soa(h), n, exit_max_distance * exit_max_distance, flags);
+    }
+    if (exit_min_distance && n > 1) {
+        LaunchScope ls(h, TC_BOUNDARY);
+        const unsigned int gx = div_up(n, 128);
+        const unsigned int gy = gx < 592u ? max(1u, min(gx, 592u / gx)) : 1u;
+        encounter_kernel<<<dim3(gx, gy), 128, 0, h->stream>>>(diag_soa(h), n, exit_min_distance * exit_min_distance, flags);
+    }
+    CU_TRY(h, cudaGetLastError());
+    unsigned int* pin = (unsigned int*)(h->pinned + 20);
+    CU_TRY(h, cudaMemcpyAsync(pin, flags, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    *escape = pin[0] != 0; *encounter = pin[1] != 0;
+    return REBCU_OK;
+}
 
 int rebcu_energy(rebcu_handle* h, const rebcu_config* cfg, double* out3) {
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");

@@ -86,6 +86,9 @@ struct rebcu_handle {
     rebcu_collision* col_list = nullptr; uint64_t col_cap = 0; uint64_t col_n = 0;
     void* col_scan_tmp = nullptr; size_t col_scan_tmp_bytes = 0;
     uint64_t* col_slots = nullptr; uint64_t col_slots_cap = 0;   // parked hits of the single-traversal tree search
+    // r->map / r->N_map / r->N_targets of the collision search (rebcu_set_collision_subset)
+    uint32_t* col_map = nullptr; uint64_t col_map_cap = 0, col_map_n = 0, col_map_max = 0; bool col_map_on = false;
+    uint64_t col_targets = REBCU_SIZE_MAX;
     // small device scratch
     double* scratch = nullptr;            // 64 doubles
     unsigned long long* counters = nullptr; // 16 counters

@@ -65,8 +65,12 @@ int shim_resident(const struct reb_simulation* r){
     /* Between the steps of reb_simulation_steps / reb_simulation_integrate only these can look at r->particles
      * (run_heartbeat and reb_simulation_step, src/simulation.c:240-274, 514-603); without them nobody sees the host
      * copy before the reb_simulation_synchronize that ends the call (:455, :511). */
+    /* exit distances: run_heartbeat's scans are evaluated on the device when nothing moves the particles between the
+     * integrator step and the heartbeat (shim_integrators.c) */
+    const int exits_ok = (!r->exit_max_distance && !r->exit_min_distance)
+                      || (r->boundary==REB_BOUNDARY_NONE && r->collision==REB_COLLISION_NONE);
     return !r->heartbeat && !r->pre_timestep_modifications && !r->post_timestep_modifications
-        && !r->exit_max_distance && !r->exit_min_distance && !r->display_data && !r->server_data;
+        && exits_ok && !r->display_data && !r->server_data;
 }
 
 void shim_fill_config(const struct reb_simulation* r, rebcu_config* c){

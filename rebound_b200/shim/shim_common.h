@@ -28,6 +28,7 @@ struct shim_state {
     size_t uploaded_N;
     void* pinned_ptr;            /* r->particles as registered with cudaHostRegister (REBOUND_B200_PIN=1) */
     size_t pinned_bytes;
+    int subset_set;              /* the engine holds a collision subset (r->map / r->N_targets) from the previous search */
 };
 
 /* Returns the per-simulation state (creating the rebcu handle on first use); NULL + reb_simulation_error

@@ -9,7 +9,7 @@
  *   reb_collision_search                            src/collision.c:49
  * The reference's own definitions are compiled under the names *_cpuref (-D renames in
  * rebound_b200/shim/Makefile); they are only used for the modes outside the GPU hot path
- * (REB_COLLISION_LINE/LINETREE, r->map / N_targets subsets, track_energy_offset, free_particle_ap).
+ * (track_energy_offset, free_particle_ap, unknown collision modes).
  *
  * Default mode: host-authoritative -- every call uploads r->particles, runs on the GPU and writes
  * the result back, so every host hook of the reference keeps working unchanged.
@@ -113,12 +113,11 @@ void reb_boundary_check(struct reb_simulation* r){
 /* ---- collisions ---------------------------------------------------------------------------- */
 void reb_collision_search(struct reb_simulation* const r){
     const int gpu_mode = (r->collision==REB_COLLISION_DIRECT || r->collision==REB_COLLISION_TREE
-                          || r->collision==REB_COLLISION_LINE || r->collision==REB_COLLISION_LINETREE)
-                       && r->map==NULL && r->N_targets==SIZE_MAX;
+                          || r->collision==REB_COLLISION_LINE || r->collision==REB_COLLISION_LINETREE);
     if (r->collision==REB_COLLISION_NONE) return;               /* collision.c:52 switch: nothing to do */
     if (!gpu_mode){
-        /* outside the GPU path (r->map / N_targets subsets of MERCURIUS and TRACE, unknown modes): the reference's
-         * routine on host data; a simulation that never used the GPU does not get a device context for this */
+        /* outside the GPU path (unknown modes): the reference's routine on host data; a simulation that never
+         * used the GPU does not get a device context for this */
         struct shim_state* s0 = shim_find(r);
         if (s0){ if (shim_to_host(r, s0)) return; s0->device_valid = 0; }
         reb_collision_search_cpuref(r);
@@ -132,6 +131,15 @@ void reb_collision_search(struct reb_simulation* const r){
     if (!s->host_stale){
         int err = rebcu_upload(s->h, (const rebcu_particle*)r->particles, r->N);
         if (shim_report(r, s, err)) return;
+    }
+    /* r->map / r->N_map / r->N_targets (collision.c:53-58): MERCURIUS and TRACE search among the particles of a
+     * close encounter only.  The subset is forwarded when it is set or was set by the previous search. */
+    const int subset = r->map!=NULL || r->N_targets!=SIZE_MAX;
+    if (subset || s->subset_set){
+        int e2 = rebcu_set_collision_subset(s->h, (const uint64_t*)r->map, r->map ? r->N_map : 0,
+                                            r->N_targets==SIZE_MAX ? REBCU_SIZE_MAX : (uint64_t)r->N_targets);
+        if (shim_report(r, s, e2)) return;
+        s->subset_set = subset;
     }
     uint64_t n_found = 0;
     int err = rebcu_collision_search(s->h, &c, (rebcu_collision*)r->collisions, r->N_allocated_collisions, &n_found);

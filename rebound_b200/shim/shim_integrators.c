@@ -61,12 +61,25 @@ static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_s
     r->OMEGAZ = c.OMEGAZ;
     r->N_active = (c.N_active==REBCU_SIZE_MAX)?SIZE_MAX:(size_t)c.N_active;
     s->host_stale = 1;
-    /* run_heartbeat (src/simulation.c:240-274) scans r->particles after every step when an exit distance is set:
-     * such simulations are kept host-current even in resident mode */
-    if (shim_resident(r) && !r->exit_max_distance && !r->exit_min_distance){
+    /* run_heartbeat (src/simulation.c:240-274) scans r->particles after every step when an exit distance is set.
+     * When nothing else changes the particles between the integrator step and that scan (no boundary, no
+     * collisions, no post-timestep hook), the same predicates are evaluated on the device here and the simulation
+     * stays resident: the host scan then runs on the state of the last synchronisation, which had passed it.
+     * Otherwise such simulations are kept host-current. */
+    const int exits = r->exit_max_distance || r->exit_min_distance;
+    const int exits_on_device = exits && r->boundary==REB_BOUNDARY_NONE && r->collision==REB_COLLISION_NONE
+                                && !r->post_timestep_modifications && !r->heartbeat;
+    if (shim_resident(r) && (!exits || exits_on_device)){
         r->N = rebcu_N(s->h);            /* tree gravity + open boundary may have removed particles */
         s->uploaded_N = r->N;
         r->is_synchronized = 0;
+        if (exits){
+            int escape = 0, encounter = 0;
+            err = rebcu_exit_check(s->h, r->exit_max_distance, r->exit_min_distance, &escape, &encounter);
+            if (shim_report(r, s, err)) return;
+            if (escape) r->status = REB_STATUS_ESCAPE;             /* simulation.c:251-253 */
+            if (encounter) r->status = REB_STATUS_ENCOUNTER;       /* simulation.c:267-269 */
+        }
     }else{
         shim_to_host(r, s);
     }

@@ -131,6 +131,18 @@ class Engine:
             self._check(self.f["collisions_fetch"](self.h, abi.as_ptr(out), n.value, C.byref(n)))
         return out[: n.value]
 
+    def exit_check(self, exit_max_distance=0.0, exit_min_distance=0.0):
+        """(escape, encounter) flags of run_heartbeat's exit conditions (src/simulation.c:242-272) on the resident state."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.f["exit_check"](self.h, float(exit_max_distance), float(exit_min_distance), C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
+
+    def set_collision_subset(self, map=None, n_targets=None):
+        """r->map / r->N_map / r->N_targets for the following searches (src/collision.c:53-58); no arguments resets."""
+        m = None if map is None else np.ascontiguousarray(map, dtype=np.uint64)
+        self._check(self.f["set_collision_subset"](self.h, None if m is None else abi.as_ptr(m), 0 if m is None else len(m),
+                                                   abi.SIZE_MAX if n_targets is None else int(n_targets)))
+
     def collisions_fetch(self):
         n = C.c_uint64(0)
         self._check(self.f["collisions_fetch"](self.h, None, 0, C.byref(n)))
@@ -275,11 +287,19 @@ class Engine:
 
 
 _GRAVITY = {"none": 0, "basic": 1, "compensated": 2, "tree": 3}
-_COLLISION = {"none": 0, "direct": 1, "tree": 2}
+_COLLISION = {"none": 0, "direct": 1, "tree": 2, "line": 4, "linetree": 5}
 _BOUNDARY = {"none": 0, "open": 1, "periodic": 2, "shear": 3}
 _INTEGRATOR = {"none": 0, "leapfrog": 1, "sei": 2}
 _ENUMS = {"gravity": _GRAVITY, "collision": _COLLISION, "boundary": _BOUNDARY, "integrator": _INTEGRATOR}
 _CFG_FIELDS = {name for name, _ in abi.Config._fields_}
+
+
+class Escape(Exception):
+    """A particle is farther than exit_max_distance from the origin (the reference's rebound.Escape, REB_STATUS_ESCAPE)."""
+
+
+class Encounter(Exception):
+    """Two particles are closer than exit_min_distance (the reference's rebound.Encounter, REB_STATUS_ENCOUNTER)."""
 
 
 class Simulation:
@@ -298,6 +318,8 @@ class Simulation:
         object.__setattr__(self, "_dev_valid", False)   # device copy is current
         object.__setattr__(self, "steps_done", 0)
         object.__setattr__(self, "collision_resolve", None)
+        object.__setattr__(self, "exit_max_distance", 0.0)      # src/rebound.h: 0 = check off
+        object.__setattr__(self, "exit_min_distance", 0.0)
 
     def __setattr__(self, name, value):
         if name in _ENUMS:
@@ -372,6 +394,15 @@ class Simulation:
         object.__setattr__(self, "_host_valid", False)
         object.__setattr__(self, "steps_done", self.steps_done + int(n))
 
+    def _exit_check(self):
+        """run_heartbeat's exit conditions (src/simulation.c:242-272), tested on the device."""
+        self._to_device()
+        escape, encounter = self._engine.exit_check(self.exit_max_distance, self.exit_min_distance)
+        if encounter:       # tested after the escape condition, so its status is the one that survives
+            raise Encounter("Two particles had a close encounter (d<exit_min_distance).")
+        if escape:
+            raise Escape("A particle escaped (r>exit_max_distance).")
+
     def step(self):
         self.steps(1)
 
@@ -386,8 +417,16 @@ class Simulation:
         while (t < tmax) if c.dt > 0 else (t > tmax):
             t += c.dt
             n += 1
-        if n:
-            self.steps(n)
+        if not (self.exit_max_distance or self.exit_min_distance):
+            if n:
+                self.steps(n)
+            return
+        # the reference runs the heartbeat (and with it the exit checks) before the first step and after every
+        # step (src/simulation.c:392, 431-432); the step that trips a condition is completed
+        self._exit_check()
+        for _ in range(n):
+            self.steps(1)
+            self._exit_check()
 
     def collision_search(self):
         self._to_device()

@@ -43,6 +43,7 @@ int main(int argc, char** argv){
     struct reb_simulation* r = reb_simulation_create();
     r->rand_seed = 42;
     char sa_file[4096] = {0};
+    int use_integrate = 0;      /* reb_simulation_integrate(r, steps*dt) instead of reb_simulation_steps(r, steps) */
     if (strcmp(scen, "plummer")==0 || strcmp(scen, "plummer_comp")==0 || strcmp(scen, "archive")==0 || strcmp(scen, "edit")==0){
         /* examples/selfgravity_plummer/problem.c */
         double M=1, R=1, E=3./64.*M_PI*M*M/R, r0=16./(3.*M_PI)*R;
@@ -179,12 +180,38 @@ int main(int argc, char** argv){
             pt.m = 1./(double)N;
             reb_simulation_add(r, pt);
         }
+    }else if (strcmp(scen, "mercurius")==0 || strcmp(scen, "trace")==0){
+        /* hybrid integrators: close encounters are integrated for a subset of the particles, and the collision
+         * search runs on that subset through r->map / r->N_map (integrator_mercurius.c:404-429, integrator_trace.c:820)
+         * and, between steps, against the star only through r->N_targets = 1 (integrator_mercurius.c:909) */
+        struct reb_particle star = {0}; star.m = 1; star.r = 0.005; reb_simulation_add(r, star);
+        for (int i=0;i<N;i++) reb_simulation_add_fmt(r, "m a e omega f inc r", 3e-4, reb_random_uniform(r,1.,1.6), reb_random_uniform(r,0.0,0.3),
+                                                     reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,0.02), 0.004);
+        reb_simulation_move_to_com(r);
+        reb_simulation_set_integrator(r, scen);
+        r->dt = 0.02;
+        r->collision = REB_COLLISION_DIRECT; r->collision_resolve = reb_collision_resolve_merge;
+    }else if (strcmp(scen, "escape")==0 || strcmp(scen, "encounter")==0){
+        /* run_heartbeat's exit conditions (simulation.c:242-272): a hot cloud loses a particle past exit_max_distance,
+         * or two particles come closer than exit_min_distance; reb_simulation_integrate ends with that status */
+        reb_simulation_set_integrator(r, "leapfrog");
+        r->gravity = REB_GRAVITY_BASIC; r->softening = 0.05; r->dt = 2e-2;
+        for (int i=0;i<N;i++){
+            struct reb_particle pt = {0};
+            pt.x = reb_random_uniform(r,-1.,1.); pt.y = reb_random_uniform(r,-1.,1.); pt.z = reb_random_uniform(r,-1.,1.);
+            pt.vx = reb_random_normal(r, 1.); pt.vy = reb_random_normal(r, 1.); pt.vz = reb_random_normal(r, 1.);
+            pt.m = 1./(double)N;
+            reb_simulation_add(r, pt);
+        }
+        if (strcmp(scen, "escape")==0) r->exit_max_distance = 4.; else r->exit_min_distance = 1e-2;
+        use_integrate = 1;
     }else{ fprintf(stderr, "unknown scenario %s\n", scen); return 2; }
 
     struct timespec t_begin, t_end;
     if (getenv("DRIVER_WARMUP")) reb_simulation_steps(r, 1);      /* timing runs: CUDA context + first upload outside the clock */
     clock_gettime(CLOCK_MONOTONIC, &t_begin);
-    reb_simulation_steps(r, steps);
+    if (use_integrate){ r->exact_finish_time = 0; reb_simulation_integrate(r, r->t + steps*r->dt); }
+    else reb_simulation_steps(r, steps);
     clock_gettime(CLOCK_MONOTONIC, &t_end);
     if (strcmp(scen, "edit")==0){
         /* plain host edits between two calls, without r->did_modify_particles: legal with the reference's leapfrog */

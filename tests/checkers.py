@@ -82,6 +82,21 @@ class Checker:
             return self.collision_search(cfg, p, cap=n.value)
         return out[: n.value]
 
+    def collision_search_subset(self, cfg, p, map=None, n_targets=None, cap=None):
+        """reb_collision_search with r->map / r->N_map / r->N_targets set (collision.c:53-58)."""
+        p = p.copy()
+        c = cfg.copy()
+        cap = cap or max(64, 8 * len(p))
+        out = np.zeros(cap, dtype=abi.COLLISION_DTYPE)
+        n = C.c_uint64(0)
+        m = None if map is None else np.ascontiguousarray(map, dtype=np.uint64)
+        self._check(self.f["collision_search_subset"](
+            C.byref(c), abi.as_ptr(p), len(p), None if m is None else abi.as_ptr(m), 0 if m is None else len(m),
+            abi.SIZE_MAX if n_targets is None else n_targets, abi.as_ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            return self.collision_search_subset(cfg, p, map, n_targets, cap=n.value)
+        return out[: n.value]
+
     def steps(self, cfg, p, n_steps, resolve=0, minimum_collision_velocity=0.0):
         p = p.copy()
         c = cfg.copy()
@@ -90,6 +105,11 @@ class Checker:
         self._check(self.f["steps"](C.byref(c), abi.as_ptr(p), C.byref(n), n_steps, resolve,
                                     minimum_collision_velocity, aux))
         return p[: n.value], c, {"collisions_log_n": int(aux[0]), "collisions_plog": aux[1], "seconds": aux[2]}
+
+    def exit_check(self, cfg, p, exit_max_distance=0.0, exit_min_distance=0.0):
+        """Status after run_heartbeat's exit checks: 4 escape, 3 encounter (wins over escape), 0 neither."""
+        p = p.copy()
+        return self.f["exit_check"](C.byref(cfg.copy()), abi.as_ptr(p), len(p), float(exit_max_distance), float(exit_min_distance))
 
     def energy(self, cfg, p):
         p = p.copy()

@@ -92,3 +92,32 @@ def test_simulation_energy_tracks_the_oracle_through_steps():
 def test_fp64_peak_probe_is_plausible(eng):
     tf = eng.measure_fp64_peak()
     assert 10.0 < tf < 80.0          # B200: ~37 TFLOP/s nominal at 1.97 GHz
+
+
+def test_exit_checks_exact(eng):
+    """run_heartbeat's exit conditions (simulation.c:242-272) on the device: exact predicates, incl. thresholds that sit
+    on a particle / a pair, NaN coordinates, N = 0 and 1, and a size with several tiles per row."""
+    from test_oracle_vs_reference import exit_cases
+    for q, mx, mn in exit_cases():
+        want = checkers.oracle().exit_check(abi.default_config(), q, mx, mn)
+        if len(q) == 0:
+            continue            # nothing to upload
+        eng.upload(np.ascontiguousarray(q))
+        escape, encounter = eng.exit_check(mx, mn)
+        got = 3 if encounter else (4 if escape else 0)
+        assert got == want, (mx, mn)
+    rng = np.random.default_rng(5)
+    n = 5000
+    q = abi.particles(n)
+    for f in ("x", "y", "z"):
+        q[f] = rng.uniform(-1, 1, n)
+    eng.upload(q)
+    assert eng.exit_check(0.0, 1e-7) == (False, False)
+    q["x"][4999] = q["x"][17] + 3e-8
+    q["y"][4999] = q["y"][17]
+    q["z"][4999] = q["z"][17]
+    q["z"][1234] = 1.8
+    eng.upload(q)
+    assert eng.exit_check(1.75, 1e-7) == (True, True)
+    assert eng.exit_check(1.81, 1e-8) == (False, False)
+    assert checkers.oracle().exit_check(abi.default_config(), q, 1.75, 1e-7) == 3

@@ -15,7 +15,9 @@ pytestmark = [pytest.mark.gpu,
 
 SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8), ("sheet", 25, 400),
              ("lf4", 700, 3), ("lf6", 700, 3), ("lf8", 700, 2), ("tp0", 3000, 6), ("merge", 400, 30), ("line", 400, 30),
-             ("periodic", 1500, 6), ("open_direct", 1200, 12), ("ias15", 300, 3), ("ias15_comp", 300, 3), ("whfast", 300, 10)]
+             ("periodic", 1500, 6), ("open_direct", 1200, 12), ("ias15", 300, 3), ("ias15_comp", 300, 3), ("whfast", 300, 10),
+             # r->map / r->N_targets collision subsets of the hybrid integrators; exit conditions of run_heartbeat
+             ("mercurius", 40, 200), ("trace", 40, 200), ("escape", 500, 400), ("encounter", 500, 400)]
 
 
 def run(binary, scen, n, steps, tmp_path, env=None):
@@ -35,6 +37,13 @@ def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
     got = run("driver_dropin", scen, n, steps, tmp_path, env={"REBOUND_B200_RESIDENT": resident})
     assert len(ref) == len(got)
     assert np.array_equal(ref, got)
+    hdr = ref[:6].view(np.float64)
+    if scen in ("mercurius", "trace"):
+        assert hdr[0] < n + 1                      # particles merged during close encounters
+    if scen == "escape":
+        assert hdr[4] == 4 and hdr[1] < steps * 2e-2      # REB_STATUS_ESCAPE before tmax
+    if scen == "encounter":
+        assert hdr[4] == 3 and hdr[1] < steps * 2e-2      # REB_STATUS_ENCOUNTER before tmax
 
 
 @pytest.mark.parametrize("resident", ["0", "1", ""], ids=["host_authoritative", "resident", "auto"])

@@ -308,6 +308,35 @@ def test_line_and_linetree_collision_lists_bitwise(eng):
         assert collisions_equal(got, want, with_ri=(cfg.collision == abi.COLLISION_LINETREE)), name
 
 
+def test_collision_subset_lists_bitwise(eng):
+    """r->map / r->N_map / r->N_targets subsets (collision.c:53-58) on the GPU against the oracle, all four modes;
+    the subset is cleared again afterwards and invalid subsets are refused."""
+    from test_oracle_vs_reference import _subset_cases
+    try:
+        n_nonempty = 0
+        for name, cfg, p, sub, nt in _subset_cases():
+            want = checkers.oracle().collision_search_subset(cfg, p, sub, nt)
+            eng.set_collision_subset(sub, nt)
+            got = eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p))
+            tree = cfg.collision in (abi.COLLISION_TREE, abi.COLLISION_LINETREE)
+            assert len(got) == len(want), name
+            assert collisions_equal(got, want, with_ri=tree), name
+            n_nonempty += len(want) > 0
+        assert n_nonempty >= 20
+        name, cfg, p, sub, nt = _subset_cases()[0]
+        eng.set_collision_subset(np.array([0, len(p)], dtype=np.uint64))           # entry >= N
+        with pytest.raises(ReboundCudaError):
+            eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p))
+        eng.set_collision_subset(None, len(p) + 1)                                 # more targets than projectiles
+        with pytest.raises(ReboundCudaError):
+            eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p))
+    finally:
+        eng.set_collision_subset()
+    name, cfg, p, sub, nt = _subset_cases()[0]
+    assert collisions_equal(eng.collision_search_host(cfg.copy(), np.ascontiguousarray(p)),
+                            checkers.oracle().collision_search(cfg, p), with_ri=False)
+
+
 def _pair_keys(col):
     """(p1, p2, ghost shift) of every entry as sortable rows."""
     k = np.stack([col["p1"].astype(np.float64), col["p2"].astype(np.float64), col["gb_x"], col["gb_y"], col["gb_vy"]], axis=1)

@@ -178,6 +178,80 @@ def test_collision_list_bitwise(name, cfg, p):
     assert checkers.collisions_equal(ref, orc, with_ri=(cfg.collision == abi.COLLISION_TREE))
 
 
+def subset_cases():
+    """r->map / r->N_map / r->N_targets (collision.c:53-58): what MERCURIUS and TRACE set around encounter steps."""
+    base = {name: (cfg, p) for name, cfg, p in collision_cases()}
+    base.update({name: (cfg, p) for name, cfg, p in line_cases()})
+    rng = np.random.default_rng(17)
+    for name in ("box_open_c1", "box_per_c1", "box_open_c2", "box_2root_c2", "open_c4", "per_c4", "open_c5", "sheet_direct"):
+        cfg, p = base[name]
+        n = len(p)
+        sub = rng.permutation(n)[: (2 * n) // 3]
+        yield f"{name}_map", cfg, p, sub, None
+        yield f"{name}_map_targets", cfg, p, sub, len(sub) // 4
+        yield f"{name}_targets", cfg, p, None, n // 5
+    cfg, p = base["box_open_c1"]
+    yield "empty_map", cfg, p, np.zeros(0, dtype=np.uint64), None
+    yield "zero_targets", cfg, p, None, 0
+    yield "repeated_slots", cfg, p, np.array([5, 5, 7, 9, 7], dtype=np.uint64), None
+
+
+SUBSET_CASES = None
+
+
+def _subset_cases():
+    global SUBSET_CASES
+    if SUBSET_CASES is None:
+        SUBSET_CASES = list(subset_cases())
+    return SUBSET_CASES
+
+
+def test_collision_subset_lists_bitwise():
+    n_nonempty = 0
+    for name, cfg, p, sub, nt in _subset_cases():
+        ref = checkers.reference().collision_search_subset(cfg, p, sub, nt)
+        orc = checkers.oracle().collision_search_subset(cfg, p, sub, nt)
+        tree = cfg.collision in (abi.COLLISION_TREE, abi.COLLISION_LINETREE)
+        assert checkers.collisions_equal(ref, orc, with_ri=tree), name
+        n_nonempty += len(ref) > 0
+    assert n_nonempty >= 20
+
+
+def exit_cases():
+    """(particles, exit_max_distance, exit_min_distance) incl. thresholds that sit exactly on a particle / a pair."""
+    rng = np.random.default_rng(23)
+    n = 300
+    q = abi.particles(n)
+    for f in ("x", "y", "z"):
+        q[f] = rng.normal(0, 1, n)
+    q["m"] = 1.0 / n
+    r = np.sqrt(q["x"] * q["x"] + q["y"] * q["y"] + q["z"] * q["z"])
+    d = np.sqrt((q["x"][:, None] - q["x"][None, :]) ** 2 + (q["y"][:, None] - q["y"][None, :]) ** 2
+                + (q["z"][:, None] - q["z"][None, :]) ** 2)
+    dmin = d[np.triu_indices(n, 1)].min()
+    for mx in (0.0, r.max() * 0.999, float(r.max()), np.nextafter(r.max(), 10.0), r.max() * 2):
+        for mn in (0.0, dmin * 0.999, float(dmin), np.nextafter(dmin, 10.0), dmin * 1.5):
+            yield q, float(mx), float(mn)
+    yield q[:1], 0.5, 10.0
+    yield q[:0], 0.5, 10.0
+    w = q.copy()
+    w["x"][7] = np.nan
+    yield w, 3.0, 1e-3
+
+
+def test_exit_checks_match_reference():
+    seen = set()
+    for q, mx, mn in exit_cases():
+        ref = checkers.reference().exit_check(abi.default_config(), q, mx, mn)
+        orc = checkers.oracle().exit_check(abi.default_config(), q, mx, mn)
+        if len(q) == 0:
+            assert ref == 2 and orc == 0       # REB_STATUS_NO_PARTICLES: the reference leaves before any check
+            continue
+        assert ref == orc, (mx, mn)
+        seen.add(ref)
+    assert seen == {0, 3, 4}
+
+
 def test_sei_step_bitwise():
     p = ics.shearing_sheet(root_size=30.0, seed=8)
     cfg = ics.shearing_sheet_config(root_size=30.0, collision=abi.COLLISION_NONE)
