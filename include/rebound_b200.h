@@ -159,6 +159,11 @@ int rebcu_update_acceleration(rebcu_handle* h, rebcu_config* cfg);
 /* reb_integrator_leapfrog_step (integrator_leapfrog.c:97-209) / reb_integrator_sei_step
  * (integrator_sei.c:86-117), selected by cfg->integrator.  Advances cfg->t, sets dt_last_done. */
 int rebcu_integrator_step(rebcu_handle* h, rebcu_config* cfg);
+/* reb_gravity_basic_calculate_and_apply_jerk, src/gravity.c:850-924 (called by EOS, integrator_eos.c:101-103,
+ * right after a force evaluation): kicks the velocities with the gradient term of the modified-kick schemes,
+ * from the resident positions and accelerations; `v` is the reference's argument.  Uses cfg->G, N_active,
+ * testparticle_type, gravity_ignore_terms.  Bit-identical to the reference's serial build. */
+int rebcu_apply_jerk(rebcu_handle* h, const rebcu_config* cfg, double v);
 /* reb_boundary_check, src/boundary.c:35-141.  OPEN removes particles (order preserving,
  * N_active decremented as in particle.c:364-366): cfg->N_active and rebcu_N() change. */
 int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg);
@@ -196,6 +201,8 @@ int rebcu_tree_fetch(rebcu_handle* h, rebcu_treecell* out, uint64_t cap);
  * reb_gravity_tree_calculate_acceleration         src/gravity.c:47-106
  * Upload x,y,z,m -> kernel -> write ax,ay,az into the caller's AoS.  cfg->gravity selects. */
 int rebcu_gravity_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N);
+/* reb_gravity_basic_calculate_and_apply_jerk on a host AoS (x, v, a, m in; v out). */
+int rebcu_jerk_host(rebcu_handle* h, const rebcu_config* cfg, rebcu_particle* particles, uint64_t N, double v);
 /* reb_collision_search (search part) on a host AoS. */
 int rebcu_collision_search_host(rebcu_handle* h, const rebcu_config* cfg,
                                 const rebcu_particle* particles, uint64_t N,

@@ -130,6 +130,82 @@ static void gravity_compensated(const rebcu_config* c, rebcu_particle* p, uint64
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Jerk kick of the modified-kick schemes (EOS): src/gravity.c:850-924                          */
+/* ------------------------------------------------------------------------------------------ */
+/* One pair (i > j): velocity increments from the gradient of |a_i - a_j| terms.  `both`: also update j. */
+static void jerk_pair(rebcu_particle* p, uint64_t i, uint64_t j, double vG2, int both){
+    const double d[3]  = { p[i].x - p[j].x,   p[i].y - p[j].y,   p[i].z - p[j].z };
+    const double da[3] = { p[i].ax - p[j].ax, p[i].ay - p[j].ay, p[i].az - p[j].az };
+    const double dr = sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
+    const double alphasum = da[0]*d[0] + da[1]*d[1] + da[2]*d[2];
+    const double pf2 = vG2/(dr*dr*dr);                     /* gravity.c:876 */
+    const double pf1 = alphasum*pf2/dr*3./dr;              /* gravity.c:879 */
+    const double pf1i = pf1*p[j].m, pf2i = pf2*p[j].m;
+    double* vi = &p[i].vx; double* vj = &p[j].vx;
+    for (int k=0;k<3;k++) vi[k] += d[k]*pf1i - da[k]*pf2i;          /* gravity.c:882-884, 909-911 */
+    if (both){
+        const double pf1j = pf1*p[i].m, pf2j = pf2*p[i].m;
+        for (int k=0;k<3;k++) vj[k] += da[k]*pf2j - d[k]*pf1j;      /* gravity.c:885-887, 915-917 */
+    }
+}
+
+static void apply_jerk(const rebcu_config* c, rebcu_particle* p, uint64_t N, double v){
+    const uint64_t Na = (c->N_active==REBCU_SIZE_MAX)?N:(c->N_active<N?c->N_active:N);
+    const uint64_t starti = (c->gravity_ignore_terms==REBCU_IGNORE_TERMS_NONE)?1:2;         /* gravity.c:857 */
+    const uint64_t startj = (c->gravity_ignore_terms==REBCU_IGNORE_TERMS_INVOLVING_0)?1:0;  /* gravity.c:858 */
+    const double vG2 = 2.*v*c->G;
+    /* massive-massive pairs (gravity.c:861-889), serial order: the scatter makes the order part of the result */
+    for (uint64_t i=starti;i<Na;i++)
+        for (uint64_t j=startj;j<i;j++) jerk_pair(p, i, j, vG2, 1);
+    /* rows of the test particles: every j < i, not only the massive ones (gravity.c:892-920); the back reaction
+     * only with testparticle_type != 0 */
+    for (uint64_t i=Na;i<N;i++)
+        for (uint64_t j=startj;j<i;j++) jerk_pair(p, i, j, vG2, c->testparticle_type!=0);
+}
+
+/* The same result as a GATHER (what the CUDA kernel does; kept here so that the order analysis is checked on the
+ * CPU): in the serial scatter above, the velocity of particle k first receives its own row (partners p < k, as the
+ * i-side of the pair, ascending p) and then, as i runs on, the back reaction of every later row p > k (as the
+ * j-side, ascending p) -- i.e. one sum over ascending p.  Which pairs exist:
+ *   p < k: (i=k, j=p) needs p >= startj, and k >= starti when k is massive (test-particle rows have no starti)
+ *   p > k: (i=p, j=k) needs k >= startj, and p >= starti when p is massive, testparticle_type != 0 otherwise. */
+int orc_apply_jerk_gather(rebcu_config* c, rebcu_particle* p, uint64_t N, double v){
+    const uint64_t Na = (c->N_active==REBCU_SIZE_MAX)?N:(c->N_active<N?c->N_active:N);
+    const uint64_t starti = (c->gravity_ignore_terms==REBCU_IGNORE_TERMS_NONE)?1:2;
+    const uint64_t startj = (c->gravity_ignore_terms==REBCU_IGNORE_TERMS_INVOLVING_0)?1:0;
+    const double vG2 = 2.*v*c->G;
+    double* out = malloc(sizeof(double)*3*(N?N:1));
+    for (uint64_t k=0;k<N;k++){
+        double w[3] = { p[k].vx, p[k].vy, p[k].vz };
+        for (uint64_t q=startj;q<N;q++){
+            if (q==k) continue;
+            const int k_is_i = q<k;
+            if (k_is_i){ if (k<Na && k<starti) continue; }
+            else { if (k<startj) continue; if (q<Na ? q<starti : c->testparticle_type==0) continue; }
+            const uint64_t i = k_is_i ? k : q, j = k_is_i ? q : k;
+            const double d[3]  = { p[i].x - p[j].x,   p[i].y - p[j].y,   p[i].z - p[j].z };
+            const double da[3] = { p[i].ax - p[j].ax, p[i].ay - p[j].ay, p[i].az - p[j].az };
+            const double dr = sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
+            const double alphasum = da[0]*d[0] + da[1]*d[1] + da[2]*d[2];
+            const double pf2 = vG2/(dr*dr*dr);
+            const double pf1 = alphasum*pf2/dr*3./dr;
+            const double pf1o = pf1*p[q].m, pf2o = pf2*p[q].m;          /* scaled with the OTHER particle's mass */
+            for (int a=0;a<3;a++) w[a] += k_is_i ? (d[a]*pf1o - da[a]*pf2o) : (da[a]*pf2o - d[a]*pf1o);
+        }
+        out[3*k]=w[0]; out[3*k+1]=w[1]; out[3*k+2]=w[2];
+    }
+    for (uint64_t k=0;k<N;k++){ p[k].vx=out[3*k]; p[k].vy=out[3*k+1]; p[k].vz=out[3*k+2]; }
+    free(out);
+    return 0;
+}
+
+int orc_apply_jerk(rebcu_config* c, rebcu_particle* p, uint64_t N, double v){
+    orc_errbuf[0]=0;
+    apply_jerk(c, p, N, v);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Boundary check: src/boundary.c:35-141                                                       */
 /* ------------------------------------------------------------------------------------------ */
 static void boundary_check(rebcu_config* c, rebcu_particle* p, uint64_t* Np){

@@ -127,6 +127,17 @@ int refh_gravity(rebcu_config* c, rebcu_particle* p, uint64_t* N){
     return err;
 }
 
+/* reb_gravity_basic_calculate_and_apply_jerk (gravity.c:850) on the given positions, velocities and accelerations. */
+int refh_apply_jerk(rebcu_config* c, rebcu_particle* p, uint64_t N, double v){
+    struct reb_simulation* r = make_sim(c, p, N);
+    reb_gravity_basic_calculate_and_apply_jerk(r, v);
+    int err = collect_error(r);
+    uint64_t n = N;
+    copy_back(r, c, p, &n);
+    reb_simulation_free(r);
+    return err;
+}
+
 /* Force evaluation that also returns r->gravity_cs (src/gravity.c:293-306), 3 doubles per particle. */
 int refh_gravity_cs(rebcu_config* c, rebcu_particle* p, uint64_t* N, double* cs_out){
     struct reb_simulation* r = make_sim(c, p, *N);

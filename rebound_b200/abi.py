@@ -152,6 +152,7 @@ CHECKER_SIGNATURES = {
     "collision_search_subset": (C.c_int, [_CFG, _P, C.c_uint64, _P, C.c_uint64, C.c_uint64, _P, C.c_uint64, _U64P]),
     "steps": (C.c_int, [_CFG, _P, _U64P, C.c_uint64, C.c_int, C.c_double, _DBLP]),
     "exit_check": (C.c_int, [_CFG, _P, C.c_uint64, C.c_double, C.c_double]),
+    "apply_jerk": (C.c_int, [_CFG, _P, C.c_uint64, C.c_double]),
     "energy": (C.c_double, [_CFG, _P, C.c_uint64]),
     "com": (None, [_CFG, _P, C.c_uint64, _DBLP]),
     "angular_momentum": (None, [_CFG, _P, C.c_uint64, _DBLP]),
@@ -204,6 +205,8 @@ PRODUCT_SIGNATURES = {
     "com": (C.c_int, [_P, _DBLP]),
     "angular_momentum": (C.c_int, [_P, _DBLP]),
     "exit_check": (C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "apply_jerk": (C.c_int, [_P, _CFG, C.c_double]),
+    "jerk_host": (C.c_int, [_P, _CFG, _P, C.c_uint64, C.c_double]),
     "measure_fp64_peak": (C.c_int, [_P, _DBLP]),
     "launch_count": (C.c_uint64, [_P]),
     "timing_enable": (C.c_int, [_P, C.c_int]),

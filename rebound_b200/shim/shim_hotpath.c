@@ -5,6 +5,7 @@
  *   reb_gravity_basic_calculate_acceleration        src/gravity.c:167
  *   reb_gravity_compensated_calculate_acceleration  src/gravity.c:284
  *   reb_gravity_tree_calculate_acceleration         src/gravity.c:47
+ *   reb_gravity_basic_calculate_and_apply_jerk      src/gravity.c:850
  *   reb_boundary_check                              src/boundary.c:35
  *   reb_collision_search                            src/collision.c:49
  * The reference's own definitions are compiled under the names *_cpuref (-D renames in
@@ -73,6 +74,22 @@ void reb_gravity_tree_calculate_acceleration(struct reb_simulation* r){
         s->device_valid = 0;
     }
     gravity_gpu(r);
+}
+
+/* The jerk kick of the modified-kick schemes (gravity.c:850-924), called by EOS right after a force evaluation
+ * (integrator_eos.c:101-103): positions, velocities and the accelerations just written go up, velocities come back. */
+void reb_gravity_basic_calculate_and_apply_jerk(struct reb_simulation* r, const double v){
+    struct shim_state* s = shim_get(r);
+    if (!s) return;
+    rebcu_config c;
+    shim_fill_config(r, &c);
+    if (s->host_stale){
+        shim_report(r, s, rebcu_apply_jerk(s->h, &c, v));
+        return;
+    }
+    int err = rebcu_jerk_host(s->h, &c, (rebcu_particle*)r->particles, r->N, v);
+    s->device_valid = 0;
+    shim_report(r, s, err);
 }
 
 /* ---- boundary ------------------------------------------------------------------------------ */

@@ -118,6 +118,13 @@ class Engine:
     def boundary_check(self, cfg):
         self._check(self.f["boundary_check"](self.h, C.byref(cfg)))
 
+    def apply_jerk(self, cfg, v):
+        """reb_gravity_basic_calculate_and_apply_jerk (src/gravity.c:850-924) on the resident state."""
+        self._check(self.f["apply_jerk"](self.h, C.byref(cfg), float(v)))
+
+    def jerk_host(self, cfg, p, v):
+        self._check(self.f["jerk_host"](self.h, C.byref(cfg), abi.as_ptr(p), len(p), float(v)))
+
     def steps(self, cfg, n):
         self._check(self.f["steps"](self.h, C.byref(cfg), n))
 

@@ -12,6 +12,7 @@
 #include <time.h>
 #include "rebound.h"
 #include "integrator_leapfrog.h"
+#include "integrator_eos.h"
 
 static double restitution_bridges(const struct reb_simulation* const r, double v){
     (void)r;                                   /* examples/shearing_sheet/problem.c:96-103 */
@@ -191,6 +192,16 @@ int main(int argc, char** argv){
         reb_simulation_set_integrator(r, scen);
         r->dt = 0.02;
         r->collision = REB_COLLISION_DIRECT; r->collision_resolve = reb_collision_resolve_merge;
+    }else if (strcmp(scen, "eos")==0){
+        /* Embedded operator splitting with a modified-kick outer scheme (PMLF4): every interaction step is a force
+         * evaluation followed by reb_gravity_basic_calculate_and_apply_jerk (integrator_eos.c:96-110) */
+        struct reb_particle star = {0}; star.m = 1; reb_simulation_add(r, star);
+        for (int i=0;i<N;i++) reb_simulation_add_fmt(r, "m a e omega f inc", 1e-5, reb_random_uniform(r,1.,10.), reb_random_uniform(r,0.0,0.1),
+                                                     reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,2.*M_PI), reb_random_uniform(r,0.,0.05));
+        reb_simulation_move_to_com(r);
+        struct reb_integrator_eos_state* eos = reb_simulation_set_integrator(r, "eos");
+        eos->phi0 = REB_INTEGRATOR_EOS_TYPE_PMLF4; eos->phi1 = REB_INTEGRATOR_EOS_TYPE_LF4; eos->n = 2;
+        r->dt = 0.05;
     }else if (strcmp(scen, "escape")==0 || strcmp(scen, "encounter")==0){
         /* run_heartbeat's exit conditions (simulation.c:242-272): a hot cloud loses a particle past exit_max_distance,
          * or two particles come closer than exit_min_distance; reb_simulation_integrate ends with that status */

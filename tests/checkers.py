@@ -106,6 +106,12 @@ class Checker:
                                     minimum_collision_velocity, aux))
         return p[: n.value], c, {"collisions_log_n": int(aux[0]), "collisions_plog": aux[1], "seconds": aux[2]}
 
+    def apply_jerk(self, cfg, p, v):
+        """reb_gravity_basic_calculate_and_apply_jerk (gravity.c:850-924): velocities after the jerk kick."""
+        p = p.copy()
+        self._check(self.f["apply_jerk"](C.byref(cfg.copy()), abi.as_ptr(p), len(p), float(v)))
+        return p
+
     def exit_check(self, cfg, p, exit_max_distance=0.0, exit_min_distance=0.0):
         """Status after run_heartbeat's exit checks: 4 escape, 3 encounter (wins over escape), 0 neither."""
         p = p.copy()

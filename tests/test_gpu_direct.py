@@ -342,3 +342,25 @@ def test_type1_massive_rows_in_several_source_chunks(tmp_path):
     env = dict(os.environ, REBOUND_B200_ROWCHUNK="2048")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "CHUNKS OK" in r.stdout, r.stderr
+
+
+def test_apply_jerk_bitwise(eng):
+    """reb_gravity_basic_calculate_and_apply_jerk (gravity.c:850-924): the serial scatter order reproduced by one
+    ascending sum per particle; same cases as the oracle-vs-reference pin, host-buffer and resident entry points."""
+    from test_oracle_vs_reference import _jerk_cases
+    for name, cfg, p, v in _jerk_cases():
+        want = checkers.oracle().apply_jerk(cfg, p, v)
+        q = np.ascontiguousarray(p.copy())
+        eng.jerk_host(cfg.copy(), q, v)
+        assert bits_equal(q, want), name
+        eng.upload(np.ascontiguousarray(p))
+        eng.apply_jerk(cfg.copy(), v)
+        assert bits_equal(eng.download(), want), name + " (resident)"
+    # a size with many CTAs and several tiles per row
+    p = ics.plummer(3001, seed=21)
+    cfg = ics.plummer_config(3001)
+    p, _ = checkers.oracle().gravity(cfg, p)
+    want = checkers.oracle().apply_jerk(cfg, p, 0.01)
+    q = np.ascontiguousarray(p.copy())
+    eng.jerk_host(cfg.copy(), q, 0.01)
+    assert bits_equal(q, want)

@@ -17,7 +17,9 @@ SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 
              ("lf4", 700, 3), ("lf6", 700, 3), ("lf8", 700, 2), ("tp0", 3000, 6), ("merge", 400, 30), ("line", 400, 30),
              ("periodic", 1500, 6), ("open_direct", 1200, 12), ("ias15", 300, 3), ("ias15_comp", 300, 3), ("whfast", 300, 10),
              # r->map / r->N_targets collision subsets of the hybrid integrators; exit conditions of run_heartbeat
-             ("mercurius", 40, 200), ("trace", 40, 200), ("escape", 500, 400), ("encounter", 500, 400)]
+             ("mercurius", 40, 200), ("trace", 40, 200), ("escape", 500, 400), ("encounter", 500, 400),
+             # EOS with a modified-kick scheme: force evaluation + jerk kick per interaction step
+             ("eos", 200, 6)]
 
 
 def run(binary, scen, n, steps, tmp_path, env=None):

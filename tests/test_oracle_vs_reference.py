@@ -217,6 +217,56 @@ def test_collision_subset_lists_bitwise():
     assert n_nonempty >= 20
 
 
+def jerk_cases():
+    """reb_gravity_basic_calculate_and_apply_jerk (gravity.c:850-924): state = positions, velocities and the
+    accelerations of a preceding force evaluation."""
+    def with_acc(cfg, p):
+        q, _ = checkers.oracle().gravity(cfg, p)
+        return q
+    p = ics.plummer(700, seed=12)
+    cfg = ics.plummer_config(700)
+    yield "plummer", cfg, with_acc(cfg, p), 0.37
+    for terms in (abi.IGNORE_TERMS_BETWEEN_0_AND_1, abi.IGNORE_TERMS_INVOLVING_0):
+        c2 = ics.plummer_config(300, gravity_ignore_terms=terms)
+        yield f"plummer_ignore{terms}", c2, with_acc(c2, p[:300]), -0.21
+    q = ics.planetesimal_disk(600, seed=13)
+    q["m"][10:] = 1e-9
+    for tp in (0, 1):
+        c3 = ics.planetesimal_config(testparticle_type=tp)
+        yield f"testp_type{tp}", c3, with_acc(c3, q), 1e-3
+    c4 = ics.planetesimal_config(testparticle_type=1, N_active=0)
+    yield "no_active", c4, with_acc(ics.planetesimal_config(testparticle_type=1), q[:100]), 0.5
+    yield "two", cfg, with_acc(cfg, p[:2]), 0.1
+    yield "one", cfg, with_acc(cfg, p[:1]), 0.1
+
+
+JERK_CASES = None
+
+
+def _jerk_cases():
+    global JERK_CASES
+    if JERK_CASES is None:
+        JERK_CASES = list(jerk_cases())
+    return JERK_CASES
+
+
+def test_apply_jerk_bitwise():
+    for name, cfg, p, v in _jerk_cases():
+        ref = checkers.reference().apply_jerk(cfg, p, v)
+        orc = checkers.oracle().apply_jerk(cfg, p, v)
+        assert checkers.bits_equal(ref, orc), name
+        if len(p) > 1:
+            assert not checkers.bits_equal(orc, p, fields=("vx", "vy", "vz")), name
+        # the gather formulation the CUDA kernel uses (one ascending sum per particle) gives the same bits
+        import ctypes as C
+        g = p.copy()
+        fn = checkers.oracle().lib.orc_apply_jerk_gather
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.c_uint64, C.c_double]
+        assert fn(C.byref(cfg.copy()), abi.as_ptr(g), len(g), float(v)) == 0
+        assert checkers.bits_equal(ref, g), name + " (gather)"
+
+
 def exit_cases():
     """(particles, exit_max_distance, exit_min_distance) incl. thresholds that sit exactly on a particle / a pair."""
     rng = np.random.default_rng(23)
