@@ -116,7 +116,7 @@ def test_exit_checks_exact(eng):
     q["x"][4999] = q["x"][17] + 3e-8
     q["y"][4999] = q["y"][17]
     q["z"][4999] = q["z"][17]
-    q["z"][1234] = 1.8
+    q["x"][1234], q["y"][1234], q["z"][1234] = 0.0, 0.0, 1.8
     eng.upload(q)
     assert eng.exit_check(1.75, 1e-7) == (True, True)
     assert eng.exit_check(1.81, 1e-8) == (False, False)
