@@ -49,6 +49,9 @@ struct TreeBuffers {
     double4* walk_geo = nullptr;   // [cap_cells] (x,y,z,w) packed for the collision walk
     int2* walk_meta = nullptr;     // [cap_cells] int4 (pt, skip, depth, rootbox)
     int2* walk_meta2 = nullptr;    // [cap_cells] (leaf: pt >= 0 | internal: -(depth+1), skip): all the gravity walk needs
+    double4* walk_rec = nullptr;   // [walk_rec_cap] (mx,my,mz, meta2 as 64 bits): everything the traversal decides on, one 32-byte load
+    double* walk_m = nullptr;      // [walk_rec_cap] cell mass, read only for accepted cells
+    uint64_t walk_rec_cap = 0;
     double* quad = nullptr; uint64_t quad_cap = 0;   // [6][quad_cap] mxx mxy mxz myy myz mzz (QUADRUPOLE builds only)
     bool has_quad = false;         // the current tree carries quadrupole moments
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;

@@ -328,6 +328,7 @@ struct WalkArgs {
     double root_size;
     int windowed;            // G inside the window of the branch-free sqrt/divide (strict_math.cuh)
     const double* quad; uint64_t quad_stride;     // QUADRUPOLE builds: six arrays mxx mxy mxz myy myz mzz, else null
+    const double4* rec; const double* m;          // traversal records (mx,my,mz,meta2) + masses (variant 4), else null
 };
 
 // MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
@@ -392,6 +393,112 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
     double sx, sy, sz;
     unsigned wkey = STRICT_WINDOW_LIMIT;
     if (FAST || a.windowed) wkey = walk_one<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
+    if (!FAST && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
+    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+}
+
+// ---- shared pieces of the walks ----------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void interact(const WalkArgs& a, double negG, double dx, double dy, double dz, double r2, double m,
+                                         double& sx, double& sy, double& sz, unsigned& bad) {
+    if (MODE == 1) {
+        const double ri = rsqrt(r2 + a.soft2);
+        const double p = negG * m * (ri * ri * ri);
+        sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
+    } else if (MODE == 0) {
+        const double rs2 = s_add(r2, a.soft2);
+        bad = max(bad, strict_window_key(rs2));
+        const double r = fsqrt_rn_w(rs2);
+        const double p = s_mul(fdiv_rn_w(negG, s_mul(s_mul(r, r), r)), m);      // tree.c:292,313
+        sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
+    } else {
+        const double r = s_sqrt(s_add(r2, a.soft2));
+        const double p = s_mul(s_div(negG, s_mul(s_mul(r, r), r)), m);
+        sx = s_add(sx, s_mul(p, dx)); sy = s_add(sy, s_mul(p, dy)); sz = s_add(sz, s_mul(p, dz));
+    }
+}
+
+__device__ __forceinline__ double cell_w2(const WalkArgs& a, int depth) {
+    if (depth < W_TABLE) return a.w2[depth];
+    double w = a.root_size;
+    for (int d = 0; d < depth; d++) w = s_div(w, 2.);
+    return s_mul(w, w);
+}
+
+// ---- walk, default variant ("advance to the next accepted cell, then interact", 32-byte traversal records) ------
+// Same interaction list in the same order as walk_one (hence the same bits); what changes is how the warp spends
+// its issue slots and its loads.
+//  * walk_one evaluates one visited cell per loop trip, so a warp pays the ~35 FP64 instructions of the interaction
+//    whenever ANY lane accepts its cell while the lanes that open theirs idle.  Here every lane first runs down its
+//    own path (one load, 8 FP64 instructions and a compare per visited cell) until it holds an ACCEPTED cell, the
+//    lanes reconverge, and the interaction is evaluated once for all of them (25.4 instead of 23.8 active lanes per
+//    instruction, ncu).
+//  * The record the traversal needs next is requested BEFORE the interaction, so its latency is covered by the
+//    sqrt/divide chain (without this the restructured loop is slower than walk_one: 7.0 vs 5.3 ms).
+//  * Every visited cell used to cost two gathers (the 32-byte position record and the 8-byte meta record).  A
+//    traversal decision needs the centre of mass and the meta word but not the mass, so the build's (mx,my,mz,m) +
+//    (pt|depth, skip) arrays are repacked into (mx,my,mz,meta) + m: ONE 32-byte gather per visited cell; the mass is
+//    fetched for accepted cells only and arrives while the sqrt/divide chain runs.
+// Measured (B200, disc N=2^20 / 2^22, sheet N=2^20 with 25 ghost boxes): 4.93 / 23.5 / 1.85 ms against 5.28 / 24.8 /
+// 1.94 ms for walk_kernel (REBOUND_B200_WALK=v1), repacking included.
+__global__ void __launch_bounds__(256) walk_pack_kernel(uint64_t n_cells, const double4* __restrict__ pos, const int2* __restrict__ meta2,
+                                                        double4* __restrict__ rec, double* __restrict__ m) {
+    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cells) return;
+    const double4 q = pos[c];
+    const int2 mt = meta2[c];
+    const long long bits = (long long)(((unsigned long long)(unsigned int)mt.y << 32) | (unsigned long long)(unsigned int)mt.x);
+    rec[c] = make_double4(q.x, q.y, q.z, __longlong_as_double(bits));
+    m[c] = q.w;
+}
+
+template <int MODE>
+__device__ __forceinline__ unsigned walk_one_rec(const WalkArgs& a, uint32_t self, double px, double py, double pz,
+                                                double& sx, double& sy, double& sz) {
+    sx = sy = sz = 0.;
+    unsigned bad = 0;
+    const double negG = -a.G;
+    const int ngb = a.ghosts->n;
+    const int n_cells = (int)a.n_cells;
+    for (int g = 0; g < ngb; g++) {
+        const double gx = s_add(a.ghosts->gb[g].x, px), gy = s_add(a.ghosts->gb[g].y, py), gz = s_add(a.ghosts->gb[g].z, pz);
+        int c = 0;
+        double4 q = make_double4(0., 0., 0., 0.);
+        if (n_cells > 0) q = ld_pos256(a.rec);
+        while (true) {
+            double dx = 0., dy = 0., dz = 0., r2 = 0., m = 0.;
+            bool found = false;
+            while (c < n_cells) {
+                const long long bits = __double_as_longlong(q.w);
+                const int mx = (int)(unsigned int)(unsigned long long)bits, my = (int)(unsigned int)((unsigned long long)bits >> 32);
+                dx = s_sub(gx, q.x); dy = s_sub(gy, q.y); dz = s_sub(gz, q.z);
+                r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+                bool acc;
+                const int c0 = c;
+                if (mx < 0) {
+                    acc = !(cell_w2(a, -mx - 1) > s_mul(a.theta2, r2));                    // tree.c:284
+                    c = acc ? my : c + 1;
+                } else { acc = (uint32_t)mx != self; c = my; }                          // tree.c:311
+                if (c < n_cells) q = ld_pos256(a.rec + c);
+                if (acc) { m = a.m[c0]; found = true; break; }
+            }
+            if (!found) break;
+            interact<MODE>(a, negG, dx, dy, dz, r2, m, sx, sy, sz, bad);
+        }
+    }
+    return bad;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) walk_rec_kernel(const WalkArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (t >= a.n_work) return;
+    const uint64_t k = a.list ? a.list[t] : t;
+    const uint32_t self = a.perm[k];
+    const double px = a.x[self], py = a.y[self], pz = a.z[self];
+    double sx, sy, sz;
+    unsigned wkey = STRICT_WINDOW_LIMIT;
+    if (FAST || a.windowed) wkey = walk_one_rec<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
     if (!FAST && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
     a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
 }
@@ -565,7 +672,7 @@ void tree_free(rebcu_handle* h) {
     TreeBuffers& T = h->tree;
     cudaFree(T.keys); cudaFree(T.keys_sorted); cudaFree(T.perm); cudaFree(T.perm_in); cudaFree(T.lcp);
     cudaFree(T.cell_off); cudaFree(T.cell_cnt); cudaFree(T.cells); cudaFree(T.parent); cudaFree(T.ready);
-    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
+    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.walk_rec); cudaFree(T.walk_m); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
     cudaFree(T.shard_list); cudaFree(T.quad);
     T = TreeBuffers();
 }
@@ -723,7 +830,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     WalkArgs a;
     a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
     a.perm = T.perm; a.list = nullptr; a.n_work = n;
-    a.quad = nullptr; a.quad_stride = 0;
+    a.quad = nullptr; a.quad_stride = 0; a.rec = nullptr; a.m = nullptr;
     a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
     a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
     a.ghosts = h->ghosts_dev;
@@ -738,17 +845,30 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     }
     if (a.n_work) {
         LaunchScope ls(h, TC_TREEWALK);
-        // Both walks give identical bits.  Measured on B200 (profiles/r01_walk_ncu.txt, r01_walk_coop_ncu.txt):
-        // per-thread is L1-wavefront bound (l1tex 93 %, FP64 37 %), cooperative is FP64-issue bound (FP64 61 %,
-        // 18.7 of 32 lanes active); wall time 6.99 vs 7.24 ms at N=2^20, 2.1 vs 3.0 ms with 25 ghost boxes.
-        // Default: per-thread; REBOUND_B200_WALK=coop selects the cooperative kernel.
-        static const bool per_thread = [] { const char* e = getenv("REBOUND_B200_WALK"); return !(e && strcmp(e, "coop") == 0); }();
+        // REBOUND_B200_WALK selects a walk for A/B runs (all give identical bits): unset = records walk (walk_rec_kernel),
+        // v1 = one visited cell per trip on the build's arrays (walk_kernel), coop = warp-cooperative (walk_coop_kernel;
+        // FP64-issue bound with 18.7 of 32 lanes active, profiles/r01_walk_coop_ncu.txt).
+        static const int variant = [] { const char* e = getenv("REBOUND_B200_WALK");
+                                        return (e && strcmp(e, "coop") == 0) ? 2 : (e && strcmp(e, "v1") == 0) ? 1 : 0; }();
         const unsigned int nb = div_up(a.n_work, 128);
         if (T.has_quad) {
             a.quad = T.quad; a.quad_stride = T.quad_cap;
             if (c->mode == REBCU_MODE_FAST) walk_quad_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_quad_kernel<false><<<nb, 128, 0, h->stream>>>(a);
-        } else if (per_thread) {
+        } else if (variant == 0) {
+            if (T.walk_rec_cap < T.cap_cells) {
+                CU_TRY(h, cudaStreamSynchronize(h->stream));
+                cudaFree(T.walk_rec); cudaFree(T.walk_m); T.walk_rec = nullptr; T.walk_m = nullptr; T.walk_rec_cap = 0;
+                CU_TRY(h, cudaMalloc(&T.walk_rec, T.cap_cells * sizeof(double4)));
+                CU_TRY(h, cudaMalloc(&T.walk_m, T.cap_cells * sizeof(double)));
+                T.walk_rec_cap = T.cap_cells;
+            }
+            h->launches++;
+            walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m);
+            a.rec = T.walk_rec; a.m = T.walk_m;
+            if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
+            else walk_rec_kernel<false><<<nb, 128, 0, h->stream>>>(a);
+        } else if (variant == 1) {
             if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_kernel<false><<<nb, 128, 0, h->stream>>>(a);
         } else {

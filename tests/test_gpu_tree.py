@@ -402,3 +402,37 @@ def test_quadrupole_tree_gravity_bitwise(eng, name, cfg, p):
     f = p.copy()
     eng.gravity_host(cf, f)
     assert max_rel_acc_error(f[:n], want) <= 1e-11
+
+
+def test_walk_variants_give_identical_bits(tmp_path):
+    """REBOUND_B200_WALK = v1 / coop (the A/B kernels kept beside the default records walk) reproduce the default
+    walk's accelerations bit for bit; the variant is latched per process, hence the subprocesses."""
+    import subprocess
+    import sys
+    script = tmp_path / "walk_variant.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from rebound_b200 import abi, ics\n"
+        "from rebound_b200.simulation import Engine\n"
+        "eng = Engine(0)\n"
+        "out = []\n"
+        "for cfg, p in ((ics.selfgravity_disc_config(), ics.selfgravity_disc(20000, seed=2)),\n"
+        "               (ics.shearing_sheet_config(root_size=60.0, t=12.3), ics.shearing_sheet(root_size=60.0, seed=5))):\n"
+        "    for mode in (abi.MODE_STRICT, abi.MODE_FAST):\n"
+        "        c = cfg.copy(); c.mode = mode\n"
+        "        q = np.ascontiguousarray(p.copy())\n"
+        "        eng.gravity_host(c, q)\n"
+        "        out += [q['ax'], q['ay'], q['az']]\n"
+        "np.concatenate(out).tofile(sys.argv[1])\n")
+    res = {}
+    for variant in ("", "v1", "coop"):
+        env = dict(os.environ)
+        env["REBOUND_B200_WALK"] = variant
+        out = tmp_path / f"acc_{variant or 'default'}.bin"
+        r = subprocess.run([sys.executable, str(script), str(out)], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        res[variant] = np.fromfile(out, dtype=np.uint64)
+    assert len(res[""]) > 0
+    assert np.array_equal(res[""], res["v1"])
+    assert np.array_equal(res[""], res["coop"])
