@@ -139,8 +139,13 @@ __global__ void __launch_bounds__(128) direct_collision_kernel(ColSoa P, DirectC
 }
 
 // ---- TREE ---------------------------------------------------------------------------------------
+constexpr int COL_W_TABLE = 64;
+
 struct TreeColArgs {
-    const double4* pos; const double4* geo; const int4* meta; uint32_t n_cells;
+    const double4* rec;          // one 32-byte record per cell: everything a visit needs (see col_pack_kernel)
+    const int4* meta; uint32_t n_cells;      // meta[c].w = root box, read for reported hits only
+    double w[COL_W_TABLE];       // cell width by depth (tree.c:100: exact halvings of root_size)
+    double root_size;
     const uint32_t* perm; uint32_t n;
     const uint32_t* list; uint32_t n_work;       // sharded: work item t -> sorted position list[t] (else t)
     uint32_t n_proj;                             // only particles [0, n_proj) are projectiles (collision.c:229,:286 with r->map set)
@@ -148,6 +153,29 @@ struct TreeColArgs {
     double r2nd;          // TREE: radius of the second largest particle; LINETREE: maxdrift = dt_last_done*sqrt(max v^2)
     double dt_last_done;
 };
+
+// The search visits a cell for its geometric centre and width (internal) or for its particle (leaf), plus the meta
+// word (leaf flag / depth, skip).  The build keeps these in three arrays (32-byte centre-of-mass record, 32-byte
+// geometry record, 16-byte meta record), which costs two dependent gathers per visited cell; the width is an exact
+// halving of root_size per level, so a table indexed by depth replaces it and ONE 32-byte record per cell is enough:
+//   leaf      (x, y, z of the particle | pt, skip)            internal  (cx, cy, cz | -(depth+1), skip)
+__global__ void __launch_bounds__(256) col_pack_kernel(uint32_t n_cells, const double4* __restrict__ pos, const double4* __restrict__ geo,
+                                                       const int4* __restrict__ meta, double4* __restrict__ rec) {
+    const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cells) return;
+    const int4 mt = meta[c];                 // pt, skip, depth, rootbox
+    const double4 q = (mt.x >= 0) ? pos[c] : geo[c];
+    const int tag = (mt.x >= 0) ? mt.x : -(mt.z + 1);
+    const long long bits = (long long)(((unsigned long long)(unsigned int)mt.y << 32) | (unsigned long long)(unsigned int)tag);
+    rec[c] = make_double4(q.x, q.y, q.z, __longlong_as_double(bits));
+}
+
+__device__ __forceinline__ double col_cell_w(const TreeColArgs& a, int depth) {
+    if (depth < COL_W_TABLE) return a.w[depth];
+    double w = a.root_size;
+    for (int d = 0; d < depth; d++) w = s_div(w, 2.);
+    return w;
+}
 
 // One traversal per projectile.  Pass 0 counts the hits and parks the first COL_SLOTS of them (target, ghost
 // box, root box packed in 8 bytes) in a per-projectile slot row; after the scan, tree_slots_kernel turns the
@@ -178,26 +206,32 @@ __global__ void __launch_bounds__(128) tree_collision_kernel(ColSoa P, TreeColAr
         const rebcu_vec6d gb = a.ghosts->gb[g];
         const rebcu_vec6d s = shifted(gb, P, i);
         uint32_t c = 0;
+        double4 q = ld256(a.rec);                                    // n_cells >= 1: the tree holds this projectile
         while (c < a.n_cells) {
-            const int4 mt = a.meta[c];
-            if (mt.x >= 0) {
-                if ((uint32_t)mt.x != i) {
-                    const double4 q = ld256(a.pos + c);              // leaf: the particle's own position
-                    if (LINE ? hit_line(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x, a.dt_last_done)
-                             : hit(s, r1, q.x, q.y, q.z, P.r[mt.x], P, (uint32_t)mt.x)) {
-                        if (PASS == 1) emit(out, base + found, i, (uint32_t)mt.x, gb, (uint64_t)mt.w);
+            const long long bits = __double_as_longlong(q.w);
+            const int tag = (int)(unsigned int)(unsigned long long)bits;
+            const uint32_t skip = (uint32_t)((unsigned long long)bits >> 32);
+            const uint32_t c0 = c;
+            const double4 q0 = q;
+            if (tag >= 0) {
+                c = skip;
+                if (c < a.n_cells) q = ld256(a.rec + c);             // next record in flight during the overlap test
+                if ((uint32_t)tag != i) {
+                    if (LINE ? hit_line(s, r1, q0.x, q0.y, q0.z, P.r[tag], P, (uint32_t)tag, a.dt_last_done)
+                             : hit(s, r1, q0.x, q0.y, q0.z, P.r[tag], P, (uint32_t)tag)) {
+                        const int rootbox = a.meta[c0].w;
+                        if (PASS == 1) emit(out, base + found, i, (uint32_t)tag, gb, (uint64_t)rootbox);
                         else if (found < COL_SLOTS)
-                            slots[(uint64_t)i * COL_SLOTS + found] = (uint64_t)(uint32_t)mt.x | ((uint64_t)g << 32) | ((uint64_t)mt.w << 40);
+                            slots[(uint64_t)i * COL_SLOTS + found] = (uint64_t)(uint32_t)tag | ((uint64_t)g << 32) | ((uint64_t)rootbox << 40);
                         found++;
                     }
                 }
-                c = mt.y;
             } else {
-                const double4 q = ld256(a.geo + c);
-                const double dx = s_sub(s.x, q.x), dy = s_sub(s.y, q.y), dz = s_sub(s.z, q.z);
+                const double dx = s_sub(s.x, q0.x), dy = s_sub(s.y, q0.y), dz = s_sub(s.z, q0.z);
                 const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
-                const double rp = s_add(reach, s_mul(0.86602540378443, q.w));       // collision.c:492
-                c = (r2 < s_mul(rp, rp)) ? c + 1 : (uint32_t)mt.y;
+                const double rp = s_add(reach, s_mul(0.86602540378443, col_cell_w(a, -tag - 1)));       // collision.c:492
+                c = (r2 < s_mul(rp, rp)) ? c + 1 : skip;
+                if (c < a.n_cells) q = ld256(a.rec + c);
             }
         }
     }
@@ -357,7 +391,19 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         if ((err = ensure_lists(h, n))) return err;
         TreeBuffers& T = h->tree;
         TreeColArgs a;
-        a.pos = T.walk_pos; a.geo = T.walk_geo; a.meta = (const int4*)T.walk_meta; a.n_cells = (uint32_t)T.n_cells;
+        if (T.col_rec_cap < T.cap_cells) {
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(T.col_rec); T.col_rec = nullptr; T.col_rec_cap = 0;
+            CU_TRY(h, cudaMalloc(&T.col_rec, T.cap_cells * sizeof(double4)));
+            T.col_rec_cap = T.cap_cells;
+        }
+        {
+            LaunchScope ls(h, TC_COLLISION);
+            col_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>((uint32_t)T.n_cells, T.walk_pos, T.walk_geo, (const int4*)T.walk_meta, T.col_rec);
+        }
+        a.rec = T.col_rec; a.meta = (const int4*)T.walk_meta; a.n_cells = (uint32_t)T.n_cells;
+        a.root_size = c->root_size;
+        { double w = c->root_size; for (int d = 0; d < COL_W_TABLE; d++) { a.w[d] = w; w = w / 2.; } }
         a.perm = T.perm; a.n = (uint32_t)n; a.ghosts = h->ghosts_dev;
         a.list = nullptr; a.n_work = (uint32_t)n; a.n_proj = (uint32_t)n_proj;
         h->col_seg_n = 1; h->col_seg_stride = n;

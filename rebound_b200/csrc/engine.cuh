@@ -52,6 +52,8 @@ struct TreeBuffers {
     double4* walk_rec = nullptr;   // [walk_rec_cap] (mx,my,mz, meta2 as 64 bits): everything the traversal decides on, one 32-byte load
     double* walk_m = nullptr;      // [walk_rec_cap] cell mass, read only for accepted cells
     uint64_t walk_rec_cap = 0;
+    double4* col_rec = nullptr;    // [col_rec_cap] collision-walk records: leaf (x,y,z | pt, skip), internal (cx,cy,cz | -(depth+1), skip)
+    uint64_t col_rec_cap = 0;
     double* quad = nullptr; uint64_t quad_cap = 0;   // [6][quad_cap] mxx mxy mxz myy myz mzz (QUADRUPOLE builds only)
     bool has_quad = false;         // the current tree carries quadrupole moments
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;

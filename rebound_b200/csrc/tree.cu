@@ -672,7 +672,7 @@ void tree_free(rebcu_handle* h) {
     TreeBuffers& T = h->tree;
     cudaFree(T.keys); cudaFree(T.keys_sorted); cudaFree(T.perm); cudaFree(T.perm_in); cudaFree(T.lcp);
     cudaFree(T.cell_off); cudaFree(T.cell_cnt); cudaFree(T.cells); cudaFree(T.parent); cudaFree(T.ready);
-    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.walk_rec); cudaFree(T.walk_m); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
+    cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.walk_rec); cudaFree(T.walk_m); cudaFree(T.col_rec); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
     cudaFree(T.shard_list); cudaFree(T.quad);
     T = TreeBuffers();
 }
