@@ -259,43 +259,69 @@ __global__ void __launch_bounds__(256) overflow_flag_kernel(uint32_t n, const ui
     if (__any_sync(0xffffffffu, over) && (threadIdx.x & 31) == 0) atomicAdd(flag, 1ull);
 }
 
-// Radius of the second largest particle (reb_simulation_two_largest_particles, simulation.c:718-799).
-__global__ void __launch_bounds__(1024) second_largest_kernel(const double* __restrict__ r, uint32_t n, double* out) {
-    __shared__ double s1[1024], s2[1024];
+// Radius of the second largest particle (reb_simulation_two_largest_particles, simulation.c:718-799) and
+// max over particles of vx^2+vy^2+vz^2 (collision.c:273-277): only the VALUES are used, so the reductions are order
+// independent.  Two stages: RED_BLOCKS blocks leave their partial results in `part`, one block combines them.
+constexpr int RED_BLOCKS = 128;
+
+// two largest of the multiset {a1 >= a2} U {b1 >= b2}
+__device__ __forceinline__ void top2_merge(double& a1, double& a2, double b1, double b2) {
+    const double m1 = a1 > b1 ? a1 : b1;
+    const double lo = a1 > b1 ? b1 : a1;
+    const double hi2 = a1 > b1 ? a2 : b2;
+    a1 = m1; a2 = lo > hi2 ? lo : hi2;
+}
+
+__device__ __forceinline__ void top2_block(double& l1, double& l2, double* s1, double* s2) {
+    for (int o = 16; o > 0; o >>= 1) top2_merge(l1, l2, __shfl_down_sync(0xffffffffu, l1, o), __shfl_down_sync(0xffffffffu, l2, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s1[w] = l1; s2[w] = l2; }
+    __syncthreads();
+    if (w == 0) {
+        l1 = (l < (int)(blockDim.x >> 5)) ? s1[l] : -1.0; l2 = (l < (int)(blockDim.x >> 5)) ? s2[l] : -1.0;
+        for (int o = 16; o > 0; o >>= 1) top2_merge(l1, l2, __shfl_down_sync(0xffffffffu, l1, o), __shfl_down_sync(0xffffffffu, l2, o));
+    }
+}
+
+__global__ void __launch_bounds__(256) second_largest_kernel(const double* __restrict__ r, uint32_t n, double* __restrict__ part) {
+    __shared__ double s1[8], s2[8];
     double l1 = -1.0, l2 = -1.0;
-    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const double v = r[i];
         if (v > l1) { l2 = l1; l1 = v; } else if (v > l2) l2 = v;
     }
-    s1[threadIdx.x] = l1; s2[threadIdx.x] = l2;
-    __syncthreads();
-    for (int w = 512; w > 0; w >>= 1) {
-        if (threadIdx.x < w) {
-            const double a1 = s1[threadIdx.x], a2 = s2[threadIdx.x], b1 = s1[threadIdx.x + w], b2 = s2[threadIdx.x + w];
-            // two largest of the multiset {a1,a2,b1,b2}
-            const double m1 = a1 > b1 ? a1 : b1;
-            const double lo = a1 > b1 ? b1 : a1;
-            const double hi2 = a1 > b1 ? a2 : b2;
-            s1[threadIdx.x] = m1; s2[threadIdx.x] = lo > hi2 ? lo : hi2;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = (n >= 2) ? s2[0] : 0.0;
+    top2_block(l1, l2, s1, s2);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = l1; part[2 * blockIdx.x + 1] = l2; }
 }
 
-// max over particles of vx^2+vy^2+vz^2 (collision.c:273-277)
-__global__ void __launch_bounds__(1024) vmax2_kernel(ColSoa P, uint32_t n, double* out) {
-    __shared__ double sm[1024];
+__global__ void __launch_bounds__(RED_BLOCKS) second_largest_final_kernel(const double* __restrict__ part, int n_part, uint32_t n, double* out) {
+    __shared__ double s1[RED_BLOCKS / 32], s2[RED_BLOCKS / 32];
+    double l1 = -1.0, l2 = -1.0;
+    if ((int)threadIdx.x < n_part) { l1 = part[2 * threadIdx.x]; l2 = part[2 * threadIdx.x + 1]; }
+    top2_block(l1, l2, s1, s2);
+    if (threadIdx.x == 0) out[0] = (n >= 2) ? l2 : 0.0;       // collision.c:222-225: no second particle, radius 0
+}
+
+__global__ void __launch_bounds__(256) vmax2_kernel(ColSoa P, uint32_t n, double* __restrict__ part) {
+    __shared__ double sm[8];
     double m = 0.;
-    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const double vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
         const double v2 = s_add(s_add(s_mul(vx, vx), s_mul(vy, vy)), s_mul(vz, vz));
-        m = (m > v2) ? m : v2;
+        m = (m > v2) ? m : v2;                                // MAX(vmax2, v2), collision.c:44
     }
-    sm[threadIdx.x] = m;
+    for (int o = 16; o > 0; o >>= 1) { const double b = __shfl_down_sync(0xffffffffu, m, o); m = (m > b) ? m : b; }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
     __syncthreads();
-    for (int w = 512; w > 0; w >>= 1) {
-        if (threadIdx.x < w) { const double a = sm[threadIdx.x], b = sm[threadIdx.x + w]; sm[threadIdx.x] = (a > b) ? a : b; }
+    if (threadIdx.x == 0) { for (int w = 1; w < 8; w++) m = (m > sm[w]) ? m : sm[w]; part[blockIdx.x] = m; }
+}
+
+__global__ void __launch_bounds__(RED_BLOCKS) vmax2_final_kernel(const double* __restrict__ part, int n_part, double* out) {
+    __shared__ double sm[RED_BLOCKS];
+    sm[threadIdx.x] = ((int)threadIdx.x < n_part) ? part[threadIdx.x] : 0.;
+    __syncthreads();
+    for (int w = RED_BLOCKS / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) { const double a = sm[threadIdx.x], b = sm[threadIdx.x + w]; sm[threadIdx.x] = (a > b) ? a : b; }
         __syncthreads();
     }
     if (threadIdx.x == 0) out[0] = sm[0];
@@ -415,8 +441,16 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
         }
         {
             LaunchScope ls(h, TC_COLLISION, 2);
-            if (line) vmax2_kernel<<<1, 1024, 0, h->stream>>>(P, (uint32_t)n_proj, h->scratch);      // collision.c:273-277
-            else second_largest_kernel<<<1, 1024, 0, h->stream>>>(P.r, (uint32_t)n, h->scratch);
+            double* part = h->scratch_big;        // 2 x RED_BLOCKS doubles of the 3584 (the fused test-particle step is not running)
+            if (line) {                                                                           // collision.c:273-277
+                const int nb = (int)min((unsigned int)RED_BLOCKS, max(1u, div_up(n_proj, 256)));
+                vmax2_kernel<<<nb, 256, 0, h->stream>>>(P, (uint32_t)n_proj, part);
+                vmax2_final_kernel<<<1, RED_BLOCKS, 0, h->stream>>>(part, nb, h->scratch);
+            } else {
+                const int nb = (int)min((unsigned int)RED_BLOCKS, max(1u, div_up(n, 256)));
+                second_largest_kernel<<<nb, 256, 0, h->stream>>>(P.r, (uint32_t)n, part);
+                second_largest_final_kernel<<<1, RED_BLOCKS, 0, h->stream>>>(part, nb, (uint32_t)n, h->scratch);
+            }
         }
         double* pin = (double*)(h->pinned + 8);
         CU_TRY(h, cudaMemcpyAsync(pin, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
