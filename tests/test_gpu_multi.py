@@ -199,3 +199,71 @@ def test_two_gpu_sharded_steps_bitwise(case, tmp_path):
     p, cfg, steps = make_case(case)
     want, _, _ = checkers.oracle().steps(cfg, p, steps)
     assert checkers.bits_equal(got, want)
+
+
+def _extras_setup():
+    p = ics.shearing_sheet(root_size=40.0, seed=5)
+    cfg = ics.shearing_sheet_config(root_size=40.0, t=55.5, collision=abi.COLLISION_NONE)
+    rng = np.random.default_rng(11)
+    sub = rng.permutation(len(p))[: (2 * len(p)) // 3].astype(np.uint64)
+    return p, cfg, 2, sub, len(sub) // 2, 0.37
+
+
+def _extras_worker(rank, world, port, case, path):
+    """Sharded steps, then the jerk kick (needs every block's accelerations: exchange ALL), the exit checks (every
+    rank scans all particles) and a DIRECT collision search on an r->map / N_targets subset (slots are sharded)."""
+    import torch.distributed as dist
+
+    from rebound_b200 import distributed as D
+    from rebound_b200.simulation import Engine
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        p, cfg, steps, sub, nt, v = _extras_setup()
+        dev = torch.device("cuda", rank)
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        eng = Engine(rank, stream.cuda_stream)
+        eng.upload(np.ascontiguousarray(p))
+        D.attach(eng, dev)
+        c = cfg.copy()
+        eng.steps(c, steps)
+        eng.apply_jerk(c, v)
+        flags = eng.exit_check(30.0, 1.5)
+        c.collision = abi.COLLISION_DIRECT
+        eng.set_collision_subset(sub, nt)
+        eng.collision_search(c)
+        merged = D.gather_collisions(eng, dev)
+        eng.set_collision_subset()
+        D.gather_owned(eng, dev)
+        torch.cuda.synchronize()
+        if rank == 0:
+            np.save(path, np.frombuffer(eng.download().tobytes(), dtype=np.uint8))
+            np.save(path + ".col.npy", np.frombuffer(merged.tobytes(), dtype=np.uint8))
+            np.save(path + ".flags.npy", np.array(flags, dtype=np.int64))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_jerk_exit_checks_and_subset_search_bitwise(tmp_path):
+    path = str(tmp_path / "out.npy")
+    _run(_extras_worker, "extras", path)
+    got = np.frombuffer(np.load(path).tobytes(), dtype=abi.PARTICLE_DTYPE)
+    got_col = np.frombuffer(np.load(path + ".col.npy").tobytes(), dtype=abi.COLLISION_DTYPE)
+    flags = np.load(path + ".flags.npy")
+    p, cfg, steps, sub, nt, v = _extras_setup()
+    orc = checkers.oracle()
+    q, c1, _ = orc.steps(cfg, p, steps)
+    q = orc.apply_jerk(c1, q, v)
+    assert checkers.bits_equal(got, q)
+    status = orc.exit_check(c1, q, 30.0, 1.5)
+    assert (3 if flags[1] else (4 if flags[0] else 0)) == status and status != 0
+    c1.collision = abi.COLLISION_DIRECT
+    want_col = orc.collision_search_subset(c1, q, sub, nt)
+    assert len(want_col) > 0
+    assert checkers.collisions_equal(got_col, want_col, with_ri=False)
