@@ -106,6 +106,7 @@ typedef struct rebcu_treecell {
 } rebcu_treecell;
 
 enum {
+    REBCU_INTERRUPTED = 1,            /* rebcu_steps stopped early on the caller's interrupt flag (not an error) */
     REBCU_OK = 0,
     REBCU_ERR_CUDA = -1,              /* CUDA runtime failure */
     REBCU_ERR_ARG = -2,               /* invalid argument */
@@ -184,6 +185,11 @@ int rebcu_set_collision_subset(rebcu_handle* h, const uint64_t* map, uint64_t N_
  * collision list of the LAST step is left on the device (rebcu_collisions_fetch). */
 int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps);
 int rebcu_collisions_fetch(rebcu_handle* h, rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+/* The reference polls its global `reb_sigint` inside its long loops and leaves them when a second Ctrl-C arrives
+ * (`if (reb_sigint > 1) return;`, src/gravity.c:196, src/collision.c:75,232; declared in src/rebound.c:193).
+ * rebcu_steps tests *flag > 1 before every step: the step in progress is completed, cfg->t stands at the last
+ * completed step, and the call returns REBCU_INTERRUPTED.  NULL (default) = never. */
+int rebcu_set_interrupt_flag(rebcu_handle* h, const volatile int* flag);
 /* Hook run after each step's collision search inside rebcu_steps: the place of the shuffle + resolve
  * loop (collision.c:336-404), which stays on the host because r->collision_resolve is a user callback.
  * The callback may call rebcu_collisions_fetch / rebcu_download / rebcu_upload; non-zero aborts. */

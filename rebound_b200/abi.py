@@ -201,6 +201,7 @@ PRODUCT_SIGNATURES = {
     "exchange_request": (C.c_int, [_P]),
     "collisions_segments": (C.c_int, [_P, _U64P, C.c_uint64, _U64P]),
     "set_collision_callback": (C.c_int, [_P, _P, _P]),
+    "set_interrupt_flag": (C.c_int, [_P, _P]),
     "energy": (C.c_int, [_P, _CFG, _DBLP]),
     "com": (C.c_int, [_P, _DBLP]),
     "angular_momentum": (C.c_int, [_P, _DBLP]),

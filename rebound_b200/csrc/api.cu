@@ -66,6 +66,8 @@ int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg, rebcu_colli
 int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
+    auto interrupted = [h] { return h->interrupt && *h->interrupt > 1; };
+    if (n_steps && interrupted()) return REBCU_INTERRUPTED;
     {
         // few massive bodies + many test particles: the whole batch of steps in two launches
         const int fused = tp_steps_resident(h, cfg, n_steps);
@@ -75,7 +77,8 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
                         && cfg->collision == REBCU_COLLISION_NONE && h->exchange == nullptr;
     bool carried = false;
     for (uint64_t s = 0; s < n_steps; s++) {
-        const bool last = (s + 1 == n_steps);
+        const bool stop = interrupted();              // finish this step (a carried half-kick must be closed), then leave
+        const bool last = (s + 1 == n_steps) || stop;
         const bool carry_out = can_carry && !last;
         int err = integrator_step(h, cfg, carried, carry_out, last);
         if (err) return err;
@@ -99,6 +102,7 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
                 if (err) return err;
             }
         }
+        if (stop && s + 1 < n_steps) return REBCU_INTERRUPTED;
     }
     return REBCU_OK;
 }
@@ -134,6 +138,11 @@ int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particl
 
 int rebcu_set_exchange_callback(rebcu_handle* h, void (*cb)(void*), void* user) {
     h->exchange = cb; h->exchange_user = user;
+    return REBCU_OK;
+}
+
+int rebcu_set_interrupt_flag(rebcu_handle* h, const volatile int* flag) {
+    h->interrupt = flag;
     return REBCU_OK;
 }
 

@@ -119,6 +119,7 @@ struct rebcu_handle {
     uint64_t col_seg_n = 0, col_seg_stride = 0;     // local collision list: segments (ghost boxes) x projectiles per segment
     int (*collision_hook)(void*) = nullptr;   // called after each step's collision search (host resolve)
     void* collision_hook_user = nullptr;
+    const volatile int* interrupt = nullptr;  // rebcu_set_interrupt_flag: the caller's reb_sigint
     // pinned staging for small host<->device exchanges
     unsigned long long* pinned = nullptr;  // 32 words
 

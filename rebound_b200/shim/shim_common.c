@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "shim_common.h"
+#include "rebound_internal.h"   /* reb_sigint */
 #include "integrator_leapfrog.h"
 
 #define SHIM_MAX 256
@@ -24,7 +25,8 @@ struct shim_state* shim_get(struct reb_simulation* r){
             const char* env = getenv("REBOUND_B200_DEVICE");
             if (env) device = atoi(env);
             s->h = rebcu_create(device, NULL);
-            if (s->h) s->r = r; else s = NULL;
+            /* second Ctrl-C: leave multi-step device calls as the reference leaves its loops (src/rebound.c:193-200) */
+            if (s->h){ s->r = r; rebcu_set_interrupt_flag(s->h, (const volatile int*)&reb_sigint); } else s = NULL;
         }
     }
     pthread_mutex_unlock(&table_lock);

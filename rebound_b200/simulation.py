@@ -126,7 +126,15 @@ class Engine:
         self._check(self.f["jerk_host"](self.h, C.byref(cfg), abi.as_ptr(p), len(p), float(v)))
 
     def steps(self, cfg, n):
-        self._check(self.f["steps"](self.h, C.byref(cfg), n))
+        err = self.f["steps"](self.h, C.byref(cfg), n)
+        if err == 1:        # REBCU_INTERRUPTED: the reference's Python raises KeyboardInterrupt for REB_STATUS_SIGINT
+            raise KeyboardInterrupt
+        self._check(err)
+
+    def set_interrupt_flag(self, flag):
+        """flag: a ctypes.c_int the caller raises above 1 to stop rebcu_steps (the reference's reb_sigint), or None."""
+        self._interrupt_flag = flag      # keep it alive
+        self._check(self.f["set_interrupt_flag"](self.h, C.byref(flag) if flag is not None else None))
 
     def collision_search(self, cfg, cap=None):
         cap = cap or max(1024, 4 * self.N)

@@ -138,3 +138,36 @@ def test_independent_simulations_in_parallel_threads():
         t.join(120)
     assert not errors, errors
     assert results == serial
+
+
+def test_interrupt_flag_stops_multi_step_calls():
+    """rebcu_set_interrupt_flag: the reference leaves its long loops on a second Ctrl-C (reb_sigint > 1, src/gravity.c:196);
+    rebcu_steps tests the caller's flag before every step, completes the step in progress and returns REBCU_INTERRUPTED."""
+    import ctypes as C
+    from rebound_b200.simulation import Engine
+    eng = Engine(0)
+    try:
+        p = ics.plummer(600, seed=3)
+        cfg = ics.plummer_config(600)
+        flag = C.c_int(0)
+        eng.set_interrupt_flag(flag)
+        eng.upload(np.ascontiguousarray(p))
+        c = cfg.copy()
+        eng.steps(c, 3)                               # flag low: runs to the end
+        t3 = c.t
+        flag.value = 1                                # first Ctrl-C: the reference keeps going as well
+        eng.steps(c, 1)
+        assert c.t > t3
+        flag.value = 2
+        t4 = c.t
+        with pytest.raises(KeyboardInterrupt):
+            eng.steps(c, 5)
+        assert c.t == t4                              # nothing was started
+        want, cw, _ = checkers.oracle().steps(cfg, p, 4)
+        assert checkers.bits_equal(eng.download(), want) and c.t == cw.t
+        eng.set_interrupt_flag(None)
+        eng.steps(c, 2)
+        want, cw, _ = checkers.oracle().steps(cfg, p, 6)
+        assert checkers.bits_equal(eng.download(), want)
+    finally:
+        eng.close()
