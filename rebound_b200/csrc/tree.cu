@@ -33,6 +33,7 @@
 #include "primitives.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -328,7 +329,8 @@ struct WalkArgs {
     double root_size;
     int windowed;            // G inside the window of the branch-free sqrt/divide (strict_math.cuh)
     const double* quad; uint64_t quad_stride;     // QUADRUPOLE builds: six arrays mxx mxy mxz myy myz mzz, else null
-    const double4* rec; const double* m;          // traversal records (mx,my,mz,meta2) + masses (variant 4), else null
+    const double4* rec; const double* m;          // traversal records (mx,my,mz,meta) + masses (records walk), else null
+    uint32_t w2_lo;                               // low word of every (normal) squared cell width, see walk_pack_kernel
 };
 
 // MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
@@ -418,6 +420,13 @@ __device__ __forceinline__ void interact(const WalkArgs& a, double negG, double 
     }
 }
 
+// out-of-line copy for the rare branch of the records walk (keeps the hot loop short)
+__device__ __noinline__ double cell_w2_rare(double root_size, int depth) {
+    double w = root_size;
+    for (int d = 0; d < depth; d++) w = s_div(w, 2.);
+    return s_mul(w, w);
+}
+
 __device__ __forceinline__ double cell_w2(const WalkArgs& a, int depth) {
     if (depth < W_TABLE) return a.w2[depth];
     double w = a.root_size;
@@ -441,13 +450,24 @@ __device__ __forceinline__ double cell_w2(const WalkArgs& a, int depth) {
 //    fetched for accepted cells only and arrives while the sqrt/divide chain runs.
 // Measured (B200, disc N=2^20 / 2^22, sheet N=2^20 with 25 ghost boxes): 4.93 / 23.5 / 1.85 ms against 5.28 / 24.8 /
 // 1.94 ms for walk_kernel (REBOUND_B200_WALK=v1), repacking included.
+// Meta word of a record: low half = tag, high half = skip.  Leaf: tag = particle index (>= 0).  Internal cell: bit 31
+// set and, below it, the HIGH word of the cell's squared width w2.  Cell widths are exact halvings of root_size
+// (tree.c:100), so every w2 is fl(root_size^2) scaled by a power of four: all of them share their low word (passed as
+// a kernel argument) and the walk rebuilds w2 with one logic instruction instead of a table lookup by depth.  A width
+// so small that w2 leaves the normal range gets the marker 0x80000000 and the walk recomputes it from the depth.
 __global__ void __launch_bounds__(256) walk_pack_kernel(uint64_t n_cells, const double4* __restrict__ pos, const int2* __restrict__ meta2,
-                                                        double4* __restrict__ rec, double* __restrict__ m) {
+                                                        double4* __restrict__ rec, double* __restrict__ m, WalkArgs a) {
     const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (c >= n_cells) return;
     const double4 q = pos[c];
     const int2 mt = meta2[c];
-    const long long bits = (long long)(((unsigned long long)(unsigned int)mt.y << 32) | (unsigned long long)(unsigned int)mt.x);
+    unsigned int tag = (unsigned int)mt.x;
+    if (mt.x < 0) {
+        const double w2 = cell_w2(a, -mt.x - 1);
+        const unsigned int hi = (unsigned int)__double2hiint(w2), lo = (unsigned int)__double2loint(w2);
+        tag = (lo == a.w2_lo && (hi >> 20) != 0 && hi < 0x7ff00000u) ? (0x80000000u | hi) : 0x80000000u;
+    }
+    const long long bits = (long long)(((unsigned long long)(unsigned int)mt.y << 32) | (unsigned long long)tag);
     rec[c] = make_double4(q.x, q.y, q.z, __longlong_as_double(bits));
     m[c] = q.w;
 }
@@ -470,15 +490,16 @@ __device__ __forceinline__ unsigned walk_one_rec(const WalkArgs& a, uint32_t sel
             bool found = false;
             while (c < n_cells) {
                 const long long bits = __double_as_longlong(q.w);
-                const int mx = (int)(unsigned int)(unsigned long long)bits, my = (int)(unsigned int)((unsigned long long)bits >> 32);
+                const int tag = (int)(unsigned int)(unsigned long long)bits, skip = (int)(unsigned int)((unsigned long long)bits >> 32);
                 dx = s_sub(gx, q.x); dy = s_sub(gy, q.y); dz = s_sub(gz, q.z);
                 r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
-                bool acc;
+                const int hi = tag & 0x7fffffff;
+                double w2 = __hiloint2double(hi, (int)a.w2_lo);
+                if (tag < 0 && hi == 0) w2 = cell_w2_rare(a.root_size, -a.meta2[c].x - 1);    // beyond the normal range: by depth
+                const bool open = tag < 0 && w2 > s_mul(a.theta2, r2);                   // tree.c:284
+                const bool acc = tag < 0 ? !open : (uint32_t)tag != self;               // tree.c:311
                 const int c0 = c;
-                if (mx < 0) {
-                    acc = !(cell_w2(a, -mx - 1) > s_mul(a.theta2, r2));                    // tree.c:284
-                    c = acc ? my : c + 1;
-                } else { acc = (uint32_t)mx != self; c = my; }                          // tree.c:311
+                c = open ? c + 1 : skip;
                 if (c < n_cells) q = ld_pos256(a.rec + c);
                 if (acc) { m = a.m[c0]; found = true; break; }
             }
@@ -830,7 +851,7 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     WalkArgs a;
     a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
     a.perm = T.perm; a.list = nullptr; a.n_work = n;
-    a.quad = nullptr; a.quad_stride = 0; a.rec = nullptr; a.m = nullptr;
+    a.quad = nullptr; a.quad_stride = 0; a.rec = nullptr; a.m = nullptr; a.w2_lo = 0;
     a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
     a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
     a.ghosts = h->ghosts_dev;
@@ -864,8 +885,9 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
                 T.walk_rec_cap = T.cap_cells;
             }
             h->launches++;
-            walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m);
             a.rec = T.walk_rec; a.m = T.walk_m;
+            { const double w20 = a.w2[0]; unsigned long long u; memcpy(&u, &w20, 8); a.w2_lo = (uint32_t)u; }
+            walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m, a);
             if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_rec_kernel<false><<<nb, 128, 0, h->stream>>>(a);
         } else if (variant == 1) {
