@@ -97,7 +97,49 @@ def main():
         d[f"out_b{b}"] = raw(q)
         d[f"n_active_b{b}"] = cc.N_active
     np.savez_compressed(os.path.join(HERE, "boundary300.npz"), **d)
+
+    # 6. the searches / kicks / checks around the five configurations: LINE and LINETREE lists, r->map / N_targets
+    #    subsets in all four search modes, the jerk kick of the modified-kick schemes, run_heartbeat's exit checks
+    extras(ref)
     print("golden fixtures written to", HERE)
+
+
+def extras_inputs():
+    """Inputs of fixture 6 (shared with tests/test_oracle_golden.py and the GPU tests)."""
+    rng = np.random.default_rng(29)
+    n = 300
+    q = abi.particles(n)
+    for f in ("x", "y", "z"):
+        q[f] = rng.uniform(-4.9, 4.9, n)
+    for f in ("vx", "vy", "vz"):
+        q[f] = rng.normal(0, 3, n)
+    q["r"] = rng.uniform(0.05, 0.35, n)
+    q["m"] = rng.uniform(0.5, 1.5, n) / n
+    sub = rng.permutation(n)[:200].astype(np.uint64)
+    base = dict(root_size=10.0, boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=1, N_ghost_y=1, N_ghost_z=0, dt_last_done=0.04)
+    return q, sub, 60, base
+
+
+def extras(ref):
+    q, sub, nt, base = extras_inputs()
+    d = {"particles_in": raw(q), "map": sub, "n_targets": nt}
+    for mode in (abi.COLLISION_DIRECT, abi.COLLISION_TREE, abi.COLLISION_LINE, abi.COLLISION_LINETREE):
+        c = abi.default_config(collision=mode, **base)
+        d[f"col_m{mode}"] = raw(ref.collision_search(c, q))
+        d[f"col_m{mode}_map"] = raw(ref.collision_search_subset(c, q, sub, None))
+        d[f"col_m{mode}_map_targets"] = raw(ref.collision_search_subset(c, q, sub, nt))
+        d[f"col_m{mode}_targets"] = raw(ref.collision_search_subset(c, q, None, nt))
+    cj = abi.default_config(softening=0.05, N_active=100, testparticle_type=1)
+    qa, _ = ref.gravity(cj, q)
+    d["jerk_in"] = raw(qa)
+    d["jerk_out"] = raw(ref.apply_jerk(cj, qa, 0.37))
+    cj2 = abi.default_config(softening=0.05, gravity_ignore_terms=abi.IGNORE_TERMS_INVOLVING_0)
+    d["jerk_out_ignore0"] = raw(ref.apply_jerk(cj2, qa, -0.11))
+    r = np.sqrt(q["x"] ** 2 + q["y"] ** 2 + q["z"] ** 2)
+    d["exit_max"] = np.array([float(r.max()), float(np.nextafter(r.max(), 0.0)), 2.0, 0.0])
+    d["exit_min"] = np.array([0.0, 0.05, 0.5])
+    d["exit_status"] = np.array([[ref.exit_check(cj, q, mx, mn) for mn in d["exit_min"]] for mx in d["exit_max"]])
+    np.savez_compressed(os.path.join(HERE, "extras300.npz"), **d)
 
 
 if __name__ == "__main__":

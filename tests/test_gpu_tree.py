@@ -436,3 +436,40 @@ def test_walk_variants_give_identical_bits(tmp_path):
     assert len(res[""]) > 0
     assert np.array_equal(res[""], res["v1"])
     assert np.array_equal(res[""], res["coop"])
+
+
+def test_extras_golden(eng):
+    """The committed reference vectors of tests/golden/extras300.npz through the C ABI: LINE / LINETREE lists, r->map /
+    N_targets subsets in all four search modes, the jerk kick, the exit checks (no oracle involved)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import extras_inputs
+    g = np.load(os.path.join(GOLD, "extras300.npz"))
+    q, sub, nt, base = extras_inputs()
+    q = np.ascontiguousarray(q)
+    try:
+        for mode in (abi.COLLISION_DIRECT, abi.COLLISION_TREE, abi.COLLISION_LINE, abi.COLLISION_LINETREE):
+            c = abi.default_config(collision=mode, **base)
+            tree = mode in (abi.COLLISION_TREE, abi.COLLISION_LINETREE)
+            for key, m, t in ((f"col_m{mode}", None, None), (f"col_m{mode}_map", sub, None),
+                              (f"col_m{mode}_map_targets", sub, nt), (f"col_m{mode}_targets", None, nt)):
+                eng.set_collision_subset(m, t)
+                got = eng.collision_search_host(c.copy(), q.copy())
+                want = np.frombuffer(g[key].tobytes(), dtype=abi.COLLISION_DTYPE)
+                assert collisions_equal(got, want, with_ri=tree), key
+    finally:
+        eng.set_collision_subset()
+    qa = np.frombuffer(g["jerk_in"].tobytes(), dtype=abi.PARTICLE_DTYPE).copy()
+    cj = abi.default_config(softening=0.05, N_active=100, testparticle_type=1)
+    out = qa.copy()
+    eng.jerk_host(cj.copy(), out, 0.37)
+    assert bits_equal(out, np.frombuffer(g["jerk_out"].tobytes(), dtype=abi.PARTICLE_DTYPE))
+    cj2 = abi.default_config(softening=0.05, gravity_ignore_terms=abi.IGNORE_TERMS_INVOLVING_0)
+    out = qa.copy()
+    eng.jerk_host(cj2.copy(), out, -0.11)
+    assert bits_equal(out, np.frombuffer(g["jerk_out_ignore0"].tobytes(), dtype=abi.PARTICLE_DTYPE))
+    eng.upload(q)
+    for i, mx in enumerate(g["exit_max"]):
+        for j, mn in enumerate(g["exit_min"]):
+            escape, encounter = eng.exit_check(float(mx), float(mn))
+            assert (3 if encounter else (4 if escape else 0)) == int(g["exit_status"][i, j])

@@ -90,3 +90,33 @@ def test_boundary_golden(b):
     out, cc = checkers.oracle().boundary_check(c, p)
     assert out.tobytes() == as_particles(g[f"out_b{b}"]).tobytes()
     assert cc.N_active == int(g[f"n_active_b{b}"])
+
+
+def test_extras_golden():
+    """LINE / LINETREE lists, r->map / N_targets subsets in all four search modes, the jerk kick, the exit checks."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import extras_inputs
+    g = load("extras300.npz")
+    q, sub, nt, base = extras_inputs()
+    assert q.tobytes() == as_particles(g["particles_in"]).tobytes() and np.array_equal(sub, g["map"]) and nt == int(g["n_targets"])
+    orc = checkers.oracle()
+    n_hits = 0
+    for mode in (abi.COLLISION_DIRECT, abi.COLLISION_TREE, abi.COLLISION_LINE, abi.COLLISION_LINETREE):
+        c = abi.default_config(collision=mode, **base)
+        tree = mode in (abi.COLLISION_TREE, abi.COLLISION_LINETREE)
+        for key, got in ((f"col_m{mode}", orc.collision_search(c, q)),
+                         (f"col_m{mode}_map", orc.collision_search_subset(c, q, sub, None)),
+                         (f"col_m{mode}_map_targets", orc.collision_search_subset(c, q, sub, nt)),
+                         (f"col_m{mode}_targets", orc.collision_search_subset(c, q, None, nt))):
+            want = np.frombuffer(g[key].tobytes(), dtype=abi.COLLISION_DTYPE)
+            assert checkers.collisions_equal(got, want, with_ri=tree), key
+            n_hits += len(want)
+    assert n_hits > 100
+    cj = abi.default_config(softening=0.05, N_active=100, testparticle_type=1)
+    qa = as_particles(g["jerk_in"])
+    assert orc.apply_jerk(cj, qa, 0.37).tobytes() == as_particles(g["jerk_out"]).tobytes()
+    cj2 = abi.default_config(softening=0.05, gravity_ignore_terms=abi.IGNORE_TERMS_INVOLVING_0)
+    assert orc.apply_jerk(cj2, qa, -0.11).tobytes() == as_particles(g["jerk_out_ignore0"]).tobytes()
+    got = np.array([[orc.exit_check(cj, q, mx, mn) for mn in g["exit_min"]] for mx in g["exit_max"]])
+    assert np.array_equal(got, g["exit_status"]) and set(got.ravel()) == {0, 3, 4}
