@@ -50,6 +50,9 @@ enum { SHIM_HOST_AUTHORITATIVE = 0, SHIM_RESIDENT = 1, SHIM_AUTO = 2 };
 int shim_residency(void);
 int shim_resident(const struct reb_simulation* r);
 
+/* The simulation's integrator is one of the two this library provides (leapfrog, sei) and its step would run on the device. */
+int shim_is_device_integrator(const struct reb_simulation* r);
+
 void shim_fill_config(const struct reb_simulation* r, rebcu_config* c);
 /* Forwards a rebcu error to reb_simulation_error (src/simulation.c:82-86); returns err. */
 int shim_report(struct reb_simulation* r, struct shim_state* s, int err);

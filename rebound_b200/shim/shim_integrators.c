@@ -98,6 +98,10 @@ static void synchronize(struct reb_simulation* r, void* state){
 static void leapfrog_step(struct reb_simulation* r, void* state){ device_step(r, reb_integrator_leapfrog_step, state); }
 static void sei_step(struct reb_simulation* r, void* state){ device_step(r, reb_integrator_sei_step, state); }
 
+int shim_is_device_integrator(const struct reb_simulation* r){
+    return (r->integrator.callbacks.step==leapfrog_step || r->integrator.callbacks.step==sei_step) && device_step_possible(r);
+}
+
 const struct reb_integrator reb_integrator_leapfrog = {
     .documentation = "Leapfrog (drift-kick-drift), orders 2, 4, 6 and 8; kick/drift run as fused CUDA kernels on the resident particle arrays.",
     .step = leapfrog_step,

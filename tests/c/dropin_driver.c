@@ -45,6 +45,7 @@ int main(int argc, char** argv){
     r->rand_seed = 42;
     char sa_file[4096] = {0};
     int use_integrate = 0;      /* reb_simulation_integrate(r, steps*dt) instead of reb_simulation_steps(r, steps) */
+    double integrate_sign = 1.;
     if (strcmp(scen, "plummer")==0 || strcmp(scen, "plummer_comp")==0 || strcmp(scen, "archive")==0 || strcmp(scen, "edit")==0){
         /* examples/selfgravity_plummer/problem.c */
         double M=1, R=1, E=3./64.*M_PI*M*M/R, r0=16./(3.*M_PI)*R;
@@ -192,6 +193,33 @@ int main(int argc, char** argv){
         reb_simulation_set_integrator(r, scen);
         r->dt = 0.02;
         r->collision = REB_COLLISION_DIRECT; r->collision_resolve = reb_collision_resolve_merge;
+    }else if (strncmp(scen, "integ_", 6)==0){
+        /* reb_simulation_integrate on a simulation nothing observes between steps (the drop-in batches the whole steps
+         * on the device and leaves the end of the run to the reference's exit logic): integ_exact ends on tmax with a
+         * shortened last step (exact_finish_time=1), integ_over steps past it, integ_back runs backwards in time,
+         * integ_tree is the disc with tree gravity and an open boundary */
+        reb_simulation_set_integrator(r, "leapfrog");
+        if (strcmp(scen, "integ_tree")==0){
+            r->gravity = REB_GRAVITY_TREE; r->boundary = REB_BOUNDARY_OPEN; r->opening_angle2 = 0.25;
+            r->softening = 0.02; r->dt = 3e-2; r->root_size = 10.2;
+            struct reb_particle star = {0}; star.m = 1; reb_simulation_add(r, star);
+            for (int i=0;i<N;i++){
+                struct reb_particle pt = {0};
+                double a = reb_random_powerlaw(r, 1.02, 4.25, -1.5), phi = reb_random_uniform(r, 0,2.*M_PI);
+                pt.x = a*cos(phi); pt.y = a*sin(phi); pt.z = a*reb_random_normal(r, 0.001);
+                double vkep = sqrt(1.1/a)*reb_random_uniform(r, 0.9, 3.0);       /* some particles leave the box */
+                pt.vx = vkep*sin(phi); pt.vy = -vkep*cos(phi); pt.m = 0.2/(double)N;
+                reb_simulation_add(r, pt);
+            }
+        }else{
+            double M=1, R=1, E=3./64.*M_PI*M*M/R, r0=16./(3.*M_PI)*R;
+            double t0 = r->G*pow(M,5./2.)*pow(4.*E,-3./2.)*(double)N/log(0.4*(double)N);
+            r->dt = 2e-5*t0; r->softening = 0.01*r0;
+            reb_simulation_add_plummer(r, N, M, R);
+        }
+        use_integrate = 2;
+        r->exact_finish_time = strcmp(scen, "integ_over")==0 ? 0 : 1;
+        if (strcmp(scen, "integ_back")==0) integrate_sign = -1.;
     }else if (strcmp(scen, "eos")==0){
         /* Embedded operator splitting with a modified-kick outer scheme (PMLF4): every interaction step is a force
          * evaluation followed by reb_gravity_basic_calculate_and_apply_jerk (integrator_eos.c:96-110) */
@@ -221,7 +249,11 @@ int main(int argc, char** argv){
     struct timespec t_begin, t_end;
     if (getenv("DRIVER_WARMUP")) reb_simulation_steps(r, 1);      /* timing runs: CUDA context + first upload outside the clock */
     clock_gettime(CLOCK_MONOTONIC, &t_begin);
-    if (use_integrate){ r->exact_finish_time = 0; reb_simulation_integrate(r, r->t + steps*r->dt); }
+    if (use_integrate==2){
+        /* a final time that is not a whole number of steps away, reached in two calls */
+        reb_simulation_integrate(r, r->t + integrate_sign*(0.4*steps + 0.37)*r->dt);
+        reb_simulation_integrate(r, r->t + integrate_sign*(0.6*steps + 0.21)*fabs(r->dt));
+    }else if (use_integrate){ r->exact_finish_time = 0; reb_simulation_integrate(r, r->t + steps*r->dt); }
     else reb_simulation_steps(r, steps);
     clock_gettime(CLOCK_MONOTONIC, &t_end);
     if (strcmp(scen, "edit")==0){

@@ -19,7 +19,10 @@ SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 
              # r->map / r->N_targets collision subsets of the hybrid integrators; exit conditions of run_heartbeat
              ("mercurius", 40, 200), ("trace", 40, 200), ("escape", 500, 400), ("encounter", 500, 400),
              # EOS with a modified-kick scheme: force evaluation + jerk kick per interaction step
-             ("eos", 200, 6)]
+             ("eos", 200, 6),
+             # reb_simulation_integrate with its exit logic around device batches; long reb_simulation_steps runs in pieces
+             ("integ_exact", 800, 40), ("integ_over", 800, 40), ("integ_back", 800, 40), ("integ_tree", 3000, 80),
+             ("testparticles", 1500, 4200)]
 
 
 def run(binary, scen, n, steps, tmp_path, env=None):
@@ -35,6 +38,8 @@ def run(binary, scen, n, steps, tmp_path, env=None):
 @pytest.mark.parametrize("scen,n,steps", SCENARIOS, ids=[f"{s[0]}-{s[1]}-{s[2]}" for s in SCENARIOS])
 @pytest.mark.parametrize("resident", ["0", "1", ""], ids=["host_authoritative", "resident", "auto"])
 def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
+    if steps > 1000 and resident != "":
+        pytest.skip("long runs exercise the device batches of the automatic mode only")
     ref = run("driver_ref", scen, n, steps, tmp_path)
     got = run("driver_dropin", scen, n, steps, tmp_path, env={"REBOUND_B200_RESIDENT": resident})
     assert len(ref) == len(got)
@@ -42,6 +47,8 @@ def test_dropin_matches_reference_bitwise(scen, n, steps, resident, tmp_path):
     hdr = ref[:6].view(np.float64)
     if scen in ("mercurius", "trace"):
         assert hdr[0] < n + 1                      # particles merged during close encounters
+    if scen == "integ_tree":
+        assert hdr[0] < n + 1                      # particles left the open box during the batched steps
     if scen == "escape":
         assert hdr[4] == 4 and hdr[1] < steps * 2e-2      # REB_STATUS_ESCAPE before tmax
     if scen == "encounter":
