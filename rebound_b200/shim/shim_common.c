@@ -101,8 +101,9 @@ void shim_fill_config(const struct reb_simulation* r, rebcu_config* c){
     }else if (r->integrator.name && strcmp(r->integrator.name, "sei")==0){
         c->integrator = REBCU_INTEGRATOR_SEI;
     }
-    const char* mode = getenv("REBOUND_B200_MODE");
-    c->mode = (mode && strcmp(mode, "fast")==0) ? REBCU_MODE_FAST : REBCU_MODE_STRICT;
+    static int mode = -1;            /* read once: this runs before every replaced call */
+    if (mode < 0){ const char* e = getenv("REBOUND_B200_MODE"); mode = (e && strcmp(e, "fast")==0) ? REBCU_MODE_FAST : REBCU_MODE_STRICT; }
+    c->mode = mode;
 }
 
 int shim_report(struct reb_simulation* r, struct shim_state* s, int err){
