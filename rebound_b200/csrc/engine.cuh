@@ -62,6 +62,7 @@ struct TreeBuffers {
     uint32_t* shard_list = nullptr; // [cap_n] sorted positions owned by this rank (multi-GPU walk)
     int* flags = nullptr;          // device error flags [8]
     int built_for_n = -1;
+    bool prefix_ok = true;         // sorting on a key prefix has not hit a long tie run yet (see tree_build)
 };
 
 struct rebcu_handle {

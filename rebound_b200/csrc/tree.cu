@@ -39,11 +39,13 @@ namespace {
 
 constexpr int MAX_DESCENT = 1200;   // below 2^-1074 x root_size a cell has width zero (tree.c:107-111)
 constexpr int W_TABLE = 64;
+constexpr int TIE_RUN_MAX = 16;     // longest run of equal key prefixes the prefix-sorted build accepts
 
 struct TreeParams {
     double root_size;
     int Nx, Ny, Nz;
     int L0;        // octant levels stored in the key
+    int prefix;    // L0 was cut short to save sort passes: tie runs longer than TIE_RUN_MAX abort the build (flags[4])
     int rbits;     // bits of root box index above the path
     uint64_t n;
 };
@@ -126,7 +128,10 @@ __global__ void __launch_bounds__(256) tie_kernel(TreeParams P, const uint64_t* 
     if (keys[k] != keys[k + 1]) return;
     if (k > 0 && keys[k - 1] == keys[k]) return;     // not the run start
     uint64_t e = k + 1;
-    while (e + 1 < P.n && keys[e + 1] == keys[k]) e++;
+    while (e + 1 < P.n && keys[e + 1] == keys[k]) {
+        e++;
+        if (P.prefix && e - k >= TIE_RUN_MAX) { atomicMin(&flags[4], 1); return; }      // too clustered for this prefix
+    }
     for (uint64_t a = k + 1; a <= e; a++) {
         const uint32_t pa = perm[a];
         const double ax = x[pa], ay = y[pa], az = z[pa];
@@ -724,6 +729,24 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
     while ((1ull << P.rbits) < n_root) P.rbits++;
     P.L0 = (63 - P.rbits) / 3;
     if (P.L0 < 1) return rebcu_fail(h, REBCU_ERR_ARG, "too many root boxes");
+    // Key prefix: the radix sort costs one pass per 8 key bits, and all 63 path bits are only needed to separate
+    // particles closer than 2^-21 of the box.  With log2(N)/2 + 2 levels (a surface distribution fills ~4^level cells)
+    // most particles already have a cell of their own; the few that share one form short runs of equal keys, which the
+    // exact pairwise descent of tie_kernel / lcp_kernel orders anyway (the same code that handles paths deeper than 21
+    // levels).  A run longer than TIE_RUN_MAX (clustered input) aborts the build, which then falls back to full keys
+    // for this simulation.  REBOUND_B200_KEY_LEVELS=<n> forces a prefix (tests), =0 switches the prefix off.
+    P.prefix = 0;
+    {
+        static const int forced = [] { const char* e = getenv("REBOUND_B200_KEY_LEVELS"); return e ? atoi(e) : -1; }();
+        int want = 0;
+        if (forced > 0) want = forced;
+        else if (forced < 0 && T.prefix_ok && n >= 65536) {
+            want = 2; for (uint64_t q = n; q > 1; q >>= 2) want++;            // ceil-ish log4(N) + 2
+            const int over = (P.rbits + 3 * want) % 8;
+            if (over >= 1 && over <= 3 && want > 8) want--;                   // one level less saves a whole pass
+        }
+        if (want >= 1 && want < P.L0 && (forced > 0 ? T.prefix_ok : true)) { P.L0 = want; P.prefix = 1; }
+    }
 
     if (T.cap_n < n) {
         CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -762,13 +785,17 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
     CU_TRY(h, cudaGetLastError());
     // cell count and error flags back to the host
     int* pin = (int*)h->pinned;
-    CU_TRY(h, cudaMemcpyAsync(pin, T.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(pin + 4, T.cell_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(pin, T.flags, 5 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(pin + 5, T.cell_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (P.prefix && pin[4] != 0x7f7f7f7f) {          // a long tie run: this input needs the full keys
+        T.prefix_ok = false;
+        return tree_build(h, c);
+    }
     int f[4];
     for (int k = 0; k < 4; k++) f[k] = (pin[k] == 0x7f7f7f7f) ? 0x7fffffff : pin[k];
     if (f[0] != 0x7fffffff || f[1] != 0x7fffffff || f[2] != 0x7fffffff || f[3] != 0x7fffffff) return tree_error(h, f);
-    const uint64_t n_cells = (uint32_t)pin[4];
+    const uint64_t n_cells = (uint32_t)pin[5];
     if (T.cap_cells < n_cells) {
         const uint64_t cap = n_cells + n_cells / 8 + 1024;
         int err;

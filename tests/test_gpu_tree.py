@@ -473,3 +473,46 @@ def test_extras_golden(eng):
         for j, mn in enumerate(g["exit_min"]):
             escape, encounter = eng.exit_check(float(mx), float(mn))
             assert (3 if encounter else (4 if escape else 0)) == int(g["exit_status"][i, j])
+
+
+def test_key_prefix_builds_give_identical_trees(tmp_path):
+    """The build sorts on a key prefix (fewer radix passes) and orders the particles that share it by exact pairwise
+    descent; a prefix that is too short for the input aborts the build and falls back to full keys.  Forced prefixes
+    of 2, 5 and 9 levels (REBOUND_B200_KEY_LEVELS, latched per process) must reproduce the full-key tree and
+    accelerations bit for bit: 2 levels trips the fallback, 5 and 9 exercise long and short tie runs."""
+    import subprocess
+    import sys
+    script = tmp_path / "prefix.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from rebound_b200 import abi, ics\n"
+        "from rebound_b200.simulation import Engine\n"
+        "eng = Engine(0)\n"
+        "out = []\n"
+        "p3 = ics.plummer(6000, seed=4)\n"
+        "cases = [(ics.selfgravity_disc_config(), ics.selfgravity_disc(30000, seed=2)),\n"
+        "         (ics.shearing_sheet_config(root_size=60.0, t=12.3), ics.shearing_sheet(root_size=60.0, seed=5)),\n"
+        "         (ics.plummer_config(6000, gravity=abi.GRAVITY_TREE, root_size=200.0, opening_angle2=0.25), p3),\n"
+        "         (ics.plummer_config(6000, gravity=abi.GRAVITY_TREE, root_size=50.0, N_root_x=2, N_root_y=3, N_root_z=2,\n"
+        "                             boundary=abi.BOUNDARY_PERIODIC, N_ghost_x=1, N_ghost_y=1, N_ghost_z=1), p3)]\n"
+        "for cfg, p in cases:\n"
+        "    q = np.ascontiguousarray(p.copy())\n"
+        "    n = eng.gravity_host(cfg.copy(), q)\n"
+        "    out += [np.frombuffer(q[:n].tobytes(), dtype=np.uint8)]\n"
+        "    eng.upload(np.ascontiguousarray(q[:n]))\n"
+        "    out += [np.frombuffer(eng.tree(cfg.copy()).tobytes(), dtype=np.uint8)]\n"
+        "    col = eng.collision_search_host(cfg.copy(), np.ascontiguousarray(q[:n]))\n"
+        "    out += [np.frombuffer(col.tobytes(), dtype=np.uint8)]\n"
+        "np.concatenate(out).tofile(sys.argv[1])\n")
+    res = {}
+    for levels in ("0", "2", "5", "9"):
+        env = dict(os.environ)
+        env["REBOUND_B200_KEY_LEVELS"] = levels
+        out = tmp_path / f"tree_{levels}.bin"
+        r = subprocess.run([sys.executable, str(script), str(out)], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        res[levels] = np.fromfile(out, dtype=np.uint8)
+    assert len(res["0"]) > 1000000
+    for levels in ("2", "5", "9"):
+        assert np.array_equal(res["0"], res[levels]), levels
