@@ -106,3 +106,56 @@ def test_random_quadrupole_gravity(d):
     a, _ = ref.gravity(c, p)
     b, _ = checkers.oracle().gravity(c, p)
     assert len(a) == len(b) and bits_equal(a, b)
+
+
+subset_st = st.fixed_dictionaries({
+    "map_frac": st.sampled_from([None, 0.3, 0.7, 1.0]),       # None: no r->map
+    "targets_frac": st.sampled_from([None, 0.0, 0.4, 1.0]),   # None: N_targets = SIZE_MAX
+    "mseed": st.integers(0, 2**31 - 1),
+})
+
+
+def make_subset(s, n):
+    """(map or None, N_targets or None) for n particles: a random selection in random order, targets <= projectiles."""
+    rng = np.random.default_rng(s["mseed"])
+    sub = None
+    n_proj = n
+    if s["map_frac"] is not None:
+        n_proj = int(round(s["map_frac"] * n))
+        sub = rng.permutation(n)[:n_proj].astype(np.uint64)
+    nt = None if s["targets_frac"] is None else int(s["targets_frac"] * n_proj)
+    return sub, nt
+
+
+@SET
+@given(cfg_st, st.sampled_from([abi.COLLISION_DIRECT, abi.COLLISION_TREE, abi.COLLISION_LINE, abi.COLLISION_LINETREE]),
+       st.sampled_from([0.05, -0.2]), subset_st)
+def test_random_collision_subsets(d, col, dtl, s):
+    c, p = make(d, collision=col, dt_last_done=dtl)
+    sub, nt = make_subset(s, len(p))
+    a = checkers.reference().collision_search_subset(c, p, sub, nt)
+    b = checkers.oracle().collision_search_subset(c, p, sub, nt)
+    assert collisions_equal(a, b, with_ri=(col in (abi.COLLISION_TREE, abi.COLLISION_LINETREE)))
+
+
+@SET
+@given(cfg_st, st.integers(0, 1), st.integers(0, 2), st.sampled_from([None, 0, 1, 2, 5]), st.sampled_from([0.37, -0.2, 1e-3]))
+def test_random_jerk(d, tptype, terms, nactive, v):
+    """reb_gravity_basic_calculate_and_apply_jerk on random states (the accelerations are whatever the state holds)."""
+    c, p = make(d, gravity=abi.GRAVITY_BASIC, testparticle_type=tptype, gravity_ignore_terms=terms)
+    if nactive is not None:
+        c.N_active = min(nactive, len(p))
+    rng = np.random.default_rng(d["seed"] ^ 0x5a5a)
+    for f in ("ax", "ay", "az"):
+        p[f] = rng.normal(0, 1, len(p))
+    a = checkers.reference().apply_jerk(c, p, v)
+    b = checkers.oracle().apply_jerk(c, p, v)
+    assert bits_equal(a, b)
+
+
+@SET
+@given(cfg_st, st.sampled_from([0.0, 0.3, 0.45, 0.8]), st.sampled_from([0.0, 1e-3, 0.02, 0.2]))
+def test_random_exit_checks(d, fmax, fmin):
+    c, p = make(d)
+    scale = d["root_size"] * max(d["nroot"])
+    assert checkers.reference().exit_check(c, p, fmax * scale, fmin * scale) == checkers.oracle().exit_check(c, p, fmax * scale, fmin * scale)
