@@ -91,6 +91,21 @@ def test_integrate_hands_whole_steps_to_one_batch_and_keeps_the_exit_logic(mock_
     assert off["step_calls"] == off["steps"] >= 40
 
 
+def test_long_runs_are_cut_into_pieces(mock_driver, tmp_path):
+    """More than 4096 steps in one call: reb_simulation_steps and reb_simulation_integrate hand them over in pieces
+    (shim_steps.c); the results stay bit-identical and every piece is one engine call."""
+    ref = run(os.path.join(DROPIN, "driver_ref"), "testparticles", 40, 9000, tmp_path / "ref.bin")
+    got = run(mock_driver, "testparticles", 40, 9000, tmp_path / "mock.bin", env={"REBOUND_B200_RESIDENT": ""})
+    assert np.array_equal(ref, got)
+    s = stats(mock_driver, "testparticles", 40, 9000, tmp_path, REBOUND_B200_RESIDENT="")
+    assert s == {"uploads": 3, "downloads": 3, "step_calls": 3, "steps": 9000}
+    ref = run(os.path.join(DROPIN, "driver_ref"), "integ_over", 30, 12000, tmp_path / "ref2.bin")
+    got = run(mock_driver, "integ_over", 30, 12000, tmp_path / "mock2.bin", env={"REBOUND_B200_RESIDENT": ""})
+    assert np.array_equal(ref, got)
+    s = stats(mock_driver, "integ_over", 30, 12000, tmp_path, REBOUND_B200_RESIDENT="")
+    assert s["steps"] >= 12000 and s["step_calls"] <= 12
+
+
 def test_observers_keep_the_simulation_host_current(mock_driver, tmp_path):
     """plummer installs a heartbeat: in automatic mode every step ends with the particles on the host."""
     steps = 5
@@ -99,3 +114,111 @@ def test_observers_keep_the_simulation_host_current(mock_driver, tmp_path):
     # exit distances without boundary / collisions: checked on the device, the simulation stays resident
     e = stats(mock_driver, "escape", 300, 300, tmp_path, REBOUND_B200_RESIDENT="")
     assert e["uploads"] == 1 and e["downloads"] == 1 and e["steps"] > 10
+
+
+PY_SCRIPT = r"""
+import math, random, sys
+import rebound
+print("LIB", rebound.__libpath__)
+
+def cloud(sim, n, seed, vel=0.3, radius=0.0):
+    rng = random.Random(seed)
+    for _ in range(n):
+        sim.add(m=1.0 / n, x=rng.uniform(-1, 1), y=rng.uniform(-1, 1), z=rng.uniform(-1, 1),
+                vx=rng.gauss(0, vel), vy=rng.gauss(0, vel), vz=rng.gauss(0, vel), r=radius)
+
+def dump(tag, sim):
+    import hashlib
+    h = hashlib.sha256()
+    for p in sim.particles:
+        for v in (p.x, p.y, p.z, p.vx, p.vy, p.vz, p.ax, p.ay, p.az):
+            h.update(v.hex().encode())
+    print(tag, sim.N, sim.t.hex(), sim.dt.hex(), sim.steps_done, h.hexdigest()[:24])
+
+# 1. integrate() to a time that is not a whole number of steps away, forwards then backwards
+sim = rebound.Simulation(); sim.integrator = "leapfrog"; sim.softening = 0.05; sim.dt = 0.01
+cloud(sim, 120, 1)
+sim.integrate(0.4567); dump("A1", sim)
+sim.integrate(0.9); dump("A2", sim)
+sim.integrate(0.33); dump("A3", sim)
+sim.exact_finish_time = 0
+sim.integrate(0.71); dump("A4", sim)
+
+# 2. exit_max_distance raises Escape from integrate()
+sim = rebound.Simulation(); sim.integrator = "leapfrog"; sim.softening = 0.05; sim.dt = 0.02
+cloud(sim, 150, 2, vel=1.0)
+sim.exit_max_distance = 3.0
+try:
+    sim.integrate(50.0)
+    print("B no escape")
+except rebound.Escape as e:
+    dump("B escape", sim)
+
+# 4. tree gravity in an open box, steps()
+sim = rebound.Simulation(); sim.integrator = "leapfrog"; sim.gravity = "tree"; sim.boundary = "open"
+sim.root_size = 6.0; sim.opening_angle2 = 0.3; sim.softening = 0.05; sim.dt = 0.05
+cloud(sim, 300, 4, vel=1.5)
+sim.steps(40); dump("D", sim)
+
+# 5. direct collisions with merging
+sim = rebound.Simulation(); sim.integrator = "leapfrog"; sim.softening = 0.01; sim.dt = 0.02
+sim.collision = "direct"; sim.collision_resolve = "merge"; sim.rand_seed = 42     # the seed of the collision shuffle defaults to time + pid
+cloud(sim, 150, 5, vel=0.05, radius=0.06)
+sim.integrate(1.0); dump("E", sim)
+
+# 6. Simulationarchive snapshot and restart
+sim = rebound.Simulation(); sim.integrator = "leapfrog"; sim.softening = 0.05; sim.dt = 0.01
+cloud(sim, 80, 6)
+sim.integrate(0.2)
+sim.save_to_file(sys.argv[1], delete_file=True)
+sim.integrate(0.5); dump("F1", sim)
+sim2 = rebound.Simulation(sys.argv[1])
+sim2.integrate(0.5); dump("F2", sim2)
+
+# 7. shearing sheet: SEI, tree gravity, tree collisions, hard spheres, ghost boxes
+sim = rebound.Simulation(); sim.integrator = "sei"; sim.gravity = "tree"; sim.collision = "tree"; sim.boundary = "shear"
+sim.collision_resolve = "hardsphere"; sim.opening_angle2 = 0.5; sim.rand_seed = 42
+sim.OMEGA = 0.00013143527; sim.G = 6.67428e-11; sim.softening = 0.1; sim.dt = 1e-3 * 2 * math.pi / sim.OMEGA
+sim.root_size = 30.0; sim.N_root_x = 2; sim.N_root_y = 2; sim.N_root_z = 1; sim.N_ghost_x = 2; sim.N_ghost_y = 2; sim.N_ghost_z = 0
+rng = random.Random(7)
+for _ in range(250):
+    x = rng.uniform(-30, 30); rad = rng.uniform(1.0, 2.0)
+    sim.add(m=400.0 * 4.0 / 3.0 * math.pi * rad**3, r=rad, x=x, y=rng.uniform(-30, 30), z=rng.gauss(0, 1.0), vy=-1.5 * x * sim.OMEGA)
+sim.steps(15); dump("G", sim)
+"""
+
+
+def _python_env(tmp_path, libfile, extra=()):
+    lib_dir = tmp_path / ("lib_" + os.path.basename(os.path.dirname(libfile)))
+    lib_dir.mkdir(parents=True, exist_ok=True)
+    import shutil
+    shutil.copy(libfile, lib_dir / "librebound.so")
+    for f in extra:
+        shutil.copy(f, lib_dir / os.path.basename(f))
+    return dict(os.environ, PYTHONPATH=f"{lib_dir}:/root/reference"), lib_dir
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rebound"), reason="needs the reference's Python package")
+def test_reference_python_package_on_the_mock_dropin_matches_the_reference_library(mock_driver, tmp_path):
+    """The reference's own Python package (ctypes) driving (a) the unmodified reference library and (b) the drop-in with
+    the mock engine: integrate() with its exit logic, Escape, tree gravity with an open boundary,
+    merging collisions, a Simulationarchive restart, a shearing sheet.  Every printed state must be identical."""
+    import sys
+    outs = {}
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+    mock = (os.path.join(BUILD, "librebound.so"), (os.path.join(BUILD, "librebound_b200.so"),))
+    for name, lib, extra in (("ref", ref_lib, ()), ("mock", *mock), ("mock0", *mock), ("mock1", *mock)):
+        env, lib_dir = _python_env(tmp_path, lib, extra)
+        if name.startswith("mock"):
+            env["REBOUND_B200_RESIDENT"] = name[4:]
+            env["LD_LIBRARY_PATH"] = f"{lib_dir}:{os.path.join(ROOT, 'oracle')}:" + env.get("LD_LIBRARY_PATH", "")
+        r = subprocess.run([sys.executable, "-c", PY_SCRIPT, str(tmp_path / f"{name}.sa")], capture_output=True, text=True,
+                           env=env, timeout=600, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr[-3000:]
+        lines = [l for l in r.stdout.splitlines() if not l.startswith("LIB")]
+        assert f"LIB {lib_dir}" in r.stdout
+        outs[name] = lines
+    assert len(outs["ref"]) >= 10
+    assert any(l.startswith("B escape") for l in outs["ref"])
+    for name in ("mock", "mock0", "mock1"):          # automatic, host-authoritative, resident
+        assert outs["ref"] == outs[name], name
