@@ -1,0 +1,142 @@
+/*
+ * hostlogic_driver.c -- call sequences that stress the HOST side of the drop-in (particle arrays that grow, shrink and
+ * move between calls, integrator switches, copies of resident simulations, several simulations in one process and in
+ * several threads, error paths), written against the reference's public API only.  tests/test_hostlogic_cpu.py
+ * runs it once on the unmodified reference and once on the drop-in with the mock engine (all residency modes) and
+ * compares the dumps bit for bit.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <pthread.h>
+#include "rebound.h"
+
+static FILE* out;
+static void dump(const char* tag, struct reb_simulation* r){
+    double hdr[5] = {(double)r->N, r->t, r->dt_last_done, (double)r->status, (double)r->steps_done};
+    fwrite(tag, 1, 4, out);
+    fwrite(hdr, sizeof(double), 5, out);
+    for (size_t i=0;i<r->N;i++) fwrite(&r->particles[i], sizeof(double), 11, out);
+}
+
+static void cloud(struct reb_simulation* r, int n, double vel, double radius){
+    for (int i=0;i<n;i++){
+        struct reb_particle p = {0};
+        p.x = reb_random_uniform(r,-1.,1.); p.y = reb_random_uniform(r,-1.,1.); p.z = reb_random_uniform(r,-1.,1.);
+        p.vx = reb_random_normal(r, vel); p.vy = reb_random_normal(r, vel); p.vz = reb_random_normal(r, vel);
+        p.m = 1./(double)n; p.r = radius;
+        reb_simulation_add(r, p);
+    }
+}
+
+static struct reb_simulation* make(unsigned int seed, int n){
+    struct reb_simulation* r = reb_simulation_create();
+    r->rand_seed = seed;
+    reb_simulation_set_integrator(r, "leapfrog");
+    r->softening = 0.05; r->dt = 0.01;
+    cloud(r, n, 0.3, 0.);
+    return r;
+}
+
+static void* thread_main(void* arg){
+    struct reb_simulation* r = arg;
+    reb_simulation_steps(r, 7);
+    reb_simulation_integrate(r, r->t + 0.0555);
+    return NULL;
+}
+
+int main(int argc, char** argv){
+    if (argc<3){ fprintf(stderr, "usage: %s scenario outfile [N]\n", argv[0]); return 2; }
+    const char* scen = argv[1];
+    const int N = argc>3 ? atoi(argv[3]) : 100;
+    out = fopen(argv[2], "wb");
+    if (!out) return 3;
+    if (strcmp(scen, "addremove")==0){
+        /* the particle array grows (realloc may move it), shrinks and is edited between calls */
+        struct reb_simulation* r = make(1, N);
+        reb_simulation_steps(r, 3); dump("ar1 ", r);
+        cloud(r, 3*N, 0.2, 0.);                          /* grows past N_allocated: r->particles moves */
+        reb_simulation_steps(r, 3); dump("ar2 ", r);
+        reb_simulation_remove_particle(r, 2);
+        reb_simulation_remove_particle(r, r->N-1);
+        reb_simulation_integrate(r, r->t + 0.0333); dump("ar3 ", r);
+        r->particles[5].vx += 0.25; r->particles[0].m *= 2.;     /* raw edits after a synchronised call ... */
+        r->did_modify_particles = 1;                             /* ... flagged as the reference asks for integrators that keep state (rebound.h:247) */
+        reb_simulation_steps(r, 2); dump("ar4 ", r);
+        reb_simulation_move_to_com(r);
+        reb_simulation_steps(r, 2); dump("ar5 ", r);
+        reb_simulation_free(r);
+    }else if (strcmp(scen, "switch")==0){
+        /* integrators and gravity modes change between calls */
+        struct reb_simulation* r = make(2, N);
+        reb_simulation_steps(r, 3); dump("sw1 ", r);
+        reb_simulation_set_integrator(r, "ias15"); r->dt = 0.001;
+        reb_simulation_steps(r, 2); dump("sw2 ", r);
+        reb_simulation_set_integrator(r, "leapfrog"); r->dt = 0.01; r->gravity = REB_GRAVITY_COMPENSATED;
+        reb_simulation_integrate(r, r->t + 0.047); dump("sw3 ", r);
+        r->gravity = REB_GRAVITY_TREE; r->root_size = 40.; r->opening_angle2 = 0.3;
+        reb_simulation_steps(r, 3); dump("sw4 ", r);
+        r->gravity = REB_GRAVITY_NONE;
+        reb_simulation_steps(r, 2); dump("sw5 ", r);
+        r->gravity = REB_GRAVITY_BASIC; r->N_active = N/4; r->testparticle_type = 1;
+        reb_simulation_steps(r, 3); dump("sw6 ", r);
+        r->testparticle_type = 0;
+        reb_simulation_integrate(r, r->t + 0.05); dump("sw7 ", r);
+        reb_simulation_free(r);
+    }else if (strcmp(scen, "copy")==0){
+        /* copies and diffs of a simulation between calls; two simulations advance side by side */
+        struct reb_simulation* r = make(3, N);
+        reb_simulation_steps(r, 4);
+        struct reb_simulation* r2 = reb_simulation_copy(r);
+        reb_simulation_steps(r, 3);
+        reb_simulation_steps(r2, 3);
+        const int differ = reb_simulation_diff(r, r2, 2);
+        fwrite(&differ, sizeof(int), 1, out);
+        dump("cp1 ", r); dump("cp2 ", r2);
+        struct reb_simulation* r3 = make(33, N/2);
+        for (int k=0;k<4;k++){ reb_simulation_steps(r, 2); reb_simulation_steps(r3, 3); }
+        dump("cp3 ", r); dump("cp4 ", r3);
+        reb_simulation_free(r); reb_simulation_free(r2); reb_simulation_free(r3);
+    }else if (strcmp(scen, "error")==0){
+        /* tree gravity with a particle outside the box: the error ends an integration with REB_STATUS_GENERIC_ERROR */
+        struct reb_simulation* r = make(4, N);
+        r->save_messages = 1;
+        r->gravity = REB_GRAVITY_TREE; r->root_size = 4.; r->opening_angle2 = 0.3;
+        reb_simulation_steps(r, 2); dump("er1 ", r);
+        r->particles[7].x = 9.;                          /* outside */
+        r->did_modify_particles = 1;
+        enum REB_STATUS st = reb_simulation_integrate(r, r->t + 0.2);
+        const int sti = (int)st;
+        fwrite(&sti, sizeof(int), 1, out);
+        int n_err = 0;
+        if (r->messages) for (int i=0;i<10;i++) if (r->messages[i] && r->messages[i][0]=='e') n_err++;
+        const int has_err = n_err>0;
+        fwrite(&has_err, sizeof(int), 1, out);
+        double hdr[2] = {(double)r->N, (double)r->status};
+        fwrite(hdr, sizeof(double), 2, out);
+        reb_simulation_free(r);
+    }else if (strcmp(scen, "short")==0){
+        /* integrations shorter than a step, to the current time, and of exactly a few steps */
+        struct reb_simulation* r = make(5, N);
+        reb_simulation_integrate(r, r->t); dump("sh1 ", r);
+        reb_simulation_integrate(r, 0.0042); dump("sh2 ", r);
+        reb_simulation_integrate(r, r->t + 3.*r->dt); dump("sh3 ", r);
+        reb_simulation_integrate(r, r->t + 5.*r->dt); dump("sh4 ", r);
+        r->exact_finish_time = 0;
+        reb_simulation_integrate(r, r->t + 4.5*r->dt); dump("sh5 ", r);
+        reb_simulation_integrate(r, r->t - 6.2*fabs(r->dt)); dump("sh6 ", r);
+        reb_simulation_steps(r, 1); dump("sh7 ", r);
+        reb_simulation_free(r);
+    }else if (strcmp(scen, "threads")==0){
+        /* independent simulations stepped from several threads */
+        enum { NT = 4 };
+        struct reb_simulation* sims[NT]; pthread_t th[NT];
+        for (int k=0;k<NT;k++) sims[k] = make(10+k, N + 7*k);
+        for (int k=0;k<NT;k++) pthread_create(&th[k], NULL, thread_main, sims[k]);
+        for (int k=0;k<NT;k++) pthread_join(th[k], NULL);
+        for (int k=0;k<NT;k++){ dump("thr ", sims[k]); reb_simulation_free(sims[k]); }
+    }else{ fprintf(stderr, "unknown scenario %s\n", scen); return 2; }
+    fclose(out);
+    return 0;
+}
