@@ -244,3 +244,21 @@ def test_host_side_call_sequences_match_the_reference_bitwise(mock_driver, scen,
         r = subprocess.run([os.path.join(BUILD, "hl_mock"), scen, str(out), "60"], capture_output=True, text=True, env=e, timeout=300)
         assert r.returncode == 0, r.stderr
         assert out.read_bytes() == ref, (scen, name)
+
+
+def test_quadrupole_dropin_on_the_mock_engine(mock_driver, tmp_path):
+    """A -DQUADRUPOLE build of the reference sources and the shim (rebound_b200/shim/Makefile QUADRUPOLE=1): the shim
+    tells the engine to carry the quadrupole tensors (rebcu_config.quadrupole); tree-gravity scenarios must match the
+    reference compiled the same way (oracle/_ref/libref_harness_quad.so) and differ from the monopole build."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_harness_quad.so")):
+        pytest.skip("oracle/_ref/libref_harness_quad.so not built")
+    r = subprocess.run(["make", "-C", HOSTLOGIC, "quad"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    quad = os.path.join(BUILD, "quad")
+    for scen, n, steps in (("disc", 600, 4), ("sheet", 25, 20), ("periodic", 300, 4)):
+        ref = run(os.path.join(quad, "driver_ref"), scen, n, steps, tmp_path / "refq.bin")
+        mono = run(os.path.join(DROPIN, "driver_ref"), scen, n, steps, tmp_path / "ref0.bin")
+        assert not np.array_equal(ref, mono), scen
+        for value, name in MODES:
+            got = run(os.path.join(quad, "driver_mock"), scen, n, steps, tmp_path / f"mockq_{name}.bin", env={"REBOUND_B200_RESIDENT": value})
+            assert np.array_equal(ref, got), (scen, name)
