@@ -7,47 +7,61 @@
 #include "rebound_internal.h"   /* reb_sigint */
 #include "integrator_leapfrog.h"
 
-#define SHIM_MAX 256
-static struct shim_state table[SHIM_MAX];
-static int table_n = 0;
+/* One entry per simulation that has used the replaced hot path.  Entries are individually allocated (their addresses
+ * are handed out and must stay valid while the table grows) and released when the simulation is freed
+ * (reb_simulation_free / reb_simulation_free_pointers, shim_steps.c), so neither a long parameter sweep nor a large
+ * list of simultaneously alive simulations runs into a limit. */
+static struct shim_state** table = NULL;
+static int table_n = 0, table_cap = 0;
 static pthread_mutex_t table_lock = PTHREAD_MUTEX_INITIALIZER;
 
 struct shim_state* shim_get(struct reb_simulation* r){
     pthread_mutex_lock(&table_lock);
     struct shim_state* s = NULL;
-    for (int i=0;i<table_n;i++) if (table[i].r==r){ s = &table[i]; break; }
+    for (int i=0;i<table_n;i++) if (table[i] && table[i]->r==r){ s = table[i]; break; }
     if (!s){
-        for (int i=0;i<table_n && !s;i++) if (table[i].r==NULL) s = &table[i];
-        if (!s && table_n<SHIM_MAX) s = &table[table_n++];
-        if (s){
-            memset(s, 0, sizeof(*s));
+        int slot = -1;
+        for (int i=0;i<table_n && slot<0;i++) if (table[i]==NULL) slot = i;
+        if (slot<0){
+            if (table_n==table_cap){
+                const int cap = table_cap ? 2*table_cap : 64;
+                struct shim_state** t = realloc(table, cap*sizeof(*t));
+                if (t){ table = t; table_cap = cap; }
+            }
+            if (table_n<table_cap) slot = table_n++;
+        }
+        if (slot>=0){
+            s = calloc(1, sizeof(*s));
+            table[slot] = NULL;
             int device = 0;
             const char* env = getenv("REBOUND_B200_DEVICE");
             if (env) device = atoi(env);
-            s->h = rebcu_create(device, NULL);
+            if (s) s->h = rebcu_create(device, NULL);
             /* second Ctrl-C: leave multi-step device calls as the reference leaves its loops (src/rebound.c:193-200) */
-            if (s->h){ s->r = r; rebcu_set_interrupt_flag(s->h, (const volatile int*)&reb_sigint); } else s = NULL;
+            if (s && s->h){ s->r = r; rebcu_set_interrupt_flag(s->h, (const volatile int*)&reb_sigint); table[slot] = s; }
+            else { free(s); s = NULL; }
         }
     }
     pthread_mutex_unlock(&table_lock);
-    if (!s) reb_simulation_error(r, "rebound_b200: no usable CUDA device (or too many simulations); the GPU hot path has no CPU fallback.");
+    if (!s) reb_simulation_error(r, "rebound_b200: no usable CUDA device; the GPU hot path has no CPU fallback.");
     return s;
 }
 
 struct shim_state* shim_find(struct reb_simulation* r){
     pthread_mutex_lock(&table_lock);
     struct shim_state* s = NULL;
-    for (int i=0;i<table_n;i++) if (table[i].r==r){ s = &table[i]; break; }
+    for (int i=0;i<table_n;i++) if (table[i] && table[i]->r==r){ s = table[i]; break; }
     pthread_mutex_unlock(&table_lock);
     return s;
 }
 
 void shim_forget(struct reb_simulation* r){
     pthread_mutex_lock(&table_lock);
-    for (int i=0;i<table_n;i++) if (table[i].r==r){
-        if (table[i].pinned_ptr) rebcu_host_unregister(table[i].pinned_ptr);
-        rebcu_destroy(table[i].h);
-        memset(&table[i], 0, sizeof(table[i]));
+    for (int i=0;i<table_n;i++) if (table[i] && table[i]->r==r){
+        if (table[i]->pinned_ptr) rebcu_host_unregister(table[i]->pinned_ptr);
+        rebcu_destroy(table[i]->h);
+        free(table[i]);
+        table[i] = NULL;
     }
     pthread_mutex_unlock(&table_lock);
 }

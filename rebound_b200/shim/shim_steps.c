@@ -101,6 +101,14 @@ static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
     return 0;
 }
 
+/* The device state of a simulation goes with the simulation (reb_simulation_free, src/simulation.c:124-198; the Python
+ * package calls it from Simulation.__del__, rebound/simulation.py:154-158): its handle is released first. */
+void reb_simulation_free_cpuref(struct reb_simulation* const r);
+void reb_simulation_free(struct reb_simulation* const r){
+    if (r) shim_forget(r);
+    reb_simulation_free_cpuref(r);
+}
+
 void reb_simulation_steps(struct reb_simulation* const r, size_t N_steps){
     if (N_steps >= 2 && batch_possible(r)){
         /* run_heartbeat has nothing to do here (no heartbeat, no exit distances); the call ends synchronised.  An

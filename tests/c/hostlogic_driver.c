@@ -136,6 +136,33 @@ int main(int argc, char** argv){
         for (int k=0;k<NT;k++) pthread_create(&th[k], NULL, thread_main, sims[k]);
         for (int k=0;k<NT;k++) pthread_join(th[k], NULL);
         for (int k=0;k<NT;k++){ dump("thr ", sims[k]); reb_simulation_free(sims[k]); }
+    }else if (strcmp(scen, "many")==0){
+        /* a parameter sweep: hundreds of short-lived simulations, created and freed one after the other (and a few
+         * kept alive), each using the replaced hot path */
+        struct reb_simulation* keep[8] = {0};
+        for (int k=0;k<700;k++){
+            struct reb_simulation* r = make(100+k, 8 + k%5);
+            r->save_messages = 1;
+            reb_simulation_steps(r, 2);
+            int n_err = 0;
+            if (r->messages) for (int i=0;i<10;i++) if (r->messages[i] && r->messages[i][0]=='e') n_err++;
+            if (n_err){ fprintf(stderr, "simulation %d: error message queued\n", k); return 5; }
+            if (k%97==0) dump("mny ", r);
+            if (k%100==3 && k/100<8) keep[k/100] = r; else reb_simulation_free(r);
+        }
+        for (int k=0;k<8;k++) if (keep[k]){ reb_simulation_steps(keep[k], 1); dump("kep ", keep[k]); reb_simulation_free(keep[k]); }
+        /* ... and a list of simulations that are all alive at once, advanced round-robin */
+        enum { NLIVE = 600 };
+        static struct reb_simulation* live[NLIVE];
+        for (int k=0;k<NLIVE;k++){ live[k] = make(1000+k, 6 + k%4); live[k]->save_messages = 1; }
+        for (int round=0;round<2;round++) for (int k=0;k<NLIVE;k++) reb_simulation_steps(live[k], 2);
+        for (int k=0;k<NLIVE;k++){
+            int n_err = 0;
+            if (live[k]->messages) for (int i=0;i<10;i++) if (live[k]->messages[i] && live[k]->messages[i][0]=='e') n_err++;
+            if (n_err){ fprintf(stderr, "live simulation %d: error message queued\n", k); return 6; }
+            if (k%59==0) dump("liv ", live[k]);
+            reb_simulation_free(live[k]);
+        }
     }else{ fprintf(stderr, "unknown scenario %s\n", scen); return 2; }
     fclose(out);
     return 0;

@@ -224,14 +224,16 @@ def test_reference_python_package_on_the_mock_dropin_matches_the_reference_libra
         assert outs["ref"] == outs[name], name
 
 
-HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads"]
+HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many"]
 
 
 @pytest.mark.parametrize("scen", HL_SCENARIOS)
 def test_host_side_call_sequences_match_the_reference_bitwise(mock_driver, scen, tmp_path):
     """tests/c/hostlogic_driver.c: particle arrays that grow (and move), shrink and are edited between calls, integrator
     and gravity switches, copies and diffs, an error that ends an integration, integrations shorter than a step or to the
-    current time or backwards, several simulations interleaved and in threads -- on the unmodified reference and on the
+    current time or backwards, several simulations interleaved and in threads, a sweep of 700 short-lived simulations and
+    600 simulations alive at once (the shim's side table grows and is released with reb_simulation_free) -- on the
+    unmodified reference and on the
     drop-in with the mock engine in the three residency modes."""
     ref_out = tmp_path / "ref.bin"
     r = subprocess.run([os.path.join(BUILD, "hl_ref"), scen, str(ref_out), "60"], capture_output=True, text=True, timeout=300)
