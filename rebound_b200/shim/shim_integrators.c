@@ -91,8 +91,11 @@ static void synchronize(struct reb_simulation* r, void* state){
     if (!s){ r->is_synchronized = 1; return; }
     if (shim_to_host(r, s)) return;
     r->is_synchronized = 1;
-    /* automatic residency: the call is over, the host copy is the truth again (it may be edited without any flag) */
-    if (shim_residency()==SHIM_AUTO) s->device_valid = 0;
+    /* automatic residency: the call is over, the host copy is the truth again (it may be edited without any flag).
+     * Explicit residency keeps the device copy across synchronisations (host edits are flagged with
+     * r->did_modify_particles) -- except when timestep-modification hooks are installed: the reference synchronises
+     * right before it calls them (src/simulation.c:521-524, 562-565) precisely so that they can edit the particles. */
+    if (shim_residency()==SHIM_AUTO || r->pre_timestep_modifications || r->post_timestep_modifications) s->device_valid = 0;
 }
 
 static void leapfrog_step(struct reb_simulation* r, void* state){ device_step(r, reb_integrator_leapfrog_step, state); }

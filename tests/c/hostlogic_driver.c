@@ -39,6 +39,23 @@ static struct reb_simulation* make(unsigned int seed, int n){
     return r;
 }
 
+/* user callbacks of the "hooks" scenario */
+static void drag(struct reb_simulation* r){                    /* additional_forces: reads velocities, adds to a */
+    for (size_t i=0;i<r->N;i++){
+        r->particles[i].ax -= 0.3*r->particles[i].vx; r->particles[i].ay -= 0.3*r->particles[i].vy; r->particles[i].az -= 0.3*r->particles[i].vz;
+    }
+}
+static void pre_mod(struct reb_simulation* r){ r->particles[1].vz += 1e-3; }
+static void post_mod(struct reb_simulation* r){ r->particles[2].m *= 1.0001; }
+static int n_resolved = 0;
+static enum REB_COLLISION_RESOLVE_OUTCOME eat(struct reb_simulation* const r, struct reb_collision c){
+    /* the heavier particle swallows the other one's mass; the lighter one is removed */
+    n_resolved++;
+    struct reb_particle* a = &r->particles[c.p1]; struct reb_particle* b = &r->particles[c.p2];
+    if (a->m >= b->m){ a->m += b->m; return REB_COLLISION_RESOLVE_OUTCOME_REMOVE_P2; }
+    b->m += a->m; return REB_COLLISION_RESOLVE_OUTCOME_REMOVE_P1;
+}
+
 static void* thread_main(void* arg){
     struct reb_simulation* r = arg;
     reb_simulation_steps(r, 7);
@@ -136,6 +153,39 @@ int main(int argc, char** argv){
         for (int k=0;k<NT;k++) pthread_create(&th[k], NULL, thread_main, sims[k]);
         for (int k=0;k<NT;k++) pthread_join(th[k], NULL);
         for (int k=0;k<NT;k++){ dump("thr ", sims[k]); reb_simulation_free(sims[k]); }
+    }else if (strcmp(scen, "hooks")==0){
+        /* host callbacks between and inside the steps: additional_forces (the reference's host step runs, only its
+         * force call is replaced), pre/post_timestep_modifications, a collision_resolve callback that removes
+         * particles, an open boundary that tracks the energy of lost particles, variational particles (MEGNO) */
+        struct reb_simulation* r = make(6, N);
+        r->additional_forces = drag; r->force_is_velocity_dependent = 1;
+        reb_simulation_steps(r, 4); dump("hk1 ", r);
+        r->additional_forces = NULL;
+        r->pre_timestep_modifications = pre_mod; r->post_timestep_modifications = post_mod;
+        reb_simulation_integrate(r, r->t + 0.045); dump("hk2 ", r);
+        r->pre_timestep_modifications = NULL; r->post_timestep_modifications = NULL;
+        for (size_t i=0;i<r->N;i++) r->particles[i].r = 0.09;
+        r->did_modify_particles = 1;
+        r->collision = REB_COLLISION_DIRECT; r->collision_resolve = eat;
+        reb_simulation_steps(r, 6); dump("hk3 ", r);
+        fwrite(&n_resolved, sizeof(int), 1, out);
+        r->collision = REB_COLLISION_NONE;
+        r->boundary = REB_BOUNDARY_OPEN; r->root_size = 2.2; r->track_energy_offset = 1;
+        for (size_t i=0;i<r->N;i+=3){ r->particles[i].vx *= 8.; r->particles[i].vy *= 8.; }
+        r->did_modify_particles = 1;
+        reb_simulation_steps(r, 25); dump("hk4 ", r);
+        fwrite(&r->energy_offset, sizeof(double), 1, out);
+        r->gravity = REB_GRAVITY_TREE; r->opening_angle2 = 0.3;
+        reb_simulation_steps(r, 10); dump("hk5 ", r);
+        fwrite(&r->energy_offset, sizeof(double), 1, out);
+        reb_simulation_free(r);
+        struct reb_simulation* v = make(7, 12);
+        reb_simulation_init_megno_seed(v, 99);
+        reb_simulation_integrate(v, 0.08);
+        const double megno = reb_simulation_megno(v);
+        fwrite(&megno, sizeof(double), 1, out);
+        dump("hk6 ", v);
+        reb_simulation_free(v);
     }else if (strcmp(scen, "many")==0){
         /* a parameter sweep: hundreds of short-lived simulations, created and freed one after the other (and a few
          * kept alive), each using the replaced hot path */

@@ -224,7 +224,7 @@ def test_reference_python_package_on_the_mock_dropin_matches_the_reference_libra
         assert outs["ref"] == outs[name], name
 
 
-HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many"]
+HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many", "hooks"]
 
 
 @pytest.mark.parametrize("scen", HL_SCENARIOS)
@@ -232,7 +232,9 @@ def test_host_side_call_sequences_match_the_reference_bitwise(mock_driver, scen,
     """tests/c/hostlogic_driver.c: particle arrays that grow (and move), shrink and are edited between calls, integrator
     and gravity switches, copies and diffs, an error that ends an integration, integrations shorter than a step or to the
     current time or backwards, several simulations interleaved and in threads, a sweep of 700 short-lived simulations and
-    600 simulations alive at once (the shim's side table grows and is released with reb_simulation_free) -- on the
+    600 simulations alive at once (the shim's side table grows and is released with reb_simulation_free), host callbacks
+    (additional_forces, pre/post_timestep_modifications, a collision_resolve that removes particles), an open boundary
+    with track_energy_offset, MEGNO with variational particles -- on the
     unmodified reference and on the
     drop-in with the mock engine in the three residency modes."""
     ref_out = tmp_path / "ref.bin"
