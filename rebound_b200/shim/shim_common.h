@@ -52,6 +52,9 @@ int shim_resident(const struct reb_simulation* r);
 
 /* The simulation's integrator is one of the two this library provides (leapfrog, sei) and its step would run on the device. */
 int shim_is_device_integrator(const struct reb_simulation* r);
+/* Brings the integrator's own state (the SEI cache) to where the reference's step would leave it; 0 = this step has to
+ * run through the reference's host step (a stale cache the reference would keep using). */
+int shim_prepare_integrator_state(struct reb_simulation* r);
 
 void shim_fill_config(const struct reb_simulation* r, rebcu_config* c);
 /* Forwards a rebcu error to reb_simulation_error (src/simulation.c:82-86); returns err. */

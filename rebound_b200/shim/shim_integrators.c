@@ -16,6 +16,7 @@
  * `synchronize` callback (called by reb_simulation_synchronize at src/simulation.c:331,336,455,511,521,562)
  * brings r->particles up to date -- the protocol of the reference's WHFast integrators.
  */
+#include <math.h>
 #include <string.h>
 #include "shim_common.h"
 #include "integrator_leapfrog.h"
@@ -30,6 +31,8 @@ void* reb_integrator_sei_create();
 void reb_integrator_sei_free(void* p);
 extern const struct reb_binarydata_field_descriptor reb_integrator_sei_field_descriptor_list[];
 
+static void sei_step(struct reb_simulation* r, void* state);
+
 static int device_step_possible(const struct reb_simulation* r){
     if (r->N_var || r->additional_forces) return 0;
     switch (r->gravity){
@@ -41,8 +44,32 @@ static int device_step_possible(const struct reb_simulation* r){
     return 1;
 }
 
+/* The SEI state is a cache the reference fills at the top of its step and serialises with the simulation
+ * (struct reb_integrator_sei_state is private to src/integrator_sei.c:33-39: lastdt, sindt, tandt, sindtz, tandtz; the
+ * Python package exposes it as sim.integrator.lastdt).  The device step recomputes the same four numbers from OMEGA,
+ * OMEGAZ and dt with the same libm calls, so the cache is kept exactly as the reference would leave it
+ * (integrator_sei.c:91-101).  Returns 0 in the one case where the device step would NOT do what the reference
+ * does: a cache that is valid for this dt but was computed for another OMEGA (the reference keeps using it). */
+struct shim_sei_state { double lastdt, sindt, tandt, sindtz, tandtz; };
+int shim_prepare_integrator_state(struct reb_simulation* r){
+    if (r->integrator.callbacks.step!=sei_step || r->integrator.state==NULL) return 1;
+    struct shim_sei_state* sei = r->integrator.state;
+    if (sei->lastdt!=r->dt){
+        if (r->OMEGAZ==-1) r->OMEGAZ = r->OMEGA;
+        sei->sindt = sin(r->OMEGA*(-r->dt/2.));
+        sei->tandt = tan(r->OMEGA*(-r->dt/4.));
+        sei->sindtz = sin(r->OMEGAZ*(-r->dt/2.));
+        sei->tandtz = tan(r->OMEGAZ*(-r->dt/4.));
+        sei->lastdt = r->dt;
+        return 1;
+    }
+    const double oz = (r->OMEGAZ==-1) ? r->OMEGA : r->OMEGAZ;       /* what the device step would use */
+    return sei->sindt==sin(r->OMEGA*(-r->dt/2.)) && sei->tandt==tan(r->OMEGA*(-r->dt/4.))
+        && sei->sindtz==sin(oz*(-r->dt/2.)) && sei->tandtz==tan(oz*(-r->dt/4.)) && r->OMEGAZ!=-1;
+}
+
 static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_simulation*, void*), void* state){
-    if (!device_step_possible(r)){
+    if (!device_step_possible(r) || !shim_prepare_integrator_state(r)){
         struct shim_state* s = shim_find(r);
         if (s){ if (shim_to_host(r, s)) return; s->device_valid = 0; }
         host_step(r, state);

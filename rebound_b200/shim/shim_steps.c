@@ -58,6 +58,7 @@ static int batch_possible(const struct reb_simulation* r){
 static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
     struct shim_state* s = shim_get(r);
     if (!s) return -1;
+    if (!shim_prepare_integrator_state(r)) return -2;   /* not a step the device may take: the caller goes step by step */
     if (shim_to_host(r, s)) return -1;                 /* a device copy that is ahead comes home first */
     rebcu_config c;
     shim_fill_config(r, &c);
@@ -118,7 +119,9 @@ void reb_simulation_steps(struct reb_simulation* const r, size_t N_steps){
         size_t left = N_steps;
         while (left){
             const size_t n = left < piece ? left : piece;
-            if (run_batch(r, n, one_call)) return;
+            const int rc = run_batch(r, n, one_call);
+            if (rc==-2){ reb_simulation_steps_cpuref(r, left); return; }
+            if (rc) return;
             left -= n;
             if (left && !batch_possible(r)){ reb_simulation_steps_cpuref(r, left); return; }
         }

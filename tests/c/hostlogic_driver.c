@@ -186,6 +186,32 @@ int main(int argc, char** argv){
         fwrite(&megno, sizeof(double), 1, out);
         dump("hk6 ", v);
         reb_simulation_free(v);
+    }else if (strcmp(scen, "seicache")==0){
+        /* SEI caches sin/tan of OMEGA*dt in its state and refreshes them only when dt changes (integrator_sei.c:91-101):
+         * the cache must look the same after device steps, and a changed OMEGA with an unchanged dt keeps the OLD
+         * rotation in the reference -- the drop-in has to reproduce that, too */
+        struct reb_simulation* r = reb_simulation_create();
+        r->rand_seed = 8;
+        reb_simulation_set_integrator(r, "sei");
+        r->OMEGA = 1.0; r->dt = 1e-2; r->softening = 0.05; r->G = 1e-3;
+        cloud(r, N, 0.1, 0.);
+        reb_simulation_steps(r, 3); dump("se1 ", r);
+        fwrite(r->integrator.state, sizeof(double), 5, out);
+        fwrite(&r->OMEGAZ, sizeof(double), 1, out);
+        r->OMEGA = 1.7;                                    /* dt unchanged: stale cache */
+        reb_simulation_steps(r, 3); dump("se2 ", r);
+        fwrite(r->integrator.state, sizeof(double), 5, out);
+        r->dt = 2e-2;                                      /* refresh */
+        reb_simulation_integrate(r, r->t + 0.11); dump("se3 ", r);
+        fwrite(r->integrator.state, sizeof(double), 5, out);
+        r->OMEGAZ = 2.5;
+        reb_simulation_steps(r, 2); dump("se4 ", r);
+        fwrite(r->integrator.state, sizeof(double), 5, out);
+        r->OMEGAZ = -1;
+        reb_simulation_steps(r, 2); dump("se5 ", r);
+        fwrite(r->integrator.state, sizeof(double), 5, out);
+        fwrite(&r->OMEGAZ, sizeof(double), 1, out);
+        reb_simulation_free(r);
     }else if (strcmp(scen, "many")==0){
         /* a parameter sweep: hundreds of short-lived simulations, created and freed one after the other (and a few
          * kept alive), each using the replaced hot path */

@@ -224,7 +224,7 @@ def test_reference_python_package_on_the_mock_dropin_matches_the_reference_libra
         assert outs["ref"] == outs[name], name
 
 
-HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many", "hooks"]
+HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many", "hooks", "seicache"]
 
 
 @pytest.mark.parametrize("scen", HL_SCENARIOS)
@@ -266,3 +266,39 @@ def test_quadrupole_dropin_on_the_mock_engine(mock_driver, tmp_path):
         for value, name in MODES:
             got = run(os.path.join(quad, "driver_mock"), scen, n, steps, tmp_path / f"mockq_{name}.bin", env={"REBOUND_B200_RESIDENT": value})
             assert np.array_equal(ref, got), (scen, name)
+
+
+# the reference's own Python tests for the hot path and its callers (SURVEY.md section 8c lists them as behavioural pins)
+REFERENCE_TESTS = ["test_gravity.py", "test_collisions.py", "test_shearingsheet.py", "test_boundary.py", "test_leapfrog.py",
+                   "test_simulation.py", "test_eos.py", "test_mercurius.py", "test_trace.py", "test_additional_forces.py",
+                   "test_post_timestep_modifications.py", "test_copy.py", "test_simulationarchive.py",
+                   "test_fpcontract.py", "test_size_of_simulation.py", "test_whfast.py"]
+# explicit resident mode: the files that drive leapfrog / SEI, where residency changes what the shim does
+REFERENCE_TESTS_RESIDENT = ["test_gravity.py", "test_collisions.py", "test_shearingsheet.py", "test_boundary.py", "test_leapfrog.py",
+                            "test_simulation.py", "test_post_timestep_modifications.py", "test_additional_forces.py"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rebound/tests"), reason="needs the reference's Python tests")
+@pytest.mark.parametrize("resident", ["", "1"], ids=["auto", "resident"])
+def test_the_references_own_python_tests_pass_on_the_mock_dropin(mock_driver, resident, tmp_path):
+    """The reference's unit tests, unmodified, with `import rebound` resolving to the drop-in on the mock engine: what
+    passes on the reference's own library must pass here (same counts), in automatic and in explicit resident mode."""
+    import sys
+    files = [os.path.join("/root/reference/rebound/tests", f) for f in (REFERENCE_TESTS_RESIDENT if resident else REFERENCE_TESTS)]
+    files = [f for f in files if os.path.exists(f)]
+    assert len(files) >= 8
+    counts = {}
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+    mock = (os.path.join(BUILD, "librebound.so"), (os.path.join(BUILD, "librebound_b200.so"),))
+    for name, lib, extra in (("ref", ref_lib, ()), ("mock", *mock)):
+        env, lib_dir = _python_env(tmp_path, lib, extra)
+        env["OMP_NUM_THREADS"] = "1"          # tiny systems, thousands of calls: the oracle's OpenMP teams only cost time
+        if name == "mock":
+            env["REBOUND_B200_RESIDENT"] = resident
+            env["LD_LIBRARY_PATH"] = f"{lib_dir}:{os.path.join(ROOT, 'oracle')}:" + env.get("LD_LIBRARY_PATH", "")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--no-header", "-x", *files],
+                           capture_output=True, text=True, env=env, timeout=1500, cwd=str(tmp_path))
+        tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+        assert r.returncode == 0, (name, r.stdout[-3000:])
+        counts[name] = tail.split(" in ")[0]
+    assert "passed" in counts["ref"] and counts["ref"] == counts["mock"]
