@@ -56,6 +56,9 @@ static enum REB_COLLISION_RESOLVE_OUTCOME eat(struct reb_simulation* const r, st
     b->m += a->m; return REB_COLLISION_RESOLVE_OUTCOME_REMOVE_P1;
 }
 
+static int heartbeat_calls = 0;
+static void heartbeat_count(struct reb_simulation* r){ (void)r; heartbeat_calls++; }
+
 static void* thread_main(void* arg){
     struct reb_simulation* r = arg;
     reb_simulation_steps(r, 7);
@@ -211,6 +214,46 @@ int main(int argc, char** argv){
         reb_simulation_steps(r, 2); dump("se5 ", r);
         fwrite(r->integrator.state, sizeof(double), 5, out);
         fwrite(&r->OMEGAZ, sizeof(double), 1, out);
+        reb_simulation_free(r);
+    }else if (strncmp(scen, "fuzz", 4)==0){
+        /* a pseudo-random sequence of public-API calls (seed = the digits after "fuzz"): stepping and integrating in
+         * both directions, adding / removing / editing particles, switching gravity, integrator, collisions, boundary,
+         * heartbeat, exit distance and test-particle settings, copying the simulation, reading diagnostics */
+        unsigned int seed = (unsigned int)atoi(scen+4) * 2654435761u + 12345u;
+        #define RND() (seed = seed*1664525u + 1013904223u, (seed>>8))
+        struct reb_simulation* r = make(50 + (unsigned int)atoi(scen+4), N);
+        r->root_size = 60.;
+        int hb_on = 0;
+        for (int op=0; op<60; op++){
+            const unsigned int k = RND()%15;
+            switch (k){
+                case 0: case 1: reb_simulation_steps(r, 1 + RND()%6); break;
+                case 2: { const double f = 0.3 + (RND()%740)/100.; const double sgn = (RND()%5==0) ? -1. : 1.;
+                          reb_simulation_integrate(r, r->t + sgn*f*fabs(r->dt)); break; }
+                case 3: cloud(r, 1 + RND()%4, 0.2, r->collision ? 0.05 : 0.); break;
+                case 4: if (r->N > 12) reb_simulation_remove_particle(r, RND()%r->N); break;
+                case 5: if (r->N){ r->particles[RND()%r->N].vy += 0.05; r->did_modify_particles = 1; } break;
+                case 6: { const unsigned int g = RND()%4;
+                          r->gravity = g==0 ? REB_GRAVITY_BASIC : g==1 ? REB_GRAVITY_COMPENSATED : g==2 ? REB_GRAVITY_TREE : REB_GRAVITY_NONE; break; }
+                case 7: if (RND()%2){ reb_simulation_set_integrator(r, "ias15"); r->dt = 2e-3; }
+                        else { reb_simulation_set_integrator(r, "leapfrog"); r->dt = copysign(0.01, r->dt); } break;
+                case 8: hb_on = !hb_on; r->heartbeat = hb_on ? heartbeat_count : NULL; break;
+                case 9: r->exit_max_distance = r->exit_max_distance ? 0. : 25.; break;
+                case 10: if (RND()%2){ r->N_active = r->N/2; r->testparticle_type = (int)(RND()%2); } else { r->N_active = SIZE_MAX; } break;
+                case 11: { struct reb_simulation* c2 = reb_simulation_copy(r); reb_simulation_free(r); r = c2;
+                           r->heartbeat = hb_on ? heartbeat_count : NULL; break; }
+                case 12: reb_simulation_move_to_com(r); break;
+                case 13: { const double e = reb_simulation_energy(r); fwrite(&e, sizeof(double), 1, out); break; }
+                case 14: if (r->collision){ r->collision = REB_COLLISION_NONE; }
+                         else { r->collision = (RND()%2) ? REB_COLLISION_DIRECT : REB_COLLISION_TREE; r->collision_resolve = reb_collision_resolve_merge;
+                                for (size_t i=0;i<r->N;i++) r->particles[i].r = 0.03; r->did_modify_particles = 1; } break;
+            }
+            if (r->status > 0 && r->status != REB_STATUS_SUCCESS) r->status = REB_STATUS_SUCCESS;     /* an escape ends one call, not the sequence */
+            double hdr[4] = {(double)k, (double)r->N, r->t, (double)r->steps_done};
+            fwrite(hdr, sizeof(double), 4, out);
+        }
+        dump("fuz ", r);
+        fwrite(&heartbeat_calls, sizeof(int), 1, out);
         reb_simulation_free(r);
     }else if (strcmp(scen, "many")==0){
         /* a parameter sweep: hundreds of short-lived simulations, created and freed one after the other (and a few
