@@ -56,6 +56,7 @@ static enum REB_COLLISION_RESOLVE_OUTCOME eat(struct reb_simulation* const r, st
     b->m += a->m; return REB_COLLISION_RESOLVE_OUTCOME_REMOVE_P1;
 }
 
+#define RND() (seed = seed*1664525u + 1013904223u, (seed>>8))
 static int heartbeat_calls = 0;
 static void heartbeat_count(struct reb_simulation* r){ (void)r; heartbeat_calls++; }
 
@@ -215,12 +216,55 @@ int main(int argc, char** argv){
         fwrite(r->integrator.state, sizeof(double), 5, out);
         fwrite(&r->OMEGAZ, sizeof(double), 1, out);
         reb_simulation_free(r);
+    }else if (strncmp(scen, "fuzs", 4)==0){
+        /* the same idea for the shearing-sheet family: SEI, shear boundary, tree / direct gravity and collisions with the
+         * reference's hard-sphere resolver, ghost boxes; the sequence also changes dt (SEI refreshes its cache) and OMEGA
+         * (it does not), the ghost rings and the root-box grid */
+        unsigned int seed = (unsigned int)atoi(scen+4) * 2246822519u + 777u;
+        struct reb_simulation* r = reb_simulation_create();
+        r->rand_seed = 70 + (unsigned int)atoi(scen+4);
+        reb_simulation_set_integrator(r, "sei");
+        r->boundary = REB_BOUNDARY_SHEAR; r->gravity = REB_GRAVITY_TREE; r->opening_angle2 = 0.5;
+        r->OMEGA = 1.0; r->G = 2e-3; r->softening = 0.02; r->dt = 2e-2;
+        r->root_size = 4.; r->N_root_x = 2; r->N_root_y = 2; r->N_ghost_x = 1; r->N_ghost_y = 1;
+        r->collision_resolve = reb_collision_resolve_hardsphere; r->collision = REB_COLLISION_TREE;
+        for (int i=0;i<N;i++){
+            struct reb_particle p = {0};
+            p.x = reb_random_uniform(r,-3.9,3.9); p.y = reb_random_uniform(r,-3.9,3.9); p.z = reb_random_normal(r, 0.05);
+            p.vy = -1.5*p.x*r->OMEGA; p.vx = reb_random_normal(r, 0.02);
+            p.r = reb_random_uniform(r, 0.15, 0.3); p.m = p.r*p.r*p.r;
+            reb_simulation_add(r, p);
+        }
+        for (int op=0; op<50; op++){
+            const unsigned int k = RND()%12;
+            switch (k){
+                case 0: case 1: case 2: reb_simulation_steps(r, 1 + RND()%5); break;
+                case 3: reb_simulation_integrate(r, r->t + (0.4 + (RND()%500)/100.)*r->dt); break;
+                case 4: { struct reb_particle p = {0};
+                          p.x = reb_random_uniform(r,-3.9,3.9); p.y = reb_random_uniform(r,-3.9,3.9); p.z = 0.3 + 0.01*op;
+                          p.vy = -1.5*p.x*r->OMEGA; p.r = 0.06; p.m = 2e-4; reb_simulation_add(r, p); break; }
+                case 5: if (r->N > 10) reb_simulation_remove_particle(r, RND()%r->N); break;
+                case 6: { const unsigned int c = RND()%3;
+                          r->collision = c==0 ? REB_COLLISION_TREE : c==1 ? REB_COLLISION_DIRECT : REB_COLLISION_NONE; break; }
+                case 7: r->dt = (RND()%2) ? 2e-2 : 1.5e-2; break;                      /* the SEI cache is refreshed */
+                case 8: r->OMEGA = (RND()%2) ? 1.0 : 1.25; break;                      /* ... and here it is not */
+                case 9: r->N_ghost_x = r->N_ghost_y = 1 + (int)(RND()%2); break;
+                case 10: { struct reb_simulation* c2 = reb_simulation_copy(r); reb_simulation_free(r); r = c2; break; }
+                /* (no REB_GRAVITY_BASIC here: with ghost boxes the reference's serial build applies the shifted pairs
+                 * antisymmetrically and differs from its own OpenMP build, and from the gather form, in the last bit) */
+                case 11: r->gravity = (RND()%3==0) ? REB_GRAVITY_NONE : REB_GRAVITY_TREE; break;
+            }
+            double hdr[5] = {(double)k, (double)r->N, r->t, (double)r->steps_done, (double)r->collisions_log_n};
+            fwrite(hdr, sizeof(double), 5, out);
+        }
+        dump("fzs ", r);
+        fwrite(r->integrator.state, sizeof(double), 5, out);
+        reb_simulation_free(r);
     }else if (strncmp(scen, "fuzz", 4)==0){
         /* a pseudo-random sequence of public-API calls (seed = the digits after "fuzz"): stepping and integrating in
          * both directions, adding / removing / editing particles, switching gravity, integrator, collisions, boundary,
          * heartbeat, exit distance and test-particle settings, copying the simulation, reading diagnostics */
         unsigned int seed = (unsigned int)atoi(scen+4) * 2654435761u + 12345u;
-        #define RND() (seed = seed*1664525u + 1013904223u, (seed>>8))
         struct reb_simulation* r = make(50 + (unsigned int)atoi(scen+4), N);
         r->root_size = 60.;
         int hb_on = 0;

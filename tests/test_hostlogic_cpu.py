@@ -311,10 +311,14 @@ def test_fuzzed_api_sequences_match_the_reference_bitwise(mock_driver, tmp_path)
     leave the same trace as the unmodified reference in every residency mode.  (Seeds on which the reference itself
     does not finish within the time limit are skipped: 4 of the first 120.)"""
     checked = 0
-    for seed in range(1, 41):
+    cases = [(f"fuzz{seed}", "30") for seed in range(1, 41)]
+    # the shearing-sheet family: SEI (cache refreshed by dt changes, kept across OMEGA changes), shear boundary, ghost
+    # rings, tree / direct collision searches with the reference's hard-sphere resolver
+    cases += [(f"fuzs{seed}", "120") for seed in range(1, 21)]
+    for scen, n in cases:
         ref_out = tmp_path / "ref.bin"
         try:
-            r = subprocess.run([os.path.join(BUILD, "hl_ref"), f"fuzz{seed}", str(ref_out), "30"], capture_output=True, timeout=20)
+            r = subprocess.run([os.path.join(BUILD, "hl_ref"), scen, str(ref_out), n], capture_output=True, timeout=30)
         except subprocess.TimeoutExpired:
             continue
         assert r.returncode == 0
@@ -322,8 +326,8 @@ def test_fuzzed_api_sequences_match_the_reference_bitwise(mock_driver, tmp_path)
         for value, name in MODES:
             out = tmp_path / "mock.bin"
             e = dict(os.environ, REBOUND_B200_RESIDENT=value)
-            r = subprocess.run([os.path.join(BUILD, "hl_mock"), f"fuzz{seed}", str(out), "30"], capture_output=True, env=e, timeout=60)
-            assert r.returncode == 0, (seed, name, r.stderr[-500:])
-            assert out.read_bytes() == ref, (seed, name)
+            r = subprocess.run([os.path.join(BUILD, "hl_mock"), scen, str(out), n], capture_output=True, env=e, timeout=120)
+            assert r.returncode == 0, (scen, name, r.stderr[-500:])
+            assert out.read_bytes() == ref, (scen, name)
         checked += 1
-    assert checked >= 35
+    assert checked >= 55
