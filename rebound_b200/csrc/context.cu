@@ -179,7 +179,9 @@ static rebcu_vec6d ghostbox_host(const rebcu_config* c, int i, int j, int k) {
 }
 
 // Offsets for the rings [-gx,gx] x [-gy,gy] x [-gz,gz] in the reference's loop order (x outermost).
+// More boxes than REBCU_MAX_GHOST: out->n = -1 (the callers report REBCU_ERR_ARG through engine_upload_ghosts).
 void engine_ghost_shifts(const rebcu_config* c, int gx, int gy, int gz, GhostShifts* out) {
+    if ((long long)(2 * gx + 1) * (2 * gy + 1) * (2 * gz + 1) > REBCU_MAX_GHOST || gx < 0 || gy < 0 || gz < 0) { out->n = -1; return; }
     int n = 0;
     for (int i = -gx; i <= gx; i++)
         for (int j = -gy; j <= gy; j++)
@@ -189,6 +191,7 @@ void engine_ghost_shifts(const rebcu_config* c, int gx, int gy, int gz, GhostShi
 }
 
 int engine_upload_ghosts(rebcu_handle* h, const GhostShifts* g) {
+    if (g->n < 0) return rebcu_fail(h, REBCU_ERR_ARG, "too many ghost boxes: (2*N_ghost_x+1)(2*N_ghost_y+1)(2*N_ghost_z+1) must not exceed 729");
     // Skip the copy when the device already holds these offsets (always the case without a shear
     // boundary); otherwise stage through a pinned ring so that no stream synchronisation is needed.
     const size_t bytes = offsetof(GhostShifts, gb) + sizeof(rebcu_vec6d) * (size_t)g->n;

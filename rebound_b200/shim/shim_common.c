@@ -86,7 +86,8 @@ int shim_resident(const struct reb_simulation* r){
     const int exits_ok = (!r->exit_max_distance && !r->exit_min_distance)
                       || (r->boundary==REB_BOUNDARY_NONE && r->collision==REB_COLLISION_NONE);
     return !r->heartbeat && !r->pre_timestep_modifications && !r->post_timestep_modifications
-        && exits_ok && !r->display_data && !r->server_data;
+        && exits_ok && !r->display_data && !r->server_data
+        && !r->N_odes;     /* user ODEs are integrated on the host after every step and read r->particles (simulation.c:531-556) */
 }
 
 void shim_fill_config(const struct reb_simulation* r, rebcu_config* c){

@@ -96,7 +96,9 @@ static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_s
     const int exits = r->exit_max_distance || r->exit_min_distance;
     const int exits_on_device = exits && r->boundary==REB_BOUNDARY_NONE && r->collision==REB_COLLISION_NONE
                                 && !r->post_timestep_modifications && !r->heartbeat;
-    if (shim_resident(r) && (!exits || exits_on_device)){
+    /* user ODEs are integrated on the host right after this callback returns and read r->particles
+     * (src/simulation.c:531-556): in every residency mode the host copy must be current then */
+    if (shim_resident(r) && !r->N_odes && (!exits || exits_on_device)){
         r->N = rebcu_N(s->h);            /* tree gravity + open boundary may have removed particles */
         s->uploaded_N = r->N;
         r->is_synchronized = 0;

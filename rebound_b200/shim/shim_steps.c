@@ -12,9 +12,9 @@
  *
  * reb_simulation_integrate keeps its exit logic: the batch stops at least two steps short of tmax and the
  * reference's own loop (reb_check_exit, :290-351: exact_finish_time, the shortened last step, the status codes)
- * finishes the run.  SIGINT is handled as in the reference (:371-372): the handler is installed before the batch,
- * batches are cut into pieces, and a pending interrupt hands control to the reference's loop, which ends the run
- * with REB_STATUS_SIGINT after its next step.
+ * finishes the run.  SIGINT is handled as in the reference (:371-372, :346-349): the handler is installed before the
+ * batch, batches are cut into pieces, and an interrupt that arrives during a batch ends the run right there with
+ * REB_STATUS_SIGINT (the reference's loop would reset reb_sigint on entry, :371, and lose it).
  *
  * Only in automatic residency mode (REBOUND_B200_RESIDENT unset); the explicit modes keep their per-step behaviour.
  */
@@ -73,6 +73,15 @@ static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
         if (!err) err = rebcu_steps(s->h, &c, n);
         if (!err){ N = rebcu_N(s->h); err = rebcu_download(s->h, (rebcu_particle*)r->particles, N); }
     }
+    int interrupted = 0;
+    if (err==REBCU_INTERRUPTED){
+        /* a second Ctrl-C stopped the engine between two steps: not an error.  The state of the last completed step
+         * comes home (rebcu_steps_host returns before its download) and c.t tells how many steps were done. */
+        interrupted = 1;
+        N = rebcu_N(s->h);
+        err = rebcu_download(s->h, (rebcu_particle*)r->particles, N);
+        if (c.dt != 0.){ const double done = floor((c.t - r->t)/c.dt + 0.5); n = (done > 0. && done < (double)n) ? (size_t)done : (done <= 0. ? 0 : n); }
+    }
     s->device_valid = 0; s->host_stale = 0;
     if (shim_report(r, s, err)) return -1;
     gettimeofday(&t1, NULL);
@@ -89,7 +98,7 @@ static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
     r->is_synchronized = 1;
     /* walltime bookkeeping, simulation.c:588-600 */
     const double el = (double)(t1.tv_sec-t0.tv_sec) + (double)(t1.tv_usec-t0.tv_usec)/1e6;
-    r->walltime_last_step = el/(double)n;
+    r->walltime_last_step = el/(double)(n ? n : 1);
     r->walltime_last_steps_sum += el;
     r->walltime_last_steps_N += n;
     if (r->walltime_last_steps_sum > 0.1){
@@ -99,6 +108,7 @@ static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
     }
     r->walltime += el;
     r->steps_done += n;                                 /* simulation.c:603 */
+    if (interrupted){ if (reb_sigint < 2) reb_sigint = 2; return 1; }
     return 0;
 }
 
@@ -150,6 +160,13 @@ enum REB_STATUS reb_simulation_integrate(struct reb_simulation* const r, double 
                 const double left = floor((tmax - r->t)/dt) - 2.;
                 if (left < nf) nf = left;
                 if (!batch_possible(r)) break;                              /* e.g. the last particle left an open box */
+            }
+            if (reb_sigint){
+                /* what reb_check_exit does with a pending interrupt (simulation.c:346-349) and the end of
+                 * reb_simulation_integrate_raw (:455-459): synchronise, report, leave */
+                reb_simulation_synchronize(r);
+                r->status = REB_STATUS_SIGINT;                  /* reb_sigint stays set, as the reference leaves it */
+                return r->status;
             }
         }
     }

@@ -427,10 +427,18 @@ class Simulation:
         c = self._cfg
         if c.dt == 0:
             raise RuntimeError("dt is zero")
+        if tmax == c.t:
+            return
+        # simulation.c:377-380: dt takes the sign of the direction of integration
+        c.dt = float(np.copysign(c.dt, tmax - c.t))
+        # count the steps with the integrator's own update of t: two half drifts per step (integrator_leapfrog.c:81,
+        # integrator_sei.c:107,116), which round differently from t += dt
+        half = c.dt / 2.0
         n = 0
         t = c.t
         while (t < tmax) if c.dt > 0 else (t > tmax):
-            t += c.dt
+            t += half
+            t += half
             n += 1
         if not (self.exit_max_distance or self.exit_min_distance):
             if n:

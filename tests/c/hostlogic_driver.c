@@ -60,6 +60,15 @@ static enum REB_COLLISION_RESOLVE_OUTCOME eat(struct reb_simulation* const r, st
 static int heartbeat_calls = 0;
 static void heartbeat_count(struct reb_simulation* r){ (void)r; heartbeat_calls++; }
 
+/* user ODE coupled to the particles ("odes" scenario): dy/dt = -y * |x_0|^2, reads r->particles every step */
+static void ode_rhs(struct reb_ode* const ode, double* const yDot, const double* const y, const double t){
+    (void)t;
+    const struct reb_particle* p = &ode->r->particles[0];
+    const double w = p->x*p->x + p->y*p->y + p->z*p->z;
+    yDot[0] = -y[0]*w; yDot[1] = y[0]*p->vx;
+}
+static void ode_pre(struct reb_ode* const ode, const double* const y0){ (void)y0; ode->y[1] += 1e-3*ode->r->particles[1].x; }
+
 static void* thread_main(void* arg){
     struct reb_simulation* r = arg;
     reb_simulation_steps(r, 7);
@@ -298,6 +307,27 @@ int main(int argc, char** argv){
         }
         dump("fuz ", r);
         fwrite(&heartbeat_calls, sizeof(int), 1, out);
+        reb_simulation_free(r);
+    }else if (strcmp(scen, "odes")==0){
+        /* a user ODE whose right-hand side and pre_timestep hook read r->particles: integrated on the host after every
+         * N-body step (simulation.c:531-556), so the host copy must be current at every step */
+        struct reb_simulation* r = make(21, N);
+        struct reb_ode* ode = reb_ode_create(r, 2);
+        ode->derivatives = ode_rhs; ode->pre_timestep = ode_pre; ode->needs_nbody = 0;
+        ode->y[0] = 1.0; ode->y[1] = 0.0;
+        reb_simulation_steps(r, 6); dump("od1 ", r); fwrite(ode->y, sizeof(double), 2, out);
+        reb_simulation_integrate(r, r->t + 0.0777); dump("od2 ", r); fwrite(ode->y, sizeof(double), 2, out);
+        reb_ode_free(ode);
+        reb_simulation_steps(r, 5); dump("od3 ", r);
+        reb_simulation_free(r);
+    }else if (strcmp(scen, "sigint")==0){
+        /* Ctrl-C during a long integration (the test harness makes the mock engine raise SIGINT in the middle of a
+         * device batch): the run must end there with REB_STATUS_SIGINT, synchronised, short of tmax */
+        struct reb_simulation* r = make(22, N);
+        const enum REB_STATUS st = reb_simulation_integrate(r, 50000.*r->dt);
+        double info[4] = {(double)st, (double)r->status, r->t, (double)r->steps_done};
+        fwrite(info, sizeof(double), 4, out);
+        dump("sig ", r);
         reb_simulation_free(r);
     }else if (strcmp(scen, "many")==0){
         /* a parameter sweep: hundreds of short-lived simulations, created and freed one after the other (and a few

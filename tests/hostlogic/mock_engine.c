@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <signal.h>
 #include "../../include/rebound_b200.h"
 
 const char* orc_last_error(void);
@@ -123,6 +124,11 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps){
         const int err = from_oracle(h, orc_steps(cfg, h->p, &h->N, 1, 0, 0., NULL));
         if (err) return err;
         n_steps_total++;
+        {   /* MOCK_SIGINT_AT_STEP=<k>[,<times>]: the user's Ctrl-C arrives while the k-th step of the process runs */
+            static long at = -2; static int times = 1;
+            if (at == -2){ const char* e = getenv("MOCK_SIGINT_AT_STEP"); at = e ? atol(e) : -1; const char* c = e ? strchr(e, ',') : NULL; if (c) times = atoi(c+1); }
+            if (at >= 0 && (long)n_steps_total == at) for (int k=0;k<times;k++) raise(SIGINT);
+        }
     }
     return 0;
 }

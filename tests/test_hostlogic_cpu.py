@@ -224,7 +224,7 @@ def test_reference_python_package_on_the_mock_dropin_matches_the_reference_libra
         assert outs["ref"] == outs[name], name
 
 
-HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many", "hooks", "seicache"]
+HL_SCENARIOS = ["addremove", "switch", "copy", "error", "short", "threads", "many", "hooks", "seicache", "odes"]
 
 
 @pytest.mark.parametrize("scen", HL_SCENARIOS)
@@ -331,3 +331,28 @@ def test_fuzzed_api_sequences_match_the_reference_bitwise(mock_driver, tmp_path)
             assert out.read_bytes() == ref, (scen, name)
         checked += 1
     assert checked >= 55
+
+
+@pytest.mark.parametrize("times", [1, 2])
+def test_ctrl_c_during_a_device_batch_ends_the_integration(mock_driver, times, tmp_path):
+    """A SIGINT that arrives while a device batch of reb_simulation_integrate runs (once: the batch piece finishes;
+    twice: the engine stops between two steps and returns REBCU_INTERRUPTED) ends the run with REB_STATUS_SIGINT,
+    synchronised and short of tmax -- it must not fall through to the reference's loop, which clears reb_sigint."""
+    hl = os.path.join(BUILD, "hl_mock")
+    out = tmp_path / "sig.bin"
+    e = dict(os.environ)
+    e.update({"REBOUND_B200_RESIDENT": "", "MOCK_SIGINT_AT_STEP": f"300,{times}", "MOCK_ENGINE_STATS": str(tmp_path / "st.json")})
+    r = subprocess.run([hl, "sigint", str(out), "40"], capture_output=True, text=True, env=e, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(out, dtype=np.uint8)
+    info = raw[:32].view(np.float64)
+    REB_STATUS_SIGINT = 6          # src/rebound.h:217-233
+    assert info[0] == REB_STATUS_SIGINT and info[1] == REB_STATUS_SIGINT
+    st = json.loads((tmp_path / "st.json").read_text())
+    if times == 1:
+        assert st["steps"] == 4096 and info[3] == 4096           # the piece in flight is completed, nothing after it
+    else:
+        assert st["steps"] == 300 and info[3] == 300              # stopped between two steps
+    assert abs(info[2] - info[3] * 0.01) < 1e-9 and info[2] < 500.0
+    hdr = raw[32 + 4:32 + 4 + 40].view(np.float64)
+    assert hdr[0] == 40 and hdr[1] == info[2]
