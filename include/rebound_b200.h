@@ -272,6 +272,35 @@ void rebcu_shard_range(const rebcu_handle* h, uint64_t* begin, uint64_t* end);
  * box of the innermost ring for DIRECT/LINE, a single segment otherwise). */
 int rebcu_collisions_segments(rebcu_handle* h, uint64_t* counts, uint64_t cap, uint64_t* n_segments);
 
+/* ---- native exchange: NCCL (or in-process peer copies) inside the engine ------------------------------------
+ * With a communicator attached, the engine performs the exchange itself wherever it would have called the exchange
+ * callback: in-place all-gather of the owners' blocks of the requested fields, enqueued on the handle's stream between
+ * the drift and the force kernels (the place of reb_communication_mpi_distribute_particles, src/gravity.c:58-61).
+ *   one process per GPU:    rank 0 calls rebcu_comm_unique_id, ships the 128 bytes to the other ranks by any means
+ *                           (torch.distributed, MPI, a file), every rank calls rebcu_comm_init_rank.
+ *   one process, many GPUs: rebcu_comm_init_all on the handles (one per device); every handle must then be driven
+ *                           by its own host thread, all threads making the same sequence of calls.
+ * Both also set the shard (rebcu_set_shard).  transport: NCCL needs distinct devices; LOCAL (peer copies fenced by
+ * events and host barriers) also works for handles that share a device -- how sharded runs are tested on one GPU. */
+#define REBCU_TRANSPORT_AUTO 0
+#define REBCU_TRANSPORT_NCCL 1
+#define REBCU_TRANSPORT_LOCAL 2
+int rebcu_comm_unique_id(void* out128);
+/* The exchange on demand: afterwards every rank holds the owners' current values of the fields `need` names
+ * (REBCU_EXCHANGE_* mask; e.g. ALL before rank 0 downloads a complete state). */
+int rebcu_exchange(rebcu_handle* h, int need);
+/* Sharded residency: each rank's host memory holds only ITS block of r->particles (rebcu_shard_range of N_total), the
+ * way a rank of the reference's MPI build owns only its particles.  Upload = own block over PCIe + one exchange of all
+ * fields over NVLink; download = own block.  (rebcu_upload / rebcu_download move the whole array on every rank.) */
+int rebcu_upload_shard(rebcu_handle* h, const rebcu_particle* block, uint64_t N_total);
+int rebcu_download_shard(rebcu_handle* h, rebcu_particle* block, uint64_t cap);
+int rebcu_comm_init_rank(rebcu_handle* h, const void* id128, int rank, int world);
+int rebcu_comm_init_all(rebcu_handle** handles, int n, int transport);
+int rebcu_comm_destroy(rebcu_handle* h);
+/* Bytes this rank received through the exchange and the number of exchanges since the communicator was created;
+ * *transport = REBCU_TRANSPORT_* in use (0: none).  Exchange time is timing class 7 of rebcu_timing_read. */
+int rebcu_comm_stats(const rebcu_handle* h, uint64_t* bytes_received, uint64_t* exchanges, int* transport);
+
 /* ---- diagnostics on the resident state ----------------------------------------- */
 /* reb_simulation_energy, src/tools.c:108-162: out3 = {kinetic, potential, kinetic + potential}
  * (r->energy_offset is host state and is not added).  Uses cfg->G, N_active, testparticle_type.
@@ -302,6 +331,12 @@ uint64_t rebcu_launch_count(const rebcu_handle* h);
 int rebcu_timing_enable(rebcu_handle* h, int on);
 int rebcu_timing_read(rebcu_handle* h, double* ms_out, uint64_t* launches_out, int n_classes);
 int rebcu_timing_reset(rebcu_handle* h);
+/* Work counters of the tree walk on the current tree (call right after a TREE force evaluation with the same cfg);
+ * what bench.py derives its FP64 roofline figures from.  out6 = {interactions of the per-particle criterion
+ * (src/tree.c:284: what the reference and the STRICT walk evaluate) summed over this rank's particles and ghost boxes,
+ * cells those walks visit, list entries summed over the groups of the last FAST group walk (each entry is evaluated by
+ * 32 lanes), cells its traversals tested, number of groups, cells in the tree}. */
+int rebcu_tree_walk_stats(rebcu_handle* h, const rebcu_config* cfg, uint64_t* out6);
 /* Device self-test of the STRICT kernels' branch-free sqrt/divide against __dsqrt_rn/__ddiv_rn on
  * n_samples pseudo-random operand pairs: result4 = {sqrt mismatches, divide mismatches (both must be 0),
  * sqrt / divide operands of the ordinary families that were sent to the generic path}. */

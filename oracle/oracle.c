@@ -129,6 +129,55 @@ static void gravity_compensated(const rebcu_config* c, rebcu_particle* p, uint64
     }
 }
 
+/* Selected rows of the direct sum (full-size spot checks: one row of N = 2^22 is 4e6 pair terms): the accelerations of
+ * particles rows[0..n_rows) from all their sources, by the loop bodies above (tests/test_oracle_vs_reference.py checks
+ * that the rows equal the full evaluation bit for bit).  out = ax,ay,az per row.  BASIC without ghost boxes or COMPENSATED. */
+int orc_gravity_rows(rebcu_config* c, rebcu_particle* p, uint64_t N, const uint64_t* rows, uint64_t n_rows, double* out){
+    const double G = c->G;
+    const double soft2 = c->softening*c->softening;
+    if (c->gravity!=REBCU_GRAVITY_BASIC && c->gravity!=REBCU_GRAVITY_COMPENSATED) return orc_fail(REBCU_ERR_ARG, "orc_gravity_rows: direct summation only");
+    if (c->N_ghost_x || c->N_ghost_y || c->N_ghost_z) return orc_fail(REBCU_ERR_ARG, "orc_gravity_rows: no ghost boxes");
+    const rebcu_vec6d gb0 = ghostbox(c, 0, 0, 0);
+#pragma omp parallel for schedule(dynamic,1)
+    for (uint64_t k=0;k<n_rows;k++){
+        const uint64_t i = rows[k];
+        const uint64_t ns = source_count(c, N, i);
+        if (c->gravity==REBCU_GRAVITY_BASIC){
+            double ax=0., ay=0., az=0.;
+            const double xi = gb0.x + p[i].x, yi = gb0.y + p[i].y, zi = gb0.z + p[i].z;
+            for (uint64_t j=0;j<ns;j++){
+                if (ignored(c->gravity_ignore_terms, i, j)) continue;
+                const double dx = xi - p[j].x;
+                const double dy = yi - p[j].y;
+                const double dz = zi - p[j].z;
+                const double rr = sqrt(dx*dx + dy*dy + dz*dz + soft2);
+                const double pre = -G/(rr*rr*rr)*p[j].m;
+                ax += pre*dx; ay += pre*dy; az += pre*dz;
+            }
+            out[3*k] = ax; out[3*k+1] = ay; out[3*k+2] = az;
+        }else{
+            double s[3] = {0.,0.,0.}, e[3] = {0.,0.,0.};
+            for (uint64_t j=0;j<ns;j++){
+                if (ignored(c->gravity_ignore_terms, i, j)) continue;
+                double d[3] = { p[i].x - p[j].x, p[i].y - p[j].y, p[i].z - p[j].z };
+                const double r2 = d[0]*d[0] + d[1]*d[1] + d[2]*d[2] + soft2;
+                const double rr = sqrt(r2);
+                const double pre = G/(r2*rr);
+                const double prej = -pre*p[j].m;
+                for (int q=0;q<3;q++){
+                    const double term = prej*d[q];
+                    const double y = term - e[q];
+                    const double t = s[q] + y;
+                    e[q] = (t - s[q]) - y;
+                    s[q] = t;
+                }
+            }
+            out[3*k] = s[0]; out[3*k+1] = s[1]; out[3*k+2] = s[2];
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* Jerk kick of the modified-kick schemes (EOS): src/gravity.c:850-924                          */
 /* ------------------------------------------------------------------------------------------ */

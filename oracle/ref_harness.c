@@ -373,3 +373,98 @@ int refh_make_plummer(uint64_t N, double M, double R, unsigned int seed, rebcu_p
     reb_simulation_free(r);
     return 0;
 }
+
+/* ---- bounded samples of the large tree workloads (bench.py: cpu_baseline and --impl reference) ------------------
+ * A full step of BASELINE.json's C4 (N = 2^24) takes the reference minutes.  A session runs the serial phases of
+ * reb_gravity_tree_calculate_acceleration (gravity.c:47-106) once on the FULL problem, each timed -- boundary check,
+ * reb_tree_construct, reb_tree_calculate_gravity_data -- and then walks the tree for a SAMPLE of the particles
+ * (every stride-th one, all ghost boxes, the reference's own per-particle function and OpenMP schedule), so that
+ *   seconds per step ~= t_boundary + t_construct + t_gravity_data + t_walk_sample * N / n_sample + t_delete + t_rest
+ * with every term measured on the real 2^24-particle tree.  t_rest = one reb_simulation_steps(r,1) with gravity
+ * switched off (drift, kick, drift, boundary check). */
+struct refh_session { struct reb_simulation* r; };
+
+void* refh_tree_open(rebcu_config* c, rebcu_particle* p, uint64_t N, double* sec3){
+    struct refh_session* s = calloc(1, sizeof(*s));
+    s->r = make_sim(c, p, N);
+    struct reb_simulation* r = s->r;
+    struct timespec t0, t1, t2, t3;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    reb_boundary_check(r);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    reb_tree_construct(r);
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+    if (collect_error(r) || !r->tree_root){ reb_simulation_free(r); free(s); return NULL; }
+    reb_tree_calculate_gravity_data(r);
+    clock_gettime(CLOCK_MONOTONIC, &t3);
+    sec3[0] = (t1.tv_sec-t0.tv_sec) + 1e-9*(t1.tv_nsec-t0.tv_nsec);
+    sec3[1] = (t2.tv_sec-t1.tv_sec) + 1e-9*(t2.tv_nsec-t1.tv_nsec);
+    sec3[2] = (t3.tv_sec-t2.tv_sec) + 1e-9*(t3.tv_nsec-t2.tv_nsec);
+    return s;
+}
+
+uint64_t refh_tree_session_N(void* session){ return ((struct refh_session*)session)->r->N; }
+
+/* The walk of gravity.c:76-99 for particles offset, offset+stride, ...; returns the wall seconds and the count. */
+int refh_tree_walk_sample(void* session, uint64_t stride, uint64_t offset, double* sec, uint64_t* n_walked){
+    struct reb_simulation* r = ((struct refh_session*)session)->r;
+    struct reb_particle* const particles = r->particles;
+    const size_t N = r->N;
+    if (stride == 0) stride = 1;
+    const size_t n_s = offset < N ? (N - offset + stride - 1)/stride : 0;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel for schedule(guided)
+    for (size_t k=0; k<n_s; k++){
+        const size_t i = offset + k*stride;
+        particles[i].ax = 0; particles[i].ay = 0; particles[i].az = 0;
+    }
+    for (int gbx=-r->N_ghost_x; gbx<=r->N_ghost_x; gbx++){
+        for (int gby=-r->N_ghost_y; gby<=r->N_ghost_y; gby++){
+            for (int gbz=-r->N_ghost_z; gbz<=r->N_ghost_z; gbz++){
+#pragma omp parallel for schedule(guided)
+                for (size_t k=0; k<n_s; k++){
+                    const size_t i = offset + k*stride;
+                    struct reb_vec6d gb = reb_boundary_get_ghostbox(r, gbx,gby,gbz);
+                    gb.x += particles[i].x;
+                    gb.y += particles[i].y;
+                    gb.z += particles[i].z;
+                    reb_tree_calculate_acceleration_for_particle(r, (int)i, gb);
+                }
+            }
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *sec = (t1.tv_sec-t0.tv_sec) + 1e-9*(t1.tv_nsec-t0.tv_nsec);
+    *n_walked = n_s;
+    return 0;
+}
+
+/* Accelerations of the sampled particles (parity spot checks at full size): out = ax,ay,az per sampled particle. */
+int refh_tree_sample_acc(void* session, uint64_t stride, uint64_t offset, double* out, uint64_t cap){
+    struct reb_simulation* r = ((struct refh_session*)session)->r;
+    uint64_t k = 0;
+    for (size_t i=offset; i<r->N && k<cap; i+=stride, k++){
+        out[3*k] = r->particles[i].ax; out[3*k+1] = r->particles[i].ay; out[3*k+2] = r->particles[i].az;
+    }
+    return (int)k;
+}
+
+/* sec2 = {reb_tree_delete, one reb_simulation_steps(r,1) with gravity and collisions switched off}. */
+int refh_tree_close(void* session, double* sec2){
+    struct refh_session* s = session;
+    struct reb_simulation* r = s->r;
+    struct timespec t0, t1, t2;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    reb_tree_delete(r);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    r->gravity = REB_GRAVITY_NONE; r->collision = REB_COLLISION_NONE;
+    reb_simulation_steps(r, 1);
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+    sec2[0] = (t1.tv_sec-t0.tv_sec) + 1e-9*(t1.tv_nsec-t0.tv_nsec);
+    sec2[1] = (t2.tv_sec-t1.tv_sec) + 1e-9*(t2.tv_nsec-t1.tv_nsec);
+    reb_simulation_free(r);
+    free(s);
+    return 0;
+}
+

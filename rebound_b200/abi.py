@@ -40,6 +40,7 @@ IGNORE_TERMS_NONE, IGNORE_TERMS_BETWEEN_0_AND_1, IGNORE_TERMS_INVOLVING_0 = 0, 1
 INTEGRATOR_NONE, INTEGRATOR_LEAPFROG, INTEGRATOR_SEI = 0, 1, 2
 MODE_STRICT, MODE_FAST = 0, 1
 EXCHANGE_POSITIONS, EXCHANGE_VELOCITIES, EXCHANGE_ALL = 1, 2, 4
+TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_LOCAL = 0, 1, 2
 N_FIELDS = 14  # x y z vx vy vz ax ay az m r name ap sim
 
 ERRORS = {
@@ -213,6 +214,15 @@ PRODUCT_SIGNATURES = {
     "timing_enable": (C.c_int, [_P, C.c_int]),
     "timing_read": (C.c_int, [_P, _DBLP, _U64P, C.c_int]),
     "timing_reset": (C.c_int, [_P]),
+    "tree_walk_stats": (C.c_int, [_P, _CFG, _U64P]),
+    "comm_unique_id": (C.c_int, [_P]),
+    "exchange": (C.c_int, [_P, C.c_int]),
+    "upload_shard": (C.c_int, [_P, _P, C.c_uint64]),
+    "download_shard": (C.c_int, [_P, _P, C.c_uint64]),
+    "comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "comm_init_all": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    "comm_destroy": (C.c_int, [_P]),
+    "comm_stats": (C.c_int, [_P, _U64P, _U64P, C.POINTER(C.c_int)]),
     "selftest_math": (C.c_int, [_P, C.c_uint64, C.c_uint64, _U64P]),
     "selftest_sort": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
     "selftest_scan": (C.c_int, [_P, _P, C.c_uint64]),

@@ -74,7 +74,7 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
         if (fused <= 0) return fused;
     }
     const bool can_carry = cfg->integrator == REBCU_INTEGRATOR_LEAPFROG && cfg->boundary == REBCU_BOUNDARY_NONE
-                        && cfg->collision == REBCU_COLLISION_NONE && h->exchange == nullptr;
+                        && cfg->collision == REBCU_COLLISION_NONE && h->exchange == nullptr && h->comm == nullptr;
     bool carried = false;
     for (uint64_t s = 0; s < n_steps; s++) {
         const bool stop = interrupted();              // finish this step (a carried half-kick must be closed), then leave
@@ -85,8 +85,8 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
         carried = carry_out;
         if (h->world > 1 && cfg->boundary == REBCU_BOUNDARY_OPEN) {
             // every rank must see every particle's final position to agree on what left the box
-            engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
-            err = boundary_check_full(h, cfg);
+            err = engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
+            if (!err) err = boundary_check_full(h, cfg);
         } else {
             err = boundary_check(h, cfg);
         }
@@ -134,6 +134,46 @@ int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particl
     if (err) return err;
     *N = h->N;
     return rebcu_download(h, particles, *N);
+}
+
+// The exchange on demand (what the engine does by itself between drift and force): after it every rank holds the
+// owners' current values of the requested fields.
+int rebcu_exchange(rebcu_handle* h, int need) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (h->world <= 1) return REBCU_OK;
+    return engine_exchange(h, need);
+}
+
+// Sharded residency: every rank's host memory holds only its own block of r->particles (as in the reference's MPI
+// build, where a rank owns the particles of its root boxes).  Upload: own block over PCIe, everything else over the
+// exchange transport (all 14 fields once; afterwards only positions travel per step).  Download: own block only.
+int rebcu_upload_shard(rebcu_handle* h, const rebcu_particle* block, uint64_t N_total) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    int err = engine_reserve(h, N_total);
+    if (err) return err;
+    h->N = N_total; h->resident = true; h->tree.built_for_n = -1;
+    uint64_t b, e; engine_shard(h, &b, &e);
+    if (e > b) {
+        CU_TRY(h, cudaMemcpyAsync(h->aos + b, block, (e - b) * sizeof(rebcu_particle), cudaMemcpyHostToDevice, h->stream));
+        if ((err = engine_upload_range(h, h->stream, nullptr, h->stream, nullptr, b, e))) return err;
+    }
+    if (h->world > 1) return engine_exchange(h, REBCU_EXCHANGE_ALL);
+    return REBCU_OK;
+}
+
+int rebcu_download_shard(rebcu_handle* h, rebcu_particle* block, uint64_t cap) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    CU_TRY(h, cudaSetDevice(h->device));
+    uint64_t b, e; engine_shard(h, &b, &e);
+    if (cap < e - b) return rebcu_fail(h, REBCU_ERR_CAPACITY, "host block buffer too small");
+    if (e > b) {
+        int err = engine_download_range(h, h->stream, nullptr, h->stream, nullptr, b, e);
+        if (err) return err;
+        CU_TRY(h, cudaMemcpyAsync(block, h->aos + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return REBCU_OK;
 }
 
 int rebcu_set_exchange_callback(rebcu_handle* h, void (*cb)(void*), void* user) {

@@ -126,10 +126,11 @@ int boundary_check(rebcu_handle* h, rebcu_config* c) {
         // Sharded: every rank found the same particles outside (positions are replicated), but it only owns the
         // velocities / accelerations / tags of its own block, and the compaction moves particles across block
         // borders.  Gather every field from its owner first; all ranks then compact identical arrays.
-        if (!h->exchange) return rebcu_fail(h, REBCU_ERR_ARG, "open-boundary removal while sharded over several GPUs needs the exchange callback");
+        if (!h->exchange && !h->comm) return rebcu_fail(h, REBCU_ERR_ARG, "open-boundary removal while sharded over several GPUs needs the exchange callback");
         h->rank = h->full_check_rank; h->world = h->full_check_world;
-        engine_exchange(h, REBCU_EXCHANGE_ALL);
+        const int xerr = engine_exchange(h, REBCU_EXCHANGE_ALL);
         h->rank = 0; h->world = 1;
+        if (xerr) return xerr;
     }
     // order-preserving compaction into a second SoA block, then swap
     if (!h->compact_buf) CU_TRY(h, cudaMalloc(&h->compact_buf, h->cap * F_COUNT * sizeof(double)));

@@ -371,7 +371,7 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
     if (!direct && c->collision != REBCU_COLLISION_TREE && c->collision != REBCU_COLLISION_LINETREE)
         return rebcu_fail(h, REBCU_ERR_ARG, "Collision routine not implemented.");
     // Sharded: the overlap tests read the target's velocity, which only its owner has kept current.
-    if (h->world > 1) engine_exchange(h, REBCU_EXCHANGE_POSITIONS | REBCU_EXCHANGE_VELOCITIES);
+    if (h->world > 1) { const int xerr = engine_exchange(h, REBCU_EXCHANGE_POSITIONS | REBCU_EXCHANGE_VELOCITIES); if (xerr) return xerr; }
     if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "collision search supports N < 2^31");
     // r->map / r->N_map / r->N_targets (collision.c:53-58)
     const uint32_t* map = h->col_map_on ? h->col_map : nullptr;

@@ -65,6 +65,7 @@ void rebcu_destroy(rebcu_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    comm_free(h);
     tree_free(h);
     cudaFree(h->soa); cudaFree(h->aos); cudaFree(h->ghosts_dev); cudaFree(h->scratch); cudaFree(h->counters); cudaFree(h->scratch_big);
     cudaFree(h->col_count); cudaFree(h->col_off); cudaFree(h->col_list); cudaFree(h->col_scan_tmp); cudaFree(h->col_slots); cudaFree(h->col_map);
@@ -244,18 +245,20 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(uint64_t* __restrict
 
 // Range versions on an arbitrary stream, for the chunk-pipelined host-buffer path (integrate.cu).
 // Runs the caller's exchange callback with the set of fields it has to gather (rebcu_exchange_request).
-void engine_exchange(rebcu_handle* h, int need) {
-    if (!h->exchange) return;
+int engine_exchange(rebcu_handle* h, int need) {
+    if (h->comm) return comm_exchange(h, need);        // native transport (comm.cu)
+    if (!h->exchange) return REBCU_OK;
     h->exchange_need = need;
     h->exchange(h->exchange_user);
     h->exchange_need = REBCU_EXCHANGE_POSITIONS;
+    return REBCU_OK;
 }
 
 // b must be a multiple of PACK_THREADS.  The copy runs on s_copy, the AoS<->SoA kernel on s_kernel, chained by
 // `ev`: a copy stream then carries nothing but back-to-back DMA transfers and never waits for an SM to free up.
 int engine_upload_range(rebcu_handle* h, cudaStream_t s_copy, cudaEvent_t ev, cudaStream_t s_kernel, const rebcu_particle* particles, uint64_t b, uint64_t e) {
     if (e <= b) return REBCU_OK;
-    CU_TRY(h, cudaMemcpyAsync(h->aos + b, particles + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyHostToDevice, s_copy));
+    if (particles) CU_TRY(h, cudaMemcpyAsync(h->aos + b, particles + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyHostToDevice, s_copy));
     if (s_copy != s_kernel) { CU_TRY(h, cudaEventRecord(ev, s_copy)); CU_TRY(h, cudaStreamWaitEvent(s_kernel, ev, 0)); }
     h->launches++;
     unpack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s_kernel>>>((const uint64_t*)(h->aos + b), (uint64_t*)h->soa + b, h->cap, e - b);
@@ -269,7 +272,7 @@ int engine_download_range(rebcu_handle* h, cudaStream_t s_kernel, cudaEvent_t ev
     pack_kernel<<<div_up(e - b, PACK_THREADS), PACK_THREADS, 0, s_kernel>>>((uint64_t*)(h->aos + b), (const uint64_t*)h->soa + b, h->cap, e - b);
     CU_TRY(h, cudaGetLastError());
     if (s_copy != s_kernel) { CU_TRY(h, cudaEventRecord(ev, s_kernel)); CU_TRY(h, cudaStreamWaitEvent(s_copy, ev, 0)); }
-    CU_TRY(h, cudaMemcpyAsync(particles + b, h->aos + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyDeviceToHost, s_copy));
+    if (particles) CU_TRY(h, cudaMemcpyAsync(particles + b, h->aos + b, (e - b) * sizeof(rebcu_particle), cudaMemcpyDeviceToHost, s_copy));
     return REBCU_OK;
 }
 

@@ -193,7 +193,7 @@ int rebcu_exit_check(rebcu_handle* h, double exit_max_distance, double exit_min_
     const uint64_t n = h->N;
     // the reference tests the distances for truth (`if (r->exit_max_distance)`): zero switches a check off
     if (n == 0 || (!exit_max_distance && !exit_min_distance)) return REBCU_OK;
-    if (h->world > 1) engine_exchange(h, REBCU_EXCHANGE_POSITIONS);     // every rank scans all particles
+    if (h->world > 1) { const int xerr = engine_exchange(h, REBCU_EXCHANGE_POSITIONS); if (xerr) return xerr; }     // every rank scans all particles
     unsigned int* flags = (unsigned int*)(h->counters + 12);
     CU_TRY(h, cudaMemsetAsync(flags, 0, 2 * sizeof(unsigned int), h->stream));
     if (exit_max_distance) {

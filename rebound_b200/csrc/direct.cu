@@ -18,6 +18,7 @@
 // Bound: FP64 pipe.  HBM traffic is 32 B read per source per CTA tile + 24 B written per particle.
 #include "engine.cuh"
 #include "strict_math.cuh"
+#include "fast_math.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -349,30 +350,64 @@ __global__ void __launch_bounds__(32 * SPLIT_W) direct_strict_split_kernel(const
 // ------------------------------------------------------------------------------------------------
 // FAST
 // ------------------------------------------------------------------------------------------------
-// Block = 32 particles x W warps.  Warp w handles source chunks w, w+W, ... of 32 sources each,
-// staged in a private shared-memory slab (double buffered through registers).
-template <bool KAHAN, int W>
-__global__ void __launch_bounds__(32 * W) direct_fast_kernel(const DirectArgs a) {
-    __shared__ double4 slab[W][32];
-    __shared__ double red[W][6][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t i0 = a.i_begin + (uint64_t)blockIdx.x * 32;
-    const uint64_t i = i0 + lane;
-    const bool valid = i < a.i_end;
-    uint64_t ns = 0, skip0 = NO_SKIP, skip1 = NO_SKIP;
-    double pxi = 0, pyi = 0, pzi = 0;
-    if (valid) {
-        source_set(a, i, ns, skip0, skip1);
-        pxi = a.x[i]; pyi = a.y[i]; pzi = a.z[i];
+// Block = 32*IPT particles x W warps: every lane owns IPT particles (register tiling: one shared-memory read of a
+// source serves IPT pair terms), warp w handles source chunks w, w+W, ... of 32 sources each, staged in a private
+// shared-memory slab (double buffered through registers), and the W partial sums are combined in warp order.
+// The pair term is fast_math.cuh's: 17 FP64 instructions (26 with the Kahan update), -G folded into the staged mass.
+// Chunks that every particle of the block uses in full -- inside the common source range, not holding any of the
+// block's own particles nor a source excluded by gravity_ignore_terms -- run a loop without any per-pair predicate;
+// the few remaining chunks (the block's diagonal, the end of the range) select mass 0 / r2 1 for the excluded pairs.
+template <bool KAHAN>
+__device__ __forceinline__ void fast_accumulate(double f, double dx, double dy, double dz, double& sx, double& sy, double& sz,
+                                                double& cx, double& cy, double& cz) {
+    if (!KAHAN) {
+        sx = fma(f, dx, sx); sy = fma(f, dy, sy); sz = fma(f, dz, sz);
+    } else {
+        double y, t;
+        y = fma(f, dx, -cx); t = sx + y; cx = (t - sx) - y; sx = t;
+        y = fma(f, dy, -cy); t = sy + y; cy = (t - sy) - y; sy = t;
+        y = fma(f, dz, -cz); t = sz + y; cz = (t - sz) - y; sz = t;
     }
-    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;
+}
+
+template <bool KAHAN, int W, int IPT>
+__global__ void __launch_bounds__(32 * W) direct_fast_kernel(const DirectArgs a) {
+    constexpr int NR = KAHAN ? 6 : 3;
+    __shared__ double4 slab[W][32];
+    __shared__ double red[W][IPT][NR][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t i0 = a.i_begin + (uint64_t)blockIdx.x * (32 * IPT);
+    uint64_t i[IPT], ns[IPT], skip0[IPT], skip1[IPT];
+    bool valid[IPT];
+    double pxi[IPT], pyi[IPT], pzi[IPT];
+    double sx[IPT], sy[IPT], sz[IPT], cx[IPT], cy[IPT], cz[IPT];
+#pragma unroll
+    for (int q = 0; q < IPT; q++) {
+        i[q] = i0 + (uint64_t)q * 32 + lane;
+        valid[q] = i[q] < a.i_end;
+        ns[q] = 0; skip0[q] = NO_SKIP; skip1[q] = NO_SKIP;
+        pxi[q] = pyi[q] = pzi[q] = 0;
+        if (valid[q]) {
+            source_set(a, i[q], ns[q], skip0[q], skip1[q]);
+            pxi[q] = a.x[i[q]]; pyi[q] = a.y[i[q]]; pzi[q] = a.z[i[q]];
+        }
+        sx[q] = sy[q] = sz[q] = cx[q] = cy[q] = cz[q] = 0;
+    }
+    const uint64_t i_last = ((i0 + 32 * IPT < a.i_end) ? i0 + 32 * IPT : a.i_end) - 1;
+    const uint64_t ns_blk = (a.type && i0 < a.Na) ? a.N : a.Na;          // the longest source range in the block
+    uint64_t ns_lo = (a.type && i_last < a.Na) ? a.N : a.Na;              // the range every particle of the block uses
+    if (a.terms == REBCU_IGNORE_TERMS_INVOLVING_0 && i0 == 0) ns_lo = 0;  // particle 0 has no sources at all
+    const bool has_terms = a.terms != REBCU_IGNORE_TERMS_NONE;
     const double negG = -a.G;
-    double sx = 0, sy = 0, sz = 0, cx = 0, cy = 0, cz = 0;
 
     const int ngb = a.use_ghosts ? a.ghosts->n : 1;
     for (int g = 0; g < ngb; g++) {
-        double xi = pxi, yi = pyi, zi = pzi;
-        if (a.use_ghosts) { xi += a.ghosts->gb[g].x; yi += a.ghosts->gb[g].y; zi += a.ghosts->gb[g].z; }
+        double xi[IPT], yi[IPT], zi[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; q++) {
+            xi[q] = pxi[q]; yi[q] = pyi[q]; zi[q] = pzi[q];
+            if (a.use_ghosts) { xi[q] += a.ghosts->gb[g].x; yi[q] += a.ghosts->gb[g].y; zi[q] += a.ghosts->gb[g].z; }
+        }
         uint64_t t0 = (uint64_t)w * 32;
         double4 pre = make_double4(0, 0, 0, 0);
         if (t0 + lane < ns_blk) { const uint64_t j = t0 + lane; pre = make_double4(a.x[j], a.y[j], a.z[j], negG * a.m[j]); }
@@ -383,44 +418,58 @@ __global__ void __launch_bounds__(32 * W) direct_fast_kernel(const DirectArgs a)
             const uint64_t tn = t0 + 32 * W + lane;
             pre = make_double4(0, 0, 0, 0);
             if (tn < ns_blk) pre = make_double4(a.x[tn], a.y[tn], a.z[tn], negG * a.m[tn]);
-            const int jn = (ns_blk - t0 < 32ull) ? (int)(ns_blk - t0) : 32;
-#pragma unroll 8
-            for (int jj = 0; jj < jn; jj++) {
-                const uint64_t j = t0 + jj;
-                const double4 s = slab[w][jj];
-                const double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
-                const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
-                const double ri = rsqrt(r2);
-                const bool ok = (j < ns) & (j != skip0) & (j != skip1);
-                const double p = ok ? s.w * (ri * ri * ri) : 0.0;
-                if (!KAHAN) {
-                    sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
-                } else {
-                    double y, t;
-                    y = fma(p, dx, -cx); t = sx + y; cx = (t - sx) - y; sx = t;
-                    y = fma(p, dy, -cy); t = sy + y; cy = (t - sy) - y; sy = t;
-                    y = fma(p, dz, -cz); t = sz + y; cz = (t - sz) - y; sz = t;
+            const bool plain = (t0 + 32 <= ns_lo) && (t0 + 32 <= i0 || t0 > i_last) && !(has_terms && t0 < 2);
+            if (plain) {
+#pragma unroll 4
+                for (int jj = 0; jj < 32; jj++) {
+                    const double4 s = slab[w][jj];
+#pragma unroll
+                    for (int q = 0; q < IPT; q++) {
+                        const double dx = xi[q] - s.x, dy = yi[q] - s.y, dz = zi[q] - s.z;
+                        const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
+                        const double f = fast_m_over_r3(r2, s.w);
+                        fast_accumulate<KAHAN>(f, dx, dy, dz, sx[q], sy[q], sz[q], cx[q], cy[q], cz[q]);
+                    }
+                }
+            } else {
+                const int jn = (ns_blk - t0 < 32ull) ? (int)(ns_blk - t0) : 32;
+                for (int jj = 0; jj < jn; jj++) {
+                    const uint64_t j = t0 + jj;
+                    const double4 s = slab[w][jj];
+#pragma unroll
+                    for (int q = 0; q < IPT; q++) {
+                        const bool ok = (j < ns[q]) & (j != skip0[q]) & (j != skip1[q]);
+                        const double dx = xi[q] - s.x, dy = yi[q] - s.y, dz = zi[q] - s.z;
+                        const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
+                        const double f = fast_m_over_r3(ok ? r2 : 1.0, ok ? s.w : 0.0);
+                        fast_accumulate<KAHAN>(f, dx, dy, dz, sx[q], sy[q], sz[q], cx[q], cy[q], cz[q]);
+                    }
                 }
             }
         }
     }
     // combine the W partial sums in warp order (fixed => deterministic)
-    red[w][0][lane] = sx; red[w][1][lane] = sy; red[w][2][lane] = sz;
-    red[w][3][lane] = cx; red[w][4][lane] = cy; red[w][5][lane] = cz;
+#pragma unroll
+    for (int q = 0; q < IPT; q++) {
+        red[w][q][0][lane] = sx[q]; red[w][q][1][lane] = sy[q]; red[w][q][2][lane] = sz[q];
+        if (KAHAN) { red[w][q][3][lane] = cx[q]; red[w][q][4][lane] = cy[q]; red[w][q][5][lane] = cz[q]; }
+    }
     __syncthreads();
-    if (w == 0 && valid) {
+#pragma unroll
+    for (int q = 0; q < IPT; q++) {
+        if ((q % W) != w || !valid[q]) continue;
         double tx = 0, ty = 0, tz = 0, ex = 0, ey = 0, ez = 0;
         for (int k = 0; k < W; k++) {
             // two-sum of the partials; the per-warp Kahan residuals are folded into the error term
             double v, t, bb;
-            v = red[k][0][lane]; t = tx + v; bb = t - tx; ex += (tx - (t - bb)) + (v - bb) - red[k][3][lane]; tx = t;
-            v = red[k][1][lane]; t = ty + v; bb = t - ty; ey += (ty - (t - bb)) + (v - bb) - red[k][4][lane]; ty = t;
-            v = red[k][2][lane]; t = tz + v; bb = t - tz; ez += (tz - (t - bb)) + (v - bb) - red[k][5][lane]; tz = t;
+            v = red[k][q][0][lane]; t = tx + v; bb = t - tx; ex += (tx - (t - bb)) + (v - bb) - (KAHAN ? red[k][q][3][lane] : 0.0); tx = t;
+            v = red[k][q][1][lane]; t = ty + v; bb = t - ty; ey += (ty - (t - bb)) + (v - bb) - (KAHAN ? red[k][q][4][lane] : 0.0); ty = t;
+            v = red[k][q][2][lane]; t = tz + v; bb = t - tz; ez += (tz - (t - bb)) + (v - bb) - (KAHAN ? red[k][q][5][lane] : 0.0); tz = t;
         }
         const double fx = tx + ex, fy = ty + ey, fz = tz + ez;
-        a.ax[i] = fx; a.ay[i] = fy; a.az[i] = fz;
+        a.ax[i[q]] = fx; a.ay[i[q]] = fy; a.az[i[q]] = fz;
         // what the last addition lost, in the sign convention of a Kahan compensation (true sum = a - cs)
-        if (KAHAN && a.csx) { a.csx[i] = (fx - tx) - ex; a.csy[i] = (fy - ty) - ey; a.csz[i] = (fz - tz) - ez; }
+        if (KAHAN && a.csx) { a.csx[i[q]] = (fx - tx) - ex; a.csy[i[q]] = (fy - ty) - ey; a.csz[i[q]] = (fz - tz) - ez; }
     }
 }
 
@@ -588,8 +637,8 @@ __global__ void __launch_bounds__(128) row_fast_kernel(const RowArgs R, double* 
         for (int k = 0; k < 8; k++) {
             const double dx = ri.x - src[k].x, dy = ri.y - src[k].y, dz = ri.z - src[k].z;
             const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
-            const double q = rsqrt(r2);
             const bool ok = (jj[k] < R.j1) & (jj[k] < ns) & (jj[k] != skip0) & (jj[k] != skip1);
+            const double q = fast_rsqrt(ok ? r2 : 1.0);
             const double p = ok ? src[k].w * (q * q * q) : 0.0;
             px = fma(p, dx, px); py = fma(p, dy, py); pz = fma(p, dz, pz);
         }
@@ -646,15 +695,23 @@ void launch_strict(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
     else direct_strict_kernel<KAHAN, 32, 4><<<div_up(n_i, 32), 32, 0, h->stream>>>(a);
 }
 
-template <bool KAHAN>
-void launch_fast(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
-    const unsigned int blocks = div_up(n_i, 32);
+template <bool KAHAN, int IPT>
+void launch_fast_ipt(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
+    const unsigned int blocks = div_up(n_i, 32 * IPT);
     // aim for >= 16 warps per SM
     const uint64_t want = (148ull * 16 + blocks - 1) / blocks;
-    if (want >= 8 && a.Na >= 2048) direct_fast_kernel<KAHAN, 8><<<blocks, 256, 0, h->stream>>>(a);
-    else if (want >= 4 && a.Na >= 1024) direct_fast_kernel<KAHAN, 4><<<blocks, 128, 0, h->stream>>>(a);
-    else if (want >= 2 && a.Na >= 512) direct_fast_kernel<KAHAN, 2><<<blocks, 64, 0, h->stream>>>(a);
-    else direct_fast_kernel<KAHAN, 1><<<blocks, 32, 0, h->stream>>>(a);
+    if (want >= 8 && a.Na >= 2048) direct_fast_kernel<KAHAN, 8, IPT><<<blocks, 256, 0, h->stream>>>(a);
+    else if (want >= 4 && a.Na >= 1024) direct_fast_kernel<KAHAN, 4, IPT><<<blocks, 128, 0, h->stream>>>(a);
+    else if (want >= 2 && a.Na >= 512) direct_fast_kernel<KAHAN, 2, IPT><<<blocks, 64, 0, h->stream>>>(a);
+    else direct_fast_kernel<KAHAN, 1, IPT><<<blocks, 32, 0, h->stream>>>(a);
+}
+
+template <bool KAHAN>
+void launch_fast(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
+    // two particles per lane once there are enough particles to fill the machine that way (REBOUND_B200_FAST_IPT=1|2 forces)
+    static const int forced = [] { const char* e = getenv("REBOUND_B200_FAST_IPT"); return e ? atoi(e) : 0; }();
+    const bool two = forced ? forced == 2 : n_i >= 148ull * 64 * 2;
+    if (two) launch_fast_ipt<KAHAN, 2>(h, a, n_i); else launch_fast_ipt<KAHAN, 1>(h, a, n_i);
 }
 
 }  // namespace

@@ -18,12 +18,15 @@
 #include "../../include/rebound_b200.h"
 
 enum { F_X = 0, F_Y, F_Z, F_VX, F_VY, F_VZ, F_AX, F_AY, F_AZ, F_M, F_R, F_NAME, F_AP, F_SIM, F_COUNT };
-enum { TC_DIRECT = 0, TC_KICKDRIFT, TC_TREEBUILD, TC_TREEWALK, TC_COLLISION, TC_BOUNDARY, TC_PACK, TC_COUNT };
+enum { TC_DIRECT = 0, TC_KICKDRIFT, TC_TREEBUILD, TC_TREEWALK, TC_COLLISION, TC_BOUNDARY, TC_PACK, TC_EXCHANGE, TC_COUNT };
 
 #define REBCU_MAX_GHOST 729   // (2*4+1)^3
 #define GHOST_RING 8
 #define AUX_STREAMS 6
 #define PIPE_RANGES 130
+#define REBCU_MAX_RANKS 16
+
+struct EngineComm;           // comm.cu: NCCL communicator or in-process peer group
 
 struct GhostShifts {          // ghost-box offsets, computed on the host exactly as src/boundary.c:145-201
     int n;
@@ -116,6 +119,9 @@ struct rebcu_handle {
     void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)
     void* exchange_user = nullptr;
     int exchange_need = REBCU_EXCHANGE_POSITIONS;   // what the running exchange callback must gather
+    EngineComm* comm = nullptr;           // native exchange (rebcu_comm_init_rank / rebcu_comm_init_all); takes precedence over the callback
+    uint64_t* comm_view[F_COUNT] = {};    // LOCAL transport: the arrays the peers pull from during the running exchange
+    int comm_view_n = 0;
     int full_check_rank = 0, full_check_world = 0;  // real shard while a full-range boundary check runs (else world 0)
     uint64_t col_seg_n = 0, col_seg_stride = 0;     // local collision list: segments (ghost boxes) x projectiles per segment
     int (*collision_hook)(void*) = nullptr;   // called after each step's collision search (host resolve)
@@ -146,7 +152,10 @@ struct LaunchScope {
 
 // internal entry points (one per translation unit)
 int engine_reserve(rebcu_handle* h, uint64_t n);
-void engine_exchange(rebcu_handle* h, int need);
+int engine_exchange(rebcu_handle* h, int need);
+int comm_exchange(rebcu_handle* h, int need);
+int comm_gather_words(rebcu_handle* h, uint64_t* array, uint64_t n_total);
+void comm_free(rebcu_handle* h);
 int boundary_check_full(rebcu_handle* h, rebcu_config* c);
 int collision_resolve_device(rebcu_handle* h, const rebcu_config* c);
 int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work);

@@ -9,6 +9,7 @@
 // (x,v,a in; x,v out), fused test-particle step 96 (x,v in; x,v out; accelerations stay in registers).
 #include "engine.cuh"
 #include "strict_math.cuh"
+#include "fast_math.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <stdio.h>
@@ -147,7 +148,7 @@ __device__ __forceinline__ void tp_force_fast(const double4* src, int Na, int se
         const double4 sj = src[j];
         const double dx = xi - sj.x, dy = yi - sj.y, dz = zi - sj.z;
         const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
-        const double ri = rsqrt(r2);
+        const double ri = fast_rsqrt(r2);
         const double p = negG * sj.w * (ri * ri * ri);
         if (!kahan) { ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az); }
         else {
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(TP_PAIR_MAX * TP_PAIR_MAX) tp_history_pair_ker
             if (FAST) {
                 dx = xi - sj.x; dy = yi - sj.y; dz = zi - sj.z;
                 const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
-                const double ri = rsqrt(r2);
+                const double ri = fast_rsqrt(r2);
                 p = negG * sj.w * (ri * ri * ri);
             } else {
                 dx = s_sub(xi, sj.x); dy = s_sub(yi, sj.y); dz = s_sub(zi, sj.z);
@@ -503,8 +504,9 @@ int leapfrog_step_ex(rebcu_handle* h, rebcu_config* c, bool carry_in, bool carry
             drift_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(s, drift[0], b, e);
         }
         c->t += drift[k];
-        engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
-        int err = update_acceleration(h, c);
+        int err = engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
+        if (err) return err;
+        err = update_acceleration(h, c);
         if (err) return err;
         engine_shard(h, &b, &e);   // N may shrink (tree gravity + open boundary)
         s = soa_of(h);
@@ -697,8 +699,9 @@ int sei_step(rebcu_handle* h, rebcu_config* c) {
         sei_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(soa_of(h), k, 0, b, e);
     }
     c->t += c->dt / 2.;
-    engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
-    int err = update_acceleration(h, c);
+    int err = engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
+    if (err) return err;
+    err = update_acceleration(h, c);
     if (err) return err;
     engine_shard(h, &b, &e);
     if (e > b) {

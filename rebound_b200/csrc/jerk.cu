@@ -87,7 +87,7 @@ int apply_jerk(rebcu_handle* h, const rebcu_config* c, double v) {
     if (n < 2) return REBCU_OK;
     if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "jerk supports N < 2^31");
     // sharded: the kick needs the accelerations of every block, which only their owners hold
-    if (h->world > 1) engine_exchange(h, REBCU_EXCHANGE_ALL);
+    if (h->world > 1) { const int xerr = engine_exchange(h, REBCU_EXCHANGE_ALL); if (xerr) return xerr; }
     uint64_t ib, ie; engine_shard(h, &ib, &ie);
     if (ie == ib) return REBCU_OK;
     JerkArgs a;

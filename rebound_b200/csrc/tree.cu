@@ -30,6 +30,7 @@
 // cells ~1.5/particle x 80 B out); the walk is FP64-pipe / L2-latency bound.
 #include "engine.cuh"
 #include "strict_math.cuh"
+#include "fast_math.cuh"
 #include "primitives.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -336,6 +337,7 @@ struct WalkArgs {
     const double* quad; uint64_t quad_stride;     // QUADRUPOLE builds: six arrays mxx mxy mxz myy myz mzz, else null
     const double4* rec; const double* m;          // traversal records (mx,my,mz,meta) + masses (records walk), else null
     uint32_t w2_lo;                               // low word of every (normal) squared cell width, see walk_pack_kernel
+    int gw_stack;                                 // traversal stack entries the group walk may use (<= GW_STACK)
 };
 
 // MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
@@ -365,7 +367,7 @@ __device__ __forceinline__ unsigned walk_one(const WalkArgs& a, uint32_t self, d
                 if (w2 > s_mul(a.theta2, r2)) { c++; continue; }          // tree.c:284: open the cell
             } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }    // tree.c:311
             if (MODE == 1) {
-                const double ri = rsqrt(r2 + a.soft2);
+                const double ri = fast_rsqrt(r2 + a.soft2);
                 const double p = negG * q.w * (ri * ri * ri);
                 sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
             } else if (MODE == 0) {
@@ -409,7 +411,7 @@ template <int MODE>
 __device__ __forceinline__ void interact(const WalkArgs& a, double negG, double dx, double dy, double dz, double r2, double m,
                                          double& sx, double& sy, double& sz, unsigned& bad) {
     if (MODE == 1) {
-        const double ri = rsqrt(r2 + a.soft2);
+        const double ri = fast_rsqrt(r2 + a.soft2);
         const double p = negG * m * (ri * ri * ri);
         sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
     } else if (MODE == 0) {
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(128) walk_quad_kernel(const WalkArgs a) {
                 if (w2 > s_mul(a.theta2, r2)) { c++; continue; }
             } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }
             if (FAST) {
-                const double ri = rsqrt(r2 + a.soft2);
+                const double ri = fast_rsqrt(r2 + a.soft2);
                 const double ri2 = ri * ri, ri3 = ri2 * ri;
                 const double prefact = negG * q.w * ri3;
                 if (internal) {
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
                 } else if ((uint32_t)mt.x == self) interact = false;                     // tree.c:311
                 if (interact) {
                     if (MODE == 1) {
-                        const double ri = rsqrt(r2 + a.soft2);
+                        const double ri = fast_rsqrt(r2 + a.soft2);
                         const double p = negG * q.w * (ri * ri * ri);
                         sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
                     } else if (MODE == 0) {
@@ -671,6 +673,189 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
     if (!live) return;
     if (MODE == 0 && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
     a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+}
+
+// ---- FAST group walk: one warp = 32 key-adjacent particles, shared traversal, list-based evaluation -------------------
+// north_star's "warp-cooperative Barnes-Hut walk" for REBCU_MODE_FAST.  The per-particle walks above keep every
+// particle's own interaction list (bit parity), which leaves the warp divergent: 25 of 32 lanes active and the FP64
+// pipe 53 % busy (profiles/r01_walk_rec_ncu.txt).  Here the 32 particles of a warp share ONE traversal and ONE list:
+//  * traversal   lane-parallel over a shared-memory stack of sibling ranges (cell, end): each lane pops one range,
+//                tests its first cell against the GROUP's bounding box, and pushes the rest of the range (skip, end)
+//                and, if the cell has to be opened, its children (cell+1, skip).  32 cells are tested per trip on the
+//                pre-order records the build already emits (no child table needed).
+//  * criterion   a cell is accepted iff  w^2 <= theta^2 * d^2  with d the distance from its centre of mass to the
+//                nearest point of the group's bounding box: d <= |x_i - com| for every particle i of the group, so
+//                the cell would also be accepted by each particle's own test (src/tree.c:284) -- the group criterion
+//                is at least as strict, the error against direct summation at most the reference's.
+//  * list        accepted cells and leaves are compacted (ballot + popc) into a shared-memory list (x,y,z,m | particle
+//                index of a leaf) with the ghost-box shift already removed; whenever the list cannot take 32 more
+//                entries, ALL 32 lanes evaluate every entry for their own particle (broadcast LDS, 17 FP64
+//                instructions per pair, fast_math.cuh).  The own leaf and its ghost images (src/tree.c:311) are
+//                skipped by an integer compare that zeroes the mass.
+// The traversal costs a few instructions per visited cell per warp; the evaluation is pure FP64-pipe work with all
+// lanes active.  The sum order differs from the reference's, so this is FAST mode only (tolerance stated in the tests).
+// A stack that would overflow (trees deeper than ~GW_STACK levels) sends the warp to the per-particle FAST walk.
+constexpr int GW_WARPS = 4;
+constexpr int GW_STACK = 352;
+constexpr int GW_LIST = 160;
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ void gw_evaluate(const double4* __restrict__ ent, const int* __restrict__ tagv, int n, int self,
+                                            double px, double py, double pz, double soft2, double& sx, double& sy, double& sz) {
+#pragma unroll 4
+    for (int j = 0; j < n; j++) {
+        const double4 s = ent[j];
+        const bool me = tagv[j] == self;                     // own leaf or one of its ghost images: tree.c:311
+        const double dx = px - s.x, dy = py - s.y, dz = pz - s.z;
+        double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
+        r2 = me ? 1.0 : r2;
+        const double f = fast_m_over_r3(r2, me ? 0.0 : s.w);
+        sx = fma(f, dx, sx); sy = fma(f, dy, sy); sz = fma(f, dz, sz);
+    }
+}
+
+__global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArgs a, unsigned long long* __restrict__ stats) {
+    __shared__ int2 s_stack[GW_WARPS][GW_STACK];
+    __shared__ double4 s_ent[GW_WARPS][GW_LIST];
+    __shared__ int s_tag[GW_WARPS][GW_LIST];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t t0 = ((uint64_t)blockIdx.x * GW_WARPS + w) * 32;
+    if (t0 >= a.n_work) return;                              // warp-uniform; no block-wide barrier below
+    const uint64_t t = t0 + lane;
+    const bool live = t < a.n_work;
+    const uint64_t tt = live ? t : a.n_work - 1;             // idle lanes shadow the last particle (keeps the box tight)
+    const uint64_t k = a.list ? a.list[tt] : tt;
+    const int self = (int)a.perm[k];
+    const double px = a.x[self], py = a.y[self], pz = a.z[self];
+    const double lox = warp_min_d(px), hix = warp_max_d(px);
+    const double loy = warp_min_d(py), hiy = warp_max_d(py);
+    const double loz = warp_min_d(pz), hiz = warp_max_d(pz);
+    const double cxg = 0.5 * (lox + hix), cyg = 0.5 * (loy + hiy), czg = 0.5 * (loz + hiz);
+    // half extents, rounded up so that the box certainly contains every particle of the group
+    const double hxg = fmax(hix - cxg, cxg - lox), hyg = fmax(hiy - cyg, cyg - loy), hzg = fmax(hiz - czg, czg - loz);
+    int2* stack = s_stack[w];
+    double4* ent = s_ent[w];
+    int* tagv = s_tag[w];
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_cells = (int)a.n_cells;
+    const int ngb = a.ghosts->n;
+    double sx = 0., sy = 0., sz = 0.;
+    int nl = 0;
+    bool overflow = false;
+    unsigned long long n_ent = 0, n_vis = 0;
+    for (int g = 0; g < ngb && !overflow; g++) {
+        const double gbx = a.ghosts->gb[g].x, gby = a.ghosts->gb[g].y, gbz = a.ghosts->gb[g].z;
+        const double bx = cxg + gbx, by = cyg + gby, bz = czg + gbz;      // centre of the shifted group box (gravity.c:93-97)
+        int sp = 0;
+        if (n_cells > 0) { if (lane == 0) stack[0] = make_int2(0, n_cells); sp = 1; }
+        __syncwarp();
+        while (sp > 0) {
+            int n = sp < 32 ? sp : 32;
+            if (n > a.gw_stack - sp) n = a.gw_stack - sp;     // every popped range may push two
+            if (n < 1) { overflow = true; break; }
+            int c = -1, end = 0;
+            if (lane < n) { const int2 e = stack[sp - 1 - lane]; c = e.x; end = e.y; }
+            sp -= n;
+            __syncwarp();
+            bool open = false;
+            int skip = 0, tag = 0;
+            double4 q = make_double4(0., 0., 0., 0.);
+            if (c >= 0) {
+                q = ld_pos256(a.rec + c);
+                const long long bits = __double_as_longlong(q.w);
+                tag = (int)(unsigned int)(unsigned long long)bits;
+                skip = (int)(unsigned int)((unsigned long long)bits >> 32);
+                if (tag < 0) {
+                    const int hi = tag & 0x7fffffff;
+                    double w2 = __hiloint2double(hi, (int)a.w2_lo);
+                    if (hi == 0) w2 = cell_w2_rare(a.root_size, -a.meta2[c].x - 1);
+                    const double ex = fmax(fabs(q.x - bx) - hxg, 0.), ey = fmax(fabs(q.y - by) - hyg, 0.), ez = fmax(fabs(q.z - bz) - hzg, 0.);
+                    const double d2 = fma(ex, ex, fma(ey, ey, ez * ez));
+                    open = w2 > a.theta2 * d2;
+                }
+            }
+            const bool acc = c >= 0 && !open;
+            const bool sib = c >= 0 && skip < end;
+            const unsigned m_sib = __ballot_sync(0xffffffffu, sib), m_open = __ballot_sync(0xffffffffu, open);
+            const unsigned m_acc = __ballot_sync(0xffffffffu, acc);
+            const int n_sib = __popc(m_sib), n_acc = __popc(m_acc);
+            // siblings below, children on top: the next trip continues depth-first (the records it touches are neighbours)
+            if (sib) stack[sp + __popc(m_sib & lt)] = make_int2(skip, end);
+            if (open) stack[sp + n_sib + __popc(m_open & lt)] = make_int2(c + 1, skip);
+            sp += n_sib + __popc(m_open);
+            if (nl + n_acc > GW_LIST) {
+                __syncwarp();
+                gw_evaluate(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
+                n_ent += nl;
+                nl = 0;
+                __syncwarp();
+            }
+            if (acc) {
+                const int slot = nl + __popc(m_acc & lt);
+                ent[slot] = make_double4(q.x - gbx, q.y - gby, q.z - gbz, a.m[c]);
+                tagv[slot] = tag < 0 ? -1 : tag;
+            }
+            nl += n_acc;
+            n_vis += n;
+            __syncwarp();
+        }
+    }
+    if (overflow) {
+        // deeper than the stack: every lane walks on its own (same FAST arithmetic class, per-particle criterion)
+        double fx, fy, fz;
+        walk_one_rec<1>(a, (uint32_t)self, px, py, pz, fx, fy, fz);
+        if (live) { a.ax[self] = fx; a.ay[self] = fy; a.az[self] = fz; }
+        return;
+    }
+    __syncwarp();
+    gw_evaluate(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
+    n_ent += nl;
+    const double negG = -a.G;
+    if (live) { a.ax[self] = negG * sx; a.ay[self] = negG * sy; a.az[self] = negG * sz; }
+    if (stats && lane == 0) { atomicAdd(&stats[0], n_ent); atomicAdd(&stats[1], n_vis); atomicAdd(&stats[2], 1ull); }
+}
+
+// Interaction count of the per-particle criterion (what the reference and the STRICT walk evaluate): accepted cells and
+// leaves summed over the work items; instrumentation for the roofline figures of bench.py, not part of a step.
+__global__ void __launch_bounds__(128) walk_count_kernel(const WalkArgs a, unsigned long long* __restrict__ stats) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    unsigned long long n_acc = 0, n_vis = 0;
+    if (t < a.n_work) {
+        const uint64_t k = a.list ? a.list[t] : t;
+        const uint32_t self = a.perm[k];
+        const double px = a.x[self], py = a.y[self], pz = a.z[self];
+        const int n_cells = (int)a.n_cells;
+        for (int g = 0; g < a.ghosts->n; g++) {
+            const double gx = s_add(a.ghosts->gb[g].x, px), gy = s_add(a.ghosts->gb[g].y, py), gz = s_add(a.ghosts->gb[g].z, pz);
+            int c = 0;
+            while (c < n_cells) {
+                const double4 q = ld_pos256(a.rec + c);
+                const long long bits = __double_as_longlong(q.w);
+                const int tag = (int)(unsigned int)(unsigned long long)bits, skip = (int)(unsigned int)((unsigned long long)bits >> 32);
+                const double dx = s_sub(gx, q.x), dy = s_sub(gy, q.y), dz = s_sub(gz, q.z);
+                const double r2 = s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz));
+                const int hi = tag & 0x7fffffff;
+                double w2 = __hiloint2double(hi, (int)a.w2_lo);
+                if (tag < 0 && hi == 0) w2 = cell_w2_rare(a.root_size, -a.meta2[c].x - 1);
+                const bool open = tag < 0 && w2 > s_mul(a.theta2, r2);
+                n_vis++;
+                if (tag < 0 ? !open : (uint32_t)tag != self) n_acc++;
+                c = open ? c + 1 : skip;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o); n_vis += __shfl_xor_sync(0xffffffffu, n_vis, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[0], n_acc); atomicAdd(&stats[1], n_vis); }
 }
 
 __global__ void __launch_bounds__(256) shard_flag_kernel(uint64_t n, const uint32_t* __restrict__ perm, uint32_t b, uint32_t e,
@@ -861,6 +1046,43 @@ int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work) {
     return REBCU_OK;
 }
 
+static int walk_args_fill(rebcu_handle* h, const rebcu_config* c, WalkArgs& a) {
+    TreeBuffers& T = h->tree;
+    a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
+    a.perm = T.perm; a.list = nullptr; a.n_work = h->N;
+    a.quad = nullptr; a.quad_stride = 0; a.rec = nullptr; a.m = nullptr; a.w2_lo = 0;
+    a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
+    a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
+    a.ghosts = h->ghosts_dev;
+    a.G = c->G; a.soft2 = c->softening * c->softening; a.theta2 = c->opening_angle2;
+    a.root_size = c->root_size;
+    a.windowed = strict_window_ok(c->G) ? 1 : 0;
+    double w = c->root_size;
+    for (int d = 0; d < W_TABLE; d++) { a.w2[d] = w * w; w = w / 2.; }
+    { const double w20 = a.w2[0]; unsigned long long u; memcpy(&u, &w20, 8); a.w2_lo = (uint32_t)u; }
+    // REBOUND_B200_GW_STACK=<n> shrinks the group walk's traversal stack (tests of the overflow path)
+    static const int gw_stack = [] { const char* e = getenv("REBOUND_B200_GW_STACK"); const int v = e ? atoi(e) : 0;
+                                     return (v >= 2 && v <= 352) ? v : 352; }();
+    a.gw_stack = gw_stack;
+    return REBCU_OK;
+}
+
+// (mx,my,mz | tag, skip) traversal records + masses of the current tree (walk_pack_kernel)
+static int walk_records(rebcu_handle* h, WalkArgs& a) {
+    TreeBuffers& T = h->tree;
+    if (T.walk_rec_cap < T.cap_cells) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(T.walk_rec); cudaFree(T.walk_m); T.walk_rec = nullptr; T.walk_m = nullptr; T.walk_rec_cap = 0;
+        CU_TRY(h, cudaMalloc(&T.walk_rec, T.cap_cells * sizeof(double4)));
+        CU_TRY(h, cudaMalloc(&T.walk_m, T.cap_cells * sizeof(double)));
+        T.walk_rec_cap = T.cap_cells;
+    }
+    h->launches++;
+    a.rec = T.walk_rec; a.m = T.walk_m;
+    walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m, a);
+    return REBCU_OK;
+}
+
 int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     // gravity.c:56.  Every rank holds all positions at this point (they were exchanged after the drift), and
     // the replicated tree needs all of them wrapped, so the check covers the full range on every rank.
@@ -876,46 +1098,30 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     err = engine_upload_ghosts(h, &g);
     if (err) return err;
     WalkArgs a;
-    a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
-    a.perm = T.perm; a.list = nullptr; a.n_work = n;
-    a.quad = nullptr; a.quad_stride = 0; a.rec = nullptr; a.m = nullptr; a.w2_lo = 0;
-    a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
-    a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
-    a.ghosts = h->ghosts_dev;
-    a.G = c->G; a.soft2 = c->softening * c->softening; a.theta2 = c->opening_angle2;
-    a.root_size = c->root_size;
-    a.windowed = strict_window_ok(c->G) ? 1 : 0;
-    double w = c->root_size;
-    for (int d = 0; d < W_TABLE; d++) { a.w2[d] = w * w; w = w / 2.; }
+    walk_args_fill(h, c, a);
     if (h->world > 1) {
         // walk only the particles of this rank's index block, visited in key order
         if ((err = tree_shard_list(h, &a.list, &a.n_work))) return err;
     }
     if (a.n_work) {
         LaunchScope ls(h, TC_TREEWALK);
-        // REBOUND_B200_WALK selects a walk for A/B runs (all give identical bits): unset = records walk (walk_rec_kernel),
-        // v1 = one visited cell per trip on the build's arrays (walk_kernel), coop = warp-cooperative (walk_coop_kernel;
-        // FP64-issue bound with 18.7 of 32 lanes active, profiles/r01_walk_coop_ncu.txt).
+        // REBOUND_B200_WALK selects a walk for A/B runs: unset = records walk (walk_rec_kernel; in FAST mode the group
+        // walk, walk_group_kernel), rec = records walk also in FAST mode, v1 = one visited cell per trip on the build's
+        // arrays (walk_kernel), coop = warp-cooperative with per-lane lists (walk_coop_kernel; FP64-issue bound with
+        // 18.7 of 32 lanes active, profiles/r01_walk_coop_ncu.txt).  All but the group walk give identical bits.
         static const int variant = [] { const char* e = getenv("REBOUND_B200_WALK");
-                                        return (e && strcmp(e, "coop") == 0) ? 2 : (e && strcmp(e, "v1") == 0) ? 1 : 0; }();
+                                        return (e && strcmp(e, "coop") == 0) ? 2 : (e && strcmp(e, "v1") == 0) ? 1 : (e && strcmp(e, "rec") == 0) ? 3 : 0; }();
         const unsigned int nb = div_up(a.n_work, 128);
         if (T.has_quad) {
             a.quad = T.quad; a.quad_stride = T.quad_cap;
             if (c->mode == REBCU_MODE_FAST) walk_quad_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_quad_kernel<false><<<nb, 128, 0, h->stream>>>(a);
-        } else if (variant == 0) {
-            if (T.walk_rec_cap < T.cap_cells) {
-                CU_TRY(h, cudaStreamSynchronize(h->stream));
-                cudaFree(T.walk_rec); cudaFree(T.walk_m); T.walk_rec = nullptr; T.walk_m = nullptr; T.walk_rec_cap = 0;
-                CU_TRY(h, cudaMalloc(&T.walk_rec, T.cap_cells * sizeof(double4)));
-                CU_TRY(h, cudaMalloc(&T.walk_m, T.cap_cells * sizeof(double)));
-                T.walk_rec_cap = T.cap_cells;
-            }
-            h->launches++;
-            a.rec = T.walk_rec; a.m = T.walk_m;
-            { const double w20 = a.w2[0]; unsigned long long u; memcpy(&u, &w20, 8); a.w2_lo = (uint32_t)u; }
-            walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m, a);
-            if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
+        } else if (variant == 0 || variant == 3) {
+            if ((err = walk_records(h, a))) return err;
+            if (c->mode == REBCU_MODE_FAST && variant == 0) {
+                CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
+                walk_group_kernel<<<div_up(a.n_work, 32 * GW_WARPS), 32 * GW_WARPS, 0, h->stream>>>(a, h->counters + 8);
+            } else if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_rec_kernel<false><<<nb, 128, 0, h->stream>>>(a);
         } else if (variant == 1) {
             if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<nb, 128, 0, h->stream>>>(a);
@@ -927,5 +1133,32 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
         }
     }
     CU_TRY(h, cudaGetLastError());
+    return REBCU_OK;
+}
+
+// Work counters of the tree walk on the CURRENT tree (call right after a TREE force evaluation with the same cfg):
+//   out[0] interactions of the per-particle criterion (accepted cells + leaves, summed over this rank's particles and
+//          ghost boxes: what the reference and the STRICT walk evaluate), out[1] cells those walks visit,
+//   out[2] list entries summed over the groups of the last FAST group walk (each is evaluated by 32 lanes),
+//   out[3] cells its traversals tested, out[4] number of groups, out[5] cells in the tree.
+extern "C" int rebcu_tree_walk_stats(rebcu_handle* h, const rebcu_config* c, uint64_t* out6) {
+    TreeBuffers& T = h->tree;
+    for (int k = 0; k < 6; k++) out6[k] = 0;
+    if (!h->resident || T.n_cells == 0 || T.built_for_n != (int)h->N) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no current tree: call after a TREE force evaluation");
+    CU_TRY(h, cudaSetDevice(h->device));
+    WalkArgs a;
+    walk_args_fill(h, c, a);
+    int err;
+    if (h->world > 1 && (err = tree_shard_list(h, &a.list, &a.n_work))) return err;
+    if ((err = walk_records(h, a))) return err;
+    unsigned long long host[8] = {0};
+    CU_TRY(h, cudaMemcpyAsync(host + 2, h->counters + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->counters + 12, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (a.n_work) walk_count_kernel<<<div_up(a.n_work, 128), 128, 0, h->stream>>>(a, h->counters + 12);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(host, h->counters + 12, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 5; k++) out6[k] = host[k];
+    out6[5] = T.n_cells;
     return REBCU_OK;
 }

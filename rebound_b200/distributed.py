@@ -1,18 +1,26 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed for the exchange.
+"""Multi-GPU plumbing.
 
 Direct summation and the tree walk shard the *targets*: rank r of W owns the contiguous index block
 [N*r/W, N*(r+1)/W) (`rebcu_set_shard`) and computes forces, kicks and drifts only for it.  Between the
 drift and the force evaluation every rank needs the other blocks' new positions: that is the one real
 exchange step of the path -- an all-gather of x, y, z (24 B per particle), the role the reference's MPI
 build gives to reb_communication_mpi_distribute_* (src/communication_mpi.c:109-181, 354-438).
-The engine calls back into `BlockExchange.__call__` at exactly that point (rebcu_set_exchange_callback).
-Two rarer events widen the exchange (rebcu_exchange_request): a collision search also needs the other
-blocks' velocities, and an open-boundary removal needs every field, because the compaction shifts particles
-across block borders.  The collision lists themselves are merged on the host (`gather_collisions`).
+Two rarer events widen the exchange: a collision search also needs the other blocks' velocities, and an
+open-boundary removal needs every field, because the compaction shifts particles across block borders.
 
-Everything here is plumbing on torch tensors; it runs on CPU tensors with the gloo backend as well, which
-is how tests/test_distributed_cpu.py covers it without a GPU.
+The exchange itself runs INSIDE the engine (csrc/comm.cu): ncclAllGather on the engine's stream, ordered
+between the drift and the force kernels without any host round trip.  What is left here is plumbing:
+  * `attach`       one process per GPU: ships NCCL's unique id from rank 0 to the others over
+                   torch.distributed and hands it to rebcu_comm_init_rank;
+  * `LocalGroup`   several engines in ONE process (one thread each), NCCL via ncclCommInitAll or -- when engines
+                   share a device, e.g. to test the sharded kernels on a single GPU -- the LOCAL transport;
+  * `attach(..., transport="callback")`  the exchange as a Python callback on torch tensors (`BlockExchange`);
+                   runs on CPU tensors with the gloo backend, which is how tests/test_distributed_cpu.py
+                   covers the block arithmetic without a GPU;
+  * collision lists are merged on the host (`gather_collisions`, `merge_collision_segments`).
 """
+import threading
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -79,16 +87,48 @@ class BlockExchange:
                         dist.broadcast(f[rb:re], src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
 
 
-def attach(engine, device, group=None):
-    """Shards `engine` over the process group and installs the position exchange.  Call after upload."""
+class ExchangeState:
+    """What `attach` returns: counters of the exchange.  state["calls"] = exchanges so far, state["fields"] = 8-byte
+    fields gathered so far (3 per position exchange, 6 with velocities, 14 for everything)."""
+
+    def __init__(self, engine, counters=None):
+        self.engine = engine
+        self.counters = counters
+
+    def _native(self):
+        st = self.engine.comm_stats()
+        n = self.engine.N
+        b, e = self.engine.shard_range()
+        other = max(1, n - (e - b))
+        return {"calls": st["exchanges"], "fields": st["bytes_received"] // (8 * other), "bytes_received": st["bytes_received"],
+                "transport": st["transport"]}
+
+    def __getitem__(self, key):
+        return (self.counters if self.counters is not None else self._native())[key]
+
+    def get(self, key, default=None):
+        d = self.counters if self.counters is not None else self._native()
+        return d.get(key, default)
+
+
+def attach(engine, device, group=None, transport="nccl"):
+    """Shards `engine` over the process group (one process per GPU) and installs the exchange.  Call after upload.
+    transport "nccl": the engine's own NCCL communicator (rank 0's unique id travels over torch.distributed);
+    "callback": the exchange as a Python callback on torch tensors (any torch.distributed backend)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if transport == "nccl":
+        uid = [engine.comm_unique_id() if rank == 0 else None]
+        src = dist.get_global_rank(group, 0) if group else 0
+        dist.broadcast_object_list(uid, src=src, group=group)
+        engine.comm_init_rank(uid[0], rank, world)
+        return ExchangeState(engine)
     engine.set_shard(rank, world)
-    state = {"calls": 0}
+    state = {"calls": 0, "fields": 0}
 
     def exchange():
         # The engine must launch on torch's current stream (pass torch.cuda.current_stream().cuda_stream
-        # of an explicit stream to Engine) so that NCCL orders behind the drift kernel.  Views are rebuilt
+        # of an explicit stream to Engine) so that the collective orders behind the drift kernel.  Views are rebuilt
         # per call: the engine may swap its SoA block (open-boundary compaction) or change N.
         n = engine.N
         ks = exchange_fields(engine.exchange_request)       # x, y, z unless a collision search / removal asks for more
@@ -96,18 +136,61 @@ def attach(engine, device, group=None):
         fields = [device_view(engine.device_field(k), n, device, "<i8") for k in ks]
         BlockExchange(fields, group)()
         state["calls"] += 1
-        state["fields"] = state.get("fields", 0) + len(ks)
+        state["fields"] += len(ks)
 
     engine.set_exchange_callback(exchange)
-    return state
+    return ExchangeState(engine, state)
 
 
-def gather_owned(engine, device, group=None):
-    """After stepping: every rank's owned block of x..vz (and ax..az) gathered everywhere, so that rank 0
-    can download a complete state.  Returns nothing; the engine's arrays are updated in place."""
+def gather_owned(engine, device=None, group=None):
+    """After stepping: every rank's owned block of every field gathered everywhere, so that rank 0 can download a
+    complete state.  Native transport: rebcu_exchange(ALL); callback transport: the same through the callback."""
+    if engine.comm_stats()["transport"] is not None:
+        engine.exchange(abi.EXCHANGE_ALL)
+        return
     n = engine.N
     fields = [device_view(engine.device_field(k), n, device) for k in range(9)]
     BlockExchange(fields, group)()
+
+
+class LocalGroup:
+    """Several engines driven by the threads of ONE process: `run(fn)` calls fn(rank, engine) on every engine from its
+    own thread (the engine's calls block in barriers / collectives until all ranks have made them).  Engines on
+    distinct devices use NCCL (ncclCommInitAll); engines that share a device use the LOCAL transport."""
+
+    def __init__(self, engines, transport=abi.TRANSPORT_AUTO):
+        import ctypes as C
+
+        self.engines = list(engines)
+        arr = (C.c_void_p * len(self.engines))(*[e.h for e in self.engines])
+        err = self.engines[0].f["comm_init_all"](arr, len(self.engines), int(transport))
+        if err != 0:
+            self.engines[0]._check(err)
+
+    def run(self, fn):
+        out = [None] * len(self.engines)
+        errs = []
+
+        def work(r):
+            try:
+                out[r] = fn(r, self.engines[r])
+            except BaseException as e:      # noqa: BLE001 -- re-raised in the caller's thread
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(r,)) for r in range(len(self.engines))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def collisions(self):
+        """The complete collision list of the last sharded search in the reference's serial order."""
+        lists = [e.collisions_fetch() for e in self.engines]
+        segs = [e.collisions_segments() for e in self.engines]
+        return merge_collision_segments(lists, segs)
 
 
 def merge_collision_segments(lists, segments):

@@ -223,6 +223,36 @@ class Engine:
         self.f["shard_range"](self.h, C.byref(b), C.byref(e))
         return b.value, e.value
 
+    # native exchange (csrc/comm.cu)
+    def comm_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        if self.f["comm_unique_id"](buf) != 0:
+            raise ReboundCudaError(-1, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init_rank(self, unique_id, rank, world):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self.f["comm_init_rank"](self.h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._check(self.f["comm_destroy"](self.h))
+
+    def comm_stats(self):
+        b, n, t = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        self._check(self.f["comm_stats"](self.h, C.byref(b), C.byref(n), C.byref(t)))
+        return {"bytes_received": int(b.value), "exchanges": int(n.value), "transport": {0: None, 1: "nccl", 2: "local"}[t.value]}
+
+    def exchange(self, need=abi.EXCHANGE_ALL):
+        self._check(self.f["exchange"](self.h, int(need)))
+
+    def upload_shard(self, block, n_total):
+        assert block.dtype == abi.PARTICLE_DTYPE and block.flags.c_contiguous
+        self._check(self.f["upload_shard"](self.h, abi.as_ptr(block), int(n_total)))
+
+    def download_shard(self, out):
+        self._check(self.f["download_shard"](self.h, abi.as_ptr(out), len(out)))
+        return out
+
     def set_exchange_callback(self, fn):
         cb = EXCHANGE_CB(lambda _u: fn()) if fn else None
         self._keep.append(cb)
@@ -263,6 +293,13 @@ class Engine:
         self._check(self.f["angular_momentum"](self.h, out))
         return out[0], out[1], out[2]
 
+    def tree_walk_stats(self, cfg):
+        """Work counters of the tree walk on the current tree (rebcu_tree_walk_stats)."""
+        out = (C.c_uint64 * 6)()
+        self._check(self.f["tree_walk_stats"](self.h, C.byref(cfg), out))
+        keys = ("interactions", "visits", "group_entries", "group_visits", "groups", "cells")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def measure_fp64_peak(self):
         out = C.c_double(0)
         self._check(self.f["measure_fp64_peak"](self.h, C.byref(out)))
@@ -294,10 +331,10 @@ class Engine:
         self._check(self.f["timing_reset"](self.h))
 
     def timing_read(self):
-        ms = (C.c_double * 7)()
-        n = (C.c_uint64 * 7)()
-        self._check(self.f["timing_read"](self.h, ms, n, 7))
-        names = ("direct", "kickdrift", "treebuild", "treewalk", "collision", "boundary", "pack")
+        ms = (C.c_double * 8)()
+        n = (C.c_uint64 * 8)()
+        self._check(self.f["timing_read"](self.h, ms, n, 8))
+        names = ("direct", "kickdrift", "treebuild", "treewalk", "collision", "boundary", "pack", "exchange")
         return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
 
 

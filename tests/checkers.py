@@ -146,11 +146,72 @@ class Checker:
                 return out[: n.value]
             cap = n.value
 
+    def gravity_rows(self, cfg, p, rows):
+        """Oracle port only: accelerations (n_rows, 3) of the given particles from all their sources (direct sum)."""
+        fn = self.lib.orc_gravity_rows
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros((max(len(rows), 1), 3), dtype=np.float64)
+        self._check(fn(C.byref(cfg.copy()), abi.as_ptr(p), len(p), abi.as_ptr(rows), len(rows), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[: len(rows)]
+
+    def tree_session(self, cfg, p):
+        """Reference only: the serial phases of one tree force evaluation on the full problem, each timed, and a tree
+        that stays alive for sampled walks (oracle/ref_harness.c: refh_tree_open / _walk_sample / _close)."""
+        return TreeSession(self, cfg, p)
+
     def threads(self):
         return self.f["openmp_threads"]()
 
     def set_threads(self, n):
         self.f["set_threads"](n)
+
+
+class TreeSession:
+    def __init__(self, chk, cfg, p):
+        lib = chk.lib
+        lib.refh_tree_open.restype = C.c_void_p
+        lib.refh_tree_open.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
+        lib.refh_tree_session_N.restype = C.c_uint64
+        lib.refh_tree_session_N.argtypes = [C.c_void_p]
+        lib.refh_tree_walk_sample.restype = C.c_int
+        lib.refh_tree_walk_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        lib.refh_tree_sample_acc.restype = C.c_int
+        lib.refh_tree_sample_acc.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.c_uint64]
+        lib.refh_tree_close.restype = C.c_int
+        lib.refh_tree_close.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.lib = lib
+        sec = (C.c_double * 3)()
+        c = cfg.copy()
+        self.h = lib.refh_tree_open(C.byref(c), abi.as_ptr(p), len(p), sec)
+        if not self.h:
+            raise CheckerError(-1, chk.f["last_error"]().decode())
+        self.seconds = {"boundary": sec[0], "construct": sec[1], "gravity_data": sec[2]}
+        self.N = int(lib.refh_tree_session_N(self.h))
+
+    def walk_sample(self, stride, offset=0):
+        """Walks every stride-th particle from `offset`: (seconds, number walked)."""
+        sec = C.c_double(0)
+        n = C.c_uint64(0)
+        self.lib.refh_tree_walk_sample(self.h, stride, offset, C.byref(sec), C.byref(n))
+        return sec.value, int(n.value)
+
+    def sample_acc(self, stride, offset=0):
+        n = (self.N - offset + stride - 1) // stride if offset < self.N else 0
+        out = np.zeros((max(n, 1), 3), dtype=np.float64)
+        k = self.lib.refh_tree_sample_acc(self.h, stride, offset, out.ctypes.data_as(C.POINTER(C.c_double)), n)
+        return out[:k]
+
+    def close(self):
+        """{delete, rest}: reb_tree_delete, and one reb_simulation_steps(r,1) without gravity (drift, kick, drift,
+        boundary check)."""
+        if self.h:
+            sec = (C.c_double * 2)()
+            self.lib.refh_tree_close(self.h, sec)
+            self.h = None
+            self.seconds.update({"delete": sec[0], "rest": sec[1]})
+        return self.seconds
 
 
 def build_oracle():

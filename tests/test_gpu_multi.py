@@ -77,6 +77,7 @@ def _collision_worker(rank, world, port, case, path):
         fields_before = state.get("fields", 0)
         local = eng.collision_search(c)
         assert state["fields"] - fields_before == 6          # x y z vx vy vz were gathered for the search
+        assert state["transport"] == "nccl"
         b, e = eng.shard_range()
         assert np.all((local["p1"] >= b) & (local["p1"] < e))
         merged = D.gather_collisions(eng, dev)

@@ -39,6 +39,35 @@ def test_direct_gravity_bitwise(name, cfg, p):
     assert bits_equal(orc, ref)
 
 
+@pytest.mark.parametrize("name,cfg,p", list(cases_direct()), ids=lambda v: v if isinstance(v, str) else "")
+def test_direct_gravity_rows_equal_the_reference(name, cfg, p):
+    """orc_gravity_rows (the oracle's row-sampled direct sum used for the full-size spot checks of C3) gives the
+    reference's bits for every row it is asked for."""
+    ref, _ = checkers.reference().gravity(cfg, p)
+    rows = np.array([0, 1, 2, len(p) // 2, len(p) - 1], dtype=np.uint64)
+    got = checkers.oracle().gravity_rows(cfg, p, rows)
+    want = np.stack([ref["ax"], ref["ay"], ref["az"]], 1)[rows.astype(np.int64)]
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_tree_session_samples_equal_the_full_evaluation():
+    """The reference harness's sampled tree walk (bench.py's bounded CPU sample and the full-size spot checks of C4)
+    leaves, on the sampled particles, exactly the accelerations of reb_gravity_tree_calculate_acceleration."""
+    cfg = ics.selfgravity_disc_config()
+    p = ics.selfgravity_disc(3000, seed=5)
+    full, _ = checkers.reference().gravity(cfg, p)
+    for chk in (checkers.reference(), checkers.reference(openmp=True)):
+        s = chk.tree_session(cfg, p)
+        assert s.N == len(full)
+        sec, n = s.walk_sample(7, 3)
+        assert n == len(range(3, s.N, 7)) and sec >= 0
+        got = s.sample_acc(7, 3)
+        t = s.close()
+        want = np.stack([full["ax"], full["ay"], full["az"]], 1)[3::7]
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+        assert set(t) == {"boundary", "construct", "gravity_data", "delete", "rest"}
+
+
 def test_basic_ghostboxes_matches_openmp_build():
     # With ghost boxes the reference's serial build applies the shifted pair antisymmetrically
     # (gravity.c:199-212) and is NOT bitwise equal to its own OpenMP build; the gather form is the

@@ -72,6 +72,9 @@ def main():
                "launches_per_step": {k: v["launches"] / steps for k, v in tim.items() if v["launches"]}}
         if inter:
             out["interactions_per_s"] = inter * steps / wall
+        if cfg.gravity == abi.GRAVITY_TREE:
+            eng.update_acceleration(c)
+            out["walk_stats"] = eng.tree_walk_stats(c)
         if device_resolve:
             out["resolve"] = eng.collision_stats()
             eng.set_device_resolve(False)
