@@ -272,6 +272,20 @@ void rebcu_shard_range(const rebcu_handle* h, uint64_t* begin, uint64_t* end);
  * box of the innermost ring for DIRECT/LINE, a single segment otherwise). */
 int rebcu_collisions_segments(rebcu_handle* h, uint64_t* counts, uint64_t cap, uint64_t* n_segments);
 
+/* ---- several GPUs behind one handle ------------------------------------------------------------------------------
+ * One engine handle per device, joined by the native exchange below and driven by one worker thread each; the returned
+ * LEADER handle is used like any other handle: every hot-path call on it (upload, download, update_acceleration,
+ * integrator_step, boundary_check, steps, steps_host, gravity_host, collision_search, apply_jerk, exit_check, ...)
+ * fans out to the ranks, each working on its target block and moving only its block of the host array over PCIe.
+ * This is how a single-threaded program written against the reference's C API -- one struct reb_simulation, one call
+ * to reb_simulation_integrate -- shards over the GPUs of a node: the drop-in creates a group when the environment
+ * variable REBOUND_B200_DEVICES names several devices ("0-7", "0,1,2,3").  A device may be listed more than once
+ * (the ranks then exchange through peer copies instead of NCCL).  Not available on a group: the diagnostics
+ * (rebcu_energy / _com / _angular_momentum), rebcu_download_gravity_cs, the device-side resolve, the tree
+ * inspection calls and a host collision callback inside rebcu_steps.  rebcu_destroy on the leader releases everything. */
+rebcu_handle* rebcu_create_group(const int* devices, int n);
+int rebcu_group_size(const rebcu_handle* h);
+
 /* ---- native exchange: NCCL (or in-process peer copies) inside the engine ------------------------------------
  * With a communicator attached, the engine performs the exchange itself wherever it would have called the exchange
  * callback: in-place all-gather of the owners' blocks of the requested fields, enqueued on the handle's stream between
@@ -297,6 +311,11 @@ int rebcu_download_shard(rebcu_handle* h, rebcu_particle* block, uint64_t cap);
 int rebcu_comm_init_rank(rebcu_handle* h, const void* id128, int rank, int world);
 int rebcu_comm_init_all(rebcu_handle** handles, int n, int transport);
 int rebcu_comm_destroy(rebcu_handle* h);
+/* Tree builds of a sharded run (several ranks, native exchange): 0 = every rank builds the whole tree (replicated),
+ * 1 = every rank sorts and builds only the subtrees of its own key range and the ranks all-gather the traversal records
+ * (csrc/tree.cu: tree_build_sharded; falls back to the replicated build for quadrupole trees, trees deeper than 480
+ * levels and collision searches), 2 (default) = 1 when N >= 2^18.  The accelerations are the same bits either way. */
+int rebcu_set_sharded_build(rebcu_handle* h, int mode);
 /* Bytes this rank received through the exchange and the number of exchanges since the communicator was created;
  * *transport = REBCU_TRANSPORT_* in use (0: none).  Exchange time is timing class 7 of rebcu_timing_read. */
 int rebcu_comm_stats(const rebcu_handle* h, uint64_t* bytes_received, uint64_t* exchanges, int* transport);

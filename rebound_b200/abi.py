@@ -215,6 +215,8 @@ PRODUCT_SIGNATURES = {
     "timing_read": (C.c_int, [_P, _DBLP, _U64P, C.c_int]),
     "timing_reset": (C.c_int, [_P]),
     "tree_walk_stats": (C.c_int, [_P, _CFG, _U64P]),
+    "create_group": (_P, [C.POINTER(C.c_int), C.c_int]),
+    "group_size": (C.c_int, [_P]),
     "comm_unique_id": (C.c_int, [_P]),
     "exchange": (C.c_int, [_P, C.c_int]),
     "upload_shard": (C.c_int, [_P, _P, C.c_uint64]),
@@ -222,6 +224,7 @@ PRODUCT_SIGNATURES = {
     "comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "comm_init_all": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
     "comm_destroy": (C.c_int, [_P]),
+    "set_sharded_build": (C.c_int, [_P, C.c_int]),
     "comm_stats": (C.c_int, [_P, _U64P, _U64P, C.POINTER(C.c_int)]),
     "selftest_math": (C.c_int, [_P, C.c_uint64, C.c_uint64, _U64P]),
     "selftest_sort": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),

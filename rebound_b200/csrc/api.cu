@@ -25,24 +25,34 @@ static int integrator_step(rebcu_handle* h, rebcu_config* c, bool carry_in, bool
 extern "C" {
 
 int rebcu_update_acceleration(rebcu_handle* h, rebcu_config* cfg) {
+    if (group_active(h)) return group_cfg_call(h, cfg, [](rebcu_handle* s, rebcu_config* c) { return rebcu_update_acceleration(s, c); });
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     return update_acceleration(h, cfg);
 }
 
 int rebcu_integrator_step(rebcu_handle* h, rebcu_config* cfg) {
+    if (group_active(h)) return group_cfg_call(h, cfg, [](rebcu_handle* s, rebcu_config* c) { return rebcu_integrator_step(s, c); });
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     return integrator_step(h, cfg, false, false, true);
 }
 
 int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg) {
+    if (group_active(h)) {
+        // the sharded check: every rank must see every particle's position to agree on what left the box
+        return group_cfg_call(h, cfg, [](rebcu_handle* s, rebcu_config* c) {
+            if (c->boundary == REBCU_BOUNDARY_OPEN) { const int e = rebcu_exchange(s, REBCU_EXCHANGE_POSITIONS); if (e) return e; return boundary_check_full(s, c); }
+            return rebcu_boundary_check(s, c);
+        });
+    }
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     return boundary_check(h, cfg);
 }
 
 int rebcu_collisions_fetch(rebcu_handle* h, rebcu_collision* out, uint64_t cap, uint64_t* n_found) {
+    if (group_active(h)) return group_collisions_fetch(h, out, cap, n_found);
     *n_found = h->col_n;
     const uint64_t n = h->col_n < cap ? h->col_n : cap;
     if (n && out) {
@@ -53,6 +63,11 @@ int rebcu_collisions_fetch(rebcu_handle* h, rebcu_collision* out, uint64_t cap, 
 }
 
 int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg, rebcu_collision* out, uint64_t cap, uint64_t* n_found) {
+    if (group_active(h)) {
+        const int e = group_run(h, [cfg](rebcu_handle* s, int) { uint64_t n = 0; return rebcu_collision_search(s, cfg, nullptr, 0, &n); });
+        if (e) return e;
+        return group_collisions_fetch(h, out, cap, n_found);
+    }
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     int err = collision_search(h, cfg);
@@ -64,6 +79,11 @@ int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg, rebcu_colli
 // integrator (:527-529), boundary check (:575), collision search (:584).  Consecutive leapfrog steps
 // share one kick+drift+drift launch when nothing observes the state in between.
 int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
+    if (group_active(h)) {
+        if (h->collision_hook && cfg->collision != REBCU_COLLISION_NONE)
+            return rebcu_fail(h, REBCU_ERR_ARG, "a host collision callback inside rebcu_steps is not available on a multi-GPU group handle");
+        return group_cfg_call(h, cfg, [n_steps](rebcu_handle* s, rebcu_config* c) { return rebcu_steps(s, c, n_steps); });
+    }
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     auto interrupted = [h] { return h->interrupt && *h->interrupt > 1; };
@@ -110,7 +130,7 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
 int rebcu_gravity_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N) {
     int err = rebcu_upload(h, particles, *N);
     if (err) return err;
-    err = update_acceleration(h, cfg);
+    err = group_active(h) ? rebcu_update_acceleration(h, cfg) : update_acceleration(h, cfg);
     if (err) return err;
     *N = h->N;
     return rebcu_download(h, particles, *N);
@@ -124,6 +144,13 @@ int rebcu_collision_search_host(rebcu_handle* h, const rebcu_config* cfg, const 
 }
 
 int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particles, uint64_t* N, uint64_t n_steps) {
+    if (group_active(h)) {
+        int err = rebcu_upload(h, particles, *N);
+        if (!err) err = rebcu_steps(h, cfg, n_steps);
+        if (err) return err;
+        *N = h->N;
+        return rebcu_download(h, particles, *N);
+    }
     CU_TRY(h, cudaSetDevice(h->device));
     // few massive bodies + many test particles: chunked, copies overlapped with the kernels
     const int piped = tp_steps_host_pipelined(h, cfg, particles, *N, n_steps);
@@ -139,6 +166,7 @@ int rebcu_steps_host(rebcu_handle* h, rebcu_config* cfg, rebcu_particle* particl
 // The exchange on demand (what the engine does by itself between drift and force): after it every rank holds the
 // owners' current values of the requested fields.
 int rebcu_exchange(rebcu_handle* h, int need) {
+    if (group_active(h)) return group_run(h, [need](rebcu_handle* s, int) { return rebcu_exchange(s, need); });
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     if (h->world <= 1) return REBCU_OK;
@@ -182,6 +210,7 @@ int rebcu_set_exchange_callback(rebcu_handle* h, void (*cb)(void*), void* user) 
 }
 
 int rebcu_set_interrupt_flag(rebcu_handle* h, const volatile int* flag) {
+    if (group_active(h)) return group_run(h, [flag](rebcu_handle* s, int) { return rebcu_set_interrupt_flag(s, flag); });
     h->interrupt = flag;
     return REBCU_OK;
 }
@@ -192,6 +221,7 @@ int rebcu_set_collision_callback(rebcu_handle* h, int (*cb)(void*), void* user) 
 }
 
 int rebcu_tree_build(rebcu_handle* h, const rebcu_config* cfg) {
+    GROUP_UNSUPPORTED(h, "rebcu_tree_build");
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     return tree_build(h, cfg);

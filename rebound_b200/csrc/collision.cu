@@ -491,6 +491,7 @@ int collision_search(rebcu_handle* h, const rebcu_config* c) {
 
 // r->map / r->N_map / r->N_targets of the next searches (src/rebound.h:257-258,344; collision.c:53-58).
 extern "C" int rebcu_set_collision_subset(rebcu_handle* h, const uint64_t* map, uint64_t N_map, uint64_t N_targets) {
+    if (group_active(h)) return group_run(h, [=](rebcu_handle* s, int) { return rebcu_set_collision_subset(s, map, N_map, N_targets); });
     CU_TRY(h, cudaSetDevice(h->device));
     h->col_targets = N_targets;
     h->col_map_on = map != nullptr;

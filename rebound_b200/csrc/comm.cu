@@ -54,27 +54,31 @@ static int exchange_fields(int need, int* fields) {
     return n;
 }
 
-// All-gathers the owners' blocks of arbitrary device arrays of 8-byte words laid out like the particle fields
-// (element i belongs to the rank whose block holds i).  `ptrs` are this rank's arrays; in LOCAL mode `slot` tells the
-// peers which of their arrays corresponds (field index, or -1-k for the k-th auxiliary array registered in aux_ptrs).
-static int gather_blocks(rebcu_handle* h, uint64_t** ptrs, const int* slots, int n_arrays, uint64_t n_total) {
+// All-gathers rank-owned ranges of device arrays.  Array a has elements of `bytes[a]` bytes; rank r owns the elements
+// [bounds[r], bounds[r+1]) of every array (same bounds for all arrays of a call); afterwards every rank holds every
+// owner's range.  In place.  Equal ranges of 8-byte elements use ncclAllGather, everything else one ncclBroadcast per
+// (array, owner), all inside one NCCL group.
+static int gather_ranges(rebcu_handle* h, void** ptrs, const int* bytes, int n_arrays, const uint64_t* bounds) {
     EngineComm* C = h->comm;
     const int W = h->world, me = h->rank;
-    if (W <= 1 || n_total == 0) return REBCU_OK;
-    uint64_t b[REBCU_MAX_RANKS + 1];
-    for (int r = 0; r <= W; r++) b[r] = n_total * (uint64_t)r / (uint64_t)W;
+    if (W <= 1 || bounds[W] == bounds[0]) return REBCU_OK;
+    if (n_arrays > F_COUNT) return rebcu_fail(h, REBCU_ERR_ARG, "too many arrays in one exchange");
     LaunchScope ls(h, TC_EXCHANGE, 0);
     C->calls++;
-    C->bytes += (uint64_t)n_arrays * 8ull * (n_total - (b[me + 1] - b[me]));
+    bool even = bounds[0] == 0;
+    for (int r = 0; r < W; r++) if (bounds[r + 1] - bounds[r] != bounds[1] - bounds[0]) even = false;
+    for (int a = 0; a < n_arrays; a++) C->bytes += (uint64_t)bytes[a] * ((bounds[W] - bounds[0]) - (bounds[me + 1] - bounds[me]));
     if (C->kind == 1) {
-        const bool even = (n_total % (uint64_t)W) == 0;
         NCCL_TRY(h, ncclGroupStart());
         for (int a = 0; a < n_arrays; a++) {
+            char* base = (char*)ptrs[a];
+            const uint64_t eb = (uint64_t)bytes[a];
             if (even) {
-                NCCL_TRY(h, ncclAllGather(ptrs[a] + b[me], ptrs[a], n_total / W, ncclUint64, C->nccl, h->stream));
+                NCCL_TRY(h, ncclAllGather(base + bounds[me] * eb, base, (bounds[1] - bounds[0]) * eb, ncclChar, C->nccl, h->stream));
             } else {
                 for (int r = 0; r < W; r++)
-                    if (b[r + 1] > b[r]) NCCL_TRY(h, ncclBroadcast(ptrs[a] + b[r], ptrs[a] + b[r], b[r + 1] - b[r], ncclUint64, r, C->nccl, h->stream));
+                    if (bounds[r + 1] > bounds[r])
+                        NCCL_TRY(h, ncclBroadcast(base + bounds[r] * eb, base + bounds[r] * eb, (bounds[r + 1] - bounds[r]) * eb, ncclChar, r, C->nccl, h->stream));
             }
         }
         NCCL_TRY(h, ncclGroupEnd());
@@ -82,38 +86,39 @@ static int gather_blocks(rebcu_handle* h, uint64_t** ptrs, const int* slots, int
     }
     LocalGroup* G = C->grp;
     CU_TRY(h, cudaEventRecord(G->ready[me], h->stream));
-    // what the peers read from this handle
-    for (int a = 0; a < n_arrays; a++) h->comm_view[a] = ptrs[a];
+    for (int a = 0; a < n_arrays; a++) h->comm_view[a] = (uint64_t*)ptrs[a];      // what the peers read from this handle
     h->comm_view_n = n_arrays;
-    (void)slots;
     pthread_barrier_wait(&G->bar);
     for (int r = 0; r < W; r++) {
-        if (r == me || b[r + 1] == b[r]) continue;
+        if (r == me || bounds[r + 1] == bounds[r]) continue;
         rebcu_handle* peer = G->hs[r];
         CU_TRY(h, cudaStreamWaitEvent(h->stream, G->ready[r], 0));
-        for (int a = 0; a < n_arrays; a++)
-            CU_TRY(h, cudaMemcpyPeerAsync(ptrs[a] + b[r], h->device, peer->comm_view[a] + b[r], peer->device,
-                                          (b[r + 1] - b[r]) * sizeof(uint64_t), h->stream));
+        for (int a = 0; a < n_arrays; a++) {
+            const uint64_t eb = (uint64_t)bytes[a];
+            CU_TRY(h, cudaMemcpyPeerAsync((char*)ptrs[a] + bounds[r] * eb, h->device, (const char*)peer->comm_view[a] + bounds[r] * eb, peer->device,
+                                          (bounds[r + 1] - bounds[r]) * eb, h->stream));
+        }
     }
     CU_TRY(h, cudaEventRecord(G->pulled[me], h->stream));
     pthread_barrier_wait(&G->bar);
-    // an owner must not overwrite its block (next kick/drift) before every peer has pulled it
+    // an owner must not overwrite its range (next kick/drift, next build) before every peer has pulled it
     for (int r = 0; r < W; r++) if (r != me) CU_TRY(h, cudaStreamWaitEvent(h->stream, G->pulled[r], 0));
     return REBCU_OK;
 }
 
 int comm_exchange(rebcu_handle* h, int need) {
-    int fields[F_COUNT];
+    int fields[F_COUNT], bytes[F_COUNT];
     const int nf = exchange_fields(need, fields);
-    uint64_t* ptrs[F_COUNT];
-    for (int k = 0; k < nf; k++) ptrs[k] = h->tag(fields[k]);
-    return gather_blocks(h, ptrs, fields, nf, h->N);
+    void* ptrs[F_COUNT];
+    for (int k = 0; k < nf; k++) { ptrs[k] = h->tag(fields[k]); bytes[k] = 8; }
+    uint64_t bounds[REBCU_MAX_RANKS + 1];
+    for (int r = 0; r <= h->world; r++) bounds[r] = h->N * (uint64_t)r / (uint64_t)h->world;
+    return gather_ranges(h, ptrs, bytes, nf, bounds);
 }
 
-int comm_gather_words(rebcu_handle* h, uint64_t* array, uint64_t n_total) {
+int comm_gather_ranges(rebcu_handle* h, void** ptrs, const int* bytes, int n_arrays, const uint64_t* bounds) {
     if (!h->comm) return rebcu_fail(h, REBCU_ERR_ARG, "no communicator");
-    int slot = -1;
-    return gather_blocks(h, &array, &slot, 1, n_total);
+    return gather_ranges(h, ptrs, bytes, n_arrays, bounds);
 }
 
 static void comm_release(rebcu_handle* h) {

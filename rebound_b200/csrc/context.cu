@@ -63,6 +63,7 @@ rebcu_handle* rebcu_create(int device, void* stream) {
 
 void rebcu_destroy(rebcu_handle* h) {
     if (!h) return;
+    if (h->group) group_destroy(h);          // leader: stops the workers and releases the other ranks' handles
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     comm_free(h);
@@ -91,6 +92,7 @@ const char* rebcu_last_error(const rebcu_handle* h) { return h ? h->err : "inval
 void* rebcu_stream(const rebcu_handle* h) { return (void*)h->stream; }
 
 int rebcu_synchronize(rebcu_handle* h) {
+    if (group_active(h)) return group_run(h, [](rebcu_handle* s, int) { return rebcu_synchronize(s); });
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return REBCU_OK;
 }
@@ -279,6 +281,7 @@ int engine_download_range(rebcu_handle* h, cudaStream_t s_kernel, cudaEvent_t ev
 extern "C" {
 
 int rebcu_upload(rebcu_handle* h, const rebcu_particle* particles, uint64_t N) {
+    if (group_active(h)) return group_upload(h, particles, N);
     CU_TRY(h, cudaSetDevice(h->device));
     int err = engine_reserve(h, N);
     if (err) return err;
@@ -296,6 +299,7 @@ int rebcu_upload(rebcu_handle* h, const rebcu_particle* particles, uint64_t N) {
 }
 
 int rebcu_download(rebcu_handle* h, rebcu_particle* particles, uint64_t N) {
+    if (group_active(h)) return group_download(h, particles, N);
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     if (N < h->N) return rebcu_fail(h, REBCU_ERR_CAPACITY, "host particle buffer too small");
     if (h->N == 0) return REBCU_OK;

@@ -187,6 +187,14 @@ extern "C" {
 
 // The exit checks run_heartbeat makes after every step (src/simulation.c:242-272).
 int rebcu_exit_check(rebcu_handle* h, double exit_max_distance, double exit_min_distance, int* escape, int* encounter) {
+    if (group_active(h)) {
+        // every rank scans all particles (positions are exchanged inside); the leader's verdict is returned
+        int esc[REBCU_MAX_RANKS] = {0}, enc[REBCU_MAX_RANKS] = {0};
+        int* pe = esc; int* pn = enc;
+        const int err = group_run(h, [=](rebcu_handle* s, int r) { return rebcu_exit_check(s, exit_max_distance, exit_min_distance, &pe[r], &pn[r]); });
+        *escape = esc[0]; *encounter = enc[0];
+        return err;
+    }
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     *escape = 0; *encounter = 0;
@@ -215,6 +223,7 @@ int rebcu_exit_check(rebcu_handle* h, double exit_max_distance, double exit_min_
 }
 
 int rebcu_energy(rebcu_handle* h, const rebcu_config* cfg, double* out3) {
+    GROUP_UNSUPPORTED(h, "rebcu_energy");
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     out3[0] = out3[1] = out3[2] = 0.;
@@ -250,6 +259,7 @@ int rebcu_energy(rebcu_handle* h, const rebcu_config* cfg, double* out3) {
 }
 
 int rebcu_com(rebcu_handle* h, double* out10) {
+    GROUP_UNSUPPORTED(h, "rebcu_com");
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     for (int q = 0; q < 10; q++) out10[q] = 0.;
@@ -264,6 +274,7 @@ int rebcu_com(rebcu_handle* h, double* out10) {
 }
 
 int rebcu_angular_momentum(rebcu_handle* h, double* out3) {
+    GROUP_UNSUPPORTED(h, "rebcu_angular_momentum");
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     out3[0] = out3[1] = out3[2] = 0.;

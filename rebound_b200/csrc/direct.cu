@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(256) interleave3_kernel(const double* __restri
 
 // r->gravity_cs of the last COMPENSATED force evaluation as struct reb_vec3d[N] (x,y,z interleaved).
 extern "C" int rebcu_download_gravity_cs(rebcu_handle* h, double* out_xyz, uint64_t N) {
+    GROUP_UNSUPPORTED(h, "rebcu_download_gravity_cs");
     if (!h->resident || !h->gravity_cs_valid) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no compensation terms: the last force evaluation was not REB_GRAVITY_COMPENSATED");
     if (N < h->N) return rebcu_fail(h, REBCU_ERR_CAPACITY, "gravity_cs buffer too small");
     if (h->N == 0) return REBCU_OK;

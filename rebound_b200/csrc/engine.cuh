@@ -27,6 +27,7 @@ enum { TC_DIRECT = 0, TC_KICKDRIFT, TC_TREEBUILD, TC_TREEWALK, TC_COLLISION, TC_
 #define REBCU_MAX_RANKS 16
 
 struct EngineComm;           // comm.cu: NCCL communicator or in-process peer group
+struct rebcu_group;          // group.cu: several GPUs behind one (leader) handle
 
 struct GhostShifts {          // ghost-box offsets, computed on the host exactly as src/boundary.c:145-201
     int n;
@@ -66,6 +67,21 @@ struct TreeBuffers {
     int* flags = nullptr;          // device error flags [8]
     int built_for_n = -1;
     bool prefix_ok = true;         // sorting on a key prefix has not hit a long tie run yet (see tree_build)
+    // sharded build (tree_build_sharded): every rank sorts and builds the subtrees of its own key range
+    bool rec_ready = false;        // walk_rec / walk_m already hold the complete tree (no walk_pack needed)
+    bool complete = true;          // the build's cell arrays (walk_pos, walk_geo, walk_meta) hold the whole tree
+    bool shard_ok = true;          // this simulation has not needed the replicated build yet (very deep trees)
+    int shard_mode = 2;            // 0 never, 1 whenever possible, 2 when N is large enough to pay (rebcu_set_sharded_build)
+    uint64_t* sh_keys = nullptr; uint32_t* sh_idx = nullptr; uint64_t sh_cap_n = 0;    // compacted (key, index) of this rank's key range
+    uint32_t* sh_hist = nullptr;   // [n_buckets] particles per bucket
+    uint64_t* sh_pstart = nullptr; // [n_buckets+1] sorted position where a bucket starts
+    uint64_t* sh_tab = nullptr;    // [n_buckets + 8 W] gathered per-rank status words + per-bucket (first, end) local cell offsets
+    uint32_t* sh_level = nullptr;  // 3 level arrays (count, cells, start) of the top tree
+    long long* sh_delta = nullptr; // [n_buckets] global cell index of a bucket's subtree minus its local offset
+    int4* sh_top = nullptr;        // [n_top] top cells: index, depth, skip, count
+    uint32_t* sh_info = nullptr;   // small result block (see tree.cu)
+    uint64_t sh_buckets_cap = 0;
+    uint64_t last_build_cells_local = 0;
 };
 
 struct rebcu_handle {
@@ -119,6 +135,7 @@ struct rebcu_handle {
     void (*exchange)(void*) = nullptr;    // multi-GPU position exchange hook (see rebcu_set_exchange_callback)
     void* exchange_user = nullptr;
     int exchange_need = REBCU_EXCHANGE_POSITIONS;   // what the running exchange callback must gather
+    rebcu_group* group = nullptr;         // set on the leader handle of a multi-GPU group (group.cu)
     EngineComm* comm = nullptr;           // native exchange (rebcu_comm_init_rank / rebcu_comm_init_all); takes precedence over the callback
     uint64_t* comm_view[F_COUNT] = {};    // LOCAL transport: the arrays the peers pull from during the running exchange
     int comm_view_n = 0;
@@ -135,6 +152,18 @@ struct rebcu_handle {
 };
 
 int rebcu_fail(rebcu_handle* h, int code, const char* msg);
+
+// ---- multi-GPU group (group.cu): calls on the leader fan out to one worker thread per device ----
+#include <functional>
+bool group_active(const rebcu_handle* h);       // h leads a group and the caller is not one of its workers
+int group_run(rebcu_handle* leader, const std::function<int(rebcu_handle*, int)>& fn);
+int group_cfg_call(rebcu_handle* leader, rebcu_config* cfg, const std::function<int(rebcu_handle*, rebcu_config*)>& call);
+int group_upload(rebcu_handle* leader, const rebcu_particle* particles, uint64_t N);
+int group_download(rebcu_handle* leader, rebcu_particle* particles, uint64_t N);
+int group_collisions_fetch(rebcu_handle* leader, rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+int group_size(const rebcu_handle* h);
+void group_destroy(rebcu_handle* leader);
+#define GROUP_UNSUPPORTED(h, what) do { if (group_active(h)) return rebcu_fail((h), REBCU_ERR_ARG, what " is not available on a multi-GPU group handle"); } while (0)
 int rebcu_cuda_fail(rebcu_handle* h, cudaError_t e, const char* where);
 
 #define CU_TRY(h, expr)                                                       \
@@ -154,7 +183,7 @@ struct LaunchScope {
 int engine_reserve(rebcu_handle* h, uint64_t n);
 int engine_exchange(rebcu_handle* h, int need);
 int comm_exchange(rebcu_handle* h, int need);
-int comm_gather_words(rebcu_handle* h, uint64_t* array, uint64_t n_total);
+int comm_gather_ranges(rebcu_handle* h, void** ptrs, const int* bytes, int n_arrays, const uint64_t* bounds);
 void comm_free(rebcu_handle* h);
 int boundary_check_full(rebcu_handle* h, rebcu_config* c);
 int collision_resolve_device(rebcu_handle* h, const rebcu_config* c);

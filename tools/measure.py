@@ -22,6 +22,12 @@ def case(name):
         if "fast" in name:
             cfg.mode = abi.MODE_FAST
         return ics.plummer(n, seed=42), cfg, 5, n * n - n
+    if name.startswith("d"):            # direct BASIC, Plummer sphere, N = 2^k  (d17, d17fast, ...)
+        n = 1 << int(name[1:].replace("fast", ""))
+        cfg = ics.plummer_config(n)
+        if "fast" in name:
+            cfg.mode = abi.MODE_FAST
+        return ics.plummer(n, seed=42), cfg, 2, n * n - n
     if name.startswith("c3s"):          # C3 recipe on one GPU at reduced N
         n = 1 << int(name.split("_")[1].replace("fast","")) if "_" in name else 1 << 18
         cfg = ics.plummer_config(n, gravity=abi.GRAVITY_COMPENSATED)
