@@ -152,8 +152,7 @@ int group_collisions_fetch(rebcu_handle* leader, rebcu_collision* out, uint64_t 
             for (uint64_t k = 0; k < cnt; k++, total++) if (out && total < cap) out[total] = lists[r][pos[r] + k];
             pos[r] += cnt;
         }
-    *n_found = total;
-    leader->col_n = total;
+    *n_found = total;            // (the leader is rank 0's own handle: its col_n stays the count of rank 0's list)
     return REBCU_OK;
 }
 

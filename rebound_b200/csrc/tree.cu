@@ -710,9 +710,9 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
 // a list that grows past gw_abort entries: 32 key-adjacent particles that straddle a large cell boundary have a bounding
 // box many cells wide, against which hardly any cell can be accepted -- a few such groups (lists of 1e5 entries and more)
 // took longer than all others together (97 ms instead of ~3 at N = 2^20, profiles/r02_walk_group_v1_ncu.txt).
-constexpr int GW_WARPS = 4;
-constexpr int GW_STACK = 352;
-constexpr int GW_LIST = 160;
+// Shape of the kernel (template parameters; REBOUND_B200_GW_VARIANT selects one for A/B runs): warps (= groups) per
+// CTA, unroll of the evaluation loop, resident CTAs per SM the register allocation aims at, list / stack entries per warp.
+constexpr int GW_STACK_MAX = 352;
 
 __device__ __forceinline__ double warp_min_d(double v) {
 #pragma unroll
@@ -725,9 +725,10 @@ __device__ __forceinline__ double warp_max_d(double v) {
     return v;
 }
 
+template <int UNROLL>
 __device__ __forceinline__ void gw_evaluate(const double4* __restrict__ ent, const int* __restrict__ tagv, int n, int self,
                                             double px, double py, double pz, double soft2, double& sx, double& sy, double& sz) {
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int j = 0; j < n; j++) {
         const double4 s = ent[j];
         const bool me = tagv[j] == self;                     // own leaf or one of its ghost images: tree.c:311
@@ -739,12 +740,15 @@ __device__ __forceinline__ void gw_evaluate(const double4* __restrict__ ent, con
     }
 }
 
-__global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArgs a, unsigned long long* __restrict__ stats) {
-    __shared__ int2 s_stack[GW_WARPS][GW_STACK];
-    __shared__ double4 s_ent[GW_WARPS][GW_LIST];
-    __shared__ int s_tag[GW_WARPS][GW_LIST];
+// retry: [0] = number of groups that gave up, [1...] = their first work item; walk_retry_kernel finishes them.
+template <int WARPS, int UNROLL, int MINB, int LIST, int STACK>
+__global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const WalkArgs a, unsigned long long* __restrict__ stats,
+                                                                      unsigned int* __restrict__ retry) {
+    __shared__ int2 s_stack[WARPS][STACK];
+    __shared__ double4 s_ent[WARPS][LIST];
+    __shared__ int s_tag[WARPS][LIST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t t0 = ((uint64_t)blockIdx.x * GW_WARPS + w) * 32;
+    const uint64_t t0 = ((uint64_t)blockIdx.x * WARPS + w) * 32;
     if (t0 >= a.n_work) return;                              // warp-uniform; no block-wide barrier below
     const uint64_t t = t0 + lane;
     const bool live = t < a.n_work;
@@ -764,10 +768,11 @@ __global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArg
     const unsigned lt = (1u << lane) - 1u;
     const int n_cells = (int)a.n_cells;
     const int ngb = a.ghosts->n;
+    const int stack_cap = a.gw_stack < STACK ? a.gw_stack : STACK;
     double sx = 0., sy = 0., sz = 0.;
     int nl = 0;
     bool overflow = false;
-    unsigned long long n_ent = 0, n_vis = 0;
+    unsigned int n_ent = 0, n_vis = 0;
     for (int g = 0; g < ngb && !overflow; g++) {
         const double gbx = a.ghosts->gb[g].x, gby = a.ghosts->gb[g].y, gbz = a.ghosts->gb[g].z;
         const double bx = cxg + gbx, by = cyg + gby, bz = czg + gbz;      // centre of the shifted group box (gravity.c:93-97)
@@ -776,7 +781,7 @@ __global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArg
         __syncwarp();
         while (sp > 0) {
             int n = sp < 32 ? sp : 32;
-            if (n > a.gw_stack - sp) n = a.gw_stack - sp;     // every popped range may push two
+            if (n > stack_cap - sp) n = stack_cap - sp;       // every popped range may push two
             if (n < 1) { overflow = true; break; }
             int c = -1, end = 0;
             if (lane < n) { const int2 e = stack[sp - 1 - lane]; c = e.x; end = e.y; }
@@ -810,9 +815,9 @@ __global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArg
             if (sib) stack[sp + __popc(m_sib & lt)] = make_int2(skip, end);
             if (open) stack[sp + n_sib + __popc(m_open & lt)] = make_int2(c + 1, skip);
             sp += n_sib + __popc(m_open);
-            if (nl + n_acc > GW_LIST) {
+            if (nl + n_acc > LIST) {
                 __syncwarp();
-                gw_evaluate(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
+                gw_evaluate<UNROLL>(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
                 n_ent += nl;
                 nl = 0;
                 __syncwarp();
@@ -829,18 +834,31 @@ __global__ void __launch_bounds__(32 * GW_WARPS) walk_group_kernel(const WalkArg
         }
     }
     if (overflow) {
-        // deeper than the stack: every lane walks on its own (same FAST arithmetic class, per-particle criterion)
-        double fx, fy, fz;
-        walk_one_rec<1>(a, (uint32_t)self, px, py, pz, fx, fy, fz);
-        if (live) { a.ax[self] = fx; a.ay[self] = fy; a.az[self] = fz; }
+        // too deep for the stack, or a list far longer than its particles' own lists would be: the group is finished
+        // particle by particle (walk_retry_kernel) -- outside this kernel, so that the slow groups do not hold an SM
+        if (lane == 0) retry[1 + atomicAdd(&retry[0], 1u)] = (unsigned int)(t0 / 32);
         return;
     }
     __syncwarp();
-    gw_evaluate(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
+    gw_evaluate<UNROLL>(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
     n_ent += nl;
     const double negG = -a.G;
     if (live) { a.ax[self] = negG * sx; a.ay[self] = negG * sy; a.az[self] = negG * sz; }
-    if (stats && lane == 0) { atomicAdd(&stats[0], n_ent); atomicAdd(&stats[1], n_vis); atomicAdd(&stats[2], 1ull); }
+    if (stats && lane == 0) { atomicAdd(&stats[0], (unsigned long long)n_ent); atomicAdd(&stats[1], (unsigned long long)n_vis); atomicAdd(&stats[2], 1ull); }
+}
+
+// The particles of the groups that gave up, one thread each, per-particle criterion, FAST arithmetic.  Launched with a
+// grid for the worst case; CTAs beyond the retry count leave at once (no host round trip for the count).
+__global__ void __launch_bounds__(128) walk_retry_kernel(const WalkArgs a, const unsigned int* __restrict__ retry) {
+    const uint64_t slot = ((uint64_t)blockIdx.x * 128 + threadIdx.x) / 32;
+    if (slot >= retry[0]) return;
+    const uint64_t t = (uint64_t)retry[1 + slot] * 32 + (threadIdx.x & 31);
+    if (t >= a.n_work) return;
+    const uint64_t k = a.list ? a.list[t] : t;
+    const uint32_t self = a.perm[k];
+    double sx, sy, sz;
+    walk_one_rec<1>(a, self, a.x[self], a.y[self], a.z[self], sx, sy, sz);
+    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
 }
 
 // Interaction count of the per-particle criterion (what the reference and the STRICT walk evaluate): accepted cells and
@@ -1463,7 +1481,7 @@ static int walk_args_fill(rebcu_handle* h, const rebcu_config* c, WalkArgs& a) {
     { const double w20 = a.w2[0]; unsigned long long u; memcpy(&u, &w20, 8); a.w2_lo = (uint32_t)u; }
     // REBOUND_B200_GW_STACK=<n> shrinks the group walk's traversal stack (tests of the overflow path)
     static const int gw_stack = [] { const char* e = getenv("REBOUND_B200_GW_STACK"); const int v = e ? atoi(e) : 0;
-                                     return (v >= 2 && v <= 352) ? v : 352; }();
+                                     return (v >= 2 && v <= GW_STACK_MAX) ? v : GW_STACK_MAX; }();
     a.gw_stack = gw_stack;
     // a group whose list passes ~6 typical per-particle lists (60 log2 N entries at theta^2 = 0.25, ~theta^-3) is cheaper
     // to finish particle by particle; REBOUND_B200_GW_ABORT=<entries> overrides
@@ -1533,7 +1551,22 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
             if ((err = walk_records(h, a))) return err;
             if (c->mode == REBCU_MODE_FAST && variant == 0) {
                 CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
-                walk_group_kernel<<<div_up(a.n_work, 32 * GW_WARPS), 32 * GW_WARPS, 0, h->stream>>>(a, h->counters + 8);
+                // groups that give up are listed in the (now unused) cell-count array and finished by walk_retry_kernel
+                unsigned int* retry = T.cell_cnt;
+                CU_TRY(h, cudaMemsetAsync(retry, 0, sizeof(unsigned int), h->stream));
+                static const int gv = [] { const char* e = getenv("REBOUND_B200_GW_VARIANT"); return e ? (e[0] | 32) - 'a' : -1; }();
+                const unsigned int ng = div_up(a.n_work, 32);
+                h->launches++;
+                switch (gv) {
+                    case 1:  walk_group_kernel<1, 4, 20, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 2:  walk_group_kernel<1, 4, 32, 96, 224><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 3:  walk_group_kernel<2, 4, 12, 160, 352><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 4:  walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 5:  walk_group_kernel<4, 4, 8, 96, 224><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 6:  walk_group_kernel<1, 2, 32, 96, 224><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    default: walk_group_kernel<4, 4, 5, 160, 352><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                }
+                walk_retry_kernel<<<div_up((uint64_t)ng * 32, 128), 128, 0, h->stream>>>(a, retry);
             } else if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_rec_kernel<false><<<nb, 128, 0, h->stream>>>(a);
         } else if (variant == 1) {

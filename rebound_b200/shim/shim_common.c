@@ -76,6 +76,7 @@ struct shim_state* shim_find(struct reb_simulation* r){
 void shim_forget(struct reb_simulation* r){
     pthread_mutex_lock(&table_lock);
     for (int i=0;i<table_n;i++) if (table[i] && table[i]->r==r){
+        shim_lazy_forget(table[i]);
         if (table[i]->pinned_ptr) rebcu_host_unregister(table[i]->pinned_ptr);
         rebcu_destroy(table[i]->h);
         free(table[i]);
@@ -103,7 +104,8 @@ int shim_resident(const struct reb_simulation* r){
      * integrator step and the heartbeat (shim_integrators.c) */
     const int exits_ok = (!r->exit_max_distance && !r->exit_min_distance)
                       || (r->boundary==REB_BOUNDARY_NONE && r->collision==REB_COLLISION_NONE);
-    return !r->heartbeat && !r->pre_timestep_modifications && !r->post_timestep_modifications
+    /* a heartbeat alone does not end the residency when the particle array can be fetched on demand (shim_lazy.c) */
+    return (!r->heartbeat || shim_lazy_possible(r)) && !r->pre_timestep_modifications && !r->post_timestep_modifications
         && exits_ok && !r->display_data && !r->server_data
         && !r->N_odes;     /* user ODEs are integrated on the host after every step and read r->particles (simulation.c:531-556) */
 }
@@ -161,6 +163,9 @@ static void shim_pin(struct reb_simulation* r, struct shim_state* s){
 }
 
 int shim_to_device(struct reb_simulation* r, struct shim_state* s){
+    /* a protected host copy that the device copy cannot replace (edited / moved / resized array): open it before the upload reads it */
+    if (s->lazy && !(shim_resident(r) && s->device_valid && !r->did_modify_particles && s->uploaded_from==r->particles && s->uploaded_N==r->N))
+        shim_lazy_open(s, 0);
     shim_pin(r, s);
     /* Only a resident simulation trusts the device copy across calls; otherwise every call uploads. */
     if (shim_resident(r) && s->device_valid && !r->did_modify_particles && s->uploaded_from==r->particles && s->uploaded_N==r->N) return 0;
@@ -173,6 +178,7 @@ int shim_to_device(struct reb_simulation* r, struct shim_state* s){
 }
 
 int shim_to_host(struct reb_simulation* r, struct shim_state* s){
+    if (s->lazy) shim_lazy_open(s, 1);      /* lifts the protection and downloads if the host is behind */
     if (!s->host_stale) return 0;
     const uint64_t n = rebcu_N(s->h);
     if (n > r->N_allocated) return shim_report(r, s, REBCU_ERR_CAPACITY);

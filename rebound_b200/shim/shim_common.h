@@ -29,6 +29,8 @@ struct shim_state {
     void* pinned_ptr;            /* r->particles as registered with cudaHostRegister (REBOUND_B200_PIN=1) */
     size_t pinned_bytes;
     int subset_set;              /* the engine holds a collision subset (r->map / r->N_targets) from the previous search */
+    int lazy;                    /* r->particles is page-protected while the device copy is ahead (shim_lazy.c) */
+    unsigned long lazy_faults;   /* downloads triggered by somebody touching the protected array */
 };
 
 /* Returns the per-simulation state (creating the rebcu handle on first use); NULL + reb_simulation_error
@@ -65,6 +67,12 @@ int shim_report(struct reb_simulation* r, struct shim_state* s, int err);
 int shim_to_device(struct reb_simulation* r, struct shim_state* s);
 /* Make r->particles current: downloads if the device is ahead. */
 int shim_to_host(struct reb_simulation* r, struct shim_state* s);
+
+/* Lazy host copy under a heartbeat (shim_lazy.c). */
+int shim_lazy_possible(const struct reb_simulation* r);
+void shim_lazy_protect(struct reb_simulation* r, struct shim_state* s);
+void shim_lazy_open(struct shim_state* s, int keep_device);
+void shim_lazy_forget(struct shim_state* s);
 
 #pragma GCC visibility pop
 #endif

@@ -31,6 +31,7 @@ void reb_collision_search_cpuref(struct reb_simulation* const r);
 static void gravity_gpu(struct reb_simulation* r){
     struct shim_state* s = shim_get(r);
     if (!s) return;
+    if (s->lazy && !s->host_stale) shim_lazy_open(s, 0);      /* host copy current but read-only (shim_lazy.c): the host path below writes it */
     rebcu_config c;
     shim_fill_config(r, &c);
     if (s->host_stale){
@@ -81,6 +82,7 @@ void reb_gravity_tree_calculate_acceleration(struct reb_simulation* r){
 void reb_gravity_basic_calculate_and_apply_jerk(struct reb_simulation* r, const double v){
     struct shim_state* s = shim_get(r);
     if (!s) return;
+    if (s->lazy && !s->host_stale) shim_lazy_open(s, 0);      /* host copy current but read-only (shim_lazy.c): the host path below writes it */
     rebcu_config c;
     shim_fill_config(r, &c);
     if (s->host_stale){
@@ -97,6 +99,7 @@ void reb_boundary_check(struct reb_simulation* r){
     if (r->boundary==REB_BOUNDARY_NONE) return;
     struct shim_state* s = shim_get(r);
     if (!s) return;
+    if (s->lazy && !s->host_stale) shim_lazy_open(s, 0);      /* host copy current but read-only (shim_lazy.c): the host path below writes it */
     if (r->boundary==REB_BOUNDARY_OPEN && (r->track_energy_offset || r->free_particle_ap || r->integrator.callbacks.will_remove_particle)){
         if (shim_to_host(r, s)) return;
         reb_boundary_check_cpuref(r);
@@ -142,6 +145,7 @@ void reb_collision_search(struct reb_simulation* const r){
     }
     struct shim_state* s = shim_get(r);
     if (!s) return;
+    if (s->lazy && !s->host_stale) shim_lazy_open(s, 0);      /* host copy current but read-only (shim_lazy.c): the host path below writes it */
     r->N_collisions = 0;
     rebcu_config c;
     shim_fill_config(r, &c);

@@ -102,6 +102,7 @@ static void device_step(struct reb_simulation* r, void (*host_step)(struct reb_s
         r->N = rebcu_N(s->h);            /* tree gravity + open boundary may have removed particles */
         s->uploaded_N = r->N;
         r->is_synchronized = 0;
+        if (r->heartbeat && shim_residency()==SHIM_AUTO) shim_lazy_protect(r, s);   /* the heartbeat may look: fetch on demand */
         if (exits){
             int escape = 0, encounter = 0;
             err = rebcu_exit_check(s->h, r->exit_max_distance, r->exit_min_distance, &escape, &encounter);

@@ -39,6 +39,7 @@ static int batching_disabled(void){
 static int batch_possible(const struct reb_simulation* r){
     if (batching_disabled() || shim_residency()!=SHIM_AUTO) return 0;
     if (!shim_resident(r)) return 0;                               /* heartbeat, timestep hooks, viewer, exit distances with boundary/collisions */
+    if (r->heartbeat) return 0;                                    /* called after every step */
     if (r->exit_max_distance || r->exit_min_distance) return 0;    /* checked after every step: keep the per-step path */
     if (r->simulationarchive_filename) return 0;
     if (r->collision!=REB_COLLISION_NONE) return 0;                /* the resolve loop runs on the host after every search */

@@ -69,6 +69,27 @@ static void ode_rhs(struct reb_ode* const ode, double* const yDot, const double*
 }
 static void ode_pre(struct reb_ode* const ode, const double* const y0){ (void)y0; ode->y[1] += 1e-3*ode->r->particles[1].x; }
 
+/* heartbeats of the "lazy*" scenarios: what a heartbeat may do with r->particles */
+static double hb_sum = 0.;
+static void hb_blind(struct reb_simulation* r){ heartbeat_calls++; hb_sum += r->t; }                 /* never looks at the particles */
+static void hb_reader(struct reb_simulation* r){                                                      /* reads them every 5th step */
+    heartbeat_calls++;
+    if (r->steps_done%5==0) for (size_t i=0;i<r->N;i+=97) hb_sum += r->particles[i].x + r->particles[i].vy;
+}
+static void hb_writer(struct reb_simulation* r){                                                      /* edits them every 7th step */
+    heartbeat_calls++;
+    if (r->steps_done%7==3){ r->particles[5].vx += 1e-3; r->particles[r->N-1].z *= 1.0001; }
+}
+static void hb_grower(struct reb_simulation* r){                                                      /* adds / removes particles */
+    heartbeat_calls++;
+    if (r->steps_done==4 || r->steps_done==9){
+        struct reb_particle p = {0};
+        p.x = 0.3 + 0.01*(double)r->steps_done; p.y = -0.2; p.z = 0.1; p.m = 1e-4;
+        reb_simulation_add(r, p);
+    }
+    if (r->steps_done==6) reb_simulation_remove_particle(r, 17);
+}
+
 static void* thread_main(void* arg){
     struct reb_simulation* r = arg;
     reb_simulation_steps(r, 7);
@@ -319,6 +340,20 @@ int main(int argc, char** argv){
         reb_simulation_integrate(r, r->t + 0.0777); dump("od2 ", r); fwrite(ode->y, sizeof(double), 2, out);
         reb_ode_free(ode);
         reb_simulation_steps(r, 5); dump("od3 ", r);
+        reb_simulation_free(r);
+    }else if (strncmp(scen, "lazy", 4)==0){
+        /* a heartbeat is installed (as in every example of the reference): the particle array is large enough for
+         * the drop-in to keep it on the device and fetch the host copy only when the heartbeat touches it */
+        const int n = N < 3000 ? 3000 : N;
+        struct reb_simulation* r = make(31, n);
+        hb_sum = 0.; heartbeat_calls = 0;
+        r->heartbeat = strcmp(scen,"lazy_blind")==0 ? hb_blind : strcmp(scen,"lazy_read")==0 ? hb_reader
+                     : strcmp(scen,"lazy_write")==0 ? hb_writer : hb_grower;
+        reb_simulation_steps(r, 12); dump("lz1 ", r);
+        reb_simulation_integrate(r, r->t + 8.5*r->dt); dump("lz2 ", r);
+        fwrite(&hb_sum, sizeof(double), 1, out); fwrite(&heartbeat_calls, sizeof(int), 1, out);
+        r->heartbeat = NULL;
+        reb_simulation_steps(r, 3); dump("lz3 ", r);
         reb_simulation_free(r);
     }else if (strcmp(scen, "sigint")==0){
         /* Ctrl-C during a long integration (the test harness makes the mock engine raise SIGINT in the middle of a

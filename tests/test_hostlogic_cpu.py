@@ -356,3 +356,37 @@ def test_ctrl_c_during_a_device_batch_ends_the_integration(mock_driver, times, t
     assert abs(info[2] - info[3] * 0.01) < 1e-9 and info[2] < 500.0
     hdr = raw[32 + 4:32 + 4 + 40].view(np.float64)
     assert hdr[0] == 40 and hdr[1] == info[2]
+
+
+@pytest.mark.parametrize("scen", ["lazy_blind", "lazy_read", "lazy_write", "lazy_grow"])
+def test_heartbeat_keeps_the_particles_on_the_device_until_somebody_looks(mock_driver, scen, tmp_path):
+    """shim_lazy.c: with a heartbeat installed the automatic mode stays resident and page-protects r->particles; the host
+    copy is fetched when (and only when) the heartbeat -- or anything else -- touches it.  Results: the reference's bits
+    in every mode; transfers: a heartbeat that never looks costs one upload and one download per call, a reader one
+    download per step it reads in, a writer additionally one upload per edit."""
+    ref_out = tmp_path / "ref.bin"
+    r = subprocess.run([os.path.join(BUILD, "hl_ref"), scen, str(ref_out), "3000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    ref = ref_out.read_bytes()
+    counts = {}
+    for value, name, lazy in (("0", "host", "1"), ("1", "resident", "1"), ("", "auto", "1"), ("", "auto_nolazy", "0")):
+        if name == "resident" and scen != "lazy_blind":
+            continue        # explicit residency is WHFast's protocol: a heartbeat must call reb_simulation_synchronize before it looks
+        out = tmp_path / f"mock_{name}.bin"
+        st = tmp_path / f"st_{name}.json"
+        e = dict(os.environ, REBOUND_B200_RESIDENT=value, REBOUND_B200_LAZY=lazy, MOCK_ENGINE_STATS=str(st))
+        r = subprocess.run([os.path.join(BUILD, "hl_mock"), scen, str(out), "3000"], capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        assert out.read_bytes() == ref, (scen, name)
+        counts[name] = json.loads(st.read_text())
+    a, b = counts["auto"], counts["auto_nolazy"]
+    assert b["downloads"] >= 20 and b["uploads"] >= 20           # without the mechanism: both ways every step
+    if scen == "lazy_blind":
+        # three calls (steps, integrate incl. its shortened last step, steps): a handful of transfers in total
+        assert a["uploads"] <= 5 and a["downloads"] <= 5
+    elif scen == "lazy_read":
+        assert a["uploads"] <= 5 and 4 <= a["downloads"] <= 10     # one download per read step
+    elif scen == "lazy_write":
+        assert a["uploads"] <= 9 and a["downloads"] <= 10           # + one upload per edit
+    else:
+        assert a["uploads"] <= 9 and a["downloads"] <= 10
