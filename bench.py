@@ -602,17 +602,20 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
             cls = "treewalk"
             st = results[mname]["walk_stats"]
             k_ms = tim[cls]["ms"]                      # walk_pack + walk of one force evaluation
-            evaluated = st["group_entries"] * 32 if tag == "fast" else st["interactions"]
-            dp = (17.0 if tag == "fast" else 36.0) * evaluated
-            kern = "walk_group_kernel" if tag == "fast" else "walk_rec_kernel"
+            grouped = tag == "fast" and st["groups"] > 0        # FAST without ghost boxes: the group walk
+            evaluated = st["group_entries"] * 32 if grouped else st["interactions"]
+            # FP64-pipe instructions: 17 (FAST) / 36 (STRICT) per pair term; the per-particle walks add 8 per visited cell
+            dp = 17.0 * evaluated if grouped else (17.0 if tag == "fast" else 36.0) * evaluated + 8.0 * st["visits"]
+            kern = "walk_group_kernel" if grouped else ("walk_rec_kernel<FAST>" if tag == "fast" else "walk_rec_kernel")
             roof = fp64_roofline(kern, 20.0 * st["interactions"], k_ms, fp64_peak, dp, sm_mhz, tim[cls]["ms"] / total,
                                  traffic.get(f"{name}_{tag}"),
                                  "algorithmic work = the interactions of the reference's per-particle opening criterion on this tree "
                                  f"({st['interactions'] / max(1, n / ctx.world):.0f} per particle) x 20 flop; the group walk evaluates "
-                                 f"{st['group_entries'] * 32 / max(1, st['interactions']):.2f}x as many pair terms (stricter group criterion)" if tag == "fast" else
-                                 "algorithmic work = accepted cells + leaves of the per-particle walk x 20 flop; 36 FP64-pipe instructions per interaction + 8 per visited cell")
+                                 f"{st['group_entries'] * 32 / max(1, st['interactions']):.2f}x as many pair terms (stricter group criterion)" if grouped else
+                                 "algorithmic work = accepted cells + leaves of the per-particle walk x 20 flop; "
+                                 f"{17 if tag == 'fast' else 36} FP64-pipe instructions per interaction + 8 per visited cell")
             roof["interactions_per_particle"] = st["interactions"] / max(1, n / ctx.world)
-            if tag == "fast":
+            if grouped:
                 roof["evaluated_pair_terms_per_particle"] = st["group_entries"] * 32 / max(1, n / ctx.world)
             # the build is the HBM-bound part of the step (keys 36 B + sort 4 x 24 B + cells 1.5 x 64 + 32 B per particle)
             if "treebuild" in tim:

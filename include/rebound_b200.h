@@ -243,6 +243,31 @@ int rebcu_collision_resolve(rebcu_handle* h, const rebcu_config* cfg);
 /* r->collisions_plog, r->collisions_log_n, r->rand_seed as the device resolver advanced them; rounds of the last call. */
 int rebcu_collision_stats(const rebcu_handle* h, double* plog, uint64_t* log_n, unsigned int* rand_seed, int* rounds_last);
 
+/* ---- exact collision resolve: the device keeps the order, the caller does the arithmetic ---------------
+ * The resolve loop of reb_collision_search (src/collision.c:336-404) applied to the list of the last search WITHOUT
+ * bringing the particles to the host: the rand_r shuffle, the sequential semantics (conflict-free rounds) and the two
+ * early exits of reb_collision_resolve_hardsphere (no overlap / not approaching, :598,602; exact IEEE arithmetic) run
+ * on the device; the collisions that pass them are handed to `fn` in batches whose pairs share no particle, with the
+ * current state of both particles (s1, s2 = x y z vx vy vz m r).  fn fills v1, v2 (new velocities), plog_term (its
+ * contribution to r->collisions_plog) and logged (1 if it counted the collision in r->collisions_log_n); it may work
+ * on the batch in parallel.  The drop-in's fn runs the reference's own reb_collision_resolve_hardsphere -- with the
+ * user's coefficient_of_restitution callback -- on a two-particle scratch simulation, so velocities, collisions_plog
+ * (summed in the sequential loop's order) and collisions_log_n are the reference's bits.  Only resolvers that touch
+ * nothing but the two particles and never remove one qualify (the built-in hard-sphere resolver does).
+ * *rand_seed is advanced as r->rand_seed would be; *plog / *log_n are updated in place. */
+typedef struct rebcu_resolve_pair {
+    uint64_t k;                 /* position in the shuffled list */
+    uint64_t p1, p2;
+    rebcu_vec6d gb;
+    double s1[8], s2[8];
+    double v1[3], v2[3];
+    double plog_term;
+    uint64_t logged;
+} rebcu_resolve_pair;
+typedef int (*rebcu_pair_resolver)(void* user, rebcu_resolve_pair* pairs, uint64_t n);
+int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebcu_pair_resolver fn, void* user,
+                                  double* plog, uint64_t* log_n, int* rounds);
+
 /* ---- multi-GPU sharding ------------------------------------------------------- */
 /* Rank `rank` of `world` owns the contiguous i-block [N*rank/world, N*(rank+1)/world): the direct
  * and tree force kernels and kick/drift touch only that block; positions of the other blocks are

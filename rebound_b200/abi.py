@@ -196,6 +196,7 @@ PRODUCT_SIGNATURES = {
     "set_device_resolve": (C.c_int, [_P, C.c_int, C.POINTER(Restitution), C.c_double, C.c_uint]),
     "collision_resolve": (C.c_int, [_P, _CFG]),
     "collision_stats": (C.c_int, [_P, _DBLP, _U64P, C.POINTER(C.c_uint), C.POINTER(C.c_int)]),
+    "collision_resolve_pairs": (C.c_int, [_P, C.POINTER(C.c_uint), _P, _P, _DBLP, _U64P, C.POINTER(C.c_int)]),
     "set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "shard_range": (None, [_P, _U64P, _U64P]),
     "set_exchange_callback": (C.c_int, [_P, _P, _P]),

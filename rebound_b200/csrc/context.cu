@@ -80,6 +80,7 @@ void rebcu_destroy(rebcu_handle* h) {
     for (int k = 0; k < 3; k++) if (h->aux_ev[k]) cudaEventDestroy(h->aux_ev[k]);
     for (int k = 0; k < 3 * PIPE_RANGES; k++) if (h->pipe_ev[k]) cudaEventDestroy(h->pipe_ev[k]);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->pairs_host) cudaFreeHost(h->pairs_host);
     if (h->ghost_ring) cudaFreeHost(h->ghost_ring);
     for (int i = 0; i < GHOST_RING; i++) if (h->ghost_ring_ev[i]) cudaEventDestroy(h->ghost_ring_ev[i]);
     for (auto& r : h->ranges) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -129,6 +129,7 @@ struct rebcu_handle {
     bool resolve_on = false; rebcu_restitution resolve_rest = {0, 0, 1.0, 0, 0, 0, 1}; double resolve_min_v = 0;
     unsigned int resolve_seed = 0; double resolve_plog = 0; uint64_t resolve_log_n = 0; int resolve_rounds = 0;
     uint32_t* resolve_buf = nullptr; uint64_t resolve_cap = 0;
+    void* pairs_host = nullptr; uint64_t pairs_host_cap = 0;     // pinned staging of the exact (host-assisted) resolve
     double* row_buf = nullptr; uint64_t row_cap = 0;        // state + term buffer of the massive-row path (testparticle_type 1)
     double* diag_partial = nullptr; uint64_t diag_cap = 0;  // per-block partial sums of the diagnostics
     double* tp_hist = nullptr; uint64_t tp_hist_cap = 0;   // per-step snapshots of the massive bodies

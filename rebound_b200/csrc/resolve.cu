@@ -17,9 +17,11 @@
 // for resident simulations driven through the C ABI (rebcu_set_device_resolve), where it removes the per-step
 // download + serial host loop (C5: ~7e5 list entries per step).
 #include "engine.cuh"
+#include "strict_math.cuh"
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
+#include <algorithm>
 
 namespace {
 
@@ -131,6 +133,57 @@ __global__ void __launch_bounds__(256) plog_partial_kernel(const double* __restr
 
 }  // namespace
 
+// ---- exact resolve: the device keeps the order, the CALLER does the arithmetic ----------------------------------------
+// For the drop-in, which owes the reference's bits.  The transcendental functions of the resolver (atan2 / sin / cos in
+// reb_collision_resolve_hardsphere, pow in a user's restitution law) cannot be reproduced on the device, but everything
+// around them can: the rand_r shuffle, the conflict-free rounds that keep the sequential semantics, and the two early
+// exits of the resolver (no overlap / not approaching: src/collision.c:598,602 -- plain IEEE arithmetic, evaluated here
+// with the reference's expression order).  Only the collisions that pass them travel to the host, as small records with
+// the current state of their two particles; the caller's resolver (the reference's own function, run on a two-particle
+// scratch simulation by the shim, in parallel -- the pairs of a round share no particle) returns the new velocities, which
+// are scattered back.  Per step this moves a few tens of MB instead of the whole particle array both ways, and the host
+// loop runs on all cores instead of one.  collisions_plog is summed by the caller's order (processing position), so it
+// matches the sequential loop bit for bit as well.
+struct PairIn { uint32_t k, p1, p2, pad; rebcu_vec6d gb; double s1[8], s2[8]; };          // 192 B
+struct PairsArgs {
+    ResolveArgs R;
+    PairIn* in; unsigned int* n_pairs; unsigned int cap;
+};
+
+__global__ void __launch_bounds__(256) ready_kernel(PairsArgs P) {
+    const ResolveArgs& A = P.R;
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= A.n || A.done[k]) return;
+    const rebcu_collision c = A.list[A.order[k]];
+    const uint32_t p1 = (uint32_t)c.p1, p2 = (uint32_t)c.p2;
+    if (A.first[p1] != k || A.first[p2] != k) { atomicAdd(&A.counters[0], 1ull); return; }     // an earlier collision is pending
+    A.done[k] = 1;
+    const double x1 = A.x[p1], y1 = A.y[p1], z1 = A.z[p1], x2 = A.x[p2], y2 = A.y[p2], z2 = A.z[p2];
+    const double x21 = s_sub(s_add(x1, c.gb.x), x2), y21 = s_sub(s_add(y1, c.gb.y), y2), z21 = s_sub(s_add(z1, c.gb.z), z2);
+    const double r1 = A.r[p1], r2 = A.r[p2];
+    const double rp = s_add(r1, r2);
+    const double d2 = s_add(s_add(s_mul(x21, x21), s_mul(y21, y21)), s_mul(z21, z21));
+    if (s_mul(rp, rp) < d2) return;                                                          // collision.c:598
+    const double v1x = A.vx[p1], v1y = A.vy[p1], v1z = A.vz[p1], v2x = A.vx[p2], v2y = A.vy[p2], v2z = A.vz[p2];
+    const double vx21 = s_sub(s_add(v1x, c.gb.vx), v2x), vy21 = s_sub(s_add(v1y, c.gb.vy), v2y), vz21 = s_sub(s_add(v1z, c.gb.vz), v2z);
+    if (s_add(s_add(s_mul(vx21, x21), s_mul(vy21, y21)), s_mul(vz21, z21)) > 0) return;      // collision.c:602: not approaching
+    const unsigned int slot = atomicAdd(P.n_pairs, 1u);
+    if (slot >= P.cap) return;                            // cannot happen: cap >= N/2 pairs share no particle
+    PairIn q;
+    q.k = k; q.p1 = p1; q.p2 = p2; q.pad = 0; q.gb = c.gb;
+    q.s1[0] = x1; q.s1[1] = y1; q.s1[2] = z1; q.s1[3] = v1x; q.s1[4] = v1y; q.s1[5] = v1z; q.s1[6] = A.m[p1]; q.s1[7] = r1;
+    q.s2[0] = x2; q.s2[1] = y2; q.s2[2] = z2; q.s2[3] = v2x; q.s2[4] = v2y; q.s2[5] = v2z; q.s2[6] = A.m[p2]; q.s2[7] = r2;
+    P.in[slot] = q;
+}
+
+__global__ void __launch_bounds__(256) apply_pairs_kernel(ResolveArgs A, const rebcu_resolve_pair* __restrict__ pairs, unsigned int n) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const rebcu_resolve_pair& q = pairs[j];
+    A.vx[q.p1] = q.v1[0]; A.vy[q.p1] = q.v1[1]; A.vz[q.p1] = q.v1[2];
+    A.vx[q.p2] = q.v2[0]; A.vy[q.p2] = q.v2[1]; A.vz[q.p2] = q.v2[2];
+}
+
 // Resolves the list the last collision search left on the device.  Returns the number of rounds in *rounds (may be null).
 int collision_resolve_device(rebcu_handle* h, const rebcu_config* c) {
     (void)c;
@@ -222,6 +275,118 @@ int rebcu_collision_resolve(rebcu_handle* h, const rebcu_config* cfg) {
     CU_TRY(h, cudaSetDevice(h->device));
     if (h->world > 1) return rebcu_fail(h, REBCU_ERR_ARG, "device resolve while sharded over several GPUs is not implemented");
     return collision_resolve_device(h, cfg);
+}
+
+int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebcu_pair_resolver fn, void* user,
+                                  double* plog, uint64_t* log_n, int* rounds_out) {
+    if (!h->resident) return rebcu_fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
+    GROUP_UNSUPPORTED(h, "rebcu_collision_resolve_pairs");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (h->world > 1) return rebcu_fail(h, REBCU_ERR_ARG, "collision resolve while sharded over several GPUs is not implemented");
+    const uint64_t n = h->col_n;
+    if (rounds_out) *rounds_out = 0;
+    if (n == 0) return REBCU_OK;
+    if (n >= NONE) return rebcu_fail(h, REBCU_ERR_ARG, "device resolve supports fewer than 2^32 list entries");
+    std::vector<uint32_t> order(n);
+    for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    for (uint64_t i = 0; i < n; i++) {                     // collision.c:337-342
+        const uint64_t j = (uint64_t)rand_r(rand_seed) % n;
+        const uint32_t t = order[i]; order[i] = order[j]; order[j] = t;
+    }
+    const uint64_t pair_cap = (n < h->N / 2 + 1) ? n : h->N / 2 + 1;
+    const uint64_t words = n /*order*/ + h->cap /*first*/ + (n + 3) / 4 /*done*/ + 64
+                         + pair_cap * (sizeof(PairIn) + sizeof(rebcu_resolve_pair)) / 4;
+    if (h->resolve_cap < words) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->resolve_buf); h->resolve_buf = nullptr; h->resolve_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->resolve_buf, (words + words / 4) * sizeof(uint32_t)));
+        h->resolve_cap = words + words / 4;
+    }
+    if (h->pairs_host_cap < pair_cap) {
+        if (h->pairs_host) cudaFreeHost(h->pairs_host);
+        h->pairs_host = nullptr; h->pairs_host_cap = 0;
+        CU_TRY(h, cudaMallocHost(&h->pairs_host, (pair_cap + pair_cap / 4 + 16) * (sizeof(PairIn) + sizeof(rebcu_resolve_pair))));
+        h->pairs_host_cap = pair_cap + pair_cap / 4 + 16;
+    }
+    PairIn* in_host = (PairIn*)h->pairs_host;
+    rebcu_resolve_pair* out_host = (rebcu_resolve_pair*)(in_host + h->pairs_host_cap);
+    uint32_t* base = h->resolve_buf;
+    PairsArgs P;
+    ResolveArgs& A = P.R;
+    P.in = (PairIn*)base;                                  // 8-byte aligned first
+    rebcu_resolve_pair* out_dev = (rebcu_resolve_pair*)(P.in + pair_cap);
+    A.order = (uint32_t*)(out_dev + pair_cap);
+    A.first = (uint32_t*)A.order + n;
+    A.done = (uint8_t*)(A.first + h->cap);
+    A.plog_term = nullptr;
+    A.x = h->f(F_X); A.y = h->f(F_Y); A.z = h->f(F_Z); A.vx = h->f(F_VX); A.vy = h->f(F_VY); A.vz = h->f(F_VZ);
+    A.m = h->f(F_M); A.r = h->f(F_R);
+    A.list = h->col_list; A.n = (uint32_t)n;
+    A.counters = h->counters + 8;
+    A.rest = h->resolve_rest; A.min_v = 0;
+    P.n_pairs = (unsigned int*)(h->counters + 10);
+    P.cap = (unsigned int)pair_cap;
+    CU_TRY(h, cudaMemcpyAsync((void*)A.order, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemsetAsync(A.first, 0xff, h->cap * sizeof(uint32_t), h->stream));
+    CU_TRY(h, cudaMemsetAsync(A.done, 0, n, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
+    std::vector<double> terms;                 // (processing position, term) of the logged collisions
+    std::vector<uint32_t> term_k;
+    const unsigned nb = div_up(n, 256);
+    unsigned long long* pin = h->pinned + 20;
+    int rounds = 0;
+    for (;;) {
+        {
+            LaunchScope ls(h, TC_COLLISION, 2);
+            claim_kernel<<<nb, 256, 0, h->stream>>>(A);
+            ready_kernel<<<nb, 256, 0, h->stream>>>(P);
+        }
+        rounds++;
+        CU_TRY(h, cudaMemcpyAsync(pin, h->counters + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        const unsigned long long pending = pin[0];
+        const unsigned int np = (unsigned int)(pin[2] & 0xffffffffull);
+        if (np > pair_cap) return rebcu_fail(h, REBCU_ERR_CAPACITY, "pair buffer overflow in the exact resolve");
+        if (np) {
+            CU_TRY(h, cudaMemcpyAsync(in_host, P.in, np * sizeof(PairIn), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            for (unsigned int j = 0; j < np; j++) {
+                rebcu_resolve_pair& q = out_host[j];
+                const PairIn& s = in_host[j];
+                q.k = s.k; q.p1 = s.p1; q.p2 = s.p2; q.gb = s.gb;
+                memcpy(q.s1, s.s1, sizeof(q.s1)); memcpy(q.s2, s.s2, sizeof(q.s2));
+                q.v1[0] = s.s1[3]; q.v1[1] = s.s1[4]; q.v1[2] = s.s1[5];
+                q.v2[0] = s.s2[3]; q.v2[1] = s.s2[4]; q.v2[2] = s.s2[5];
+                q.plog_term = 0; q.logged = 0;
+            }
+            const int ferr = fn(user, out_host, np);
+            if (ferr) return rebcu_fail(h, REBCU_ERR_ARG, "the pair resolver reported an error");
+            for (unsigned int j = 0; j < np; j++) if (out_host[j].logged) { terms.push_back(out_host[j].plog_term); term_k.push_back((uint32_t)out_host[j].k); }
+            CU_TRY(h, cudaMemcpyAsync(out_dev, out_host, np * sizeof(rebcu_resolve_pair), cudaMemcpyHostToDevice, h->stream));
+            LaunchScope ls(h, TC_COLLISION, 1);
+            apply_pairs_kernel<<<div_up(np, 256), 256, 0, h->stream>>>(A, out_dev, np);
+        }
+        {
+            LaunchScope ls(h, TC_COLLISION, 1);
+            release_kernel<<<nb, 256, 0, h->stream>>>(A);
+        }
+        CU_TRY(h, cudaGetLastError());
+        if (pending == 0) break;
+        if (rounds > 100000) return rebcu_fail(h, REBCU_ERR_CUDA, "exact resolve did not terminate");
+    }
+    // collisions_plog += term, in the order of the sequential loop (collision.c:351, 655-661)
+    std::vector<uint32_t> idx(terms.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return term_k[a] < term_k[b]; });
+    double pl = *plog;
+    for (size_t i = 0; i < idx.size(); i++) pl += terms[idx[i]];
+    *plog = pl;
+    *log_n += terms.size();
+    h->resolve_rounds = rounds;
+    if (rounds_out) *rounds_out = rounds;
+    h->col_n = 0;                                           // consumed
+    return REBCU_OK;
 }
 
 int rebcu_collision_stats(const rebcu_handle* h, double* plog, uint64_t* log_n, unsigned int* rand_seed, int* rounds_last) {

@@ -725,17 +725,18 @@ __device__ __forceinline__ double warp_max_d(double v) {
     return v;
 }
 
+// soft2 > 0 always (a vanishing softening is replaced by 1e-200, which no real squared distance notices): the own leaf of a
+// lane's particle then contributes f * 0 = 0 exactly, so the list needs no per-entry "is this me" test (the kernel is only
+// used without ghost boxes, where a particle's own leaf holds exactly its own position; tree.c:311).
 template <int UNROLL>
-__device__ __forceinline__ void gw_evaluate(const double4* __restrict__ ent, const int* __restrict__ tagv, int n, int self,
-                                            double px, double py, double pz, double soft2, double& sx, double& sy, double& sz) {
+__device__ __forceinline__ void gw_evaluate(const double4* __restrict__ ent, int n, double px, double py, double pz, double soft2,
+                                            double& sx, double& sy, double& sz) {
 #pragma unroll UNROLL
     for (int j = 0; j < n; j++) {
         const double4 s = ent[j];
-        const bool me = tagv[j] == self;                     // own leaf or one of its ghost images: tree.c:311
         const double dx = px - s.x, dy = py - s.y, dz = pz - s.z;
-        double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
-        r2 = me ? 1.0 : r2;
-        const double f = fast_m_over_r3(r2, me ? 0.0 : s.w);
+        const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
+        const double f = fast_m_over_r3(r2, s.w);
         sx = fma(f, dx, sx); sy = fma(f, dy, sy); sz = fma(f, dz, sz);
     }
 }
@@ -746,7 +747,6 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
                                                                       unsigned int* __restrict__ retry) {
     __shared__ int2 s_stack[WARPS][STACK];
     __shared__ double4 s_ent[WARPS][LIST];
-    __shared__ int s_tag[WARPS][LIST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint64_t t0 = ((uint64_t)blockIdx.x * WARPS + w) * 32;
     if (t0 >= a.n_work) return;                              // warp-uniform; no block-wide barrier below
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
     const double hxg = fmax(hix - cxg, cxg - lox), hyg = fmax(hiy - cyg, cyg - loy), hzg = fmax(hiz - czg, czg - loz);
     int2* stack = s_stack[w];
     double4* ent = s_ent[w];
-    int* tagv = s_tag[w];
+    const double soft2 = a.soft2 > 0. ? a.soft2 : 1e-200;
     const unsigned lt = (1u << lane) - 1u;
     const int n_cells = (int)a.n_cells;
     const int ngb = a.ghosts->n;
@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
             sp += n_sib + __popc(m_open);
             if (nl + n_acc > LIST) {
                 __syncwarp();
-                gw_evaluate<UNROLL>(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
+                gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
                 n_ent += nl;
                 nl = 0;
                 __syncwarp();
@@ -826,7 +826,6 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
             if (acc) {
                 const int slot = nl + __popc(m_acc & lt);
                 ent[slot] = make_double4(q.x - gbx, q.y - gby, q.z - gbz, cm);
-                tagv[slot] = tag < 0 ? -1 : tag;
             }
             nl += n_acc;
             n_vis += n;
@@ -840,7 +839,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
         return;
     }
     __syncwarp();
-    gw_evaluate<UNROLL>(ent, tagv, nl, self, px, py, pz, a.soft2, sx, sy, sz);
+    gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
     n_ent += nl;
     const double negG = -a.G;
     if (live) { a.ax[self] = negG * sx; a.ay[self] = negG * sy; a.az[self] = negG * sz; }
@@ -1549,7 +1548,10 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
             else walk_quad_kernel<false><<<nb, 128, 0, h->stream>>>(a);
         } else if (variant == 0 || variant == 3) {
             if ((err = walk_records(h, a))) return err;
-            if (c->mode == REBCU_MODE_FAST && variant == 0) {
+            // the group walk pays without ghost boxes; with them every group would traverse the tree once per box (25 times
+            // for the shearing sheet: 2.8 ms against 1.8 ms per-particle at N = 2^20), and a particle's ghost images would
+            // need a per-entry identity test
+            if (c->mode == REBCU_MODE_FAST && variant == 0 && g.n == 1) {
                 CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
                 // groups that give up are listed in the (now unused) cell-count array and finished by walk_retry_kernel
                 unsigned int* retry = T.cell_cnt;
@@ -1564,7 +1566,10 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
                     case 4:  walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
                     case 5:  walk_group_kernel<4, 4, 8, 96, 224><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
                     case 6:  walk_group_kernel<1, 2, 32, 96, 224><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
-                    default: walk_group_kernel<4, 4, 5, 160, 352><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 0:  walk_group_kernel<4, 4, 5, 160, 352><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    // shapes measured at N = 2^20 / 2^22 (profiles/r02_walk_group_shapes.txt): all within 8 % -- the kernel is
+                    // bound by its instruction mix, not by occupancy; one warp per CTA with the deepest unroll is the best
+                    default: walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
                 }
                 walk_retry_kernel<<<div_up((uint64_t)ng * 32, 128), 128, 0, h->stream>>>(a, retry);
             } else if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);

@@ -68,6 +68,10 @@ int shim_to_device(struct reb_simulation* r, struct shim_state* s);
 /* Make r->particles current: downloads if the device is ahead. */
 int shim_to_host(struct reb_simulation* r, struct shim_state* s);
 
+/* Collision resolve without the particles on the host (shim_hotpath.c). */
+int shim_resolve_on_device(const struct reb_simulation* r, const struct shim_state* s);
+int shim_resolve_pairs(struct reb_simulation* r, struct shim_state* s);
+
 /* Lazy host copy under a heartbeat (shim_lazy.c). */
 int shim_lazy_possible(const struct reb_simulation* r);
 void shim_lazy_protect(struct reb_simulation* r, struct shim_state* s);

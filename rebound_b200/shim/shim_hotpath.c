@@ -131,6 +131,67 @@ void reb_boundary_check(struct reb_simulation* r){
 }
 
 /* ---- collisions ---------------------------------------------------------------------------- */
+/* The resolve loop without bringing the particles home (include/rebound_b200.h: rebcu_collision_resolve_pairs): the
+ * engine keeps the shuffled order and hands over, round by round, the collisions whose particles are free; here the
+ * reference's OWN reb_collision_resolve_hardsphere (src/collision.c:573-665) -- with the user's coefficient_of_restitution
+ * callback -- runs on a two-particle scratch simulation per pair, on all cores (the pairs of a batch share no particle). */
+#include <pthread.h>
+#include <unistd.h>
+struct pair_job { struct reb_simulation* r; rebcu_resolve_pair* pairs; uint64_t begin, end; };
+static void* pair_worker(void* arg){
+    struct pair_job* job = arg;
+    struct reb_simulation rs = *job->r;                 /* scalar settings and callbacks of the caller's simulation */
+    struct reb_particle two[2];
+    rs.particles = two; rs.N = 2; rs.N_allocated = 2;
+    for (uint64_t j=job->begin; j<job->end; j++){
+        rebcu_resolve_pair* q = &job->pairs[j];
+        memset(two, 0, sizeof(two));
+        two[0].x = q->s1[0]; two[0].y = q->s1[1]; two[0].z = q->s1[2]; two[0].vx = q->s1[3]; two[0].vy = q->s1[4]; two[0].vz = q->s1[5];
+        two[0].m = q->s1[6]; two[0].r = q->s1[7]; two[0].sim = &rs;
+        two[1].x = q->s2[0]; two[1].y = q->s2[1]; two[1].z = q->s2[2]; two[1].vx = q->s2[3]; two[1].vy = q->s2[4]; two[1].vz = q->s2[5];
+        two[1].m = q->s2[6]; two[1].r = q->s2[7]; two[1].sim = &rs;
+        struct reb_collision c;
+        memset(&c, 0, sizeof(c));
+        c.p1 = 0; c.p2 = 1;
+        memcpy(&c.gb, &q->gb, sizeof(c.gb));
+        rs.collisions_plog = 0.; rs.collisions_log_n = 0;
+        reb_collision_resolve_hardsphere(&rs, c);
+        q->v1[0] = two[0].vx; q->v1[1] = two[0].vy; q->v1[2] = two[0].vz;
+        q->v2[0] = two[1].vx; q->v2[1] = two[1].vy; q->v2[2] = two[1].vz;
+        q->plog_term = rs.collisions_plog;
+        q->logged = rs.collisions_log_n ? 1 : 0;
+    }
+    return NULL;
+}
+static int shim_pair_resolver(void* user, rebcu_resolve_pair* pairs, uint64_t n){
+    struct reb_simulation* r = user;
+    static long cores = 0;
+    if (!cores){ cores = sysconf(_SC_NPROCESSORS_ONLN); if (cores < 1) cores = 1; if (cores > 32) cores = 32; }
+    int nt = (int)(n/4096);                              /* a thread is worth a few thousand pairs */
+    if (nt > cores) nt = (int)cores;
+    if (nt <= 1){ struct pair_job job = {r, pairs, 0, n}; pair_worker(&job); return 0; }
+    pthread_t th[32]; struct pair_job jobs[32];
+    for (int t=0;t<nt;t++){
+        jobs[t].r = r; jobs[t].pairs = pairs; jobs[t].begin = n*(uint64_t)t/(uint64_t)nt; jobs[t].end = n*(uint64_t)(t+1)/(uint64_t)nt;
+        if (pthread_create(&th[t], NULL, pair_worker, &jobs[t])){ pair_worker(&jobs[t]); th[t] = 0; }
+    }
+    for (int t=0;t<nt;t++) if (th[t]) pthread_join(th[t], NULL);
+    return 0;
+}
+/* Can this simulation's collisions be resolved without the particles on the host?  The built-in hard-sphere resolver
+ * only (it touches nothing but the two particles and never removes one); REBOUND_B200_DEVICE_RESOLVE=0 switches it off. */
+int shim_resolve_on_device(const struct reb_simulation* r, const struct shim_state* s){
+    static int on = -1;
+    if (on < 0){ const char* e = getenv("REBOUND_B200_DEVICE_RESOLVE"); on = (e && e[0]=='0') ? 0 : 1; }
+    return on && r->collision_resolve==reb_collision_resolve_hardsphere && rebcu_group_size(s->h)==1;
+}
+int shim_resolve_pairs(struct reb_simulation* r, struct shim_state* s){
+    uint64_t logn = (uint64_t)r->collisions_log_n;
+    int err = rebcu_collision_resolve_pairs(s->h, &r->rand_seed, shim_pair_resolver, r, &r->collisions_plog, &logn, NULL);
+    r->collisions_log_n = (int64_t)logn;
+    return shim_report(r, s, err);
+}
+
 void reb_collision_search(struct reb_simulation* const r){
     const int gpu_mode = (r->collision==REB_COLLISION_DIRECT || r->collision==REB_COLLISION_TREE
                           || r->collision==REB_COLLISION_LINE || r->collision==REB_COLLISION_LINETREE);
@@ -163,6 +224,15 @@ void reb_collision_search(struct reb_simulation* const r){
         s->subset_set = subset;
     }
     uint64_t n_found = 0;
+    if (s->host_stale && shim_resolve_on_device(r, s)){
+        /* resident simulation + the built-in hard-sphere resolver: the list stays on the device and is resolved there,
+         * pair batches travelling to the reference's own resolver and back (no particle array download) */
+        int err = rebcu_collision_search(s->h, &c, NULL, 0, &n_found);
+        if (shim_report(r, s, err)) return;
+        r->N_collisions = 0;                            /* consumed on the device; r->collisions is not filled */
+        if (n_found) shim_resolve_pairs(r, s);
+        return;
+    }
     int err = rebcu_collision_search(s->h, &c, (rebcu_collision*)r->collisions, r->N_allocated_collisions, &n_found);
     if (shim_report(r, s, err)) return;
     if (n_found > r->N_allocated_collisions){

@@ -42,7 +42,14 @@ static int batch_possible(const struct reb_simulation* r){
     if (r->heartbeat) return 0;                                    /* called after every step */
     if (r->exit_max_distance || r->exit_min_distance) return 0;    /* checked after every step: keep the per-step path */
     if (r->simulationarchive_filename) return 0;
-    if (r->collision!=REB_COLLISION_NONE) return 0;                /* the resolve loop runs on the host after every search */
+    if (r->collision!=REB_COLLISION_NONE){
+        /* the resolve loop needs the host after every search -- unless it is the built-in hard-sphere resolver, which the
+         * engine's exact resolve serves pair batch by pair batch (shim_hotpath.c) */
+        struct shim_state* s0 = shim_get((struct reb_simulation*)r);
+        if (!s0 || !shim_resolve_on_device(r, s0)) return 0;
+        if (r->collision!=REB_COLLISION_DIRECT && r->collision!=REB_COLLISION_TREE && r->collision!=REB_COLLISION_LINE && r->collision!=REB_COLLISION_LINETREE) return 0;
+        if (r->map || r->N_targets!=SIZE_MAX) return 0;
+    }
     if (r->N_odes || r->N_var || r->additional_forces) return 0;
     if (!shim_is_device_integrator(r)) return 0;
     switch (r->gravity){
@@ -56,6 +63,12 @@ static int batch_possible(const struct reb_simulation* r){
 
 /* n steps as one device batch on r->particles; the bookkeeping of reb_simulation_step (:514-603) for n steps.
  * Returns 0 on success; on an engine error the message is already queued with reb_simulation_error. */
+static int batch_collision_cb(void* user){
+    struct reb_simulation* r = user;
+    struct shim_state* s = shim_find(r);
+    return s ? shim_resolve_pairs(r, s) : -1;
+}
+
 static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
     struct shim_state* s = shim_get(r);
     if (!s) return -1;
@@ -67,6 +80,8 @@ static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
     gettimeofday(&t0, NULL);
     uint64_t N = r->N;
     int err;
+    const int with_collisions = r->collision!=REB_COLLISION_NONE;
+    if (with_collisions){ rebcu_set_collision_subset(s->h, NULL, 0, REBCU_SIZE_MAX); s->subset_set = 0; rebcu_set_collision_callback(s->h, batch_collision_cb, r); }
     if (pipelined){
         err = rebcu_steps_host(s->h, &c, (rebcu_particle*)r->particles, &N, n);
     }else{
@@ -74,6 +89,7 @@ static int run_batch(struct reb_simulation* r, size_t n, int pipelined){
         if (!err) err = rebcu_steps(s->h, &c, n);
         if (!err){ N = rebcu_N(s->h); err = rebcu_download(s->h, (rebcu_particle*)r->particles, N); }
     }
+    if (with_collisions){ rebcu_set_collision_callback(s->h, NULL, NULL); r->N_collisions = 0; }
     int interrupted = 0;
     if (err==REBCU_INTERRUPTED){
         /* a second Ctrl-C stopped the engine between two steps: not an error.  The state of the last completed step

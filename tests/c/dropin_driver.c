@@ -90,8 +90,10 @@ int main(int argc, char** argv){
             pt.vx = vkep*sin(phi); pt.vy = -vkep*cos(phi); pt.m = disc_mass/(double)N;
             reb_simulation_add(r, pt);
         }
-    }else if (strcmp(scen, "sheet")==0){
-        /* examples/shearing_sheet/problem.c; N is the root box size in metres */
+    }else if (strcmp(scen, "sheet")==0 || strcmp(scen, "sheet_hb")==0){
+        /* examples/shearing_sheet/problem.c; N is the root box size in metres.  sheet_hb: with a heartbeat installed, as
+         * in the example (it prints the time and does not touch the particles) */
+        if (strcmp(scen, "sheet_hb")==0) r->heartbeat = heartbeat;
         r->opening_angle2 = .5;
         reb_simulation_set_integrator(r, "sei");
         r->boundary = REB_BOUNDARY_SHEAR; r->gravity = REB_GRAVITY_TREE; r->collision = REB_COLLISION_TREE;

@@ -36,6 +36,7 @@ struct rebcu_handle {
     rebcu_collision* col; uint64_t col_n, col_cap;
     uint64_t* map; uint64_t map_n; int map_on; uint64_t n_targets;
     const volatile int* interrupt;
+    int (*collision_hook)(void*); void* collision_hook_user;
     char err[512];
     /* statistics the tests read through mock_counters(): how often the shim moved the particle array */
 };
@@ -119,12 +120,26 @@ int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg){
     if (!h->resident) return fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     return from_oracle(h, orc_boundary_check(cfg, h->p, &h->N));
 }
+int rebcu_collision_search(rebcu_handle* h, const rebcu_config* cfg, rebcu_collision* out, uint64_t cap, uint64_t* n_found);
+int rebcu_set_collision_callback(rebcu_handle* h, int (*cb)(void*), void* user){ h->collision_hook = cb; h->collision_hook_user = user; return 0; }
+int rebcu_group_size(const rebcu_handle* h){ (void)h; return 1; }
+
 int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps){
     if (!h->resident) return fail(h, REBCU_ERR_NOT_RESIDENT, "no resident particles");
     n_step_calls++;
     for (uint64_t s=0; s<n_steps; s++){
         if (h->interrupt && *h->interrupt > 1) return REBCU_INTERRUPTED;
-        const int err = from_oracle(h, orc_steps(cfg, h->p, &h->N, 1, 0, 0., NULL));
+        int err;
+        if (cfg->collision != REBCU_COLLISION_NONE && h->collision_hook){
+            /* the engine's step with a collision hook: integrator step, boundary check, search, hook (csrc/api.cu) */
+            err = from_oracle(h, orc_integrator_step(cfg, h->p, &h->N));
+            if (!err) err = from_oracle(h, orc_boundary_check(cfg, h->p, &h->N));
+            uint64_t nf = 0;
+            if (!err) err = rebcu_collision_search(h, cfg, NULL, 0, &nf);
+            if (!err) err = h->collision_hook(h->collision_hook_user);
+        }else{
+            err = from_oracle(h, orc_steps(cfg, h->p, &h->N, 1, 0, 0., NULL));
+        }
         if (err) return err;
         n_steps_total++;
         {   /* MOCK_SIGINT_AT_STEP=<k>[,<times>]: the user's Ctrl-C arrives while the k-th step of the process runs */
@@ -191,4 +206,38 @@ int rebcu_jerk_host(rebcu_handle* h, const rebcu_config* cfg, rebcu_particle* pa
     if (!err) err = rebcu_apply_jerk(h, cfg, v);
     if (err) return err;
     return rebcu_download(h, particles, N);
+}
+
+/* The exact resolve of the engine (csrc/resolve.cu), sequentially: shuffle, then every collision in order -- early exits
+ * of the hard-sphere resolver here, the arithmetic in the caller's resolver, one pair per call. */
+#include <stdlib.h>
+int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebcu_pair_resolver fn, void* user,
+                                  double* plog, uint64_t* log_n, int* rounds){
+    const uint64_t n = h->col_n;
+    if (rounds) *rounds = 1;
+    for (uint64_t i=0;i<n;i++){
+        const uint64_t j = (uint64_t)rand_r(rand_seed)%n;
+        rebcu_collision c1 = h->col[i]; h->col[i] = h->col[j]; h->col[j] = c1;
+    }
+    for (uint64_t i=0;i<n;i++){
+        const rebcu_collision c = h->col[i];
+        const rebcu_particle* a = &h->p[c.p1]; const rebcu_particle* b = &h->p[c.p2];
+        const double x21 = a->x + c.gb.x - b->x, y21 = a->y + c.gb.y - b->y, z21 = a->z + c.gb.z - b->z;
+        const double rp = a->r + b->r;
+        if (rp*rp < x21*x21 + y21*y21 + z21*z21) continue;
+        const double vx21 = a->vx + c.gb.vx - b->vx, vy21 = a->vy + c.gb.vy - b->vy, vz21 = a->vz + c.gb.vz - b->vz;
+        if (vx21*x21 + vy21*y21 + vz21*z21 > 0) continue;
+        rebcu_resolve_pair q;
+        memset(&q, 0, sizeof(q));
+        q.k = i; q.p1 = c.p1; q.p2 = c.p2; q.gb = c.gb;
+        q.s1[0]=a->x; q.s1[1]=a->y; q.s1[2]=a->z; q.s1[3]=a->vx; q.s1[4]=a->vy; q.s1[5]=a->vz; q.s1[6]=a->m; q.s1[7]=a->r;
+        q.s2[0]=b->x; q.s2[1]=b->y; q.s2[2]=b->z; q.s2[3]=b->vx; q.s2[4]=b->vy; q.s2[5]=b->vz; q.s2[6]=b->m; q.s2[7]=b->r;
+        q.v1[0]=a->vx; q.v1[1]=a->vy; q.v1[2]=a->vz; q.v2[0]=b->vx; q.v2[1]=b->vy; q.v2[2]=b->vz;
+        if (fn(user, &q, 1)) return fail(h, REBCU_ERR_ARG, "the pair resolver reported an error");
+        h->p[c.p1].vx = q.v1[0]; h->p[c.p1].vy = q.v1[1]; h->p[c.p1].vz = q.v1[2];
+        h->p[c.p2].vx = q.v2[0]; h->p[c.p2].vy = q.v2[1]; h->p[c.p2].vz = q.v2[2];
+        if (q.logged){ *plog += q.plog_term; (*log_n)++; }
+    }
+    h->col_n = 0;
+    return 0;
 }

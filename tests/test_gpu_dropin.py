@@ -14,6 +14,9 @@ pytestmark = [pytest.mark.gpu,
                                  reason="rebound_b200/_dropin not built (needs the reference sources at build time)")]
 
 SCENARIOS = [("plummer", 3000, 5), ("plummer_comp", 1500, 3), ("testparticles", 2000, 4), ("disc", 5000, 4), ("sheet", 40, 8), ("sheet", 25, 400),
+             # a sheet large enough (N ~ 2300, array > 256 KB) for the lazy host copy under the example's heartbeat, with the
+             # exact device-side resolve (shim_lazy.c, rebcu_collision_resolve_pairs)
+             ("sheet_hb", 125, 12), ("sheet", 125, 12),
              ("lf4", 700, 3), ("lf6", 700, 3), ("lf8", 700, 2), ("tp0", 3000, 6), ("merge", 400, 30), ("line", 400, 30),
              ("periodic", 1500, 6), ("open_direct", 1200, 12), ("ias15", 300, 3), ("ias15_comp", 300, 3), ("whfast", 300, 10),
              # r->map / r->N_targets collision subsets of the hybrid integrators; exit conditions of run_heartbeat

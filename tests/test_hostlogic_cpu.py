@@ -20,7 +20,7 @@ pytestmark = [pytest.mark.needs_ref,
                                  reason="needs rebound_b200/_dropin/obj and the reference headers (authoring container)")]
 
 # (scenario, N, steps): tests/c/dropin_driver.c, sized for the CPU oracle
-SCENARIOS = [("plummer", 300, 4), ("plummer_comp", 200, 3), ("testparticles", 300, 4), ("disc", 600, 4), ("sheet", 25, 25),
+SCENARIOS = [("plummer", 300, 4), ("plummer_comp", 200, 3), ("testparticles", 300, 4), ("disc", 600, 4), ("sheet", 25, 25), ("sheet_hb", 25, 10),
              ("lf4", 150, 3), ("lf8", 150, 2), ("tp0", 400, 6), ("merge", 200, 20), ("line", 200, 20), ("periodic", 300, 4),
              ("open_direct", 300, 10), ("ias15", 60, 3), ("ias15_comp", 60, 3), ("whfast", 60, 8), ("mercurius", 30, 120),
              ("trace", 30, 120), ("escape", 300, 300), ("encounter", 300, 300), ("eos", 60, 5), ("edit", 200, 3),
