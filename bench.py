@@ -548,6 +548,7 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
         # warm-up happens inside time_resident; the sampler covers the timed region plus that warm-up's tail
         if sampler:
             sampler.start()
+        cs0 = eng.comm_stats() if sharded else None
         ms, launches, c_end = time_resident(ctx, cfg, inner, k, warmup if first else 1, flush_l2=not big)
         if sampler:
             clocks = sampler.stop()
@@ -561,7 +562,10 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
             results[mname]["walk_stats"] = eng.tree_walk_stats(c_end)
         if sharded:
             cs = eng.comm_stats()
-            results[mname]["_comm"] = cs
+            n_calls = k + (warmup if first else 1)
+            results[mname]["_comm"] = {"transport": cs["transport"],
+                                       "bytes_received_per_step": (cs["bytes_received"] - cs0["bytes_received"]) // max(1, n_calls),
+                                       "collectives_per_step": (cs["exchanges"] - cs0["exchanges"]) / max(1, n_calls)}
     head = modes[0][0]
     R = results[head]
     out.update({"value": R["value"], "ms_per_step": R["ms_per_step"], "mode": head + (" (FMA + rsqrt; group walk for the tree)" if head == "fast" else " (bit-identical to the reference)"),
@@ -624,7 +628,7 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
                 roof["build_hbm"] = {"bound": "hbm", "kernels": "key, radix sort, tie/lcp, emit, adopt, moment", "achieved": alg / (b_ms * 1e-3) / 1e9,
                                      "peak": hbm_peak, "unit": "GB/s", "frac": alg / (b_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                                      "algorithmic_bytes": alg, "ms": b_ms, "traffic": traffic.get(f"{name}_build"),
-                                     "note": "260 B per particle per build (SURVEY.md 8d); every rank builds the whole tree"}
+                                     "note": "260 B per particle per build (SURVEY.md 8d) x ALL particles, also when the build is sharded over the ranks"}
         if mname == head:
             out["roofline"] = roof
         else:
@@ -633,9 +637,10 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
     if sharded:
         cs = results[head].get("_comm")
         tim_x = R["kernel_ms_per_step"].get("exchange", 0.0)
-        n_x = max(1, cs["exchanges"])
-        out["exchange"] = {"transport": cs["transport"], "bytes_received_per_rank_per_exchange": cs["bytes_received"] // n_x,
-                           "exchange_ms_per_step_rank0": tim_x, "collective": "ncclAllGather of x,y,z (in place, engine stream, between drift and force)"}
+        out["exchange"] = {"transport": cs["transport"], "bytes_received_per_rank_per_step": cs["bytes_received_per_step"],
+                           "collectives_per_step": cs["collectives_per_step"], "exchange_ms_per_step_rank0": tim_x,
+                           "collectives": "ncclAllGather of x,y,z in place on the engine's stream between drift and force"
+                                          + ("; tree: bucket table, traversal records (40 B per cell) and sorted permutation of the per-rank builds" if kind == "tree" else "")}
     out["clocks"] = clocks
     return out, w
 
@@ -650,6 +655,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-build", type=int, default=2, choices=[0, 1, 2],
+                    help="tree builds of a sharded run: 0 every rank builds the whole tree, 1 per-rank subtree builds, 2 automatic (default)")
     ap.add_argument("--no-configs", action="store_true", help="skip the blocks of the other configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -665,6 +672,7 @@ def main():
         raise SystemExit(f"{name} is a single-GPU configuration; the sharded paths are c3 and c4")
     # ---- headline ----
     ctx.attach()                                   # N > 1: NCCL communicator inside the engine, one rank per GPU
+    ctx.eng.set_sharded_build(args.shard_build)
     head, w = measure_config(ctx, name, args, args.steps, args.warmup, headline=True)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -693,7 +701,9 @@ def main():
             "config": head["config"],
             "detail": {"mode": head["mode"], "l2": head["l2"],
                        "sharding": ("one problem, contiguous target blocks per rank, NCCL all-gather of x,y,z inside the engine between drift and force; "
-                                    "every rank builds the whole tree and walks its own block in key order") if world > 1 else "single GPU, no exchange",
+                                    + ("every rank builds the whole tree" if args.shard_build == 0 else "every rank sorts and builds the subtrees of its own key range, "
+                                       "traversal records all-gathered, top of the tree filled in by everyone")
+                                    + "; every rank walks its own block in key order") if world > 1 else "single GPU, no exchange",
                        "host_affinity": (f"each rank bound to the {ctx.numa_cpus} cores local to its GPU" if ctx.numa_cpus else "unbound")},
             "clocks": head["clocks"],
             "e2e": head["e2e"],

@@ -1572,8 +1572,11 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
                     default: walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
                 }
                 walk_retry_kernel<<<div_up((uint64_t)ng * 32, 128), 128, 0, h->stream>>>(a, retry);
-            } else if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
-            else walk_rec_kernel<false><<<nb, 128, 0, h->stream>>>(a);
+            } else {
+                CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));   // no group walk: its counters read 0
+                if (c->mode == REBCU_MODE_FAST) walk_rec_kernel<true><<<nb, 128, 0, h->stream>>>(a);
+                else walk_rec_kernel<false><<<nb, 128, 0, h->stream>>>(a);
+            }
         } else if (variant == 1) {
             if (c->mode == REBCU_MODE_FAST) walk_kernel<true><<<nb, 128, 0, h->stream>>>(a);
             else walk_kernel<false><<<nb, 128, 0, h->stream>>>(a);

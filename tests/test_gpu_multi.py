@@ -37,6 +37,7 @@ def _worker(rank, world, port, case, path):
         eng = Engine(rank, stream.cuda_stream)
         eng.upload(np.ascontiguousarray(p))
         state = D.attach(eng, torch.device("cuda", rank))
+        eng.set_sharded_build(1)            # tree cases: per-rank subtree builds, records gathered over NCCL (ragged broadcasts)
         c = cfg.copy()
         eng.steps(c, steps)
         D.gather_owned(eng, torch.device("cuda", rank))
