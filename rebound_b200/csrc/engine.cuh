@@ -82,6 +82,8 @@ struct TreeBuffers {
     uint32_t* sh_info = nullptr;   // small result block (see tree.cu)
     uint64_t sh_buckets_cap = 0;
     uint64_t last_build_cells_local = 0;
+    uint64_t sh_pk[REBCU_MAX_RANKS + 1] = {};   // sorted positions where the ranks' key ranges start (last sharded build)
+    double* acc_sorted = nullptr; uint64_t acc_sorted_cap = 0;   // [3][cap] accelerations in sorted order (key-range walk of a sharded run)
 };
 
 struct rebcu_handle {

@@ -20,6 +20,7 @@
 #include "strict_math.cuh"
 #include <stdlib.h>
 #include <math.h>
+#include <time.h>
 #include <vector>
 #include <algorithm>
 
@@ -287,6 +288,11 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
     if (rounds_out) *rounds_out = 0;
     if (n == 0) return REBCU_OK;
     if (n >= NONE) return rebcu_fail(h, REBCU_ERR_ARG, "device resolve supports fewer than 2^32 list entries");
+    static const bool trace = getenv("REBOUND_B200_RESOLVE_TRACE") != nullptr;      // per-call timing breakdown on stderr
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    const double t_begin = now();
+    double t_fn = 0, t_wait = 0;
+    uint64_t n_pairs_total = 0;
     std::vector<uint32_t> order(n);
     for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
     for (uint64_t i = 0; i < n; i++) {                     // collision.c:337-342
@@ -330,6 +336,7 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
     CU_TRY(h, cudaMemsetAsync(A.first, 0xff, h->cap * sizeof(uint32_t), h->stream));
     CU_TRY(h, cudaMemsetAsync(A.done, 0, n, h->stream));
     CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
+    const double t_setup = now();
     std::vector<double> terms;                 // (processing position, term) of the logged collisions
     std::vector<uint32_t> term_k;
     const unsigned nb = div_up(n, 256);
@@ -344,13 +351,15 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
         rounds++;
         CU_TRY(h, cudaMemcpyAsync(pin, h->counters + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        { const double t0 = now(); CU_TRY(h, cudaStreamSynchronize(h->stream)); t_wait += now() - t0; }
         const unsigned long long pending = pin[0];
         const unsigned int np = (unsigned int)(pin[2] & 0xffffffffull);
         if (np > pair_cap) return rebcu_fail(h, REBCU_ERR_CAPACITY, "pair buffer overflow in the exact resolve");
         if (np) {
             CU_TRY(h, cudaMemcpyAsync(in_host, P.in, np * sizeof(PairIn), cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            { const double t0 = now(); CU_TRY(h, cudaStreamSynchronize(h->stream)); t_wait += now() - t0; }
+            n_pairs_total += np;
+            const double t_fn0 = now();
             for (unsigned int j = 0; j < np; j++) {
                 rebcu_resolve_pair& q = out_host[j];
                 const PairIn& s = in_host[j];
@@ -361,6 +370,7 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
                 q.plog_term = 0; q.logged = 0;
             }
             const int ferr = fn(user, out_host, np);
+            t_fn += now() - t_fn0;
             if (ferr) return rebcu_fail(h, REBCU_ERR_ARG, "the pair resolver reported an error");
             for (unsigned int j = 0; j < np; j++) if (out_host[j].logged) { terms.push_back(out_host[j].plog_term); term_k.push_back((uint32_t)out_host[j].k); }
             CU_TRY(h, cudaMemcpyAsync(out_dev, out_host, np * sizeof(rebcu_resolve_pair), cudaMemcpyHostToDevice, h->stream));
@@ -386,6 +396,8 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
     h->resolve_rounds = rounds;
     if (rounds_out) *rounds_out = rounds;
     h->col_n = 0;                                           // consumed
+    if (trace) fprintf(stderr, "[resolve] list %llu pairs %llu rounds %d: setup %.2f ms, device waits %.2f ms, host resolver (incl. record copies) %.2f ms, total %.2f ms\n",
+                       (unsigned long long)n, (unsigned long long)n_pairs_total, rounds, 1e3 * (t_setup - t_begin), 1e3 * t_wait, 1e3 * t_fn, 1e3 * (now() - t_begin));
     return REBCU_OK;
 }
 

@@ -347,7 +347,17 @@ struct WalkArgs {
     uint32_t w2_lo;                               // low word of every (normal) squared cell width, see walk_pack_kernel
     int gw_stack;                                 // traversal stack entries the group walk may use (<= GW_STACK)
     unsigned int gw_abort;                        // list entries after which a group gives up and its lanes walk on their own
+    // sharded runs with the native exchange: a rank walks the sorted positions [k_begin, k_begin + n_work) -- a compact
+    // region of space -- and leaves the accelerations in SORTED order (three arrays of sorted_stride doubles); they are
+    // all-gathered and scattered to the index blocks afterwards (tree_gravity)
+    uint64_t k_begin;
+    double* sorted_out; uint64_t sorted_stride;
 };
+
+__device__ __forceinline__ void store_acc(const WalkArgs& a, uint32_t self, uint64_t k, double sx, double sy, double sz) {
+    if (a.sorted_out) { a.sorted_out[k] = sx; a.sorted_out[a.sorted_stride + k] = sy; a.sorted_out[2 * a.sorted_stride + k] = sz; }
+    else { a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz; }
+}
 
 // MODE 0: strict with the branch-free windowed sqrt/divide (returns the running window key),
 //      1: FAST (FMA + rsqrt), 2: strict with the generic __dsqrt_rn/__ddiv_rn.
@@ -405,14 +415,14 @@ template <bool FAST>
 __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
     const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     if (t >= a.n_work) return;
-    const uint64_t k = a.list ? a.list[t] : t;
+    const uint64_t k = a.list ? a.list[t] : a.k_begin + t;
     const uint32_t self = a.perm[k];
     const double px = a.x[self], py = a.y[self], pz = a.z[self];
     double sx, sy, sz;
     unsigned wkey = STRICT_WINDOW_LIMIT;
     if (FAST || a.windowed) wkey = walk_one<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
     if (!FAST && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
-    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+    store_acc(a, self, k, sx, sy, sz);
 }
 
 // ---- shared pieces of the walks ----------------------------------------------------------------------------------
@@ -533,14 +543,14 @@ template <bool FAST>
 __global__ void __launch_bounds__(128) walk_rec_kernel(const WalkArgs a) {
     const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     if (t >= a.n_work) return;
-    const uint64_t k = a.list ? a.list[t] : t;
+    const uint64_t k = a.list ? a.list[t] : a.k_begin + t;
     const uint32_t self = a.perm[k];
     const double px = a.x[self], py = a.y[self], pz = a.z[self];
     double sx, sy, sz;
     unsigned wkey = STRICT_WINDOW_LIMIT;
     if (FAST || a.windowed) wkey = walk_one_rec<FAST ? 1 : 0>(a, self, px, py, pz, sx, sy, sz);
     if (!FAST && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
-    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+    store_acc(a, self, k, sx, sy, sz);
 }
 
 // Walk of a QUADRUPOLE build (tree.c:286-304): accepted internal cells add the quadrupole correction, in two
@@ -550,7 +560,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(128) walk_quad_kernel(const WalkArgs a) {
     const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     if (t >= a.n_work) return;
-    const uint64_t k = a.list ? a.list[t] : t;
+    const uint64_t k = a.list ? a.list[t] : a.k_begin + t;
     const uint32_t self = a.perm[k];
     const double px = a.x[self], py = a.y[self], pz = a.z[self];
     double sx = 0., sy = 0., sz = 0.;
@@ -617,7 +627,7 @@ __global__ void __launch_bounds__(128) walk_quad_kernel(const WalkArgs a) {
             c = mt.y;
         }
     }
-    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+    store_acc(a, self, k, sx, sy, sz);
 }
 
 // Warp-cooperative walk.  ncu showed the per-thread walk bound by L1 wavefronts (l1tex data pipe 93 % busy,
@@ -633,8 +643,9 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
     const bool live = t < a.n_work;
     uint32_t self = 0xffffffffu;
     double px = 0, py = 0, pz = 0;
+    uint64_t k = 0;
     if (live) {
-        const uint64_t k = a.list ? a.list[t] : t;
+        k = a.list ? a.list[t] : a.k_begin + t;
         self = a.perm[k];
         px = a.x[self]; py = a.y[self]; pz = a.z[self];
     }
@@ -684,7 +695,7 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
     }
     if (!live) return;
     if (MODE == 0 && wkey >= STRICT_WINDOW_LIMIT) walk_generic(a, self, px, py, pz, sx, sy, sz);
-    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+    store_acc(a, self, k, sx, sy, sz);
 }
 
 // ---- FAST group walk: one warp = 32 key-adjacent particles, shared traversal, list-based evaluation -------------------
@@ -753,7 +764,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
     const uint64_t t = t0 + lane;
     const bool live = t < a.n_work;
     const uint64_t tt = live ? t : a.n_work - 1;             // idle lanes shadow the last particle (keeps the box tight)
-    const uint64_t k = a.list ? a.list[tt] : tt;
+    const uint64_t k = a.list ? a.list[tt] : a.k_begin + tt;
     const int self = (int)a.perm[k];
     const double px = a.x[self], py = a.y[self], pz = a.z[self];
     const double lox = warp_min_d(px), hix = warp_max_d(px);
@@ -842,7 +853,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
     gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
     n_ent += nl;
     const double negG = -a.G;
-    if (live) { a.ax[self] = negG * sx; a.ay[self] = negG * sy; a.az[self] = negG * sz; }
+    if (live) store_acc(a, (uint32_t)self, k, negG * sx, negG * sy, negG * sz);
     if (stats && lane == 0) { atomicAdd(&stats[0], (unsigned long long)n_ent); atomicAdd(&stats[1], (unsigned long long)n_vis); atomicAdd(&stats[2], 1ull); }
 }
 
@@ -853,11 +864,11 @@ __global__ void __launch_bounds__(128) walk_retry_kernel(const WalkArgs a, const
     if (slot >= retry[0]) return;
     const uint64_t t = (uint64_t)retry[1 + slot] * 32 + (threadIdx.x & 31);
     if (t >= a.n_work) return;
-    const uint64_t k = a.list ? a.list[t] : t;
+    const uint64_t k = a.list ? a.list[t] : a.k_begin + t;
     const uint32_t self = a.perm[k];
     double sx, sy, sz;
     walk_one_rec<1>(a, self, a.x[self], a.y[self], a.z[self], sx, sy, sz);
-    a.ax[self] = sx; a.ay[self] = sy; a.az[self] = sz;
+    store_acc(a, self, k, sx, sy, sz);
 }
 
 // Interaction count of the per-particle criterion (what the reference and the STRICT walk evaluate): accepted cells and
@@ -866,7 +877,7 @@ __global__ void __launch_bounds__(128) walk_count_kernel(const WalkArgs a, unsig
     const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     unsigned long long n_acc = 0, n_vis = 0;
     if (t < a.n_work) {
-        const uint64_t k = a.list ? a.list[t] : t;
+        const uint64_t k = a.list ? a.list[t] : a.k_begin + t;
         const uint32_t self = a.perm[k];
         const double px = a.x[self], py = a.y[self], pz = a.z[self];
         const int n_cells = (int)a.n_cells;
@@ -919,7 +930,9 @@ void tree_free(rebcu_handle* h) {
     cudaFree(T.keys); cudaFree(T.keys_sorted); cudaFree(T.perm); cudaFree(T.perm_in); cudaFree(T.lcp);
     cudaFree(T.cell_off); cudaFree(T.cell_cnt); cudaFree(T.cells); cudaFree(T.parent); cudaFree(T.ready);
     cudaFree(T.walk_pos); cudaFree(T.walk_geo); cudaFree(T.walk_meta); cudaFree(T.walk_meta2); cudaFree(T.walk_rec); cudaFree(T.walk_m); cudaFree(T.col_rec); cudaFree(T.sort_tmp); cudaFree(T.scan_tmp); cudaFree(T.flags);
-    cudaFree(T.shard_list); cudaFree(T.quad);
+    cudaFree(T.shard_list); cudaFree(T.quad); cudaFree(T.acc_sorted);
+    cudaFree(T.sh_keys); cudaFree(T.sh_idx); cudaFree(T.sh_hist); cudaFree(T.sh_pstart); cudaFree(T.sh_tab); cudaFree(T.sh_level);
+    cudaFree(T.sh_delta); cudaFree(T.sh_top); cudaFree(T.sh_info);
     T = TreeBuffers();
 }
 
@@ -1331,6 +1344,7 @@ static int tree_build_sharded(rebcu_handle* h, const rebcu_config* c, bool* used
     uint64_t Bk[REBCU_MAX_RANKS + 1], Pk[REBCU_MAX_RANKS + 1], tabB[REBCU_MAX_RANKS + 1];
     for (int r = 0; r <= W; r++) { Bk[r] = pin[I_B + r]; Pk[r] = pin[I_P + r]; tabB[r] = Bk[r] + 8ull * r; }
     tabB[W] = Bk[W] + 8ull * W;
+    for (int r = 0; r <= W; r++) T.sh_pk[r] = Pk[r];
     const uint64_t n_loc = Pk[me + 1] - Pk[me];
     uint64_t* keys_loc = T.keys_sorted + Pk[me];
     uint32_t* perm_loc = T.perm + Pk[me];
@@ -1464,11 +1478,29 @@ int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work) {
     return REBCU_OK;
 }
 
+// accelerations in sorted order -> the rank's own index block
+__global__ void __launch_bounds__(256) acc_scatter_kernel(uint64_t n, const uint32_t* __restrict__ perm, const double* __restrict__ sorted,
+                                                          uint64_t stride, uint64_t b, uint64_t e, double* ax, double* ay, double* az) {
+    const uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t i = perm[k];
+    if (i >= b && i < e) { ax[i] = sorted[k]; ay[i] = sorted[stride + k]; az[i] = sorted[2 * stride + k]; }
+}
+
+// Key-range share of a sharded walk: sorted positions [kb[r], kb[r+1]) belong to rank r (the ranges of the sharded
+// build, else equal parts).
+static void walk_key_ranges(rebcu_handle* h, uint64_t* kb) {
+    TreeBuffers& T = h->tree;
+    const int W = h->world;
+    for (int r = 0; r <= W; r++) kb[r] = (T.rec_ready && !T.complete) ? T.sh_pk[r] : h->N * (uint64_t)r / (uint64_t)W;
+}
+
 static int walk_args_fill(rebcu_handle* h, const rebcu_config* c, WalkArgs& a) {
     TreeBuffers& T = h->tree;
     a.pos = T.walk_pos; a.meta = (const int4*)T.walk_meta; a.meta2 = T.walk_meta2; a.n_cells = T.n_cells;
     a.perm = T.perm; a.list = nullptr; a.n_work = h->N;
     a.quad = nullptr; a.quad_stride = 0; a.rec = nullptr; a.m = nullptr; a.w2_lo = 0;
+    a.k_begin = 0; a.sorted_out = nullptr; a.sorted_stride = 0;
     a.x = h->f(F_X); a.y = h->f(F_Y); a.z = h->f(F_Z);
     a.ax = h->f(F_AX); a.ay = h->f(F_AY); a.az = h->f(F_AZ);
     a.ghosts = h->ghosts_dev;
@@ -1529,8 +1561,28 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
     if (err) return err;
     WalkArgs a;
     walk_args_fill(h, c, a);
-    if (h->world > 1) {
-        // walk only the particles of this rank's index block, visited in key order
+    static const int variant = [] { const char* e = getenv("REBOUND_B200_WALK");
+                                    return (e && strcmp(e, "coop") == 0) ? 2 : (e && strcmp(e, "v1") == 0) ? 1 : (e && strcmp(e, "rec") == 0) ? 3 : 0; }();
+    uint64_t kb[REBCU_MAX_RANKS + 1];
+    const bool by_key = h->world > 1 && h->comm != nullptr;
+    if (by_key) {
+        // Several ranks with the native exchange: each walks a contiguous range of SORTED positions -- a compact region of
+        // space, so that the 32 particles of a group (and of a warp of the per-particle walks) are neighbours; the
+        // particles of an index block are scattered all over the box, which lengthened the group lists by a quarter on two
+        // ranks already.  The accelerations come out in sorted order, are all-gathered (24 B per particle, like the
+        // positions) and every rank picks those of its index block.  Same bits: a particle's sum does not depend on who
+        // computes it.
+        if (T.acc_sorted_cap < T.cap_n) {
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(T.acc_sorted); T.acc_sorted = nullptr; T.acc_sorted_cap = 0;
+            CU_TRY(h, cudaMalloc(&T.acc_sorted, 3 * T.cap_n * sizeof(double)));
+            T.acc_sorted_cap = T.cap_n;
+        }
+        walk_key_ranges(h, kb);
+        a.k_begin = kb[h->rank]; a.n_work = kb[h->rank + 1] - kb[h->rank];
+        a.sorted_out = T.acc_sorted; a.sorted_stride = T.acc_sorted_cap;
+    } else if (h->world > 1) {
+        // exchange through the caller's callback: walk the particles of this rank's index block, visited in key order
         if ((err = tree_shard_list(h, &a.list, &a.n_work))) return err;
     }
     if (a.n_work) {
@@ -1539,8 +1591,6 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
         // walk, walk_group_kernel), rec = records walk also in FAST mode, v1 = one visited cell per trip on the build's
         // arrays (walk_kernel), coop = warp-cooperative with per-lane lists (walk_coop_kernel; FP64-issue bound with
         // 18.7 of 32 lanes active, profiles/r01_walk_coop_ncu.txt).  All but the group walk give identical bits.
-        static const int variant = [] { const char* e = getenv("REBOUND_B200_WALK");
-                                        return (e && strcmp(e, "coop") == 0) ? 2 : (e && strcmp(e, "v1") == 0) ? 1 : (e && strcmp(e, "rec") == 0) ? 3 : 0; }();
         const unsigned int nb = div_up(a.n_work, 128);
         if (T.has_quad) {
             a.quad = T.quad; a.quad_stride = T.quad_cap;
@@ -1587,6 +1637,15 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
         }
     }
     CU_TRY(h, cudaGetLastError());
+    if (by_key) {
+        void* ptrs[3] = {T.acc_sorted, T.acc_sorted + T.acc_sorted_cap, T.acc_sorted + 2 * T.acc_sorted_cap};
+        int bytes[3] = {8, 8, 8};
+        if ((err = comm_gather_ranges(h, ptrs, bytes, 3, kb))) return err;
+        uint64_t b, e; engine_shard(h, &b, &e);
+        LaunchScope ls(h, TC_TREEWALK);
+        acc_scatter_kernel<<<div_up(n, 256), 256, 0, h->stream>>>(n, T.perm, T.acc_sorted, T.acc_sorted_cap, b, e, a.ax, a.ay, a.az);
+        CU_TRY(h, cudaGetLastError());
+    }
     return REBCU_OK;
 }
 
@@ -1603,7 +1662,11 @@ extern "C" int rebcu_tree_walk_stats(rebcu_handle* h, const rebcu_config* c, uin
     WalkArgs a;
     walk_args_fill(h, c, a);
     int err;
-    if (h->world > 1 && (err = tree_shard_list(h, &a.list, &a.n_work))) return err;
+    if (h->world > 1 && h->comm) {
+        uint64_t kb[REBCU_MAX_RANKS + 1];
+        walk_key_ranges(h, kb);
+        a.k_begin = kb[h->rank]; a.n_work = kb[h->rank + 1] - kb[h->rank];
+    } else if (h->world > 1 && (err = tree_shard_list(h, &a.list, &a.n_work))) return err;
     if ((err = walk_records(h, a))) return err;
     unsigned long long host[8] = {0};
     CU_TRY(h, cudaMemcpyAsync(host + 2, h->counters + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
