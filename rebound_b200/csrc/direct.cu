@@ -710,7 +710,9 @@ template <bool KAHAN>
 void launch_fast(rebcu_handle* h, const DirectArgs& a, uint64_t n_i) {
     // two particles per lane once there are enough particles to fill the machine that way (REBOUND_B200_FAST_IPT=1|2 forces)
     static const int forced = [] { const char* e = getenv("REBOUND_B200_FAST_IPT"); return e ? atoi(e) : 0; }();
-    const bool two = forced ? forced == 2 : n_i >= 148ull * 64 * 2;
+    // (C1, N = 16384: 0.37 ms per evaluation with two particles per lane, 0.44 with one -- one broadcast LDS pair per
+    // pair term keeps the shared-memory pipe as busy as the FP64 pipe)
+    const bool two = forced ? forced == 2 : n_i >= 148ull * 64;
     if (two) launch_fast_ipt<KAHAN, 2>(h, a, n_i); else launch_fast_ipt<KAHAN, 1>(h, a, n_i);
 }
 

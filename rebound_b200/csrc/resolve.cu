@@ -145,10 +145,9 @@ __global__ void __launch_bounds__(256) plog_partial_kernel(const double* __restr
 // are scattered back.  Per step this moves a few tens of MB instead of the whole particle array both ways, and the host
 // loop runs on all cores instead of one.  collisions_plog is summed by the caller's order (processing position), so it
 // matches the sequential loop bit for bit as well.
-struct PairIn { uint32_t k, p1, p2, pad; rebcu_vec6d gb; double s1[8], s2[8]; };          // 192 B
 struct PairsArgs {
     ResolveArgs R;
-    PairIn* in; unsigned int* n_pairs; unsigned int cap;
+    rebcu_resolve_pair* pairs; unsigned int* n_pairs; unsigned int cap;      // 264-byte records, filled here, completed by the caller
 };
 
 __global__ void __launch_bounds__(256) ready_kernel(PairsArgs P) {
@@ -170,11 +169,12 @@ __global__ void __launch_bounds__(256) ready_kernel(PairsArgs P) {
     if (s_add(s_add(s_mul(vx21, x21), s_mul(vy21, y21)), s_mul(vz21, z21)) > 0) return;      // collision.c:602: not approaching
     const unsigned int slot = atomicAdd(P.n_pairs, 1u);
     if (slot >= P.cap) return;                            // cannot happen: cap >= N/2 pairs share no particle
-    PairIn q;
-    q.k = k; q.p1 = p1; q.p2 = p2; q.pad = 0; q.gb = c.gb;
+    rebcu_resolve_pair& q = P.pairs[slot];
+    q.k = k; q.p1 = p1; q.p2 = p2; q.gb = c.gb;
     q.s1[0] = x1; q.s1[1] = y1; q.s1[2] = z1; q.s1[3] = v1x; q.s1[4] = v1y; q.s1[5] = v1z; q.s1[6] = A.m[p1]; q.s1[7] = r1;
     q.s2[0] = x2; q.s2[1] = y2; q.s2[2] = z2; q.s2[3] = v2x; q.s2[4] = v2y; q.s2[5] = v2z; q.s2[6] = A.m[p2]; q.s2[7] = r2;
-    P.in[slot] = q;
+    q.v1[0] = v1x; q.v1[1] = v1y; q.v1[2] = v1z; q.v2[0] = v2x; q.v2[1] = v2y; q.v2[2] = v2z;
+    q.plog_term = 0.; q.logged = 0;
 }
 
 __global__ void __launch_bounds__(256) apply_pairs_kernel(ResolveArgs A, const rebcu_resolve_pair* __restrict__ pairs, unsigned int n) {
@@ -300,8 +300,7 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
         const uint32_t t = order[i]; order[i] = order[j]; order[j] = t;
     }
     const uint64_t pair_cap = (n < h->N / 2 + 1) ? n : h->N / 2 + 1;
-    const uint64_t words = n /*order*/ + h->cap /*first*/ + (n + 3) / 4 /*done*/ + 64
-                         + pair_cap * (sizeof(PairIn) + sizeof(rebcu_resolve_pair)) / 4;
+    const uint64_t words = n /*order*/ + h->cap /*first*/ + (n + 3) / 4 /*done*/ + 64 + pair_cap * sizeof(rebcu_resolve_pair) / 4;
     if (h->resolve_cap < words) {
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(h->resolve_buf); h->resolve_buf = nullptr; h->resolve_cap = 0;
@@ -311,16 +310,15 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
     if (h->pairs_host_cap < pair_cap) {
         if (h->pairs_host) cudaFreeHost(h->pairs_host);
         h->pairs_host = nullptr; h->pairs_host_cap = 0;
-        CU_TRY(h, cudaMallocHost(&h->pairs_host, (pair_cap + pair_cap / 4 + 16) * (sizeof(PairIn) + sizeof(rebcu_resolve_pair))));
+        CU_TRY(h, cudaMallocHost(&h->pairs_host, (pair_cap + pair_cap / 4 + 16) * sizeof(rebcu_resolve_pair)));
         h->pairs_host_cap = pair_cap + pair_cap / 4 + 16;
     }
-    PairIn* in_host = (PairIn*)h->pairs_host;
-    rebcu_resolve_pair* out_host = (rebcu_resolve_pair*)(in_host + h->pairs_host_cap);
+    rebcu_resolve_pair* out_host = (rebcu_resolve_pair*)h->pairs_host;
     uint32_t* base = h->resolve_buf;
     PairsArgs P;
     ResolveArgs& A = P.R;
-    P.in = (PairIn*)base;                                  // 8-byte aligned first
-    rebcu_resolve_pair* out_dev = (rebcu_resolve_pair*)(P.in + pair_cap);
+    P.pairs = (rebcu_resolve_pair*)base;                   // 8-byte aligned first
+    rebcu_resolve_pair* out_dev = P.pairs;
     A.order = (uint32_t*)(out_dev + pair_cap);
     A.first = (uint32_t*)A.order + n;
     A.done = (uint8_t*)(A.first + h->cap);
@@ -337,8 +335,8 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
     CU_TRY(h, cudaMemsetAsync(A.done, 0, n, h->stream));
     CU_TRY(h, cudaMemsetAsync(h->counters + 8, 0, 3 * sizeof(unsigned long long), h->stream));
     const double t_setup = now();
-    std::vector<double> terms;                 // (processing position, term) of the logged collisions
-    std::vector<uint32_t> term_k;
+    std::vector<double> terms(n, 0.);          // per processing position: the term of a logged collision
+    std::vector<uint8_t> logged(n, 0);
     const unsigned nb = div_up(n, 256);
     unsigned long long* pin = h->pinned + 20;
     int rounds = 0;
@@ -356,23 +354,14 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
         const unsigned int np = (unsigned int)(pin[2] & 0xffffffffull);
         if (np > pair_cap) return rebcu_fail(h, REBCU_ERR_CAPACITY, "pair buffer overflow in the exact resolve");
         if (np) {
-            CU_TRY(h, cudaMemcpyAsync(in_host, P.in, np * sizeof(PairIn), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaMemcpyAsync(out_host, out_dev, np * sizeof(rebcu_resolve_pair), cudaMemcpyDeviceToHost, h->stream));
             { const double t0 = now(); CU_TRY(h, cudaStreamSynchronize(h->stream)); t_wait += now() - t0; }
             n_pairs_total += np;
             const double t_fn0 = now();
-            for (unsigned int j = 0; j < np; j++) {
-                rebcu_resolve_pair& q = out_host[j];
-                const PairIn& s = in_host[j];
-                q.k = s.k; q.p1 = s.p1; q.p2 = s.p2; q.gb = s.gb;
-                memcpy(q.s1, s.s1, sizeof(q.s1)); memcpy(q.s2, s.s2, sizeof(q.s2));
-                q.v1[0] = s.s1[3]; q.v1[1] = s.s1[4]; q.v1[2] = s.s1[5];
-                q.v2[0] = s.s2[3]; q.v2[1] = s.s2[4]; q.v2[2] = s.s2[5];
-                q.plog_term = 0; q.logged = 0;
-            }
             const int ferr = fn(user, out_host, np);
             t_fn += now() - t_fn0;
             if (ferr) return rebcu_fail(h, REBCU_ERR_ARG, "the pair resolver reported an error");
-            for (unsigned int j = 0; j < np; j++) if (out_host[j].logged) { terms.push_back(out_host[j].plog_term); term_k.push_back((uint32_t)out_host[j].k); }
+            for (unsigned int j = 0; j < np; j++) if (out_host[j].logged) { terms[out_host[j].k] = out_host[j].plog_term; logged[out_host[j].k] = 1; }
             CU_TRY(h, cudaMemcpyAsync(out_dev, out_host, np * sizeof(rebcu_resolve_pair), cudaMemcpyHostToDevice, h->stream));
             LaunchScope ls(h, TC_COLLISION, 1);
             apply_pairs_kernel<<<div_up(np, 256), 256, 0, h->stream>>>(A, out_dev, np);
@@ -386,17 +375,15 @@ int rebcu_collision_resolve_pairs(rebcu_handle* h, unsigned int* rand_seed, rebc
         if (rounds > 100000) return rebcu_fail(h, REBCU_ERR_CUDA, "exact resolve did not terminate");
     }
     // collisions_plog += term, in the order of the sequential loop (collision.c:351, 655-661)
-    std::vector<uint32_t> idx(terms.size());
-    for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return term_k[a] < term_k[b]; });
     double pl = *plog;
-    for (size_t i = 0; i < idx.size(); i++) pl += terms[idx[i]];
+    uint64_t n_logged = 0;
+    for (uint64_t k = 0; k < n; k++) if (logged[k]) { pl += terms[k]; n_logged++; }
     *plog = pl;
-    *log_n += terms.size();
+    *log_n += n_logged;
     h->resolve_rounds = rounds;
     if (rounds_out) *rounds_out = rounds;
     h->col_n = 0;                                           // consumed
-    if (trace) fprintf(stderr, "[resolve] list %llu pairs %llu rounds %d: setup %.2f ms, device waits %.2f ms, host resolver (incl. record copies) %.2f ms, total %.2f ms\n",
+    if (trace) fprintf(stderr, "[resolve] list %llu pairs %llu rounds %d: setup %.2f ms, device waits %.2f ms, host resolver %.2f ms, total %.2f ms\n",
                        (unsigned long long)n, (unsigned long long)n_pairs_total, rounds, 1e3 * (t_setup - t_begin), 1e3 * t_wait, 1e3 * t_fn, 1e3 * (now() - t_begin));
     return REBCU_OK;
 }

@@ -140,13 +140,19 @@ def _run(target, case, path, world=2):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
-    port = _free_port()
-    procs = [ctx.Process(target=target, args=(r, world, port, case, path)) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
+    for attempt in range(3):            # the free port can be taken between the probe and the rendezvous: try another one
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port, case, path)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+        if all(p.exitcode == 0 for p in procs):
+            return
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -185,18 +191,8 @@ def test_two_gpu_sharded_collision_search_bitwise(case, tmp_path):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("case", ["plummer_basic", "plummer_comp", "testp_type1", "testp_type1_rows", "disc_tree"])
 def test_two_gpu_sharded_steps_bitwise(case, tmp_path):
-    import torch.multiprocessing as mp
-
-    world = 2
     path = str(tmp_path / "out.npy")
-    ctx = mp.get_context("spawn")
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, path)) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
+    _run(_worker, case, path)
     got = np.frombuffer(np.load(path).tobytes(), dtype=abi.PARTICLE_DTYPE)
     p, cfg, steps = make_case(case)
     want, _, _ = checkers.oracle().steps(cfg, p, steps)
