@@ -67,6 +67,20 @@ class Restitution(C.Structure):
 RESTITUTION_CONSTANT, RESTITUTION_POWERLAW = 0, 1
 
 
+class Vec6d(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("x", "y", "z", "vx", "vy", "vz")]
+
+
+class ResolvePair(C.Structure):
+    """rebcu_resolve_pair: one collision handed to the caller's resolver by rebcu_collision_resolve_pairs."""
+
+    _fields_ = [("k", C.c_uint64), ("p1", C.c_uint64), ("p2", C.c_uint64), ("gb", Vec6d), ("s1", C.c_double * 8), ("s2", C.c_double * 8),
+                ("v1", C.c_double * 3), ("v2", C.c_double * 3), ("plog_term", C.c_double), ("logged", C.c_uint64)]
+
+
+PAIR_RESOLVER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(ResolvePair), C.c_uint64)
+
+
 class Config(C.Structure):
     """rebcu_config: the scalar fields of struct reb_simulation the hot path reads."""
 

@@ -42,7 +42,13 @@ int rebcu_boundary_check(rebcu_handle* h, rebcu_config* cfg) {
     if (group_active(h)) {
         // the sharded check: every rank must see every particle's position to agree on what left the box
         return group_cfg_call(h, cfg, [](rebcu_handle* s, rebcu_config* c) {
-            if (c->boundary == REBCU_BOUNDARY_OPEN) { const int e = rebcu_exchange(s, REBCU_EXCHANGE_POSITIONS); if (e) return e; return boundary_check_full(s, c); }
+            if (c->boundary == REBCU_BOUNDARY_OPEN) {
+                bool any = true;
+                int e = boundary_open_probe(s, c, &any);
+                if (e || !any) return e;
+                if ((e = rebcu_exchange(s, REBCU_EXCHANGE_POSITIONS))) return e;
+                return boundary_check_full(s, c);
+            }
             return rebcu_boundary_check(s, c);
         });
     }
@@ -104,9 +110,14 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
         if (err) return err;
         carried = carry_out;
         if (h->world > 1 && cfg->boundary == REBCU_BOUNDARY_OPEN) {
-            // every rank must see every particle's final position to agree on what left the box
-            err = engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
-            if (!err) err = boundary_check_full(h, cfg);
+            // every rank must see every particle's final position to agree on what left the box -- but only when some
+            // block did lose a particle (8 bytes per rank say so)
+            bool any = true;
+            err = boundary_open_probe(h, cfg, &any);
+            if (!err && any) {
+                err = engine_exchange(h, REBCU_EXCHANGE_POSITIONS);
+                if (!err) err = boundary_check_full(h, cfg);
+            }
         } else {
             err = boundary_check(h, cfg);
         }

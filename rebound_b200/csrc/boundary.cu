@@ -152,6 +152,38 @@ int boundary_check(rebcu_handle* h, rebcu_config* c) {
     return REBCU_OK;
 }
 
+// Sharded runs, open boundary, after a step: did ANY rank's block lose a particle?  Every rank flags its own block
+// (whose positions it holds) and the ranks gather the W counts -- 8 bytes each instead of all positions.  Only when the
+// answer is yes does the caller exchange positions and run the full check.
+int boundary_open_probe(rebcu_handle* h, const rebcu_config* c, bool* any) {
+    *any = true;
+    if (!h->comm || h->world <= 1) return REBCU_OK;            // no native transport: the caller takes the full path
+    const uint64_t N = h->N;
+    *any = false;
+    if (N == 0) return REBCU_OK;
+    if (h->compact_cap < h->cap) { *any = true; return REBCU_OK; }      // buffers of the full check not there yet: let it allocate them
+    const double bx = c->root_size * (double)c->N_root_x, by = c->root_size * (double)c->N_root_y, bz = c->root_size * (double)c->N_root_z;
+    uint64_t b, e; engine_shard(h, &b, &e);
+    unsigned long long* tab = h->counters + 16;                 // REBCU_MAX_RANKS words behind the 16 counters
+    CU_TRY(h, cudaMemsetAsync(h->counters, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (e > b) {
+        LaunchScope ls(h, TC_BOUNDARY);
+        open_flag_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(h->f(F_X) + b, h->f(F_Y) + b, h->f(F_Z) + b, e - b, 0, bx / 2., by / 2., bz / 2.,
+                                                                  h->compact_flag + b, h->counters);
+    }
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(tab + h->rank, h->counters, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    uint64_t bounds[REBCU_MAX_RANKS + 1];
+    for (int r = 0; r <= h->world; r++) bounds[r] = (uint64_t)r;
+    void* ptr = tab; int bytes = 8;
+    int err = comm_gather_ranges(h, &ptr, &bytes, 1, bounds);
+    if (err) return err;
+    CU_TRY(h, cudaMemcpyAsync(h->pinned, tab, (size_t)h->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->world; r++) if (h->pinned[r]) *any = true;
+    return REBCU_OK;
+}
+
 // Sharded runs: every rank checks EVERY particle (the positions are replicated after the exchange), so that
 // wraps and removals are applied identically everywhere.
 int boundary_check_full(rebcu_handle* h, rebcu_config* c) {

@@ -52,7 +52,7 @@ rebcu_handle* rebcu_create(int device, void* stream) {
     }
     bool ok = cudaMalloc(&h->ghosts_dev, sizeof(GhostShifts)) == cudaSuccess
            && cudaMalloc(&h->scratch, 64 * sizeof(double)) == cudaSuccess
-           && cudaMalloc(&h->counters, 16 * sizeof(unsigned long long)) == cudaSuccess
+           && cudaMalloc(&h->counters, (16 + REBCU_MAX_RANKS) * sizeof(unsigned long long)) == cudaSuccess
            && cudaMalloc(&h->scratch_big, 2 * 7 * 256 * sizeof(double)) == cudaSuccess
            && cudaMallocHost(&h->pinned, 32 * sizeof(unsigned long long)) == cudaSuccess
            && cudaMallocHost(&h->ghost_ring, GHOST_RING * sizeof(GhostShifts)) == cudaSuccess;

@@ -189,6 +189,7 @@ int comm_exchange(rebcu_handle* h, int need);
 int comm_gather_ranges(rebcu_handle* h, void** ptrs, const int* bytes, int n_arrays, const uint64_t* bounds);
 void comm_free(rebcu_handle* h);
 int boundary_check_full(rebcu_handle* h, rebcu_config* c);
+int boundary_open_probe(rebcu_handle* h, const rebcu_config* c, bool* any);
 int collision_resolve_device(rebcu_handle* h, const rebcu_config* c);
 int tree_shard_list(rebcu_handle* h, const uint32_t** list, uint64_t* n_work);
 void engine_ghost_shifts(const rebcu_config* c, int gx, int gy, int gz, GhostShifts* out);

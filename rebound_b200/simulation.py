@@ -214,6 +214,18 @@ class Engine:
     def collision_resolve(self, cfg):
         self._check(self.f["collision_resolve"](self.h, C.byref(cfg)))
 
+    def collision_resolve_pairs(self, resolver, rand_seed, plog=0.0, log_n=0):
+        """rebcu_collision_resolve_pairs on the list of the last search: `resolver(pair)` (a Python callable) gets one
+        abi.ResolvePair at a time and fills v1, v2, plog_term, logged.  Returns (rand_seed, plog, log_n, rounds)."""
+        def batch(_user, pairs, n):
+            for j in range(n):
+                resolver(pairs[j])
+            return 0
+        cb = abi.PAIR_RESOLVER(batch)
+        seed, pl, ln, rounds = C.c_uint(rand_seed), C.c_double(plog), C.c_uint64(log_n), C.c_int(0)
+        self._check(self.f["collision_resolve_pairs"](self.h, C.byref(seed), C.cast(cb, C.c_void_p), None, C.byref(pl), C.byref(ln), C.byref(rounds)))
+        return int(seed.value), pl.value, int(ln.value), int(rounds.value)
+
     def collision_stats(self):
         plog, n, seed, rounds = C.c_double(0), C.c_uint64(0), C.c_uint(0), C.c_int(0)
         self._check(self.f["collision_stats"](self.h, C.byref(plog), C.byref(n), C.byref(seed), C.byref(rounds)))

@@ -94,3 +94,81 @@ def test_device_resolve_is_reproducible(eng):
         outs.append((eng.download().tobytes(), eng.collision_stats()))
         eng.set_device_resolve(False)
     assert outs[0] == outs[1]
+
+
+def _hardsphere_python(eps_fn, min_v):
+    """reb_collision_resolve_hardsphere (src/collision.c:573-665) on one abi.ResolvePair, expression by expression, with
+    Python floats (IEEE doubles, no contraction) and the C library's atan2 / sin / cos / sqrt behind the math module."""
+    import math
+
+    def resolve(q):
+        x1, y1, z1, vx1, vy1, vz1, m1, r1 = list(q.s1)
+        x2, y2, z2, vx2, vy2, vz2, m2, r2 = list(q.s2)
+        x21 = x1 + q.gb.x - x2; y21 = y1 + q.gb.y - y2; z21 = z1 + q.gb.z - z2
+        rp = r1 + r2
+        oldvyouter = vy1 if x21 > 0 else vy2
+        if rp * rp < x21 * x21 + y21 * y21 + z21 * z21:
+            return
+        vx21 = vx1 + q.gb.vx - vx2; vy21 = vy1 + q.gb.vy - vy2; vz21 = vz1 + q.gb.vz - vz2
+        if vx21 * x21 + vy21 * y21 + vz21 * z21 > 0:
+            return
+        theta = math.atan2(z21, y21); stheta = math.sin(theta); ctheta = math.cos(theta)
+        vy21n = ctheta * vy21 + stheta * vz21
+        y21n = ctheta * y21 + stheta * z21
+        phi = math.atan2(y21n, x21); cphi = math.cos(phi); sphi = math.sin(phi)
+        vx21nn = cphi * vx21 + sphi * vy21n
+        eps = eps_fn(vx21nn)
+        dvx2 = -(1.0 + eps) * vx21nn
+        minr = r2 if r1 > r2 else r1
+        maxr = r2 if r1 < r2 else r1
+        mindv = minr * min_v
+        rr = math.sqrt(x21 * x21 + y21 * y21 + z21 * z21)
+        mindv *= 1. - (rr - maxr) / minr
+        if mindv > maxr * min_v:
+            mindv = maxr * min_v
+        if dvx2 < mindv:
+            dvx2 = mindv
+        dvx2n = cphi * dvx2; dvy2n = sphi * dvx2; dvy2nn = ctheta * dvy2n; dvz2nn = stheta * dvy2n
+        p2pf = m1 / (m1 + m2)
+        q.v2[0] = vx2 - p2pf * dvx2n; q.v2[1] = vy2 - p2pf * dvy2nn; q.v2[2] = vz2 - p2pf * dvz2nn
+        p1pf = m2 / (m1 + m2)
+        q.v1[0] = vx1 + p1pf * dvx2n; q.v1[1] = vy1 + p1pf * dvy2nn; q.v1[2] = vz1 + p1pf * dvz2nn
+        q.plog_term = -abs(x21) * (oldvyouter - q.v1[1]) * m1 if x21 > 0 else -abs(x21) * (oldvyouter - q.v2[1]) * m2
+        q.logged = 1
+    return resolve
+
+
+@pytest.mark.parametrize("law", [1, 2])
+def test_exact_resolve_with_the_callers_arithmetic_is_bitwise(eng, law):
+    """rebcu_collision_resolve_pairs: the device keeps the shuffled order, the sequential semantics and the early exits;
+    the caller supplies the arithmetic.  With a resolver that restates the reference's expressions on the C library's
+    trigonometry the result must be the oracle's BITS (velocities, collisions_plog, collisions_log_n, rand_seed) -- the
+    drop-in uses the reference's own function in that place (tests/test_gpu_dropin.py: sheet scenarios)."""
+    import math
+    p = ics.shearing_sheet(root_size=40.0, seed=5)
+    cfg = ics.shearing_sheet_config(root_size=40.0)
+    min_v = 1.0 * ics.SHEET_OMEGA * 0.001
+    steps = 4
+    want, cw, aux = checkers.oracle().steps(cfg, p, steps, resolve=law, minimum_collision_velocity=min_v)
+    if law == 1:
+        eps_fn = lambda v: 1.0
+    else:
+        eps_fn = lambda v: min(1.0, max(0.0, 0.32 * math.pow(abs(v) * 100., -0.234)))
+    resolver = _hardsphere_python(eps_fn, min_v)
+    eng.upload(np.ascontiguousarray(p))
+    c = cfg.copy()
+    seed, plog, logn = 42, 0.0, 0
+    nocol = c.copy()
+    rounds_seen = 0
+    for _ in range(steps):
+        # one step = integrator step, boundary check, search, resolve (src/simulation.c:527-584)
+        eng.integrator_step(c)
+        eng.boundary_check(c)
+        eng.collision_search(c, cap=1)
+        seed, plog, logn, rounds = eng.collision_resolve_pairs(resolver, seed, plog, logn)
+        rounds_seen = max(rounds_seen, rounds)
+    got = eng.download()
+    assert aux["collisions_log_n"] > 0 and logn == aux["collisions_log_n"]
+    assert checkers.bits_equal(got, want)
+    assert plog == aux["collisions_plog"]
+    assert rounds_seen >= 2
