@@ -58,8 +58,8 @@ static int exchange_fields(int need, int* fields) {
 
 // All-gathers rank-owned ranges of device arrays.  Array a has elements of `bytes[a]` bytes; rank r owns the elements
 // [bounds[r], bounds[r+1]) of every array (same bounds for all arrays of a call); afterwards every rank holds every
-// owner's range.  In place.  Equal ranges of 8-byte elements use ncclAllGather, everything else one ncclBroadcast per
-// (array, owner), all inside one NCCL group.
+// owner's range.  In place.  Equal ranges use ncclAllGather directly; ragged ranges go through equal-sized staging slots
+// (one ncclAllGather per array + device copies into place); all NCCL calls of one exchange form one group.
 static int gather_ranges(rebcu_handle* h, void** ptrs, const int* bytes, int n_arrays, const uint64_t* bounds) {
     EngineComm* C = h->comm;
     const int W = h->world, me = h->rank;
