@@ -638,8 +638,7 @@ __global__ void __launch_bounds__(128) row_fast_kernel(const RowArgs R, double* 
             const double dx = ri.x - src[k].x, dy = ri.y - src[k].y, dz = ri.z - src[k].z;
             const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
             const bool ok = (jj[k] < R.j1) & (jj[k] < ns) & (jj[k] != skip0) & (jj[k] != skip1);
-            const double q = fast_rsqrt(ok ? r2 : 1.0);
-            const double p = ok ? src[k].w * (q * q * q) : 0.0;
+            const double p = fast_m_over_r3(ok ? r2 : 1.0, ok ? src[k].w : 0.0);
             px = fma(p, dx, px); py = fma(p, dy, py); pz = fma(p, dz, pz);
         }
         for (int o = 16; o > 0; o >>= 1) {

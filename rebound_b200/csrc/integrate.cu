@@ -148,8 +148,7 @@ __device__ __forceinline__ void tp_force_fast(const double4* src, int Na, int se
         const double4 sj = src[j];
         const double dx = xi - sj.x, dy = yi - sj.y, dz = zi - sj.z;
         const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
-        const double ri = fast_rsqrt(r2);
-        const double p = negG * sj.w * (ri * ri * ri);
+        const double p = fast_m_over_r3(r2, negG * sj.w);
         if (!kahan) { ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az); }
         else {
             double y, t;
@@ -306,8 +305,7 @@ __global__ void __launch_bounds__(TP_PAIR_MAX * TP_PAIR_MAX) tp_history_pair_ker
             if (FAST) {
                 dx = xi - sj.x; dy = yi - sj.y; dz = zi - sj.z;
                 const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, a.soft2)));
-                const double ri = fast_rsqrt(r2);
-                p = negG * sj.w * (ri * ri * ri);
+                p = fast_m_over_r3(r2, negG * sj.w);
             } else {
                 dx = s_sub(xi, sj.x); dy = s_sub(yi, sj.y); dz = s_sub(zi, sj.z);
                 const double r2 = s_add(s_add(s_add(s_mul(dx, dx), s_mul(dy, dy)), s_mul(dz, dz)), a.soft2);

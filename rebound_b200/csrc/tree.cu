@@ -386,8 +386,7 @@ __device__ __forceinline__ unsigned walk_one(const WalkArgs& a, uint32_t self, d
                 if (w2 > s_mul(a.theta2, r2)) { c++; continue; }          // tree.c:284: open the cell
             } else if ((uint32_t)mt.x == self) { c = mt.y; continue; }    // tree.c:311
             if (MODE == 1) {
-                const double ri = fast_rsqrt(r2 + a.soft2);
-                const double p = negG * q.w * (ri * ri * ri);
+                const double p = fast_m_over_r3(r2 + a.soft2, negG * q.w);
                 sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
             } else if (MODE == 0) {
                 const double rs2 = s_add(r2, a.soft2);
@@ -430,8 +429,7 @@ template <int MODE>
 __device__ __forceinline__ void interact(const WalkArgs& a, double negG, double dx, double dy, double dz, double r2, double m,
                                          double& sx, double& sy, double& sz, unsigned& bad) {
     if (MODE == 1) {
-        const double ri = fast_rsqrt(r2 + a.soft2);
-        const double p = negG * m * (ri * ri * ri);
+        const double p = fast_m_over_r3(r2 + a.soft2, negG * m);
         sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
     } else if (MODE == 0) {
         const double rs2 = s_add(r2, a.soft2);
@@ -752,12 +750,60 @@ __device__ __forceinline__ void gw_evaluate(const double4* __restrict__ ent, int
     }
 }
 
+// Paired evaluation (PAIR kernels).  A broadcast LDS.128 writes 512 B of registers however few distinct addresses it reads,
+// and the shared-memory pipe returns 128 B per clock: the two loads of an entry cost 8 cycles per warp against 34 cycles
+// of FP64 issue -- with four warps per SM partition the two pipes are equally busy (the situation direct_fast_kernel was
+// in with one particle per lane).  Here lane L evaluates TWO particles of the group, (L & 15) and (L & 15) + 16, against
+// the entries of parity L >> 4: one pair of loads serves two pair terms.  The halves' partial sums meet in gw_pair_finish.
+// An odd list is padded with a massless copy of its last entry.  Pair term: fast_m_over_r3 (16 FP64 instructions, full
+// precision), or with CHEAP fast_m_over_r3_tree (15; measured and not shipped, see fast_math.cuh).
+template <int UNROLL, bool CHEAP>
+__device__ __forceinline__ void gw_evaluate_pair(double4* __restrict__ ent, int n, int half, double pxa, double pya, double pza,
+                                                 double pxb, double pyb, double pzb, double soft2,
+                                                 double& sxa, double& sya, double& sza, double& sxb, double& syb, double& szb) {
+    if (n & 1) {
+        if ((threadIdx.x & 31) == 0) { double4 e = ent[n - 1]; e.w = 0.; ent[n] = e; }
+        __syncwarp();
+    }
+    const int np = (n + 1) >> 1;
+    const double4* __restrict__ mine = ent + half;
+#pragma unroll UNROLL
+    for (int j = 0; j < np; j++) {
+        const double4 s = mine[2 * j];
+        const double dxa = pxa - s.x, dya = pya - s.y, dza = pza - s.z;
+        const double dxb = pxb - s.x, dyb = pyb - s.y, dzb = pzb - s.z;
+        const double r2a = fma(dxa, dxa, fma(dya, dya, fma(dza, dza, soft2)));
+        const double r2b = fma(dxb, dxb, fma(dyb, dyb, fma(dzb, dzb, soft2)));
+        const double fa = CHEAP ? fast_m_over_r3_tree(r2a, s.w) : fast_m_over_r3(r2a, s.w);
+        const double fb = CHEAP ? fast_m_over_r3_tree(r2b, s.w) : fast_m_over_r3(r2b, s.w);
+        sxa = fma(fa, dxa, sxa); sya = fma(fa, dya, sya); sza = fma(fa, dza, sza);
+        sxb = fma(fb, dxb, sxb); syb = fma(fb, dyb, syb); szb = fma(fb, dzb, szb);
+    }
+}
+
+// lane L ends up with the complete sum of ITS particle: the a-sums for L < 16, the b-sums for L >= 16
+__device__ __forceinline__ double gw_pair_finish(double sa, double sb, int half) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+    sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+    return half ? sb : sa;
+}
+
+// Exact group criterion (EXACT kernels).  The bounding-box test is conservative: it opens every cell SOME point of the box
+// would open, and 32 key-adjacent particles fill their box sparsely (a Z-order run is L-shaped or split as often as not).
+// The tightest criterion a shared list allows is "accept iff every particle of the group accepts the cell" (tree.c:284
+// for each of them).  It is evaluated only where the box cannot decide: a cell the box accepts is accepted; a cell that
+// even the FARTHEST point of the box would open is opened; the cells in between (a third of the internal cells visited)
+// are parked in shared memory and every lane tests them against its own particle, the verdicts being OR-ed across the
+// warp.  Measured on the CPU model of the walk (disc, N = 2^17, 150 groups): list 1080 entries instead of 1430
+// (per-particle lists: 609), 1408 instead of 1916 visited cells, and the longest list 1638 instead of 6778 -- the groups
+// that had to give up with the box criterion finish here like all others.
 // retry: [0] = number of groups that gave up, [1...] = their first work item; walk_retry_kernel finishes them.
-template <int WARPS, int UNROLL, int MINB, int LIST, int STACK>
+template <int WARPS, int UNROLL, int MINB, int LIST, int STACK, bool PAIR = false, bool EXACT = false, bool CHEAP = true>
 __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const WalkArgs a, unsigned long long* __restrict__ stats,
                                                                       unsigned int* __restrict__ retry) {
     __shared__ int2 s_stack[WARPS][STACK];
-    __shared__ double4 s_ent[WARPS][LIST];
+    __shared__ double4 s_ent[WARPS][LIST + (PAIR ? 1 : 0)];
+    __shared__ double4 s_amb[EXACT ? WARPS : 1][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint64_t t0 = ((uint64_t)blockIdx.x * WARPS + w) * 32;
     if (t0 >= a.n_work) return;                              // warp-uniform; no block-wide barrier below
@@ -781,6 +827,13 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
     const int ngb = a.ghosts->n;
     const int stack_cap = a.gw_stack < STACK ? a.gw_stack : STACK;
     double sx = 0., sy = 0., sz = 0.;
+    // PAIR: this lane's two particles (see gw_evaluate_pair) and their partial sums
+    const int half = lane >> 4;
+    double pxa = 0., pya = 0., pza = 0., pxb = 0., pyb = 0., pzb = 0., sxb = 0., syb = 0., szb = 0.;
+    if (PAIR) {
+        pxa = __shfl_sync(0xffffffffu, px, lane & 15); pya = __shfl_sync(0xffffffffu, py, lane & 15); pza = __shfl_sync(0xffffffffu, pz, lane & 15);
+        pxb = __shfl_sync(0xffffffffu, px, (lane & 15) + 16); pyb = __shfl_sync(0xffffffffu, py, (lane & 15) + 16); pzb = __shfl_sync(0xffffffffu, pz, (lane & 15) + 16);
+    }
     int nl = 0;
     bool overflow = false;
     unsigned int n_ent = 0, n_vis = 0;
@@ -798,10 +851,10 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
             if (lane < n) { const int2 e = stack[sp - 1 - lane]; c = e.x; end = e.y; }
             sp -= n;
             __syncwarp();
-            bool open = false;
+            bool open = false, amb = false;
             int skip = 0, tag = 0;
             double4 q = make_double4(0., 0., 0., 0.);
-            double cm = 0.;
+            double cm = 0., w2c = 0.;
             if (c >= 0) {
                 q = ld_pos256(a.rec + c);
                 cm = a.m[c];                                  // requested together with the record: one latency, not two
@@ -812,9 +865,36 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
                     const int hi = tag & 0x7fffffff;
                     double w2 = __hiloint2double(hi, (int)a.w2_lo);
                     if (hi == 0) w2 = cell_w2_rare(a.root_size, -a.meta2[c].x - 1);
-                    const double ex = fmax(fabs(q.x - bx) - hxg, 0.), ey = fmax(fabs(q.y - by) - hyg, 0.), ez = fmax(fabs(q.z - bz) - hzg, 0.);
+                    const double ux = fabs(q.x - bx), uy = fabs(q.y - by), uz = fabs(q.z - bz);
+                    const double ex = fmax(ux - hxg, 0.), ey = fmax(uy - hyg, 0.), ez = fmax(uz - hzg, 0.);
                     const double d2 = fma(ex, ex, fma(ey, ey, ez * ez));
                     open = w2 > a.theta2 * d2;
+                    if (EXACT) {
+                        const double fx = ux + hxg, fy = uy + hyg, fz = uz + hzg;      // farthest point of the box
+                        amb = open && !(w2 > a.theta2 * fma(fx, fx, fma(fy, fy, fz * fz)));
+                        w2c = w2;
+                    }
+                }
+            }
+            if (EXACT) {
+                const unsigned m_amb = __ballot_sync(0xffffffffu, amb);
+                if (m_amb) {                                  // warp-uniform
+                    double4* parked = s_amb[w];
+                    const int mine = __popc(m_amb & lt);
+                    if (amb) parked[mine] = make_double4(q.x - gbx, q.y - gby, q.z - gbz, w2c);
+                    __syncwarp();
+                    const int na = __popc(m_amb);
+                    unsigned verdict = 0;                     // bit i: my particle would open parked cell i (tree.c:284)
+#pragma unroll 4
+                    for (int i = 0; i < na; i++) {
+                        const double4 pc = parked[i];
+                        const double dx = px - pc.x, dy = py - pc.y, dz = pz - pc.z;
+                        const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                        verdict |= (pc.w > a.theta2 * r2 ? 1u : 0u) << i;
+                    }
+                    verdict = __reduce_or_sync(0xffffffffu, verdict);
+                    if (amb) open = (verdict >> mine) & 1u;
+                    __syncwarp();
                 }
             }
             const bool acc = c >= 0 && !open;
@@ -828,7 +908,8 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
             sp += n_sib + __popc(m_open);
             if (nl + n_acc > LIST) {
                 __syncwarp();
-                gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
+                if (PAIR) gw_evaluate_pair<UNROLL, CHEAP>(ent, nl, half, pxa, pya, pza, pxb, pyb, pzb, soft2, sx, sy, sz, sxb, syb, szb);
+                else gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
                 n_ent += nl;
                 nl = 0;
                 __syncwarp();
@@ -850,7 +931,10 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) walk_group_kernel(const Walk
         return;
     }
     __syncwarp();
-    gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
+    if (PAIR) {
+        gw_evaluate_pair<UNROLL, CHEAP>(ent, nl, half, pxa, pya, pza, pxb, pyb, pzb, soft2, sx, sy, sz, sxb, syb, szb);
+        sx = gw_pair_finish(sx, sxb, half); sy = gw_pair_finish(sy, syb, half); sz = gw_pair_finish(sz, szb, half);
+    } else gw_evaluate<UNROLL>(ent, nl, px, py, pz, soft2, sx, sy, sz);
     n_ent += nl;
     const double negG = -a.G;
     if (live) store_acc(a, (uint32_t)self, k, negG * sx, negG * sy, negG * sz);
@@ -1617,9 +1701,26 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
                     case 5:  walk_group_kernel<4, 4, 8, 96, 224><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
                     case 6:  walk_group_kernel<1, 2, 32, 96, 224><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
                     case 0:  walk_group_kernel<4, 4, 5, 160, 352><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
-                    // shapes measured at N = 2^20 / 2^22 (profiles/r02_walk_group_shapes.txt): all within 8 % -- the kernel is
-                    // bound by its instruction mix, not by occupancy; one warp per CTA with the deepest unroll is the best
-                    default: walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    // shapes a-g measured at N = 2^20 / 2^22 (profiles/r02_walk_group_shapes.txt): all within 8 % -- the kernel is
+                    // bound by its instruction mix, not by occupancy.  h-q (profiles/r02_walk_group_ab.txt): paired evaluation
+                    // -7 %, exact group criterion -16 % (2^24) ... -31 % (2^20) and no group gives up any more.  The 15-instruction
+                    // pair term (h-p) would take another 6 % but misses the 1e-12 of the theta = 0 tests (the hardware seed is
+                    // good to 2^-19.5 only), so the shipped kernel keeps the 16-instruction term of the direct kernels.
+                    case 17: walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    // paired evaluation (two particles per lane, half the shared-memory loads; gw_evaluate_pair)
+                    case 7:  walk_group_kernel<1, 4, 16, 160, 352, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 8:  walk_group_kernel<1, 2, 16, 160, 352, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 9:  walk_group_kernel<1, 4, 12, 160, 352, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 10: walk_group_kernel<2, 4, 8, 160, 352, true><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    // exact group criterion (the intersection of the particles' own criteria) where the box cannot decide
+                    case 11: walk_group_kernel<1, 8, 16, 160, 352, false, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 12: walk_group_kernel<1, 4, 16, 160, 352, true, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 13: walk_group_kernel<1, 2, 16, 160, 352, true, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 14: walk_group_kernel<2, 4, 8, 160, 352, true, true><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 15: walk_group_kernel<1, 4, 12, 160, 352, true, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    // the same with the 16-instruction pair term of the direct kernels (full precision)
+                    case 16: walk_group_kernel<1, 4, 16, 160, 352, true, true, false><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    default: walk_group_kernel<2, 4, 8, 160, 352, true, true, false><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
                 }
                 walk_retry_kernel<<<div_up((uint64_t)ng * 32, 128), 128, 0, h->stream>>>(a, retry);
             } else {
