@@ -35,7 +35,7 @@ import numpy as np  # noqa: E402
 BRIDGES = (0.32, 100.0, -0.234, 0.0, 1.0)        # examples/shearing_sheet/problem.c:96-103
 FLOP_PER_INTERACTION = {"basic": 20.0, "compensated": 29.0}
 # FP64-pipe instructions per pair term (SASS counts): strict = IEEE sqrt + divide expanded
-DP_PER_PAIR = {("basic", "strict"): 36.0, ("basic", "fast"): 17.0, ("compensated", "strict"): 45.0, ("compensated", "fast"): 26.0}
+DP_PER_PAIR = {("basic", "strict"): 36.0, ("basic", "fast"): 16.0, ("compensated", "strict"): 45.0, ("compensated", "fast"): 25.0}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -608,16 +608,17 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
             k_ms = tim[cls]["ms"]                      # walk_pack + walk of one force evaluation
             grouped = tag == "fast" and st["groups"] > 0        # FAST without ghost boxes: the group walk
             evaluated = st["group_entries"] * 32 if grouped else st["interactions"]
-            # FP64-pipe instructions: 17 (FAST) / 36 (STRICT) per pair term; the per-particle walks add 8 per visited cell
-            dp = 17.0 * evaluated if grouped else (17.0 if tag == "fast" else 36.0) * evaluated + 8.0 * st["visits"]
+            # FP64-pipe instructions: 16 (FAST, fast_math.cuh) / 36 (STRICT) per pair term; the per-particle walks add 8 per
+            # visited cell (the group walk's traversal and exact-criterion tests are not counted: a lower bound)
+            dp = 16.0 * evaluated if grouped else (16.0 if tag == "fast" else 36.0) * evaluated + 8.0 * st["visits"]
             kern = "walk_group_kernel" if grouped else ("walk_rec_kernel<FAST>" if tag == "fast" else "walk_rec_kernel")
             roof = fp64_roofline(kern, 20.0 * st["interactions"], k_ms, fp64_peak, dp, sm_mhz, tim[cls]["ms"] / total,
                                  traffic.get(f"{name}_{tag}"),
                                  "algorithmic work = the interactions of the reference's per-particle opening criterion on this tree "
                                  f"({st['interactions'] / max(1, n / ctx.world):.0f} per particle) x 20 flop; the group walk evaluates "
-                                 f"{st['group_entries'] * 32 / max(1, st['interactions']):.2f}x as many pair terms (stricter group criterion)" if grouped else
+                                 f"{st['group_entries'] * 32 / max(1, st['interactions']):.2f}x as many pair terms (group criterion = every particle of the group accepts the cell)" if grouped else
                                  "algorithmic work = accepted cells + leaves of the per-particle walk x 20 flop; "
-                                 f"{17 if tag == 'fast' else 36} FP64-pipe instructions per interaction + 8 per visited cell")
+                                 f"{16 if tag == 'fast' else 36} FP64-pipe instructions per interaction + 8 per visited cell")
             roof["interactions_per_particle"] = st["interactions"] / max(1, n / ctx.world)
             if grouped:
                 roof["evaluated_pair_terms_per_particle"] = st["group_entries"] * 32 / max(1, n / ctx.world)

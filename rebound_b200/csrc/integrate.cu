@@ -138,17 +138,19 @@ __device__ __forceinline__ unsigned tp_force_strict(const double4* src, int Na, 
     return wmax;
 }
 
+// premul: the source records already hold -G*m in .w (tp_multistep_kernel writes them that way once per step and CTA,
+// which takes the multiplication out of the pair term: the same product, hence the same bits)
 __device__ __forceinline__ void tp_force_fast(const double4* src, int Na, int self, double xi, double yi, double zi,
-                                              double G, double soft2, bool kahan, double& ax, double& ay, double& az) {
+                                              double G, double soft2, bool kahan, double& ax, double& ay, double& az, bool premul = false) {
     double cx = 0, cy = 0, cz = 0;
     ax = ay = az = 0;
-    const double negG = -G;
+    const double negG = premul ? 1.0 : -G;
     for (int j = 0; j < Na; j++) {
         if (j == self) continue;
         const double4 sj = src[j];
         const double dx = xi - sj.x, dy = yi - sj.y, dz = zi - sj.z;
         const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, soft2)));
-        const double p = fast_m_over_r3(r2, negG * sj.w);
+        const double p = fast_m_over_r3(r2, premul ? sj.w : negG * sj.w);
         if (!kahan) { ax = fma(p, dx, ax); ay = fma(p, dy, ay); az = fma(p, dz, az); }
         else {
             double y, t;
@@ -228,10 +230,10 @@ struct TpMultiArgs {
 
 template <bool FAST, bool KAHAN>
 __device__ __forceinline__ void tp_force_any(const double4* src, int Na, int self, bool warp_has_self, double x, double y, double z,
-                                             const TpMultiArgs& a, double& ax, double& ay, double& az) {
+                                             const TpMultiArgs& a, double& ax, double& ay, double& az, bool premul = false) {
     double xi = x, yi = y, zi = z;
     if (!KAHAN) { xi = s_add(a.gbx, x); yi = s_add(a.gby, y); zi = s_add(a.gbz, z); }
-    if (FAST) { tp_force_fast(src, Na, self, xi, yi, zi, a.G, a.soft2, KAHAN, ax, ay, az); return; }
+    if (FAST) { tp_force_fast(src, Na, self, xi, yi, zi, a.G, a.soft2, KAHAN, ax, ay, az, premul); return; }
     unsigned w = STRICT_WINDOW_LIMIT;
     if (a.windowed) {
         if (warp_has_self) w = tp_force_strict<KAHAN, true, true>(src, Na, self, xi, yi, zi, a.G, a.soft2, ax, ay, az);
@@ -375,12 +377,12 @@ __global__ void __launch_bounds__(TP_BLOCK) tp_multistep_kernel(const TpMultiArg
             if (st == 0) {
                 sx = s_add(sx, s_mul(a.d0, hs[3 * Na + j])); sy = s_add(sy, s_mul(a.d0, hs[4 * Na + j])); sz = s_add(sz, s_mul(a.d0, hs[5 * Na + j]));
             }
-            buf[j] = make_double4(sx, sy, sz, hs[6 * Na + j]);
+            buf[j] = make_double4(sx, sy, sz, FAST ? -a.G * hs[6 * Na + j] : hs[6 * Na + j]);
         }
         __syncthreads();      // one barrier per step: the other buffer is only rewritten two steps later
         if (live) {
             if (st == 0) { x = s_add(x, s_mul(a.d0, vx)); y = s_add(y, s_mul(a.d0, vy)); z = s_add(z, s_mul(a.d0, vz)); }
-            tp_force_any<FAST, KAHAN>(buf, Na, -1, false, x, y, z, a, ax, ay, az);
+            tp_force_any<FAST, KAHAN>(buf, Na, -1, false, x, y, z, a, ax, ay, az, FAST);
             vx = s_add(vx, s_mul(a.k, ax)); vy = s_add(vy, s_mul(a.k, ay)); vz = s_add(vz, s_mul(a.k, az));
             x = s_add(x, s_mul(a.d1, vx)); y = s_add(y, s_mul(a.d1, vy)); z = s_add(z, s_mul(a.d1, vz));
             if (st + 1 < a.n_steps) { x = s_add(x, s_mul(a.d2, vx)); y = s_add(y, s_mul(a.d2, vy)); z = s_add(z, s_mul(a.d2, vz)); }

@@ -671,8 +671,7 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
                 } else if ((uint32_t)mt.x == self) interact = false;                     // tree.c:311
                 if (interact) {
                     if (MODE == 1) {
-                        const double ri = fast_rsqrt(r2 + a.soft2);
-                        const double p = negG * q.w * (ri * ri * ri);
+                        const double p = fast_m_over_r3(r2 + a.soft2, negG * q.w);
                         sx = fma(p, dx, sx); sy = fma(p, dy, sy); sz = fma(p, dz, sz);
                     } else if (MODE == 0) {
                         const double rs2 = s_add(r2, a.soft2);
@@ -1707,6 +1706,10 @@ int tree_gravity(rebcu_handle* h, rebcu_config* c) {
                     // pair term (h-p) would take another 6 % but misses the 1e-12 of the theta = 0 tests (the hardware seed is
                     // good to 2^-19.5 only), so the shipped kernel keeps the 16-instruction term of the direct kernels.
                     case 17: walk_group_kernel<1, 8, 16, 160, 352><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 18: walk_group_kernel<4, 4, 4, 160, 352, true, true, false><<<div_up(ng, 4), 128, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 19: walk_group_kernel<2, 8, 8, 160, 352, true, true, false><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 20: walk_group_kernel<2, 2, 8, 160, 352, true, true, false><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
+                    case 21: walk_group_kernel<2, 4, 8, 224, 352, true, true, false><<<div_up(ng, 2), 64, 0, h->stream>>>(a, h->counters + 8, retry); break;
                     // paired evaluation (two particles per lane, half the shared-memory loads; gw_evaluate_pair)
                     case 7:  walk_group_kernel<1, 4, 16, 160, 352, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
                     case 8:  walk_group_kernel<1, 2, 16, 160, 352, true><<<ng, 32, 0, h->stream>>>(a, h->counters + 8, retry); break;
