@@ -526,7 +526,8 @@ def measure_config(ctx, name, args, steps, warmup, headline=False):
     sharded = ctx.world > 1
     big = n * 48 > (126 << 20)                     # resident x,v larger than L2
     hbm_peak, hbm_src = load_peaks()
-    traffic = load_traffic()
+    # the captures are single-GPU launches of the default problem sizes: null on a sharded run or with --n-log2
+    traffic = {} if (sharded or args.n_log2) else load_traffic()
     out = {"metric": w["metric"], "unit": w["unit"], "config": {"workload": w["desc"], "N": int(n), "inner_steps_per_step": inner}}
     min_v = ics.SHEET_OMEGA * 0.001
     modes = [("fast", abi.MODE_FAST), ("strict", abi.MODE_STRICT)]
