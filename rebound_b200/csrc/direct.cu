@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(32 * SPLIT_W) direct_strict_split_kernel(const
 // Block = 32*IPT particles x W warps: every lane owns IPT particles (register tiling: one shared-memory read of a
 // source serves IPT pair terms), warp w handles source chunks w, w+W, ... of 32 sources each, staged in a private
 // shared-memory slab (double buffered through registers), and the W partial sums are combined in warp order.
-// The pair term is fast_math.cuh's: 17 FP64 instructions (26 with the Kahan update), -G folded into the staged mass.
+// The pair term is fast_math.cuh's: 16 FP64 instructions (25 with the Kahan update), -G folded into the staged mass.
 // Chunks that every particle of the block uses in full -- inside the common source range, not holding any of the
 // block's own particles nor a source excluded by gravity_ignore_terms -- run a loop without any per-pair predicate;
 // the few remaining chunks (the block's diagonal, the end of the range) select mass 0 / r2 1 for the excluded pairs.

@@ -703,15 +703,17 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(const WalkArgs a) {
 //                tests its first cell against the GROUP's bounding box, and pushes the rest of the range (skip, end)
 //                and, if the cell has to be opened, its children (cell+1, skip).  32 cells are tested per trip on the
 //                pre-order records the build already emits (no child table needed).
-//  * criterion   a cell is accepted iff  w^2 <= theta^2 * d^2  with d the distance from its centre of mass to the
-//                nearest point of the group's bounding box: d <= |x_i - com| for every particle i of the group, so
-//                the cell would also be accepted by each particle's own test (src/tree.c:284) -- the group criterion
-//                is at least as strict, the error against direct summation at most the reference's.
-//  * list        accepted cells and leaves are compacted (ballot + popc) into a shared-memory list (x,y,z,m | particle
-//                index of a leaf) with the ghost-box shift already removed; whenever the list cannot take 32 more
-//                entries, ALL 32 lanes evaluate every entry for their own particle (broadcast LDS, 17 FP64
-//                instructions per pair, fast_math.cuh).  The own leaf and its ghost images (src/tree.c:311) are
-//                skipped by an integer compare that zeroes the mass.
+//  * criterion   box criterion (first kernels): a cell is accepted iff  w^2 <= theta^2 * d^2  with d the distance from its
+//                centre of mass to the nearest point of the group's bounding box: d <= |x_i - com| for every particle i
+//                of the group, so the cell would also be accepted by each particle's own test (src/tree.c:284).
+//                Shipped (EXACT kernels, see below): where the box cannot decide, every particle is asked -- the group
+//                criterion is then exactly as strict as its strictest particle; either way the error against direct
+//                summation is at most the reference's.
+//  * list        accepted cells and leaves are compacted (ballot + popc) into a shared-memory list (x,y,z,m) with the
+//                ghost-box shift already removed; whenever the list cannot take 32 more entries, the warp evaluates
+//                every entry for all its particles (broadcast LDS, 16 FP64 instructions per pair, fast_math.cuh; the
+//                shipped PAIR kernels give every lane two particles and half the entries, see below).  The own leaf
+//                contributes f * 0 = 0 exactly (no per-entry identity test, see gw_evaluate).
 // The traversal costs a few instructions per visited cell per warp; the evaluation is pure FP64-pipe work with all
 // lanes active.  The sum order differs from the reference's, so this is FAST mode only (tolerance stated in the tests).
 // A stack that would overflow (trees deeper than ~GW_STACK levels) sends the warp to the per-particle FAST walk, and so does
