@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" hot-path entry points of include/rebound_b200.h that compose the kernels:
 // force dispatch, integrator step, whole steps, and the host-buffer drop-ins the shim calls.
 #include "engine.cuh"
+#include <time.h>
 
 // reb_simulation_update_acceleration, src/simulation.c:640-689 (the GPU-resident gravity modes).
 int update_acceleration(rebcu_handle* h, rebcu_config* c) {
@@ -102,12 +103,18 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
     const bool can_carry = cfg->integrator == REBCU_INTEGRATOR_LEAPFROG && cfg->boundary == REBCU_BOUNDARY_NONE
                         && cfg->collision == REBCU_COLLISION_NONE && h->exchange == nullptr && h->comm == nullptr;
     bool carried = false;
+    // REBOUND_B200_STEP_TRACE=1: per step, host wall clock of the phases with the stream drained after each (stderr)
+    static const bool trace = getenv("REBOUND_B200_STEP_TRACE") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    auto lap = [&](double& t) { if (!trace) return 0.; cudaStreamSynchronize(h->stream); const double u = now(), d = u - t; t = u; return 1e3 * d; };
     for (uint64_t s = 0; s < n_steps; s++) {
         const bool stop = interrupted();              // finish this step (a carried half-kick must be closed), then leave
         const bool last = (s + 1 == n_steps) || stop;
         const bool carry_out = can_carry && !last;
+        double t_lap = trace ? now() : 0.;
         int err = integrator_step(h, cfg, carried, carry_out, last);
         if (err) return err;
+        const double ms_step = lap(t_lap);
         carried = carry_out;
         if (h->world > 1 && cfg->boundary == REBCU_BOUNDARY_OPEN) {
             // every rank must see every particle's final position to agree on what left the box -- but only when some
@@ -122,9 +129,12 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
             err = boundary_check(h, cfg);
         }
         if (err) return err;
+        const double ms_boundary = lap(t_lap);
+        double ms_search = 0., ms_resolve = 0.;
         if (cfg->collision != REBCU_COLLISION_NONE) {
             err = collision_search(h, cfg);
             if (err) return err;
+            ms_search = lap(t_lap);
             if (h->resolve_on) {
                 err = collision_resolve_device(h, cfg);
                 if (err) return err;
@@ -132,7 +142,10 @@ int rebcu_steps(rebcu_handle* h, rebcu_config* cfg, uint64_t n_steps) {
                 err = h->collision_hook(h->collision_hook_user);
                 if (err) return err;
             }
+            ms_resolve = lap(t_lap);
         }
+        if (trace) fprintf(stderr, "[step %llu] integrator %.2f ms, boundary %.2f, collision search %.2f, resolve %.2f\n",
+                           (unsigned long long)s, ms_step, ms_boundary, ms_search, ms_resolve);
         if (stop && s + 1 < n_steps) return REBCU_INTERRUPTED;
     }
     return REBCU_OK;
